@@ -1,0 +1,512 @@
+/*
+ * Host-side building blocks of the GPU worker: PRNG for offsets, offset plans, latency histogram,
+ * live counters and the normalised configuration.
+ *
+ * Semantics follow the reference (cited per item); the code is organised for the batched
+ * pipeline of this worker: an OffsetPlan hands out (offset, length) pairs ahead of completion
+ * (aio-style accounting, LocalWorker.cpp:1870), and all counters are relaxed atomics that the
+ * stats/manager threads read while the worker runs (Worker.h:43-60).
+ */
+#ifndef ELB_HOST_H_
+#define ELB_HOST_H_
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "elbencho_b200.h"
+
+namespace elb
+{
+
+/* Error type of the worker thread; what() is the reference's WorkerException text
+ * (source/workers/WorkerException.h) */
+class WorkerError : public std::runtime_error
+{
+	public:
+		explicit WorkerError(const std::string& msg) : std::runtime_error(msg) {}
+};
+
+/* thrown when a friendly interruption request was seen (Worker.cpp:72-76) */
+class WorkerInterrupted : public std::runtime_error
+{
+	public:
+		WorkerInterrupted() :
+			std::runtime_error("Received friendly request to interrupt execution.") {}
+};
+
+/* ---- PRNG for random offsets: xoshiro256** (toolkits/random/RandAlgoXoshiro256ss.h:76-91),
+ * the reference's default "balanced_single" offset algorithm (LocalWorker.cpp:1135-1136).
+ * Seeded either from std::random_device like the reference (:22-29) or from an injected 64-bit
+ * seed expanded through splitmix64 (for reproducible runs/tests). ---- */
+class Xoshiro256ss
+{
+	public:
+		Xoshiro256ss()
+		{
+			std::random_device randDev;
+			for(uint64_t& word : state)
+				word = ( (uint64_t)randDev() << 32) | (uint32_t)randDev();
+		}
+
+		explicit Xoshiro256ss(const uint64_t initState[4])
+		{
+			std::memcpy(state, initState, sizeof(state) );
+		}
+
+		/* expansion used for injected seeds: state[i] = splitmix64 output i+1 of
+		 * (seed + rank*GOLDEN) */
+		static Xoshiro256ss fromSeed(uint64_t seed, uint64_t rank)
+		{
+			uint64_t expanded[4];
+			expandSeed(seed, rank, expanded);
+			return Xoshiro256ss(expanded);
+		}
+
+		static void expandSeed(uint64_t seed, uint64_t rank, uint64_t outState[4])
+		{
+			uint64_t counter = seed + rank * 0x9E3779B97F4A7C15ULL;
+			for(int i = 0; i < 4; i++)
+			{
+				counter += 0x9E3779B97F4A7C15ULL;
+				uint64_t z = counter;
+				z = (z ^ (z >> 30) ) * 0xBF58476D1CE4E5B9ULL;
+				z = (z ^ (z >> 27) ) * 0x94D049BB133111EBULL;
+				outState[i] = z ^ (z >> 31);
+			}
+		}
+
+		uint64_t next()
+		{
+			const uint64_t result = rotl(state[1] * 5, 7) * 9;
+			const uint64_t shifted = state[1] << 17;
+
+			state[2] ^= state[0];
+			state[3] ^= state[1];
+			state[1] ^= state[2];
+			state[0] ^= state[3];
+			state[2] ^= shifted;
+			state[3] = rotl(state[3], 45);
+
+			return result;
+		}
+
+		/* value in [minVal, maxVal] by plain modulo like RandAlgoRange.h:50-54 */
+		uint64_t nextInRange(uint64_t minVal, uint64_t maxVal)
+		{
+			return minVal + (next() % (maxVal - minVal + 1) );
+		}
+
+		const uint64_t* getState() const { return state; }
+
+	private:
+		uint64_t state[4];
+
+		static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k) ); }
+};
+
+/* ---- Offset plans (toolkits/offsetgen/OffsetGenerator.h, OffsetGenRandomAlignedFullCoverageV2.h)
+ *
+ * One class instead of the reference's hierarchy: the pipeline asks for the next (offset, len)
+ * and immediately accounts the requested length (the aio loop's rule, LocalWorker.cpp:1870,2028).
+ * ---- */
+class OffsetPlan
+{
+	public:
+		enum Kind
+		{
+			Kind_SEQUENTIAL = 0,       // OffsetGenSequential :48-102
+			Kind_REVERSE = 1,          // OffsetGenReverseSeq :107-178
+			Kind_RANDOM_UNALIGNED = 2, // OffsetGenRandom :186-243
+			Kind_RANDOM_ALIGNED = 3,   // OffsetGenRandomAligned :252-318
+			Kind_STRIDED = 4,          // OffsetGenStrided :323-378
+			Kind_FULL_COVERAGE = 5,    // OffsetGenRandomAlignedFullCoverageV2
+		};
+
+		/**
+		 * @amount bytes to submit in total for the random kinds (randomAmount share); the
+		 *    sequential kinds use rangeLen.
+		 * @lcgSeedSource produces the 32-bit start states of the full coverage permutation
+		 *    (the reference uses std::random_device for every cycle, FullCoverageV2.h:93,158).
+		 */
+		OffsetPlan(Kind kind, uint64_t amount, uint64_t rangeLen, uint64_t rangeOffset,
+			uint64_t blockSize, uint64_t numDataSetThreads, Xoshiro256ss* randAlgo,
+			uint64_t lcgSeed, bool haveLCGSeed) :
+			kind(kind), blockSize(blockSize), numDataSetThreads(numDataSetThreads),
+			randAlgo(randAlgo), lcgSeedState(lcgSeed), haveLCGSeed(haveLCGSeed)
+		{
+			const bool isRandomKind = (kind == Kind_RANDOM_UNALIGNED) ||
+				(kind == Kind_RANDOM_ALIGNED) || (kind == Kind_FULL_COVERAGE);
+
+			numBytesTotal = isRandomKind ? amount : rangeLen;
+			numBytesLeft = numBytesTotal;
+
+			setRange(rangeLen, rangeOffset);
+		}
+
+		/* reset for the next file of the same size (OffsetGenerator::reset() ) */
+		void restart()
+		{
+			numBytesLeft = numBytesTotal;
+
+			if( (kind == Kind_SEQUENTIAL) || (kind == Kind_STRIDED) )
+				currentOffset = startOffset;
+			else
+			if(kind == Kind_REVERSE)
+				initReverseStart();
+			else
+			if(kind == Kind_FULL_COVERAGE)
+				beginCoverageCycle();
+		}
+
+		/* reset(len, offset): new range; for random kinds the amount becomes len (see warning at
+		 * OffsetGenerator.h:33-34) */
+		void restart(uint64_t rangeLen, uint64_t rangeOffset)
+		{
+			numBytesTotal = rangeLen;
+			numBytesLeft = rangeLen;
+
+			setRange(rangeLen, rangeOffset);
+		}
+
+		uint64_t getNumBytesTotal() const { return numBytesTotal; }
+		uint64_t getNumBytesLeftToSubmit() const { return numBytesLeft; }
+		uint64_t getBlockSize() const { return blockSize; }
+
+		/**
+		 * Hand out the next block and account its full requested length as submitted.
+		 * @return false if nothing is left to submit.
+		 */
+		bool nextBlock(uint64_t& outOffset, uint64_t& outLen)
+		{
+			if(!numBytesLeft)
+				return false;
+
+			switch(kind)
+			{
+				case Kind_SEQUENTIAL:
+				{
+					outOffset = currentOffset;
+					outLen = std::min(numBytesLeft, blockSize);
+					currentOffset += outLen;
+				} break;
+
+				case Kind_REVERSE:
+				{ // the first (highest) block is the partial one (:164-165); steps back by blockSize
+					outOffset = currentOffset;
+					outLen = std::min(startOffset + numBytesTotal - currentOffset, blockSize);
+					currentOffset -= blockSize;
+				} break;
+
+				case Kind_STRIDED:
+				{
+					outOffset = currentOffset;
+					outLen = std::min(numBytesLeft, blockSize);
+					currentOffset += (blockSize * numDataSetThreads);
+				} break;
+
+				case Kind_RANDOM_UNALIGNED:
+				{
+					outOffset = randAlgo->nextInRange(randMin, randMax);
+					outLen = std::min(numBytesLeft, blockSize);
+				} break;
+
+				case Kind_RANDOM_ALIGNED:
+				{
+					outOffset = startOffset + (randAlgo->nextInRange(randMin, randMax) * blockSize);
+					outLen = std::min(numBytesLeft, blockSize);
+				} break;
+
+				case Kind_FULL_COVERAGE:
+				{
+					outOffset = nextCoverageIndex() * blockSize;
+					outLen = std::min(numBytesLeft, blockSize);
+				} break;
+			}
+
+			numBytesLeft -= outLen;
+
+			return true;
+		}
+
+	private:
+		const Kind kind;
+		const uint64_t blockSize;
+		const uint64_t numDataSetThreads;
+		Xoshiro256ss* randAlgo;
+
+		uint64_t numBytesTotal{0};
+		uint64_t numBytesLeft{0};
+		uint64_t startOffset{0};
+		uint64_t currentOffset{0};
+
+		uint64_t randMin{0}; // inclusive range of RandAlgoRange
+		uint64_t randMax{0};
+
+		// full coverage: LCG mod next-power-of-2 with cycle walking (FullCoverageV2.h:115-139)
+		uint64_t covFirstIdx{0};
+		uint64_t covRangeSize{1};
+		uint64_t covModulus{1};
+		uint64_t covState{0};
+		uint64_t covCount{0};
+		uint64_t lcgSeedState;
+		bool haveLCGSeed;
+
+		static const uint64_t LCG_MULT = 6364136223846793005ULL;
+		static const uint64_t LCG_INC = 1442695040888963407ULL;
+
+		void setRange(uint64_t rangeLen, uint64_t rangeOffset)
+		{
+			const uint64_t minLenAndBlockSize = std::min(blockSize, rangeLen);
+
+			switch(kind)
+			{
+				case Kind_SEQUENTIAL:
+				case Kind_STRIDED:
+					startOffset = rangeOffset;
+					currentOffset = rangeOffset;
+					break;
+
+				case Kind_REVERSE:
+					startOffset = rangeOffset;
+					initReverseStart();
+					break;
+
+				case Kind_RANDOM_UNALIGNED: // :191-193, :217-227
+					randMin = rangeOffset;
+					randMax = rangeOffset + rangeLen - minLenAndBlockSize;
+					break;
+
+				case Kind_RANDOM_ALIGNED: // :255-263, :288-302
+					startOffset = rangeOffset;
+					randMin = 0;
+					randMax = minLenAndBlockSize ?
+						( (rangeLen - minLenAndBlockSize) / minLenAndBlockSize) : 0;
+					break;
+
+				case Kind_FULL_COVERAGE: // FullCoverageV2.h:293-305
+				{
+					covFirstIdx = blockSize ? (rangeOffset / blockSize) : 0;
+					const uint64_t numBlocks = (blockSize && (rangeLen / blockSize) ) ?
+						(rangeLen / blockSize) : 1;
+					covRangeSize = numBlocks;
+					covModulus = nextPowerOfTwo(covRangeSize);
+					beginCoverageCycle();
+				} break;
+			}
+		}
+
+		void initReverseStart() // :127-146
+		{
+			if(!numBytesTotal)
+			{
+				currentOffset = 0;
+				return;
+			}
+
+			const uint64_t lastBlockRemainder = numBytesTotal % blockSize;
+
+			currentOffset = startOffset + numBytesTotal -
+				(lastBlockRemainder ? lastBlockRemainder : blockSize);
+		}
+
+		static uint64_t nextPowerOfTwo(uint64_t n) // FullCoverageV2.h:190-201
+		{
+			if(!n)
+				return 1;
+
+			n--;
+			n |= n >> 1;
+			n |= n >> 2;
+			n |= n >> 4;
+			n |= n >> 8;
+			n |= n >> 16;
+			n |= n >> 32;
+
+			return n + 1;
+		}
+
+		/* new permutation: 32-bit start state like std::random_device()() (:93,:158) */
+		void beginCoverageCycle()
+		{
+			uint32_t startVal;
+
+			if(haveLCGSeed)
+			{
+				startVal = (uint32_t)lcgSeedState;
+				lcgSeedState = lcgSeedState * LCG_MULT + LCG_INC;
+			}
+			else
+				startVal = std::random_device()();
+
+			covCount = 0;
+			covState = startVal % covModulus;
+		}
+
+		uint64_t nextCoverageIndex()
+		{
+			if(covCount >= covRangeSize)
+				beginCoverageCycle();
+
+			do
+			{
+				covState = (LCG_MULT * covState + LCG_INC) % covModulus;
+			} while(covState >= covRangeSize);
+
+			covCount++;
+
+			return covFirstIdx + covState;
+		}
+};
+
+/* ---- LatencyHistogram (source/LatencyHistogram.h) on the plain C struct of the ABI ---- */
+
+inline void histogramReset(elb_histogram& histo) // :113-123
+{
+	std::memset(histo.buckets, 0, sizeof(histo.buckets) );
+	histo.numStoredValues = 0;
+	histo.numMicroSecTotal = 0;
+	histo.minMicroSecLat = ~0ULL;
+	histo.maxMicroSecLat = 0;
+}
+
+inline size_t histogramBucketIndex(uint64_t latencyMicroSec) // :65-74
+{
+	if(!latencyMicroSec)
+		return 0;
+
+	const size_t bucketIndex = (size_t)(std::log2( (double)latencyMicroSec) * 4);
+
+	return std::min(bucketIndex, (size_t)(ELB_LATHISTO_NUMBUCKETS - 1) );
+}
+
+inline void histogramAdd(elb_histogram& histo, uint64_t latencyMicroSec) // :50-77
+{
+	histo.numStoredValues++;
+	histo.numMicroSecTotal += latencyMicroSec;
+	histo.minMicroSecLat = std::min(histo.minMicroSecLat, latencyMicroSec);
+	histo.maxMicroSecLat = std::max(histo.maxMicroSecLat, latencyMicroSec);
+	histo.buckets[histogramBucketIndex(latencyMicroSec)]++;
+}
+
+inline void histogramMerge(elb_histogram& dst, const elb_histogram& src) // :187-202
+{
+	for(size_t i = 0; i < ELB_LATHISTO_NUMBUCKETS; i++)
+		dst.buckets[i] += src.buckets[i];
+
+	dst.numStoredValues += src.numStoredValues;
+	dst.numMicroSecTotal += src.numMicroSecTotal;
+	dst.minMicroSecLat = std::min(dst.minMicroSecLat, src.minMicroSecLat);
+	dst.maxMicroSecLat = std::max(dst.maxMicroSecLat, src.maxMicroSecLat);
+}
+
+inline double histogramPercentile(const elb_histogram& histo, double percentage) // :140-159
+{
+	uint64_t numValuesSoFar = 0;
+
+	for(size_t bucketIndex = 0; bucketIndex < ELB_LATHISTO_NUMBUCKETS; bucketIndex++)
+	{
+		numValuesSoFar += histo.buckets[bucketIndex];
+
+		if( ( (double)numValuesSoFar / histo.numStoredValues) >= (percentage / 100) )
+			return std::pow(2, (bucketIndex + 1) * 0.25);
+	}
+
+	return 0;
+}
+
+inline uint64_t perSecFromUSec(uint64_t totalValue, uint64_t elapsedUSec) // UnitTk.h:48-56
+{
+	const double numUSecsPerSec = 1000000;
+	return (uint64_t)(totalValue * (numUSecsPerSec / elapsedUSec) );
+}
+
+/* ---- live counters (source/LiveOps.h:86-115) ---- */
+struct AtomicLiveOps
+{
+	std::atomic<uint64_t> numEntriesDone{0};
+	std::atomic<uint64_t> numBytesDone{0};
+	std::atomic<uint64_t> numIOPSDone{0};
+
+	void setToZero()
+	{
+		numEntriesDone.store(0, std::memory_order_relaxed);
+		numBytesDone.store(0, std::memory_order_relaxed);
+		numIOPSDone.store(0, std::memory_order_relaxed);
+	}
+
+	elb_liveops snapshot() const
+	{
+		elb_liveops ops;
+		ops.numEntriesDone = numEntriesDone.load(std::memory_order_relaxed);
+		ops.numBytesDone = numBytesDone.load(std::memory_order_relaxed);
+		ops.numIOPSDone = numIOPSDone.load(std::memory_order_relaxed);
+		return ops;
+	}
+};
+
+inline void liveOpsAdd(elb_liveops& dst, const elb_liveops& src)
+{
+	dst.numEntriesDone += src.numEntriesDone;
+	dst.numBytesDone += src.numBytesDone;
+	dst.numIOPSDone += src.numIOPSDone;
+}
+
+/* ---- normalised configuration (the rules of ProgArgs::initImplicitValues/checkArgs/
+ * checkPathDependentArgs that touch the hot path; ProgArgs.cpp:1041-1671) ---- */
+struct Config
+{
+	std::vector<std::string> paths;
+	int pathType{ELB_PATH_FILE};
+	uint32_t numThreads{1};
+	uint32_t rankOffset{0};
+	uint32_t numDataSetThreads{1};
+	uint64_t blockSize{0};
+	uint64_t fileSize{0};
+	uint32_t ioDepth{1};
+	bool useDirectIO{false};
+	int ioEngine{ELB_IOENGINE_SYNC};
+	uint64_t numDirs{0};
+	uint64_t numFiles{1};
+	bool doDirSharing{false};
+	bool doTruncate{false};
+	bool doTruncToSize{false};
+	bool doPreallocFile{false};
+	bool useRandomOffsets{false};
+	bool useRandomUnaligned{false};
+	bool useExplicitRandOffsetAlgo{false};
+	bool doReverseSeqOffsets{false};
+	bool useStridedAccess{false};
+	uint64_t randomAmount{0};
+	uint64_t randOffsetSeed{0};
+	uint64_t integrityCheckSalt{0};
+	bool doDirectVerify{false};
+	bool doReadInline{false};
+	uint32_t blockVariancePercent{0};
+	int blockVarianceAlgo{ELB_RANDALGO_SPLITMIX64};
+	uint64_t blockVarianceSeed{0};
+	uint32_t rwMixReadPercent{0};
+	std::vector<int> gpuIDs;
+	bool useCuFile{false};
+	bool useGDSBufReg{false};
+	uint32_t pipelineBatchBlocks{0};
+	uint32_t pipelineNumBatches{0};
+	bool ignoreDelErrors{false};
+	bool runAsService{false};
+	bool verifyCollectAll{false};
+
+	/* @throw WorkerError on invalid combinations */
+	static Config fromABI(const elb_cfg* cfg);
+};
+
+} // namespace elb
+
+#endif /* ELB_HOST_H_ */

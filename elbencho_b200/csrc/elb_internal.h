@@ -1,0 +1,33 @@
+/*
+ * Internal declarations shared by the translation units of libelbencho_b200.so.
+ */
+#ifndef ELB_INTERNAL_H_
+#define ELB_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "elbencho_b200.h"
+
+#define ELB_MAX_DEVICES 64
+
+void elb_set_last_error(const std::string& msg);
+
+// kernel launchers (elb_kernels.cu). totalBytesHint only sizes the grid (0 = full grid).
+// (descs == NULL => single block passed by value through inlineDesc, numDescs must be 1)
+int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, uint64_t salt, uint64_t* devCounters, uint64_t totalBytesHint,
+	cudaStream_t stream);
+int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
+	cudaStream_t stream);
+int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters,
+	uint64_t totalBytesHint, bool initResults, cudaStream_t stream);
+int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
+	uint64_t totalBytesHint, cudaStream_t stream);
+uint64_t elb_get_num_kernel_launches();
+
+#endif /* ELB_INTERNAL_H_ */

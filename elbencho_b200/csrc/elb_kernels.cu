@@ -1,0 +1,634 @@
+/*
+ * Hand-written sm_100a kernels for the on-GPU work of the LocalWorker hot path:
+ *
+ *   K1 fill_pattern   <- LocalWorker::preWriteIntegrityCheckFillBuf   (LocalWorker.cpp:2091-2128)
+ *   K2 verify_pattern <- LocalWorker::postReadIntegrityCheckVerifyBuf (LocalWorker.cpp:2137-2179)
+ *   K3 fill_random    <- LocalWorker::preWriteBufRandRefillCuda + bufFill (:2185-2203, 2236-2277)
+ *
+ * All three are HBM-bound byte/integer kernels (K1/K3: 1 byte written per payload byte, K2: 1 byte
+ * read per payload byte), so the design follows the streaming rules: 32-byte (256-bit) vector
+ * accesses per thread (LDG/STG.E.256 on sm_100), fully coalesced (a warp covers 1 KiB per access),
+ * L1 no-allocate hints, several independent accesses in flight per thread, and a grid sized to a
+ * multiple of the SM count that walks "tiles" of the whole in-flight window (many blocks per
+ * launch) so that one launch covers tens to hundreds of MiB.
+ *
+ * One launch processes an array of block descriptors {devPtr, len, fileOffset, blockCounter}.
+ * Tiles are ELB_TILE_BYTES slices of a block's 32-byte-aligned body; unaligned head/tail bytes
+ * (device address not 32-byte aligned, or odd lengths) are handled byte-wise by tile 0 of the
+ * block. Mismatch counts are reduced per warp (redux.sync) before touching global atomics.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "elb_patterns.cuh"
+#include "elb_internal.h"
+
+#define ELB_THREADS 256
+#define ELB_VEC_BYTES 32
+#define ELB_UNROLL 4
+#define ELB_TILE_BYTES (ELB_THREADS * ELB_VEC_BYTES * ELB_UNROLL) /* 32 KiB */
+
+struct __align__(32) u64x4
+{
+	uint64_t a, b, c, d;
+};
+
+__device__ __forceinline__ void st_na_256(void* ptr, const u64x4& v)
+{
+	asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};"
+		:: "l"(ptr), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+}
+
+__device__ __forceinline__ u64x4 ld_nc_na_256(const void* ptr)
+{
+	u64x4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+		: "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(ptr) );
+	return v;
+}
+
+/* number of differing bytes between two u64 */
+__device__ __forceinline__ unsigned diff_bytes64(uint64_t x, uint64_t y)
+{
+	const unsigned lo = __vcmpne4( (unsigned)x, (unsigned)y);
+	const unsigned hi = __vcmpne4( (unsigned)(x >> 32), (unsigned)(y >> 32) );
+	return (__popc(lo) + __popc(hi) ) >> 3;
+}
+
+/* index (0..7) of the first differing byte of two unequal u64 */
+__device__ __forceinline__ unsigned first_diff_byte64(uint64_t x, uint64_t y)
+{
+	return (unsigned)(__ffsll( (long long)(x ^ y) ) - 1) >> 3;
+}
+
+/* ---- generators ------------------------------------------------------------------------- */
+
+struct PatternGen
+{
+	uint64_t fileOffset; // file offset of block byte 0
+	uint64_t salt;
+
+	/* fast path is valid when the file position of every 32-byte vector is 8-byte aligned */
+	__device__ __forceinline__ bool canUseFast(uint64_t headLen) const
+		{ return ( (fileOffset + headLen) & 7) == 0; }
+
+	template<bool FAST>
+	__device__ __forceinline__ u64x4 vec32(uint64_t pos) const
+	{
+		u64x4 v;
+
+		if(FAST)
+		{ // four consecutive aligned checksum words: offset + salt (LocalWorker.cpp:2110-2112)
+			const uint64_t w = fileOffset + pos + salt;
+			v.a = w;
+			v.b = w + 8;
+			v.c = w + 16;
+			v.d = w + 24;
+		}
+		else
+		{ // block starts in the middle of a checksum word: funnel-shift neighbours together
+			const uint64_t filePos = fileOffset + pos;
+			const unsigned shiftBits = (unsigned)(filePos & 7) * 8; // != 0 here
+			const uint64_t w0 = (filePos & ~7ULL) + salt;
+			const uint64_t w1 = w0 + 8, w2 = w0 + 16, w3 = w0 + 24, w4 = w0 + 32;
+			v.a = (w0 >> shiftBits) | (w1 << (64 - shiftBits) );
+			v.b = (w1 >> shiftBits) | (w2 << (64 - shiftBits) );
+			v.c = (w2 >> shiftBits) | (w3 << (64 - shiftBits) );
+			v.d = (w3 >> shiftBits) | (w4 << (64 - shiftBits) );
+		}
+
+		return v;
+	}
+
+	__device__ __forceinline__ uint8_t byte(uint64_t pos) const
+		{ return elb_pattern_byte(fileOffset + pos, salt); }
+};
+
+struct RandomGen
+{
+	uint64_t blockKey;
+	uint64_t varFillLen;
+	uint64_t remainderVal;
+
+	/* fast path is valid when every 32-byte vector starts on a word boundary of the block */
+	__device__ __forceinline__ bool canUseFast(uint64_t headLen) const
+		{ return (headLen & 7) == 0; }
+
+	template<bool FAST>
+	__device__ __forceinline__ u64x4 vec32(uint64_t pos) const
+	{
+		u64x4 v;
+
+		if(FAST && ( (pos + ELB_VEC_BYTES) <= varFillLen) )
+		{ // four whole random words
+			const uint64_t wordIdx = pos >> 3;
+			v.a = elb_rand_word(blockKey, wordIdx);
+			v.b = elb_rand_word(blockKey, wordIdx + 1);
+			v.c = elb_rand_word(blockKey, wordIdx + 2);
+			v.d = elb_rand_word(blockKey, wordIdx + 3);
+		}
+		else if(FAST && (pos >= varFillLen) )
+		{ // constant remainder: the same rotation of the repeated u64 four times
+			const unsigned rotBits = (unsigned)( (pos - varFillLen) & 7) * 8;
+			const uint64_t val = rotBits ?
+				( (remainderVal >> rotBits) | (remainderVal << (64 - rotBits) ) ) : remainderVal;
+			v.a = v.b = v.c = v.d = val;
+		}
+		else
+		{ // boundary vector or unaligned block start
+			v.a = elb_rand_bytes8(pos, blockKey, varFillLen, remainderVal);
+			v.b = elb_rand_bytes8(pos + 8, blockKey, varFillLen, remainderVal);
+			v.c = elb_rand_bytes8(pos + 16, blockKey, varFillLen, remainderVal);
+			v.d = elb_rand_bytes8(pos + 24, blockKey, varFillLen, remainderVal);
+		}
+
+		return v;
+	}
+
+	__device__ __forceinline__ uint8_t byte(uint64_t pos) const
+		{ return elb_rand_byte(pos, blockKey, varFillLen, remainderVal); }
+};
+
+/* ---- block geometry --------------------------------------------------------------------- */
+
+struct BlockGeom
+{
+	uint8_t* ptr;      // device address of block byte 0
+	uint64_t len;
+	uint64_t headLen;  // bytes before the first 32-byte aligned address (< 32, <= len)
+	uint64_t bodyLen;  // multiple of 32
+	uint64_t tailLen;  // < 32
+	uint64_t numTiles; // >= 1 for len > 0 (tile 0 also does head/tail)
+};
+
+__device__ __forceinline__ BlockGeom make_geom(const elb_block_desc& desc)
+{
+	BlockGeom g;
+	g.ptr = (uint8_t*)desc.devPtr;
+	g.len = desc.len;
+
+	const uint64_t misalign = (uint64_t)(uintptr_t)g.ptr & (ELB_VEC_BYTES - 1);
+	uint64_t headLen = misalign ? (ELB_VEC_BYTES - misalign) : 0;
+	if(headLen > g.len)
+		headLen = g.len;
+
+	g.headLen = headLen;
+	g.bodyLen = (g.len - headLen) & ~(uint64_t)(ELB_VEC_BYTES - 1);
+	g.tailLen = g.len - headLen - g.bodyLen;
+	g.numTiles = (g.bodyLen + ELB_TILE_BYTES - 1) / ELB_TILE_BYTES;
+	if(!g.numTiles && g.len)
+		g.numTiles = 1;
+
+	return g;
+}
+
+/* ---- fill ------------------------------------------------------------------------------- */
+
+template<bool FAST, class Gen>
+__device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, uint64_t tileIdx)
+{
+	const uint64_t tileStart = tileIdx * ELB_TILE_BYTES; // within body
+	uint8_t* bodyPtr = g.ptr + g.headLen;
+
+	if( (tileStart + ELB_TILE_BYTES) <= g.bodyLen)
+	{ // full tile: no bounds checks, all stores independent
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			const uint64_t pos = g.headLen + bodyOff;
+			st_na_256(bodyPtr + bodyOff, gen.template vec32<FAST>(pos) );
+		}
+	}
+	else
+	{
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			if(bodyOff < g.bodyLen)
+			{
+				const uint64_t pos = g.headLen + bodyOff;
+				st_na_256(bodyPtr + bodyOff, gen.template vec32<FAST>(pos) );
+			}
+		}
+	}
+
+	if(!tileIdx && (g.headLen | g.tailLen) )
+	{ // unaligned head/tail bytes (at most 31 each)
+		if(threadIdx.x < g.headLen)
+			g.ptr[threadIdx.x] = gen.byte(threadIdx.x);
+
+		const uint64_t tailStart = g.headLen + g.bodyLen;
+		if(threadIdx.x < g.tailLen)
+			g.ptr[tailStart + threadIdx.x] = gen.byte(tailStart + threadIdx.x);
+	}
+}
+
+/* ---- verify ----------------------------------------------------------------------------- */
+
+/* compare one 32-byte vector; update thread-local count and first mismatch position */
+__device__ __forceinline__ void verify_vec(const u64x4& got, const u64x4& exp, uint64_t pos,
+	unsigned& numBad, uint64_t& firstBad)
+{
+	const uint64_t anyDiff = (got.a ^ exp.a) | (got.b ^ exp.b) | (got.c ^ exp.c) |
+		(got.d ^ exp.d);
+
+	if(__builtin_expect(anyDiff != 0, 0) )
+	{
+		numBad += diff_bytes64(got.a, exp.a) + diff_bytes64(got.b, exp.b) +
+			diff_bytes64(got.c, exp.c) + diff_bytes64(got.d, exp.d);
+
+		uint64_t first;
+		if(got.a != exp.a)
+			first = pos + first_diff_byte64(got.a, exp.a);
+		else if(got.b != exp.b)
+			first = pos + 8 + first_diff_byte64(got.b, exp.b);
+		else if(got.c != exp.c)
+			first = pos + 16 + first_diff_byte64(got.c, exp.c);
+		else
+			first = pos + 24 + first_diff_byte64(got.d, exp.d);
+
+		if(first < firstBad)
+			firstBad = first;
+	}
+}
+
+template<bool FAST, class Gen>
+__device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
+	uint64_t tileIdx, elb_verify_result* result, unsigned long long* counters)
+{
+	const uint64_t tileStart = tileIdx * ELB_TILE_BYTES;
+	const uint8_t* bodyPtr = g.ptr + g.headLen;
+
+	unsigned numBad = 0;
+	uint64_t firstBad = ~0ULL;
+
+	if( (tileStart + ELB_TILE_BYTES) <= g.bodyLen)
+	{ // full tile: issue all loads first, then compare
+		u64x4 got[ELB_UNROLL];
+
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			got[u] = ld_nc_na_256(bodyPtr + bodyOff);
+		}
+
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			const uint64_t pos = g.headLen + bodyOff;
+			verify_vec(got[u], gen.template vec32<FAST>(pos), pos, numBad, firstBad);
+		}
+	}
+	else
+	{
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			if(bodyOff < g.bodyLen)
+			{
+				const uint64_t pos = g.headLen + bodyOff;
+				const u64x4 got = ld_nc_na_256(bodyPtr + bodyOff);
+				verify_vec(got, gen.template vec32<FAST>(pos), pos, numBad, firstBad);
+			}
+		}
+	}
+
+	if(!tileIdx && (g.headLen | g.tailLen) )
+	{
+		if(threadIdx.x < g.headLen)
+		{
+			if(g.ptr[threadIdx.x] != gen.byte(threadIdx.x) )
+			{
+				numBad++;
+				if(threadIdx.x < firstBad)
+					firstBad = threadIdx.x;
+			}
+		}
+
+		const uint64_t tailStart = g.headLen + g.bodyLen;
+		if(threadIdx.x < g.tailLen)
+		{
+			const uint64_t pos = tailStart + threadIdx.x;
+			if(g.ptr[pos] != gen.byte(pos) )
+			{
+				numBad++;
+				if(pos < firstBad)
+					firstBad = pos;
+			}
+		}
+	}
+
+	// warp-reduced mismatch count; global atomics only on the (rare) mismatch path
+	const unsigned warpBad = __reduce_add_sync(0xffffffffu, numBad);
+
+	if(__builtin_expect(warpBad != 0, 0) )
+	{
+		// 64-bit min via two 32-bit redux steps
+		const unsigned firstHi = (unsigned)(firstBad >> 32);
+		const unsigned minHi = __reduce_min_sync(0xffffffffu, firstHi);
+		const unsigned firstLo = (firstHi == minHi) ? (unsigned)firstBad : 0xffffffffu;
+		const unsigned minLo = __reduce_min_sync(0xffffffffu, firstLo);
+
+		if( (threadIdx.x & 31) == 0)
+		{
+			atomicAdd( (unsigned long long*)&result->numMismatchBytes,
+				(unsigned long long)warpBad);
+			atomicMin( (unsigned long long*)&result->firstMismatchIdx,
+				( (unsigned long long)minHi << 32) | minLo);
+			if(counters)
+				atomicAdd(&counters[ELB_DEVCTR_VERIFY_MISMATCH_BYTES],
+					(unsigned long long)warpBad);
+		}
+	}
+}
+
+/* ---- kernels: walk all tiles of all descriptors, round-robin over the grid --------------- */
+
+enum { MODE_FILL_PATTERN = 0, MODE_VERIFY_PATTERN = 1, MODE_FILL_RANDOM = 2 };
+
+struct KernelArgs
+{
+	const elb_block_desc* descs; // device-readable array, or NULL to use inlineDesc
+	elb_block_desc inlineDesc;   // single-block launches pass the descriptor by value
+	uint32_t numDescs;
+	uint64_t salt;         // pattern
+	uint64_t seed;         // random
+	unsigned pct;          // random
+	elb_verify_result* results; // verify
+	unsigned long long* counters; // optional device counter block
+};
+
+template<int MODE>
+__global__ void __launch_bounds__(ELB_THREADS, 4)
+elb_blocks_kernel(const KernelArgs args)
+{
+	uint64_t tileBase = 0; // global index of the first tile of the current descriptor
+
+	for(uint32_t descIdx = 0; descIdx < args.numDescs; descIdx++)
+	{
+		const elb_block_desc desc = args.descs ? args.descs[descIdx] : args.inlineDesc;
+		const BlockGeom g = make_geom(desc);
+
+		// first global tile of this descriptor owned by this CTA (tiles go round-robin over CTAs)
+		const uint64_t gridSize = gridDim.x;
+		const uint64_t baseMod = tileBase % gridSize;
+		uint64_t tileIdx = (blockIdx.x + gridSize - baseMod) % gridSize;
+
+		if(tileIdx < g.numTiles)
+		{
+			if(MODE == MODE_FILL_PATTERN)
+			{
+				PatternGen gen;
+				gen.fileOffset = desc.fileOffset;
+				gen.salt = args.salt;
+
+				if(gen.canUseFast(g.headLen) )
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						fill_tile<true>(g, gen, tileIdx);
+				else
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						fill_tile<false>(g, gen, tileIdx);
+			}
+			else if(MODE == MODE_VERIFY_PATTERN)
+			{
+				PatternGen gen;
+				gen.fileOffset = desc.fileOffset;
+				gen.salt = args.salt;
+
+				if(gen.canUseFast(g.headLen) )
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						verify_tile<true>(g, gen, tileIdx, &args.results[descIdx], args.counters);
+				else
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						verify_tile<false>(g, gen, tileIdx, &args.results[descIdx],
+							args.counters);
+			}
+			else
+			{
+				RandomGen gen;
+				gen.blockKey = elb_rand_block_key(args.seed, desc.blockCounter);
+				gen.varFillLen = elb_rand_var_fill_len(desc.len, args.pct);
+				gen.remainderVal = elb_rand_remainder_val(gen.blockKey);
+
+				if(gen.canUseFast(g.headLen) )
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						fill_tile<true>(g, gen, tileIdx);
+				else
+					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
+						fill_tile<false>(g, gen, tileIdx);
+			}
+		}
+
+		// device-resident stats: one atomic per block, by the CTA that owns the block's tile 0
+		if(args.counters && g.len && (baseMod == blockIdx.x) && !threadIdx.x)
+			atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
+				ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
+				(unsigned long long)g.len);
+
+		tileBase += g.numTiles;
+	}
+}
+
+__global__ void elb_verify_init_kernel(elb_verify_result* results, uint32_t numDescs)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if(i < numDescs)
+	{
+		results[i].numMismatchBytes = 0;
+		results[i].firstMismatchIdx = ~0ULL;
+	}
+}
+
+/* ---- host side launchers ------------------------------------------------------------------ */
+
+static std::atomic<uint64_t> gNumKernelLaunches{0};
+
+thread_local std::string elbThreadLastError;
+
+void elb_set_last_error(const std::string& msg)
+{
+	elbThreadLastError = msg;
+}
+
+struct DeviceLaunchInfo
+{
+	int numSMs{0};
+	int ctasPerSM[3]{0, 0, 0};
+};
+
+static DeviceLaunchInfo gDevInfo[ELB_MAX_DEVICES];
+static std::once_flag gDevInfoOnce[ELB_MAX_DEVICES];
+
+template<int MODE>
+static int queryOccupancy()
+{
+	int numBlocks = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&numBlocks, elb_blocks_kernel<MODE>,
+		ELB_THREADS, 0);
+	return (numBlocks > 0) ? numBlocks : 1;
+}
+
+static const DeviceLaunchInfo* getDeviceLaunchInfo()
+{
+	int dev = 0;
+	cudaError_t devRes = cudaGetDevice(&dev);
+
+	if( (devRes != cudaSuccess) || (dev < 0) || (dev >= ELB_MAX_DEVICES) )
+	{
+		elb_set_last_error(std::string("cudaGetDevice failed: ") + cudaGetErrorString(devRes) );
+		return NULL;
+	}
+
+	std::call_once(gDevInfoOnce[dev], [dev]()
+	{
+		cudaDeviceGetAttribute(&gDevInfo[dev].numSMs, cudaDevAttrMultiProcessorCount, dev);
+		gDevInfo[dev].ctasPerSM[MODE_FILL_PATTERN] = queryOccupancy<MODE_FILL_PATTERN>();
+		gDevInfo[dev].ctasPerSM[MODE_VERIFY_PATTERN] = queryOccupancy<MODE_VERIFY_PATTERN>();
+		gDevInfo[dev].ctasPerSM[MODE_FILL_RANDOM] = queryOccupancy<MODE_FILL_RANDOM>();
+	});
+
+	if(gDevInfo[dev].numSMs <= 0)
+	{
+		elb_set_last_error("Unable to query CUDA device attributes (no usable GPU?)");
+		return NULL;
+	}
+
+	return &gDevInfo[dev];
+}
+
+static int checkLaunch(const char* what)
+{
+	cudaError_t res = cudaGetLastError();
+
+	if(res != cudaSuccess)
+	{
+		elb_set_last_error(std::string(what) + " kernel launch failed: " +
+			cudaGetErrorString(res) );
+		return -1;
+	}
+
+	return 0;
+}
+
+/**
+ * @totalBytesHint upper bound of bytes covered by the launch (used only to size the grid);
+ *    0 = unknown (launch a full persistent grid).
+ */
+template<int MODE>
+static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
+	cudaStream_t stream)
+{
+	if(!args.numDescs)
+		return 0;
+
+	const DeviceLaunchInfo* devInfo = getDeviceLaunchInfo();
+	if(!devInfo)
+		return -1;
+
+	// grid: a multiple of the SM count, never more CTAs than tiles
+	uint64_t gridSize = (uint64_t)devInfo->numSMs * devInfo->ctasPerSM[MODE];
+
+	if(totalBytesHint)
+	{
+		const uint64_t maxTiles =
+			(totalBytesHint + ELB_TILE_BYTES - 1) / ELB_TILE_BYTES + args.numDescs;
+		if(maxTiles < gridSize)
+			gridSize = maxTiles;
+	}
+
+	elb_blocks_kernel<MODE><<<(unsigned)gridSize, ELB_THREADS, 0, stream>>>(args);
+	gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
+
+	return checkLaunch( (MODE == MODE_FILL_PATTERN) ? "fill_pattern" :
+		(MODE == MODE_VERIFY_PATTERN) ? "verify_pattern" : "fill_random");
+}
+
+int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, uint64_t salt, uint64_t* devCounters, uint64_t totalBytesHint,
+	cudaStream_t stream)
+{
+	KernelArgs args{};
+	args.descs = descs;
+	if(inlineDesc)
+		args.inlineDesc = *inlineDesc;
+	args.numDescs = numDescs;
+	args.salt = salt;
+	args.counters = (unsigned long long*)devCounters;
+
+	return launchBlocksKernel<MODE_FILL_PATTERN>(args, totalBytesHint, stream);
+}
+
+int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
+	cudaStream_t stream)
+{
+	if(!numDescs)
+		return 0;
+
+	elb_verify_init_kernel<<<(numDescs + 255) / 256, 256, 0, stream>>>(devResults, numDescs);
+	gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
+
+	return checkLaunch("verify_init");
+}
+
+/**
+ * @initResults false if the caller knows devResults still holds {0, ~0} entries (true after any
+ *    launch that found no mismatch), which saves the init launch.
+ */
+int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters,
+	uint64_t totalBytesHint, bool initResults, cudaStream_t stream)
+{
+	if(!numDescs)
+		return 0;
+
+	if(initResults && elb_launch_verify_init(devResults, numDescs, stream) )
+		return -1;
+
+	KernelArgs args{};
+	args.descs = descs;
+	if(inlineDesc)
+		args.inlineDesc = *inlineDesc;
+	args.numDescs = numDescs;
+	args.salt = salt;
+	args.results = devResults;
+	args.counters = (unsigned long long*)devCounters;
+
+	return launchBlocksKernel<MODE_VERIFY_PATTERN>(args, totalBytesHint, stream);
+}
+
+int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
+	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
+	uint64_t totalBytesHint, cudaStream_t stream)
+{
+	KernelArgs args{};
+	args.descs = descs;
+	if(inlineDesc)
+		args.inlineDesc = *inlineDesc;
+	args.numDescs = numDescs;
+	args.seed = seed;
+	args.pct = pct;
+	args.counters = (unsigned long long*)devCounters;
+
+	return launchBlocksKernel<MODE_FILL_RANDOM>(args, totalBytesHint, stream);
+}
+
+uint64_t elb_get_num_kernel_launches()
+{
+	return gNumKernelLaunches.load(std::memory_order_relaxed);
+}

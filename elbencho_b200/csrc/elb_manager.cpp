@@ -1,0 +1,676 @@
+/*
+ * Manager (WorkerManager of the reference, source/workers/WorkerManager.cpp) and the C ABI of the
+ * worker/manager level declared in include/elbencho_b200.h.
+ */
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include "elb_worker.h"
+
+#define ELB_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
+
+namespace elb
+{
+
+/* prepareThreads (WorkerManager.cpp:142-199): open bench paths, create workers and their threads,
+ * wait until all of them finished their preparation. */
+Manager::Manager(const elb_cfg* abiCfg)
+{
+	shared.cfg = Config::fromABI(abiCfg);
+
+	prepareBenchPathFDs();
+
+	const Config& cfg = shared.cfg;
+
+	for(uint32_t i = 0; i < cfg.numThreads; i++)
+	{
+		workers.emplace_back(new Worker(&shared, cfg.rankOffset + i) );
+		shared.workers.push_back(workers.back().get() );
+	}
+
+	for(uint32_t i = 0; i < cfg.numThreads; i++)
+		threads.emplace_back(Worker::threadStart, workers[i].get() );
+
+	// wait for preparation of all workers
+	int waitRes = waitForWorkersDone(-1);
+
+	if(waitRes < 0)
+	{
+		std::string errMsg = shared.firstErrorMsg.empty() ?
+			"Worker preparation failed." : shared.firstErrorMsg;
+
+		interruptAndNotifyWorkers();
+
+		for(std::thread& thread : threads)
+			thread.join();
+
+		threads.clear();
+		closeBenchPathFDs();
+
+		throw WorkerError(errMsg);
+	}
+}
+
+Manager::~Manager()
+{
+	// BenchPhase_TERMINATE tells workers to self-terminate (Common.h:145)
+	if(!threads.empty() )
+	{
+		{
+			std::unique_lock<std::mutex> lock(shared.mutex);
+			shared.currentBenchPhase = ELB_PHASE_TERMINATE;
+			shared.currentBenchSeq++;
+			for(Worker* worker : shared.workers)
+				worker->interruptExecution();
+			shared.condition.notify_all();
+		}
+
+		for(std::thread& thread : threads)
+			thread.join();
+	}
+
+	closeBenchPathFDs();
+}
+
+/* ProgArgs::prepareBenchPathFDsVec (ProgArgs.cpp:1859-1935) */
+void Manager::prepareBenchPathFDs()
+{
+	const Config& cfg = shared.cfg;
+
+	for(const std::string& path : cfg.paths)
+	{
+		int openFlags = 0;
+
+		if(cfg.pathType == ELB_PATH_DIR)
+			openFlags |= (O_DIRECTORY | O_RDONLY);
+		else
+		{
+			openFlags |= O_RDWR;
+
+			if(cfg.useDirectIO)
+				openFlags |= O_DIRECT;
+
+			if(cfg.pathType == ELB_PATH_FILE)
+				openFlags |= O_CREAT;
+		}
+
+		int fd = open(path.c_str(), openFlags, ELB_MKFILE_MODE);
+
+		if( (fd == -1) && (cfg.pathType != ELB_PATH_DIR) &&
+			( (errno == EACCES) || (errno == EROFS) || (errno == EPERM) ) )
+		{ // read-only file: good enough for read phases
+			openFlags &= ~(O_RDWR | O_CREAT);
+			openFlags |= O_RDONLY;
+			fd = open(path.c_str(), openFlags, ELB_MKFILE_MODE);
+		}
+
+		if(fd == -1)
+		{
+			int openErrno = errno;
+			closeBenchPathFDs();
+			throw WorkerError("Unable to open benchmark path: " + path + "; "
+				"SysErr: " + strerror(openErrno) );
+		}
+
+		shared.pathFDs.push_back(fd);
+	}
+}
+
+void Manager::closeBenchPathFDs()
+{
+	for(int fd : shared.pathFDs)
+		close(fd);
+
+	shared.pathFDs.clear();
+}
+
+/* ProgArgs::prepareFileSize (ProgArgs.cpp:2071-2200) for file mode: truncate / set size /
+ * preallocate before the write phase starts */
+void Manager::prepareFilesForPhase(int benchPhase)
+{
+	const Config& cfg = shared.cfg;
+
+	if( (cfg.pathType != ELB_PATH_FILE) || (benchPhase != ELB_PHASE_CREATEFILES) )
+		return;
+
+	for(size_t i = 0; i < shared.pathFDs.size(); i++)
+	{
+		const int fd = shared.pathFDs[i];
+
+		if(cfg.doTruncate && (ftruncate(fd, 0) == -1) )
+			throw WorkerError("Unable to truncate file. Path: " + cfg.paths[i] + "; "
+				"SysErr: " + strerror(errno) );
+
+		if(cfg.doTruncToSize && (ftruncate(fd, cfg.fileSize) == -1) )
+			throw WorkerError("Unable to set file size through ftruncate. "
+				"Path: " + cfg.paths[i] + "; "
+				"Size: " + std::to_string(cfg.fileSize) + "; "
+				"SysErr: " + strerror(errno) );
+
+		if(cfg.doPreallocFile)
+		{
+			int preallocRes = posix_fallocate(fd, 0, cfg.fileSize);
+			if(preallocRes != 0)
+				throw WorkerError("Unable to preallocate file size through posix_fallocate. "
+					"File: " + cfg.paths[i] + "; "
+					"Size: " + std::to_string(cfg.fileSize) + "; "
+					"SysErr: " + strerror(preallocRes) );
+		}
+	}
+}
+
+/* startNextPhase (WorkerManager.cpp:291-324) */
+void Manager::startNextPhase(int benchPhase)
+{
+	prepareFilesForPhase(benchPhase);
+
+	std::unique_lock<std::mutex> lock(shared.mutex);
+
+	for(Worker* worker : shared.workers)
+		worker->resetStats();
+
+	shared.numWorkersDone = 0;
+	shared.numWorkersDoneWithError = 0;
+	shared.firstErrorMsg.clear();
+	shared.currentBenchPhase = benchPhase;
+	shared.currentBenchSeq++;
+	shared.phaseStartT = Clock::now();
+
+	shared.condition.notify_all();
+}
+
+/* waitForWorkersDone / checkWorkersDoneUnlocked (WorkerManager.cpp:38-70, 245-267) */
+int Manager::waitForWorkersDone(int timeoutMS)
+{
+	std::unique_lock<std::mutex> lock(shared.mutex);
+
+	const size_t numWorkersTotal = shared.workers.size();
+	const Clock::time_point deadline = Clock::now() + std::chrono::milliseconds(timeoutMS);
+
+	for( ; ; )
+	{
+		if(shared.numWorkersDoneWithError)
+		{ // a worker failed: ask the others to stop and wait for them (:54-58)
+			for(Worker* worker : shared.workers)
+				worker->interruptExecution();
+
+			while(shared.numWorkersDone < numWorkersTotal)
+				shared.condition.wait_for(lock, std::chrono::milliseconds(100) );
+
+			return -1;
+		}
+
+		if(shared.numWorkersDone >= numWorkersTotal)
+			return 1;
+
+		if(timeoutMS < 0)
+			shared.condition.wait(lock);
+		else
+		if(shared.condition.wait_until(lock, deadline) == std::cv_status::timeout)
+		{
+			if(shared.numWorkersDoneWithError)
+				continue;
+
+			return (shared.numWorkersDone >= numWorkersTotal) ? 1 : 0;
+		}
+	}
+}
+
+void Manager::interruptAndNotifyWorkers() // WorkerManager.cpp:75-90
+{
+	std::unique_lock<std::mutex> lock(shared.mutex);
+
+	for(Worker* worker : shared.workers)
+		worker->interruptExecution();
+
+	shared.currentBenchPhase = ELB_PHASE_TERMINATE;
+	shared.currentBenchSeq++;
+	shared.condition.notify_all();
+}
+
+/* Statistics::generatePhaseResults (Statistics.cpp:1641-1764) */
+void Manager::getPhaseResults(elb_phase_results& out)
+{
+	memset(&out, 0, sizeof(out) );
+	histogramReset(out.iopsLatHisto);
+	histogramReset(out.entriesLatHisto);
+
+	uint64_t firstFinishUSec = ~0ULL;
+	uint64_t lastFinishUSec = 0;
+
+	for(const std::unique_ptr<Worker>& worker : workers)
+	{
+		const uint64_t elapsedUSec = worker->getElapsedUSec();
+
+		if(elapsedUSec)
+		{
+			firstFinishUSec = std::min(firstFinishUSec, elapsedUSec);
+			lastFinishUSec = std::max(lastFinishUSec, elapsedUSec);
+		}
+
+		liveOpsAdd(out.opsTotal, worker->getLiveOps() );
+		liveOpsAdd(out.opsReadMixTotal, worker->getLiveOpsReadMix() );
+		liveOpsAdd(out.opsStoneWallTotal, worker->getStoneWallOps() );
+		histogramMerge(out.iopsLatHisto, worker->getIOPSLatHisto() );
+		histogramMerge(out.entriesLatHisto, worker->getEntriesLatHisto() );
+
+		uint64_t devCounters[ELB_DEVCTR_NUM];
+		if(!worker->snapshotDevCounters(devCounters) )
+		{
+			out.verifyMismatchBytes += devCounters[ELB_DEVCTR_VERIFY_MISMATCH_BYTES];
+			out.verifiedBytes += devCounters[ELB_DEVCTR_VERIFIED_BYTES];
+			out.filledBytes += devCounters[ELB_DEVCTR_FILLED_BYTES];
+		}
+
+		out.numKernelLaunches += worker->getNumKernelLaunches();
+		out.h2dBytes += worker->getNumH2DBytes();
+		out.d2hBytes += worker->getNumD2HBytes();
+		out.devKernelUSec += worker->getDevKernelUSec();
+	}
+
+	out.firstFinishUSec = (firstFinishUSec == ~0ULL) ? 0 : firstFinishUSec;
+	out.lastFinishUSec = lastFinishUSec;
+
+	if(out.lastFinishUSec)
+	{
+		out.opsPerSec.numEntriesDone =
+			perSecFromUSec(out.opsTotal.numEntriesDone, out.lastFinishUSec);
+		out.opsPerSec.numBytesDone = perSecFromUSec(out.opsTotal.numBytesDone, out.lastFinishUSec);
+		out.opsPerSec.numIOPSDone = perSecFromUSec(out.opsTotal.numIOPSDone, out.lastFinishUSec);
+	}
+
+	if(out.firstFinishUSec)
+	{
+		out.opsStoneWallPerSec.numEntriesDone =
+			perSecFromUSec(out.opsStoneWallTotal.numEntriesDone, out.firstFinishUSec);
+		out.opsStoneWallPerSec.numBytesDone =
+			perSecFromUSec(out.opsStoneWallTotal.numBytesDone, out.firstFinishUSec);
+		out.opsStoneWallPerSec.numIOPSDone =
+			perSecFromUSec(out.opsStoneWallTotal.numIOPSDone, out.firstFinishUSec);
+	}
+
+	std::unique_lock<std::mutex> lock(shared.mutex);
+	out.numWorkersDone = (uint32_t)shared.numWorkersDone;
+	out.numWorkersDoneWithError = (uint32_t)shared.numWorkersDoneWithError;
+}
+
+/* getPhaseNumEntriesAndBytes (WorkerManager.cpp:333-487), summed over this manager's workers */
+void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& outBytes)
+{
+	const Config& cfg = shared.cfg;
+	uint64_t entriesPerWorker = 0;
+	uint64_t bytesPerWorker = 0;
+
+	if(cfg.pathType == ELB_PATH_DIR)
+	{
+		const uint64_t numDirs = cfg.numDirs ? cfg.numDirs : 1;
+
+		switch(benchPhase)
+		{
+			case ELB_PHASE_CREATEDIRS:
+			case ELB_PHASE_DELETEDIRS:
+				entriesPerWorker = cfg.numDirs;
+				break;
+
+			case ELB_PHASE_CREATEFILES:
+			case ELB_PHASE_READFILES:
+				entriesPerWorker = numDirs * cfg.numFiles;
+				bytesPerWorker = entriesPerWorker * cfg.fileSize;
+				break;
+
+			case ELB_PHASE_DELETEFILES:
+			case ELB_PHASE_STATFILES:
+				entriesPerWorker = numDirs * cfg.numFiles;
+				break;
+
+			default:
+				break;
+		}
+	}
+	else
+	{
+		entriesPerWorker = cfg.paths.size();
+
+		if( (benchPhase == ELB_PHASE_CREATEFILES) || (benchPhase == ELB_PHASE_READFILES) )
+			bytesPerWorker = cfg.useRandomOffsets ?
+				(cfg.randomAmount / cfg.numDataSetThreads) :
+				( (entriesPerWorker * cfg.fileSize) / cfg.numDataSetThreads);
+	}
+
+	outEntries = entriesPerWorker * cfg.numThreads;
+	outBytes = bytesPerWorker * cfg.numThreads;
+}
+
+} // namespace elb
+
+/* ==============================================================================================
+ * C ABI
+ * ============================================================================================ */
+
+struct elb_mgr
+{
+	elb::Manager* impl;
+	std::string lastError;
+};
+
+/* elb_worker handles are the Worker objects themselves */
+static inline elb::Worker* toWorker(elb_worker* w)
+{
+	return reinterpret_cast<elb::Worker*>(w);
+}
+
+static thread_local std::string elbWorkerErrorTmp;
+
+extern "C" {
+
+void elb_histogram_reset(elb_histogram* h)
+{
+	elb::histogramReset(*h);
+}
+
+void elb_histogram_add_latency(elb_histogram* h, uint64_t latencyMicroSec)
+{
+	elb::histogramAdd(*h, latencyMicroSec);
+}
+
+void elb_histogram_merge(elb_histogram* dst, const elb_histogram* src)
+{
+	elb::histogramMerge(*dst, *src);
+}
+
+double elb_histogram_percentile(const elb_histogram* h, double percentage)
+{
+	return elb::histogramPercentile(*h, percentage);
+}
+
+uint64_t elb_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec)
+{
+	return elb::perSecFromUSec(totalValue, elapsedUSec);
+}
+
+uint32_t elb_cfg_struct_size(void)
+{
+	return (uint32_t)sizeof(elb_cfg);
+}
+
+uint32_t elb_phase_results_struct_size(void)
+{
+	return (uint32_t)sizeof(elb_phase_results);
+}
+
+struct elb_offset_plan_impl
+{
+	std::unique_ptr<elb::Xoshiro256ss> randAlgo;
+	std::unique_ptr<elb::OffsetPlan> plan;
+};
+
+elb_offset_plan* elb_offset_plan_create(int kind, uint64_t amount, uint64_t rangeLen,
+	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads,
+	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed)
+{
+	if( (kind < elb::OffsetPlan::Kind_SEQUENTIAL) || (kind > elb::OffsetPlan::Kind_FULL_COVERAGE) )
+	{
+		elb_set_last_error("Invalid offset plan kind: " + std::to_string(kind) );
+		return NULL;
+	}
+
+	elb_offset_plan_impl* impl = new elb_offset_plan_impl();
+
+	if(randState)
+		impl->randAlgo.reset(new elb::Xoshiro256ss(randState) );
+	else
+		impl->randAlgo.reset(new elb::Xoshiro256ss() );
+
+	impl->plan.reset(new elb::OffsetPlan( (elb::OffsetPlan::Kind)kind, amount, rangeLen,
+		rangeOffset, blockSize, numDataSetThreads, impl->randAlgo.get(), lcgSeed,
+		haveLCGSeed != 0) );
+
+	return reinterpret_cast<elb_offset_plan*>(impl);
+}
+
+void elb_offset_plan_destroy(elb_offset_plan* plan)
+{
+	delete reinterpret_cast<elb_offset_plan_impl*>(plan);
+}
+
+void elb_offset_plan_restart(elb_offset_plan* plan)
+{
+	reinterpret_cast<elb_offset_plan_impl*>(plan)->plan->restart();
+}
+
+void elb_offset_plan_restart_range(elb_offset_plan* plan, uint64_t rangeLen,
+	uint64_t rangeOffset)
+{
+	reinterpret_cast<elb_offset_plan_impl*>(plan)->plan->restart(rangeLen, rangeOffset);
+}
+
+int elb_offset_plan_next(elb_offset_plan* plan, uint64_t* outOffset, uint64_t* outLen)
+{
+	return reinterpret_cast<elb_offset_plan_impl*>(plan)->plan->nextBlock(*outOffset, *outLen) ?
+		1 : 0;
+}
+
+uint64_t elb_offset_plan_bytes_total(const elb_offset_plan* plan)
+{
+	return reinterpret_cast<const elb_offset_plan_impl*>(plan)->plan->getNumBytesTotal();
+}
+
+uint64_t elb_offset_plan_bytes_left(const elb_offset_plan* plan)
+{
+	return reinterpret_cast<const elb_offset_plan_impl*>(plan)->plan->getNumBytesLeftToSubmit();
+}
+
+void elb_expand_offset_seed(uint64_t seed, uint64_t rank, uint64_t outState[4])
+{
+	elb::Xoshiro256ss::expandSeed(seed, rank, outState);
+}
+
+elb_mgr* elb_mgr_create(const elb_cfg* cfg)
+{
+	try
+	{
+		elb_mgr* m = new elb_mgr();
+		try
+		{
+			m->impl = new elb::Manager(cfg);
+		}
+		catch(...)
+		{
+			delete m;
+			throw;
+		}
+
+		return m;
+	}
+	catch(std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return NULL;
+	}
+}
+
+void elb_mgr_destroy(elb_mgr* m)
+{
+	if(!m)
+		return;
+
+	delete m->impl;
+	delete m;
+}
+
+int elb_mgr_start_phase(elb_mgr* m, int benchPhase)
+{
+	try
+	{
+		m->impl->startNextPhase(benchPhase);
+		return 0;
+	}
+	catch(std::exception& e)
+	{
+		m->lastError = e.what();
+		elb_set_last_error(e.what() );
+		return -1;
+	}
+}
+
+int elb_mgr_wait_done(elb_mgr* m, int timeoutMS)
+{
+	int waitRes = m->impl->waitForWorkersDone(timeoutMS);
+
+	if(waitRes < 0)
+	{
+		std::unique_lock<std::mutex> lock(m->impl->shared.mutex);
+		m->lastError = m->impl->shared.firstErrorMsg.empty() ?
+			"Worker encountered error" : m->impl->shared.firstErrorMsg;
+		elb_set_last_error(m->lastError);
+	}
+
+	return waitRes;
+}
+
+int elb_mgr_run_phase(elb_mgr* m, int benchPhase)
+{
+	if(elb_mgr_start_phase(m, benchPhase) )
+		return -1;
+
+	return (elb_mgr_wait_done(m, -1) == 1) ? 0 : -1;
+}
+
+int elb_mgr_live_ops(elb_mgr* m, elb_liveops out[2])
+{
+	out[0] = elb_liveops{};
+	out[1] = elb_liveops{};
+
+	for(const std::unique_ptr<elb::Worker>& worker : m->impl->workers)
+	{
+		elb::liveOpsAdd(out[0], worker->getLiveOps() );
+		elb::liveOpsAdd(out[1], worker->getLiveOpsReadMix() );
+	}
+
+	return 0;
+}
+
+int elb_mgr_live_latency(elb_mgr* m, elb_livelat* out)
+{
+	*out = elb_livelat{};
+
+	for(const std::unique_ptr<elb::Worker>& worker : m->impl->workers)
+		worker->getAndResetLiveLatency(*out);
+
+	return 0;
+}
+
+int elb_mgr_phase_results(elb_mgr* m, elb_phase_results* out)
+{
+	m->impl->getPhaseResults(*out);
+	return 0;
+}
+
+int elb_mgr_expected_totals(elb_mgr* m, int benchPhase, uint64_t* outEntries,
+	uint64_t* outBytes)
+{
+	m->impl->getExpectedTotals(benchPhase, *outEntries, *outBytes);
+	return 0;
+}
+
+int elb_mgr_interrupt(elb_mgr* m)
+{
+	std::unique_lock<std::mutex> lock(m->impl->shared.mutex);
+
+	for(elb::Worker* worker : m->impl->shared.workers)
+		worker->interruptExecution();
+
+	m->impl->shared.condition.notify_all();
+
+	return 0;
+}
+
+uint32_t elb_mgr_num_workers(elb_mgr* m)
+{
+	return (uint32_t)m->impl->workers.size();
+}
+
+elb_worker* elb_mgr_worker(elb_mgr* m, uint32_t localIdx)
+{
+	if(localIdx >= m->impl->workers.size() )
+		return NULL;
+
+	return reinterpret_cast<elb_worker*>(m->impl->workers[localIdx].get() );
+}
+
+const char* elb_mgr_last_error(elb_mgr* m)
+{
+	return m->lastError.c_str();
+}
+
+uint64_t elb_worker_rank(elb_worker* w)
+{
+	return toWorker(w)->getRank();
+}
+
+int elb_worker_gpu_id(elb_worker* w)
+{
+	return toWorker(w)->getGPUID();
+}
+
+int elb_worker_live_ops(elb_worker* w, elb_liveops out[2])
+{
+	out[0] = toWorker(w)->getLiveOps();
+	out[1] = toWorker(w)->getLiveOpsReadMix();
+	return 0;
+}
+
+int elb_worker_stonewall_ops(elb_worker* w, elb_liveops out[2])
+{
+	out[0] = toWorker(w)->getStoneWallOps();
+	out[1] = toWorker(w)->getStoneWallOpsReadMix();
+	return 0;
+}
+
+int elb_worker_histogram(elb_worker* w, int kind, elb_histogram* out)
+{
+	switch(kind)
+	{
+		case ELB_HISTO_IOPS: *out = toWorker(w)->getIOPSLatHisto(); break;
+		case ELB_HISTO_IOPS_READMIX: *out = toWorker(w)->getIOPSLatHistoReadMix(); break;
+		case ELB_HISTO_ENTRIES: *out = toWorker(w)->getEntriesLatHisto(); break;
+		case ELB_HISTO_ENTRIES_READMIX: *out = toWorker(w)->getEntriesLatHistoReadMix(); break;
+		default:
+			elb_set_last_error("Invalid histogram kind: " + std::to_string(kind) );
+			return -1;
+	}
+
+	return 0;
+}
+
+uint64_t elb_worker_elapsed_usec(elb_worker* w)
+{
+	return toWorker(w)->getElapsedUSec();
+}
+
+int elb_worker_got_work(elb_worker* w)
+{
+	return toWorker(w)->getWorkerGotPhaseWork() ? 1 : 0;
+}
+
+int elb_worker_dev_counters(elb_worker* w, uint64_t out[ELB_DEVCTR_NUM])
+{
+	return toWorker(w)->snapshotDevCounters(out);
+}
+
+uint64_t* elb_worker_dev_counters_ptr(elb_worker* w)
+{
+	return toWorker(w)->getDevCountersPtr();
+}
+
+const char* elb_worker_last_error(elb_worker* w)
+{
+	elbWorkerErrorTmp = toWorker(w)->getLastError();
+	return elbWorkerErrorTmp.c_str();
+}
+
+} // extern "C"

@@ -1,0 +1,1778 @@
+/*
+ * GPU worker implementation. See elb_worker.h for the design and the reference counterparts.
+ */
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include <algorithm>
+
+#include "elb_patterns.cuh"
+#include "elb_worker.h"
+
+#define ELB_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
+#define ELB_MKDIR_MODE (S_IRWXU | S_IRWXG | S_IRWXO)
+#define ELB_PATH_BUF_LEN 64        /* LocalWorker.cpp:62 */
+#define ELB_INTERRUPT_CHECK_INTERVAL 128 /* LocalWorker.cpp:63 */
+#define ELB_AIO_MAX_EVENTS 64
+#define ELB_AIO_MAX_WAIT_SEC 5     /* LocalWorker.cpp:60 */
+#define ELB_DEFAULT_BATCH_BYTES (16ULL * 1024 * 1024)
+#define ELB_MAX_BATCH_BLOCKS 256
+#define ELB_SLOT_ALIGN 4096
+
+#define ELB_CUDA_CHECK(call, what) \
+	do \
+	{ \
+		cudaError_t cudaCheckRes = (call); \
+		if(cudaCheckRes != cudaSuccess) \
+			throw WorkerError(std::string(what) + " failed. " \
+				"GPU ID: " + std::to_string(gpuID) + "; " \
+				"CUDA Error: " + cudaGetErrorString(cudaCheckRes) ); \
+	} while(0)
+
+namespace elb
+{
+
+static uint64_t elapsedUSecSince(const Clock::time_point& startT)
+{
+	return std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - startT).count();
+}
+
+/* ==============================================================================================
+ * Block sources: the three file iterators of the reference as producers of block references
+ * ============================================================================================ */
+
+/* fileModeIterateFilesSeq (LocalWorker.cpp:3564-3729): contiguous global block range per rank,
+ * last rank takes the remainder, one offset plan range per file piece. */
+class FileSeqSource : public BlockSource
+{
+	public:
+		FileSeqSource(const Config& cfg, uint64_t rank, OffsetPlan& plan, uint64_t& blockCounter) :
+			cfg(cfg), plan(plan), blockCounter(blockCounter)
+		{
+			const uint64_t numFiles = cfg.paths.size();
+			const uint64_t numThreads = cfg.numDataSetThreads;
+
+			numBlocksPerFile = (cfg.fileSize / cfg.blockSize) +
+				( (cfg.fileSize % cfg.blockSize) ? 1 : 0);
+
+			const uint64_t numBlocksTotal = numBlocksPerFile * numFiles;
+			const uint64_t standardWorkerNumBlocks = numBlocksTotal / numThreads;
+
+			uint64_t thisWorkerNumBlocks = standardWorkerNumBlocks;
+			if( (rank == (numThreads - 1) ) && (numBlocksTotal % numThreads) )
+				thisWorkerNumBlocks = numBlocksTotal - (standardWorkerNumBlocks * (numThreads - 1) );
+
+			currentBlockIdx = rank * standardWorkerNumBlocks;
+			endBlock = currentBlockIdx + thisWorkerNumBlocks;
+
+			// expected bytes: walk the pieces once
+			for(uint64_t blockIdx = currentBlockIdx; blockIdx < endBlock; )
+			{
+				uint64_t pieceLen, pieceStart, fileIdx;
+				calcPiece(blockIdx, fileIdx, pieceStart, pieceLen);
+				numBytesTotal += pieceLen;
+				blockIdx += (pieceLen / cfg.blockSize) + ( (pieceLen % cfg.blockSize) ? 1 : 0);
+			}
+		}
+
+		bool hasWork() const { return currentBlockIdx < endBlock; }
+		virtual uint64_t getNumBytesTotal() const override { return numBytesTotal; }
+
+		virtual bool next(BlockRef& outBlock) override
+		{
+			while(!pieceActive || !plan.getNumBytesLeftToSubmit() )
+			{
+				if(pieceActive)
+				{ // piece done: advance global block index (:3685-3692)
+					currentBlockIdx += (currentPieceLen / cfg.blockSize) +
+						( (currentPieceLen % cfg.blockSize) ? 1 : 0);
+					pieceActive = false;
+				}
+
+				if(currentBlockIdx >= endBlock)
+					return false;
+
+				uint64_t pieceStart;
+				calcPiece(currentBlockIdx, currentFileIdx, pieceStart, currentPieceLen);
+				plan.restart(currentPieceLen, pieceStart);
+				pieceActive = true;
+			}
+
+			outBlock = BlockRef();
+			plan.nextBlock(outBlock.offset, outBlock.len);
+			outBlock.fileIdx = (uint32_t)currentFileIdx;
+			outBlock.blockCounter = blockCounter++;
+
+			return true;
+		}
+
+	private:
+		const Config& cfg;
+		OffsetPlan& plan;
+		uint64_t& blockCounter;
+		uint64_t numBlocksPerFile;
+		uint64_t currentBlockIdx;
+		uint64_t endBlock;
+		uint64_t numBytesTotal{0};
+		bool pieceActive{false};
+		uint64_t currentFileIdx{0};
+		uint64_t currentPieceLen{0};
+
+		void calcPiece(uint64_t blockIdx, uint64_t& outFileIdx, uint64_t& outStart,
+			uint64_t& outLen) const
+		{ // :3617-3629
+			outFileIdx = blockIdx / numBlocksPerFile;
+			const uint64_t blockInFile = blockIdx % numBlocksPerFile;
+			outStart = blockInFile * cfg.blockSize;
+			const uint64_t remainingWorkerLen = (endBlock - blockIdx) * cfg.blockSize;
+			const uint64_t remainingFileLen = cfg.fileSize - outStart;
+			outLen = std::min(remainingWorkerLen, remainingFileLen);
+		}
+};
+
+/* fileModeIterateFilesRand (LocalWorker.cpp:3478-3556): all files form one virtual range
+ * (calcFileIdxAndOffsetStriped, :2051-2074) */
+class FileRandSource : public BlockSource
+{
+	public:
+		FileRandSource(const Config& cfg, OffsetPlan& plan, uint64_t& blockCounter) :
+			cfg(cfg), plan(plan), blockCounter(blockCounter),
+			numBytesTotal(plan.getNumBytesTotal() ) {}
+
+		virtual uint64_t getNumBytesTotal() const override { return numBytesTotal; }
+
+		virtual bool next(BlockRef& outBlock) override
+		{
+			uint64_t virtualOffset = 0, len = 0;
+
+			if(!plan.nextBlock(virtualOffset, len) )
+				return false;
+
+			outBlock = BlockRef();
+			outBlock.len = len;
+
+			if(cfg.paths.size() == 1)
+				outBlock.offset = virtualOffset;
+			else
+			{
+				outBlock.fileIdx = (uint32_t)(virtualOffset / cfg.fileSize);
+				outBlock.offset = virtualOffset % cfg.fileSize;
+			}
+
+			outBlock.blockCounter = blockCounter++;
+
+			return true;
+		}
+
+	private:
+		const Config& cfg;
+		OffsetPlan& plan;
+		uint64_t& blockCounter;
+		const uint64_t numBytesTotal;
+};
+
+/* dirModeIterateFiles (LocalWorker.cpp:3022-3248): rank-private files, dir by dir */
+class DirSource : public BlockSource
+{
+	public:
+		DirSource(const Config& cfg, OffsetPlan& plan, uint64_t& blockCounter) :
+			cfg(cfg), plan(plan), blockCounter(blockCounter),
+			numDirs(cfg.numDirs ? cfg.numDirs : 1) {}
+
+		virtual uint64_t getNumBytesTotal() const override
+			{ return numDirs * cfg.numFiles * cfg.fileSize; }
+
+		virtual bool next(BlockRef& outBlock) override
+		{
+			if(!fileActive)
+			{
+				if(dirIndex >= numDirs)
+					return false;
+
+				plan.restart(); // :3079
+				fileActive = true;
+				isFirstBlock = true;
+			}
+
+			outBlock = BlockRef();
+			outBlock.dirIndex = dirIndex;
+			outBlock.fileIndex = fileIndex;
+			outBlock.firstOfFile = isFirstBlock;
+			isFirstBlock = false;
+
+			// (empty files still yield one zero-length block that opens and closes the file)
+			plan.nextBlock(outBlock.offset, outBlock.len);
+			outBlock.blockCounter = blockCounter++;
+
+			if(!plan.getNumBytesLeftToSubmit() )
+			{
+				outBlock.lastOfFile = true;
+				fileActive = false;
+
+				if(++fileIndex >= cfg.numFiles)
+				{
+					fileIndex = 0;
+					dirIndex++;
+				}
+			}
+
+			return true;
+		}
+
+	private:
+		const Config& cfg;
+		OffsetPlan& plan;
+		uint64_t& blockCounter;
+		const uint64_t numDirs;
+		uint64_t dirIndex{0};
+		uint64_t fileIndex{0};
+		bool fileActive{false};
+		bool isFirstBlock{false};
+};
+
+/* ==============================================================================================
+ * Worker: lifecycle
+ * ============================================================================================ */
+
+Worker::Worker(Shared* shared, uint64_t rank) : shared(shared), cfg(shared->cfg), rank(rank)
+{
+	histogramReset(iopsLatHisto);
+	histogramReset(iopsLatHistoReadMix);
+	histogramReset(entriesLatHisto);
+	histogramReset(entriesLatHistoReadMix);
+}
+
+Worker::~Worker()
+{
+}
+
+void Worker::threadStart(Worker* worker)
+{
+	worker->run();
+	worker->cleanup();
+}
+
+void Worker::resetStats() // Worker.h:92-110
+{
+	phaseFinished = false;
+	isInterruptionRequested = false;
+	workerGotPhaseWork = true;
+	elapsedUSec = 0;
+	atomicLiveOps.setToZero();
+	atomicLiveOpsReadMix.setToZero();
+	stoneWallTriggered = false;
+	stoneWallOps = elb_liveops{};
+	stoneWallOpsReadMix = elb_liveops{};
+	histogramReset(iopsLatHisto);
+	histogramReset(iopsLatHistoReadMix);
+	histogramReset(entriesLatHisto);
+	histogramReset(entriesLatHistoReadMix);
+	liveLatNumIO = 0;
+	liveLatSumIO = 0;
+	liveLatNumEntries = 0;
+	liveLatSumEntries = 0;
+	numH2DBytes = 0;
+	numD2HBytes = 0;
+	numKernelLaunches = 0;
+	devKernelUSec = 0;
+
+	std::unique_lock<std::mutex> lock(errorMutex);
+	lastError.clear();
+}
+
+void Worker::createStoneWallStats() // Worker.h createStoneWallStats
+{
+	stoneWallTriggered = true;
+	stoneWallOps = atomicLiveOps.snapshot();
+	stoneWallOpsReadMix = atomicLiveOpsReadMix.snapshot();
+}
+
+void Worker::getAndResetLiveLatency(elb_livelat& outLat)
+{
+	outLat.numAvgIOLatValues += liveLatNumIO.exchange(0);
+	outLat.avgIOLatMicroSecsSum += liveLatSumIO.exchange(0);
+	outLat.numAvgEntriesLatValues += liveLatNumEntries.exchange(0);
+	outLat.avgEntriesLatMicroSecsSum += liveLatSumEntries.exchange(0);
+}
+
+std::string Worker::getLastError()
+{
+	std::unique_lock<std::mutex> lock(errorMutex);
+	return lastError;
+}
+
+int Worker::snapshotDevCounters(uint64_t out[ELB_DEVCTR_NUM] )
+{
+	memset(out, 0, sizeof(uint64_t) * ELB_DEVCTR_NUM);
+
+	if(!devCounters)
+		return -1;
+
+	int oldDev = -1;
+	cudaGetDevice(&oldDev);
+	cudaSetDevice(gpuID);
+	cudaError_t copyRes = cudaMemcpy(out, devCounters, sizeof(uint64_t) * ELB_DEVCTR_NUM,
+		cudaMemcpyDeviceToHost);
+	if(oldDev >= 0)
+		cudaSetDevice(oldDev);
+
+	return (copyRes == cudaSuccess) ? 0 : -1;
+}
+
+void Worker::checkInterruptionRequest() // Worker.cpp:72-76
+{
+	if(isInterruptionRequested)
+		throw WorkerInterrupted();
+}
+
+/* Worker.cpp:153-164. Unlike the reference, an idle worker is not interruptible here: its thread
+ * stays alive across errors/interruptions and only ends on BenchPhase_TERMINATE. */
+void Worker::waitForNextPhase(uint64_t oldBenchSeq)
+{
+	std::unique_lock<std::mutex> lock(shared->mutex);
+
+	while(oldBenchSeq == shared->currentBenchSeq)
+		shared->condition.wait(lock);
+}
+
+void Worker::incNumWorkersDone() // Worker.cpp:33-55
+{
+	std::unique_lock<std::mutex> lock(shared->mutex);
+
+	const size_t numWorkersTotal = shared->workers.size();
+	const bool lastFinisherTrigger = cfg.runAsService ?
+		false : ( (shared->numWorkersDone + 1) == numWorkersTotal);
+	const bool triggerStoneWall = (!stoneWallTriggered &&
+		(workerGotPhaseWork || lastFinisherTrigger) );
+
+	shared->numWorkersDone++;
+
+	if(triggerStoneWall)
+		for(Worker* worker : shared->workers)
+			worker->createStoneWallStats();
+
+	shared->condition.notify_all();
+}
+
+void Worker::incNumWorkersDoneWithError() // WorkersSharedData.cpp:36-44
+{
+	std::unique_lock<std::mutex> lock(shared->mutex);
+
+	shared->numWorkersDone++;
+	shared->numWorkersDoneWithError++;
+
+	if(shared->firstErrorMsg.empty() )
+		shared->firstErrorMsg = getLastError();
+
+	shared->condition.notify_all();
+}
+
+void Worker::finishPhase() // LocalWorker.cpp:433-453
+{
+	if(!workerGotPhaseWork)
+		elapsedUSec = 0;
+	else
+		elapsedUSec = std::max( (uint64_t)1, elapsedUSecSince(shared->phaseStartT) );
+
+	phaseFinished = true;
+
+	incNumWorkersDone();
+}
+
+void Worker::run() // LocalWorker.cpp:177-396
+{
+	uint64_t currentBenchSeq = 0;
+
+	try
+	{
+		preparePhase();
+	}
+	catch(std::exception& e)
+	{
+		{
+			std::unique_lock<std::mutex> lock(errorMutex);
+			lastError = e.what();
+		}
+
+		incNumWorkersDoneWithError();
+		return;
+	}
+
+	// signal coordinator that our preparations phase is done
+	phaseFinished = true;
+	incNumWorkersDone();
+
+	for( ; ; )
+	{
+		try
+		{
+			waitForNextPhase(currentBenchSeq);
+
+			{
+				std::unique_lock<std::mutex> lock(shared->mutex);
+				currentBenchSeq = shared->currentBenchSeq;
+				benchPhase = shared->currentBenchPhase;
+			}
+
+			switch(benchPhase)
+			{
+				case ELB_PHASE_TERMINATE:
+					return;
+
+				case ELB_PHASE_CREATEDIRS:
+				case ELB_PHASE_DELETEDIRS:
+				{
+					if(cfg.pathType != ELB_PATH_DIR)
+						throw WorkerError("Directory creation and deletion are not available in "
+							"file and block device mode.");
+
+					dirModeIterateDirs();
+				} break;
+
+				case ELB_PHASE_CREATEFILES:
+				case ELB_PHASE_READFILES:
+					rwPhase();
+					break;
+
+				case ELB_PHASE_STATFILES:
+				{
+					if(cfg.pathType != ELB_PATH_DIR)
+						throw WorkerError("File stat operation not available in file and block "
+							"device mode.");
+
+					dirModeIterateFilesNoIO();
+				} break;
+
+				case ELB_PHASE_DELETEFILES:
+				{
+					if(cfg.pathType == ELB_PATH_DIR)
+						dirModeIterateFilesNoIO();
+					else
+						fileModeDeleteFiles();
+				} break;
+
+				case ELB_PHASE_SYNC:
+					anyModeSync();
+					break;
+
+				case ELB_PHASE_DROPCACHES:
+					anyModeDropCaches();
+					break;
+
+				default:
+					throw WorkerError("Unknown/invalid next phase type: " +
+						std::to_string(benchPhase) );
+			}
+
+			finishPhase();
+		}
+		catch(WorkerInterrupted& e)
+		{
+			// interrupted by friendly ask: not an error (LocalWorker.cpp:372-387)
+			if(benchPhase == ELB_PHASE_TERMINATE)
+				return;
+
+			{
+				std::unique_lock<std::mutex> lock(shared->mutex);
+				if(shared->currentBenchPhase == ELB_PHASE_TERMINATE)
+					return;
+			}
+
+			abortInFlight();
+
+			isInterruptionRequested = false;
+
+			if(!phaseFinished) // (LocalWorker.cpp:378-384)
+				finishPhase();
+		}
+		catch(std::exception& e)
+		{
+			{
+				std::unique_lock<std::mutex> lock(errorMutex);
+				lastError = e.what();
+			}
+
+			abortInFlight();
+
+			phaseFinished = true;
+			incNumWorkersDoneWithError();
+		}
+	}
+}
+
+/* ==============================================================================================
+ * Preparation: device, rings, batches (replaces allocIOBuffer/allocGPUIOBuffer, :1362-1513)
+ * ============================================================================================ */
+
+void Worker::preparePhase()
+{
+	gpuID = cfg.gpuIDs[rank % cfg.gpuIDs.size() ]; // LocalWorker.cpp:1420-1422
+
+	ELB_CUDA_CHECK(cudaSetDevice(gpuID), "Setting CUDA device");
+
+	// injected seeds make runs reproducible; 0 = self-seed like the reference
+	if(cfg.randOffsetSeed)
+		randOffsetAlgo.reset(new Xoshiro256ss(Xoshiro256ss::fromSeed(cfg.randOffsetSeed, rank) ) );
+	else
+		randOffsetAlgo.reset(new Xoshiro256ss() );
+
+	if(cfg.blockVarianceSeed)
+		blockVarianceSeed = cfg.blockVarianceSeed;
+	else
+	{
+		std::random_device randDev;
+		blockVarianceSeed = ( (uint64_t)randDev() << 32) | (uint32_t)randDev();
+	}
+
+	allocRings();
+}
+
+void Worker::allocRings()
+{
+	if(!cfg.blockSize)
+		return; // nothing to do here (LocalWorker.cpp:1364-1365)
+
+	// slots are aligned for O_DIRECT; full-size slots make a batch one contiguous staged copy
+	slotStride = ( (cfg.blockSize + ELB_SLOT_ALIGN - 1) / ELB_SLOT_ALIGN) * ELB_SLOT_ALIGN;
+
+	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
+
+	if(cfg.pipelineBatchBlocks)
+		batchBlocks = cfg.pipelineBatchBlocks;
+	else
+	if(useAio)
+		batchBlocks = std::max(1u, (cfg.ioDepth + 1) / 2); // two batches in I/O flight = iodepth
+	else
+		batchBlocks = (uint32_t)std::max( (uint64_t)1, (uint64_t)(ELB_DEFAULT_BATCH_BYTES / slotStride) );
+
+	batchBlocks = std::min(batchBlocks, (uint32_t)ELB_MAX_BATCH_BLOCKS);
+
+	numBatches = cfg.pipelineNumBatches ? cfg.pipelineNumBatches : (useAio ? 3 : 2);
+
+	const uint64_t numSlots = (uint64_t)batchBlocks * numBatches;
+	const uint64_t ringBytes = numSlots * slotStride;
+
+	ELB_CUDA_CHECK(cudaHostAlloc( (void**)&hostRing, ringBytes, cudaHostAllocDefault),
+		"Pinned host I/O ring allocation");
+	ELB_CUDA_CHECK(cudaMalloc( (void**)&devRing, ringBytes), "GPU I/O ring allocation");
+	ELB_CUDA_CHECK(cudaMalloc( (void**)&devCounters, sizeof(uint64_t) * ELB_DEVCTR_NUM),
+		"GPU counter block allocation");
+	ELB_CUDA_CHECK(cudaMemset(devCounters, 0, sizeof(uint64_t) * ELB_DEVCTR_NUM),
+		"GPU counter block init");
+
+	/* fill the host ring with random data so that it is never sparse and copy it to the device
+	   ring (LocalWorker.cpp:1388-1390, 1473) */
+	{
+		Xoshiro256ss initRand;
+		uint64_t* words = (uint64_t*)hostRing;
+		for(uint64_t i = 0; i < (ringBytes / sizeof(uint64_t) ); i++)
+			words[i] = initRand.next();
+	}
+
+	ELB_CUDA_CHECK(cudaMemcpy(devRing, hostRing, ringBytes, cudaMemcpyHostToDevice),
+		"Initialization of GPU I/O ring");
+
+	batches.resize(numBatches);
+
+	for(uint32_t i = 0; i < numBatches; i++)
+	{
+		Batch& batch = batches[i];
+		batch.index = i;
+		batch.firstSlot = i * batchBlocks;
+		batch.blocks.reserve(batchBlocks);
+
+		ELB_CUDA_CHECK(cudaStreamCreateWithFlags(&batch.stream, cudaStreamNonBlocking),
+			"CUDA stream creation");
+		ELB_CUDA_CHECK(cudaEventCreate(&batch.gpuStartEvent), "CUDA event creation");
+		ELB_CUDA_CHECK(cudaEventCreate(&batch.gpuDoneEvent), "CUDA event creation");
+		ELB_CUDA_CHECK(cudaEventCreate(&batch.kernelStartEvent), "CUDA event creation");
+		ELB_CUDA_CHECK(cudaEventCreate(&batch.kernelDoneEvent), "CUDA event creation");
+
+		ELB_CUDA_CHECK(cudaHostAlloc( (void**)&batch.hostDescs,
+			sizeof(elb_block_desc) * batchBlocks, cudaHostAllocDefault), "Pinned desc allocation");
+		ELB_CUDA_CHECK(cudaMalloc( (void**)&batch.devDescs, sizeof(elb_block_desc) * batchBlocks),
+			"GPU desc allocation");
+		ELB_CUDA_CHECK(cudaMalloc( (void**)&batch.devResults,
+			sizeof(elb_verify_result) * batchBlocks), "GPU verify result allocation");
+		ELB_CUDA_CHECK(cudaHostAlloc( (void**)&batch.hostResults,
+			sizeof(elb_verify_result) * batchBlocks, cudaHostAllocDefault),
+			"Pinned verify result allocation");
+
+		batch.iocbs.resize(batchBlocks);
+		batch.iocbPtrs.resize(batchBlocks);
+	}
+
+	if(useAio)
+	{ // initLibAio (LocalWorker.cpp:455-480) on the raw kernel ABI
+		aioContext = 0;
+		long setupRes = syscall(SYS_io_setup, (unsigned)numSlots, &aioContext);
+		if(setupRes == -1)
+			throw WorkerError(std::string("Initializing async IO (io_setup) failed. ") +
+				"SysErr: " + strerror(errno) );
+
+		aioInitialized = true;
+	}
+
+	gpuPrepared = true;
+}
+
+void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
+{
+	if(aioInitialized)
+	{
+		syscall(SYS_io_destroy, aioContext);
+		aioInitialized = false;
+	}
+
+	if(gpuID < 0)
+		return;
+
+	cudaSetDevice(gpuID);
+
+	for(Batch& batch : batches)
+	{
+		if(batch.stream)
+			cudaStreamDestroy(batch.stream);
+		if(batch.gpuStartEvent)
+			cudaEventDestroy(batch.gpuStartEvent);
+		if(batch.gpuDoneEvent)
+			cudaEventDestroy(batch.gpuDoneEvent);
+		if(batch.kernelStartEvent)
+			cudaEventDestroy(batch.kernelStartEvent);
+		if(batch.kernelDoneEvent)
+			cudaEventDestroy(batch.kernelDoneEvent);
+		if(batch.hostDescs)
+			cudaFreeHost(batch.hostDescs);
+		if(batch.devDescs)
+			cudaFree(batch.devDescs);
+		if(batch.devResults)
+			cudaFree(batch.devResults);
+		if(batch.hostResults)
+			cudaFreeHost(batch.hostResults);
+	}
+
+	batches.clear();
+
+	if(hostRing)
+		cudaFreeHost(hostRing);
+	if(devRing)
+		cudaFree(devRing);
+	if(devCounters)
+		cudaFree(devCounters);
+
+	hostRing = NULL;
+	devRing = NULL;
+	devCounters = NULL;
+	gpuPrepared = false;
+}
+
+/* after an error or interruption: let everything that is still in flight on the GPU streams and
+ * in the kernel AIO context finish, so that the rings can be reused by the next phase */
+void Worker::abortInFlight()
+{
+	if(dirModeFD != -1)
+	{
+		close(dirModeFD);
+		dirModeFD = -1;
+	}
+
+	if(gpuPrepared)
+	{
+		cudaSetDevice(gpuID);
+
+		for(Batch& batch : batches)
+		{
+			cudaStreamSynchronize(batch.stream);
+			batch.devResultsClean = false;
+			batch.numIOPending = 0;
+			batch.ioSubmitted = false;
+		}
+	}
+
+	if(aioInitialized)
+	{ // io_destroy waits for all in-flight requests
+		syscall(SYS_io_destroy, aioContext);
+		aioContext = 0;
+		aioInitialized = (syscall(SYS_io_setup, (unsigned)(batchBlocks * numBatches),
+			&aioContext) != -1);
+	}
+}
+
+void Worker::cleanup()
+{
+	if(dirModeFD != -1)
+	{
+		close(dirModeFD);
+		dirModeFD = -1;
+	}
+
+	freeRings();
+}
+
+/* ==============================================================================================
+ * Offset plan selection (initPhaseRWOffsetGen :1119-1164 + fileModeIterateFilesRand :3486-3513)
+ * ============================================================================================ */
+
+void Worker::initPhaseOffsetPlan()
+{
+	const bool isWritePhase = (benchPhase == ELB_PHASE_CREATEFILES);
+	const bool isDir = (cfg.pathType == ELB_PATH_DIR);
+	const uint64_t blockSize = cfg.blockSize;
+	const uint64_t fileSize = cfg.fileSize;
+	const uint64_t numDataSetThreads = cfg.numDataSetThreads;
+
+	// start state of the full coverage permutations: derived from the injected seed, if any
+	uint64_t lcgSeed = 0;
+	const bool haveLCGSeed = (cfg.randOffsetSeed != 0);
+
+	if(haveLCGSeed)
+	{
+		uint64_t expanded[4];
+		Xoshiro256ss::expandSeed(cfg.randOffsetSeed, rank, expanded);
+		lcgSeed = expanded[0] ^ expanded[1];
+
+		// every phase restarts the offset stream from the injected seed
+		randOffsetAlgo.reset(new Xoshiro256ss(expanded) );
+	}
+
+	OffsetPlan::Kind kind;
+	uint64_t amount, rangeLen, rangeOffset;
+
+	if(!isDir && (cfg.useRandomOffsets || cfg.useStridedAccess) )
+	{ // :3486-3513
+		const uint64_t numBlocksPerFile = fileSize / blockSize;
+		const uint64_t numBlocksTotal = numBlocksPerFile * cfg.paths.size();
+
+		amount = cfg.randomAmount / numDataSetThreads;
+		rangeLen = blockSize * (numBlocksTotal / numDataSetThreads);
+		rangeOffset = rank * blockSize * (numBlocksTotal / numDataSetThreads);
+
+		if(cfg.useStridedAccess)
+		{
+			kind = OffsetPlan::Kind_STRIDED;
+			rangeOffset = blockSize * rank;
+		}
+		else
+		if(cfg.useRandomUnaligned)
+			kind = OffsetPlan::Kind_RANDOM_UNALIGNED;
+		else
+		if(cfg.useExplicitRandOffsetAlgo || !isWritePhase)
+			kind = OffsetPlan::Kind_RANDOM_ALIGNED;
+		else
+			kind = OffsetPlan::Kind_FULL_COVERAGE;
+	}
+	else
+	{ // :1129-1163
+		amount = isDir ? fileSize : (cfg.randomAmount / numDataSetThreads);
+		rangeLen = fileSize;
+		rangeOffset = 0;
+
+		if(cfg.doReverseSeqOffsets)
+			kind = OffsetPlan::Kind_REVERSE;
+		else
+		if(!cfg.useRandomOffsets && !cfg.useStridedAccess)
+			kind = OffsetPlan::Kind_SEQUENTIAL;
+		else
+		if(cfg.useRandomUnaligned)
+			kind = OffsetPlan::Kind_RANDOM_UNALIGNED;
+		else
+		if(cfg.useExplicitRandOffsetAlgo || !isWritePhase)
+			kind = OffsetPlan::Kind_RANDOM_ALIGNED;
+		else
+			kind = OffsetPlan::Kind_FULL_COVERAGE;
+	}
+
+	offsetPlan.reset(new OffsetPlan(kind, amount, rangeLen, rangeOffset, blockSize,
+		numDataSetThreads, randOffsetAlgo.get(), lcgSeed, haveLCGSeed) );
+}
+
+/* ==============================================================================================
+ * Metadata phases (pure syscalls, no GPU work)
+ * ============================================================================================ */
+
+void Worker::dirModeIterateDirs() // LocalWorker.cpp:2778-2912
+{
+	if(!cfg.numDirs)
+		return;
+
+	char currentPath[ELB_PATH_BUF_LEN];
+	const uint64_t numDirs = cfg.numDirs;
+	const std::vector<int>& pathFDs = shared->pathFDs;
+	const bool ignoreDelErrors = cfg.doDirSharing ? true : cfg.ignoreDelErrors;
+	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
+
+	if(benchPhase == ELB_PHASE_CREATEDIRS)
+	{
+		for(size_t pathFDsIndex = 0; pathFDsIndex < pathFDs.size(); pathFDsIndex++)
+		{
+			checkInterruptionRequest();
+
+			snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu", (size_t)workerDirRank);
+
+			int mkdirRes = mkdirat(pathFDs[pathFDsIndex], currentPath, ELB_MKDIR_MODE);
+
+			if( (mkdirRes == -1) && (errno != EEXIST) )
+				throw WorkerError(std::string("Rank directory creation failed. ") +
+					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+					"SysErr: " + strerror(errno) );
+		}
+	}
+
+	for(uint64_t dirIndex = 0; dirIndex < numDirs; dirIndex++)
+	{
+		checkInterruptionRequest();
+
+		int printRes = snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu/d%zu",
+			(size_t)workerDirRank, (size_t)dirIndex);
+		if(printRes >= ELB_PATH_BUF_LEN)
+			throw WorkerError("mkdir path too long for static buffer. "
+				"Buffer size: " + std::to_string(ELB_PATH_BUF_LEN) + "; "
+				"dirIndex: " + std::to_string(dirIndex) + "; "
+				"workerRank: " + std::to_string(rank) );
+
+		const size_t pathFDsIndex = (rank + dirIndex) % pathFDs.size();
+
+		Clock::time_point ioStartT = Clock::now();
+
+		if(benchPhase == ELB_PHASE_CREATEDIRS)
+		{
+			int mkdirRes = mkdirat(pathFDs[pathFDsIndex], currentPath, ELB_MKDIR_MODE);
+
+			if( (mkdirRes == -1) && (errno != EEXIST) )
+				throw WorkerError(std::string("Directory creation failed. ") +
+					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+					"SysErr: " + strerror(errno) );
+		}
+
+		if(benchPhase == ELB_PHASE_DELETEDIRS)
+		{
+			int rmdirRes = unlinkat(pathFDs[pathFDsIndex], currentPath, AT_REMOVEDIR);
+
+			if( (rmdirRes == -1) && ( (errno != ENOENT) || !ignoreDelErrors) )
+				throw WorkerError(std::string("Directory deletion failed. ") +
+					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+					"SysErr: " + strerror(errno) );
+		}
+
+		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
+
+		histogramAdd(entriesLatHisto, ioElapsedUSec);
+		liveLatNumEntries++;
+		liveLatSumEntries += ioElapsedUSec;
+		atomicLiveOps.numEntriesDone++;
+	}
+
+	if(benchPhase == ELB_PHASE_DELETEDIRS)
+	{
+		for(size_t pathFDsIndex = 0; pathFDsIndex < pathFDs.size(); pathFDsIndex++)
+		{
+			checkInterruptionRequest();
+
+			snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu", (size_t)workerDirRank);
+
+			int rmdirRes = unlinkat(pathFDs[pathFDsIndex], currentPath, AT_REMOVEDIR);
+
+			if( (rmdirRes == -1) && ( (errno != ENOENT) || !ignoreDelErrors) )
+				throw WorkerError(std::string("Directory deletion failed. ") +
+					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+					"SysErr: " + strerror(errno) );
+		}
+	}
+}
+
+/* stat and delete phases of dirModeIterateFiles (LocalWorker.cpp:3193-3243) */
+void Worker::dirModeIterateFilesNoIO()
+{
+	char currentPath[ELB_PATH_BUF_LEN];
+	const bool haveSubdirs = (cfg.numDirs > 0);
+	const uint64_t numDirs = haveSubdirs ? cfg.numDirs : 1;
+	const std::vector<int>& pathFDs = shared->pathFDs;
+	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
+
+	for(uint64_t dirIndex = 0; dirIndex < numDirs; dirIndex++)
+	{
+		for(uint64_t fileIndex = 0; fileIndex < cfg.numFiles; fileIndex++)
+		{
+			if( (fileIndex % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
+				checkInterruptionRequest();
+
+			if(haveSubdirs)
+				snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu/d%zu/r%zu-f%zu",
+					(size_t)workerDirRank, (size_t)dirIndex, (size_t)rank, (size_t)fileIndex);
+			else
+				snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu-f%zu", (size_t)rank,
+					(size_t)fileIndex);
+
+			const size_t pathFDsIndex = (rank + dirIndex) % pathFDs.size();
+
+			Clock::time_point ioStartT = Clock::now();
+
+			if(benchPhase == ELB_PHASE_STATFILES)
+			{
+				struct stat statBuf;
+
+				if(fstatat(pathFDs[pathFDsIndex], currentPath, &statBuf, 0) == -1)
+					throw WorkerError(std::string("File stat failed. ") +
+						"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+						"SysErr: " + strerror(errno) );
+			}
+
+			if(benchPhase == ELB_PHASE_DELETEFILES)
+			{
+				int unlinkRes = unlinkat(pathFDs[pathFDsIndex], currentPath, 0);
+
+				if( (unlinkRes == -1) && (!cfg.ignoreDelErrors || (errno != ENOENT) ) )
+					throw WorkerError(std::string("File delete failed. ") +
+						"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
+						"SysErr: " + strerror(errno) );
+			}
+
+			const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
+
+			histogramAdd(entriesLatHisto, ioElapsedUSec);
+			liveLatNumEntries++;
+			liveLatSumEntries += ioElapsedUSec;
+			atomicLiveOps.numEntriesDone++;
+		}
+	}
+}
+
+void Worker::fileModeDeleteFiles() // LocalWorker.cpp:3736-3767
+{
+	const size_t numFiles = cfg.paths.size();
+
+	for(size_t fileIndex = 0; fileIndex < numFiles; fileIndex++)
+	{
+		if( (fileIndex % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
+			checkInterruptionRequest();
+
+		const std::string& path = cfg.paths[ (rank + fileIndex) % numFiles];
+
+		int unlinkRes = unlink(path.c_str() );
+
+		if( (unlinkRes == -1) && (errno != ENOENT) )
+			throw WorkerError(std::string("File delete failed. ") +
+				"Path: " + path + "; "
+				"SysErr: " + strerror(errno) );
+
+		atomicLiveOps.numEntriesDone++;
+	}
+}
+
+void Worker::anyModeSync() // LocalWorker.cpp:7780-7812
+{
+	if(rank != cfg.rankOffset)
+	{
+		workerGotPhaseWork = false;
+		return;
+	}
+
+	const std::vector<int>& pathFDs = shared->pathFDs;
+
+	for(size_t i = 0; i < pathFDs.size(); i++)
+	{
+		const size_t currentIdx = (i + rank) % pathFDs.size();
+
+		if(syncfs(pathFDs[currentIdx] ) == -1)
+			throw WorkerError(std::string("Cache sync failed. ") +
+				"Path: " + cfg.paths[currentIdx] + "; "
+				"SysErr: " + strerror(errno) );
+	}
+}
+
+void Worker::anyModeDropCaches() // LocalWorker.cpp:7822-7854
+{
+	if(rank != cfg.rankOffset)
+	{
+		workerGotPhaseWork = false;
+		return;
+	}
+
+	const char* dropCachesPath = "/proc/sys/vm/drop_caches";
+
+	int fd = open(dropCachesPath, O_WRONLY);
+
+	if(fd == -1)
+		throw WorkerError(std::string("Opening virtual drop_caches file failed. ") +
+			"Path: " + dropCachesPath + "; "
+			"SysErr: " + strerror(errno) );
+
+	ssize_t writeRes = write(fd, "3", 1);
+	int writeErrno = errno;
+
+	close(fd);
+
+	if(writeRes == -1)
+		throw WorkerError(std::string("Writing to cache drop command file failed. ") +
+			"Path: " + dropCachesPath + "; "
+			"SysErr: " + strerror(writeErrno) );
+}
+
+/* ==============================================================================================
+ * Read/write phases
+ * ============================================================================================ */
+
+void Worker::rwPhase()
+{
+	const bool isRead = (benchPhase == ELB_PHASE_READFILES);
+
+	if(!cfg.blockSize || !gpuPrepared)
+	{ // zero-sized files: only dir mode has something to do (create/open empty files)
+		if(cfg.pathType != ELB_PATH_DIR)
+		{
+			workerGotPhaseWork = false;
+			return;
+		}
+	}
+
+	ELB_CUDA_CHECK(cudaSetDevice(gpuID), "Setting CUDA device");
+
+	if(devCounters)
+		ELB_CUDA_CHECK(cudaMemset(devCounters, 0, sizeof(uint64_t) * ELB_DEVCTR_NUM),
+			"GPU counter block reset");
+
+	initPhaseOffsetPlan();
+
+	if(cfg.pathType == ELB_PATH_DIR)
+	{
+		DirSource source(cfg, *offsetPlan, numIOPSSubmitted);
+		rwBlocksPipelined(source, isRead);
+	}
+	else
+	if(cfg.useRandomOffsets || cfg.useStridedAccess)
+	{
+		FileRandSource source(cfg, *offsetPlan, numIOPSSubmitted);
+		rwBlocksPipelined(source, isRead);
+	}
+	else
+	{
+		FileSeqSource source(cfg, rank, *offsetPlan, numIOPSSubmitted);
+
+		if(!source.hasWork() )
+		{ // LocalWorker.cpp:3603-3609
+			workerGotPhaseWork = false;
+			return;
+		}
+
+		rwBlocksPipelined(source, isRead);
+	}
+}
+
+/**
+ * Fill a batch with the next blocks of the source. Dir mode batches end at a file boundary when
+ * the async engine is used (the file must be closed after its last I/O completed).
+ *
+ * @return false if the source had no more blocks (batch stays empty).
+ */
+bool Worker::collectBatch(Batch& batch, BlockSource& source)
+{
+	batch.blocks.clear();
+	batch.numBytes = 0;
+	batch.numIOPending = 0;
+	batch.ioSubmitted = false;
+
+	const bool stopAtFileEnd = (cfg.pathType == ELB_PATH_DIR) &&
+		(cfg.ioEngine == ELB_IOENGINE_AIO);
+
+	while(batch.blocks.size() < batchBlocks)
+	{
+		BlockRef block;
+
+		if(!source.next(block) )
+			break;
+
+		batch.numBytes += block.len;
+		batch.blocks.push_back(block);
+
+		if(stopAtFileEnd && block.lastOfFile)
+			break;
+	}
+
+	return !batch.blocks.empty();
+}
+
+/**
+ * The batched, double-buffered replacement of rwBlockSized/aioBlockSized
+ * (LocalWorker.cpp:1669-2037).
+ *
+ * Two stage queues. Write: stage 1 = GPU (fill + staged D2H), stage 2 = storage writes.
+ * Read: stage 1 = storage reads, stage 2 = GPU (staged H2D + verify). A new batch is started
+ * whenever a batch is free; the oldest stage-1 batch moves on as soon as its stage-1 work is
+ * complete, or is waited for when two batches are queued behind each other or nothing new can be
+ * started; stage-2 batches are retired when no free batch is left or nothing else is to do.
+ */
+void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
+{
+	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
+	const bool dirModeAio = useAio && (cfg.pathType == ELB_PATH_DIR);
+
+	std::deque<Batch*> freeBatches;
+	std::deque<Batch*> stageOneQueue;
+	std::deque<Batch*> stageTwoQueue;
+	bool sourceExhausted = false;
+
+	if(batches.empty() )
+	{ // zero block size (empty files in dir mode): walk the source for open/close only
+		BlockRef block;
+		while(source.next(block) )
+		{
+			checkInterruptionRequest();
+			if(block.firstOfFile)
+				dirModeOpenFile(block, isRead);
+			if(block.lastOfFile)
+				dirModeCloseFile();
+		}
+
+		return;
+	}
+
+	for(Batch& batch : batches)
+		freeBatches.push_back(&batch);
+
+	for( ; ; )
+	{
+		// start one new batch
+		if(!freeBatches.empty() && !sourceExhausted)
+		{
+			Batch* batch = freeBatches.front();
+
+			if(!collectBatch(*batch, source) )
+				sourceExhausted = true;
+			else
+			{
+				freeBatches.pop_front();
+
+				if(isRead)
+				{
+					if(!useAio)
+						ioRunSync(*batch, true);
+					else
+					{
+						ioSubmitAio(*batch, true);
+						if(dirModeAio)
+							ioWaitAio(*batch, true);
+					}
+				}
+				else
+					gpuLaunchWriteStage(*batch);
+
+				stageOneQueue.push_back(batch);
+			}
+		}
+
+		const bool canStartNew = !freeBatches.empty() && !sourceExhausted;
+
+		// move the oldest stage-1 batch to stage 2
+		if(!stageOneQueue.empty() )
+		{
+			Batch* batch = stageOneQueue.front();
+			bool stageOneComplete;
+
+			if(isRead)
+			{
+				if(useAio && batch->numIOPending)
+					ioReapAio(false);
+
+				stageOneComplete = !batch->numIOPending;
+			}
+			else
+				stageOneComplete = (cudaEventQuery(batch->gpuDoneEvent) == cudaSuccess);
+
+			if(stageOneComplete || (stageOneQueue.size() >= 2) || !canStartNew)
+			{
+				stageOneQueue.pop_front();
+
+				if(isRead)
+				{
+					if(useAio)
+						ioWaitAio(*batch, true);
+
+					gpuLaunchReadStage(*batch);
+				}
+				else
+				{
+					gpuWait(*batch);
+
+					if(!useAio)
+						ioRunSync(*batch, false);
+					else
+					{
+						ioSubmitAio(*batch, false);
+						if(dirModeAio)
+							ioWaitAio(*batch, false);
+					}
+				}
+
+				stageTwoQueue.push_back(batch);
+			}
+		}
+
+		// retire the oldest stage-2 batch
+		if(!stageTwoQueue.empty() &&
+			(freeBatches.empty() || (sourceExhausted && stageOneQueue.empty() ) ) )
+		{
+			Batch* batch = stageTwoQueue.front();
+			stageTwoQueue.pop_front();
+
+			if(isRead)
+				retireReadBatch(*batch);
+			else
+			if(useAio)
+				ioWaitAio(*batch, false);
+
+			freeBatches.push_back(batch);
+		}
+
+		if(sourceExhausted && stageOneQueue.empty() && stageTwoQueue.empty() )
+			break;
+	}
+}
+
+/* ---- GPU stages ---------------------------------------------------------------------------- */
+
+/**
+ * Write phase GPU stage = policy of initPhaseFunctionPointers (LocalWorker.cpp:1249-1265):
+ * pattern fill if salt != 0, else random refill if blockvarpct, else nothing; then the block goes
+ * to the host for the storage write (cudaMemcpyGPUToHost, :1249-1250).
+ */
+void Worker::gpuLaunchWriteStage(Batch& batch)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const bool doPatternFill = (cfg.integrityCheckSalt != 0);
+	const bool doRandFill = !doPatternFill && cfg.blockVariancePercent;
+
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
+
+	batch.hadKernel = false;
+
+	if(doPatternFill || doRandFill)
+	{
+		for(size_t i = 0; i < numBlocks; i++)
+		{
+			const BlockRef& block = batch.blocks[i];
+			batch.hostDescs[i] = elb_block_desc{slotDevPtr(batch, i), block.len, block.offset,
+				(rank << 40) + block.blockCounter};
+		}
+
+		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
+			sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
+			"Async copy of block descriptors");
+
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+			"CUDA event record");
+
+		int launchRes;
+
+		if(doPatternFill)
+			launchRes = elb_launch_fill_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
+				cfg.integrityCheckSalt, devCounters, batch.numBytes, batch.stream);
+		else
+			launchRes = elb_launch_fill_random(batch.devDescs, NULL, (uint32_t)numBlocks,
+				cfg.blockVariancePercent, blockVarianceSeed, devCounters, batch.numBytes,
+				batch.stream);
+
+		if(launchRes)
+			throw WorkerError(std::string("GPU block fill failed. ") + elb_last_error() );
+
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+			"CUDA event record");
+
+		batch.hadKernel = true;
+		numKernelLaunches++;
+	}
+
+	// staged copy to the pinned ring: one copy when the batch is a dense run of full slots
+	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
+		ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, 0), slotDevPtr(batch, 0),
+			batch.numBytes, cudaMemcpyDeviceToHost, batch.stream), "Async GPU to host copy");
+	else
+		for(size_t i = 0; i < numBlocks; i++)
+		{
+			if(!batch.blocks[i].len)
+				continue;
+
+			ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, i), slotDevPtr(batch, i),
+				batch.blocks[i].len, cudaMemcpyDeviceToHost, batch.stream),
+				"Async GPU to host copy");
+		}
+
+	numD2HBytes += batch.numBytes;
+
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuDoneEvent, batch.stream), "CUDA event record");
+}
+
+/**
+ * Read phase GPU stage (LocalWorker.cpp:1311-1319): host -> GPU copy of what was read, then the
+ * integrity check on the GPU (the reference verifies on the CPU); only the 16-byte results come
+ * back.
+ */
+void Worker::gpuLaunchReadStage(Batch& batch)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const bool doVerify = (cfg.integrityCheckSalt != 0);
+
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
+
+	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
+		ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, 0), slotHostPtr(batch, 0),
+			batch.numBytes, cudaMemcpyHostToDevice, batch.stream), "Async host to GPU copy");
+	else
+		for(size_t i = 0; i < numBlocks; i++)
+		{
+			if(!batch.blocks[i].len)
+				continue;
+
+			ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, i), slotHostPtr(batch, i),
+				batch.blocks[i].len, cudaMemcpyHostToDevice, batch.stream),
+				"Async host to GPU copy");
+		}
+
+	numH2DBytes += batch.numBytes;
+
+	batch.hadKernel = false;
+
+	if(doVerify)
+	{
+		for(size_t i = 0; i < numBlocks; i++)
+		{
+			const BlockRef& block = batch.blocks[i];
+			batch.hostDescs[i] = elb_block_desc{slotDevPtr(batch, i), block.len, block.offset,
+				block.blockCounter};
+		}
+
+		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
+			sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
+			"Async copy of block descriptors");
+
+		const bool initResults = !batch.devResultsClean;
+
+		if(initResults)
+		{
+			/* (all batchBlocks entries, so that later launches with more blocks stay valid) */
+			if(elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream) )
+				throw WorkerError(std::string("GPU verify init failed. ") + elb_last_error() );
+
+			numKernelLaunches++;
+		}
+
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+			"CUDA event record");
+
+		if(elb_launch_verify_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
+			cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes,
+			false /*initResults*/, batch.stream) )
+			throw WorkerError(std::string("GPU block verification failed. ") +
+				elb_last_error() );
+
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+			"CUDA event record");
+
+		batch.hadKernel = true;
+		numKernelLaunches++;
+
+		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.hostResults, batch.devResults,
+			sizeof(elb_verify_result) * numBlocks, cudaMemcpyDeviceToHost, batch.stream),
+			"Async copy of verify results");
+
+		batch.devResultsClean = true; // until a mismatch shows up at retire time
+	}
+
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuDoneEvent, batch.stream), "CUDA event record");
+}
+
+void Worker::gpuWait(Batch& batch)
+{
+	ELB_CUDA_CHECK(cudaEventSynchronize(batch.gpuDoneEvent), "Waiting for GPU batch");
+
+	batch.gpuMilliSecs = 0;
+	cudaEventElapsedTime(&batch.gpuMilliSecs, batch.gpuStartEvent, batch.gpuDoneEvent);
+
+	if(batch.hadKernel)
+	{
+		float kernelMilliSecs = 0;
+		cudaEventElapsedTime(&kernelMilliSecs, batch.kernelStartEvent, batch.kernelDoneEvent);
+		devKernelUSec += (uint64_t)(kernelMilliSecs * 1000);
+	}
+}
+
+/* the exception of postReadIntegrityCheckVerifyBuf (LocalWorker.cpp:2162-2177) */
+void Worker::throwVerifyError(Batch& batch, size_t blockIdx)
+{
+	const BlockRef& block = batch.blocks[blockIdx];
+	const uint64_t firstIdx = batch.hostResults[blockIdx].firstMismatchIdx;
+	const uint64_t badOffset = block.offset + firstIdx;
+
+	const unsigned expectedVal = elb_pattern_byte(badOffset, cfg.integrityCheckSalt);
+	const unsigned actualVal = (unsigned char)slotHostPtr(batch, blockIdx)[firstIdx];
+
+	throw WorkerError("Data verification failed. "
+		"Offset: " + std::to_string(badOffset) + "; "
+		"Expected value: " + std::to_string(expectedVal) + "; "
+		"Actual value: " + std::to_string(actualVal) );
+}
+
+/* read batch completed its GPU stage: check the integrity results in submission order, then do
+ * the per-block accounting (latency = storage time + share of the batch's GPU time, so that
+ * fill/verify stay inside the reported I/O latency like LocalWorker.cpp:1691-1755) */
+void Worker::retireReadBatch(Batch& batch)
+{
+	gpuWait(batch);
+
+	const size_t numBlocks = batch.blocks.size();
+
+	if(cfg.integrityCheckSalt)
+	{
+		for(size_t i = 0; i < numBlocks; i++)
+		{
+			if(!batch.hostResults[i].numMismatchBytes)
+				continue;
+
+			batch.devResultsClean = false;
+
+			if(!cfg.verifyCollectAll)
+				throwVerifyError(batch, i);
+		}
+	}
+
+	const uint64_t gpuShareUSec = (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+
+	for(size_t i = 0; i < numBlocks; i++)
+		ioAccountBlock(batch, batch.blocks[i], true, batch.blocks[i].ioUSec + gpuShareUSec);
+}
+
+/* ---- storage stages ------------------------------------------------------------------------ */
+
+void Worker::ioAccountBlock(Batch& batch, BlockRef& block, bool isRead, uint64_t latencyUSec)
+{
+	(void)batch;
+	(void)isRead;
+
+	if(!block.len && (cfg.pathType == ELB_PATH_DIR) )
+		return; // empty file: no I/O happened
+
+	histogramAdd(iopsLatHisto, latencyUSec);
+	liveLatNumIO++;
+	liveLatSumIO += latencyUSec;
+	atomicLiveOps.numBytesDone += block.len;
+	atomicLiveOps.numIOPSDone++;
+}
+
+std::string Worker::blockPathForLog(const BlockRef& block) const
+{
+	if(cfg.pathType == ELB_PATH_DIR)
+		return dirModeCurrentPath;
+
+	return cfg.paths[block.fileIdx];
+}
+
+/* error texts of the file iterators (LocalWorker.cpp:3657-3682, 3133-3164) */
+void Worker::throwIOError(const BlockRef& block, bool isRead, ssize_t ioRes, int errnoVal)
+{
+	const std::string path = blockPathForLog(block);
+
+	if(ioRes < 0)
+		throw WorkerError(std::string(isRead ? "File read failed. " : "File write failed. ") +
+			( (cfg.useDirectIO && (errnoVal == EINVAL) ) ?
+				"Can be caused by directIO misalignment. " : "") +
+			"Path: " + path + "; "
+			"SysErr: " + strerror(errnoVal) );
+
+	throw WorkerError(std::string(isRead ?
+			"Unexpected short file read. " : "Unexpected short file write. ") +
+		"Path: " + path + "; " +
+		(isRead ? "Bytes read: " : "Bytes written: ") + std::to_string(ioRes) + "; " +
+		(isRead ? "Expected read: " : "Expected written: ") + std::to_string(block.len) + "; "
+		"Hint: Consider initial sequential write or adding \"--trunctosize\" to ensure full "
+		"file size.");
+}
+
+/* dirModeOpenAndPrepFile (LocalWorker.cpp:7097-7161) with getDirModeOpenFlags (:7062-7082) */
+void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
+{
+	char relativePath[ELB_PATH_BUF_LEN];
+	const bool haveSubdirs = (cfg.numDirs > 0);
+	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
+	int printRes;
+
+	if(haveSubdirs)
+		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "r%zu/d%zu/r%zu-f%zu",
+			(size_t)workerDirRank, (size_t)block.dirIndex, (size_t)rank, (size_t)block.fileIndex);
+	else
+		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "r%zu-f%zu", (size_t)rank,
+			(size_t)block.fileIndex);
+
+	if(printRes >= ELB_PATH_BUF_LEN)
+		throw WorkerError("file path too long for static buffer. "
+			"Buffer size: " + std::to_string(ELB_PATH_BUF_LEN) + "; "
+			"workerRank: " + std::to_string(rank) + "; "
+			"dirIndex: " + std::to_string(block.dirIndex) + "; "
+			"fileIndex: " + std::to_string(block.fileIndex) );
+
+	const size_t pathFDsIndex = (rank + block.dirIndex) % shared->pathFDs.size();
+
+	dirModeCurrentPath = cfg.paths[pathFDsIndex] + "/" + relativePath;
+
+	int openFlags;
+
+	if(!isRead)
+	{
+		openFlags = O_CREAT | O_RDWR;
+		if(cfg.doTruncate)
+			openFlags |= O_TRUNC;
+	}
+	else
+		openFlags = O_RDONLY;
+
+	if(cfg.useDirectIO)
+		openFlags |= O_DIRECT;
+
+	dirModeFileStartT = Clock::now();
+
+	dirModeFD = openat(shared->pathFDs[pathFDsIndex], relativePath, openFlags, ELB_MKFILE_MODE);
+
+	if(dirModeFD == -1)
+		throw WorkerError(std::string("File open failed. ") +
+			"Path: " + dirModeCurrentPath + "; "
+			"SysErr: " + strerror(errno) );
+
+	if(!isRead)
+	{
+		if(cfg.doTruncToSize && (ftruncate(dirModeFD, cfg.fileSize) == -1) )
+			throw WorkerError("Unable to set file size through ftruncate. "
+				"Path: " + dirModeCurrentPath + "; "
+				"Size: " + std::to_string(cfg.fileSize) + "; "
+				"SysErr: " + strerror(errno) );
+
+		if(cfg.doPreallocFile)
+		{
+			int preallocRes = posix_fallocate(dirModeFD, 0, cfg.fileSize);
+			if(preallocRes != 0)
+				throw WorkerError("Unable to preallocate file size through posix_fallocate. "
+					"File: " + dirModeCurrentPath + "; "
+					"Size: " + std::to_string(cfg.fileSize) + "; "
+					"SysErr: " + strerror(preallocRes) );
+		}
+	}
+}
+
+/* close + entry accounting (LocalWorker.cpp:3185-3243) */
+void Worker::dirModeCloseFile()
+{
+	int closeRes = close(dirModeFD);
+	int closeErrno = errno;
+	int closedFD = dirModeFD;
+
+	dirModeFD = -1;
+
+	if(closeRes == -1)
+		throw WorkerError(std::string("File close failed. ") +
+			"Path: " + dirModeCurrentPath + "; "
+			"FD: " + std::to_string(closedFD) + "; "
+			"SysErr: " + strerror(closeErrno) );
+
+	const uint64_t entryUSec = elapsedUSecSince(dirModeFileStartT);
+
+	histogramAdd(entriesLatHisto, entryUSec);
+	liveLatNumEntries++;
+	liveLatSumEntries += entryUSec;
+	atomicLiveOps.numEntriesDone++;
+}
+
+int Worker::resolveFD(const BlockRef& block, bool isRead)
+{
+	if(cfg.pathType != ELB_PATH_DIR)
+		return shared->pathFDs[block.fileIdx];
+
+	if(block.firstOfFile)
+		dirModeOpenFile(block, isRead);
+
+	return dirModeFD;
+}
+
+/**
+ * Synchronous storage stage (pread/pwrite wrappers, LocalWorker.cpp:2501-2530). For writes the
+ * per-block accounting happens here (latency = share of the batch's GPU time + storage time);
+ * reads are accounted when their GPU stage retires.
+ */
+void Worker::ioRunSync(Batch& batch, bool isRead)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const uint64_t gpuShareUSec = isRead ?
+		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		BlockRef& block = batch.blocks[i];
+
+		checkInterruptionRequest();
+
+		const int fd = resolveFD(block, isRead);
+
+		if(block.len)
+		{
+			Clock::time_point ioStartT = Clock::now();
+
+			ssize_t ioRes = isRead ?
+				pread(fd, slotHostPtr(batch, i), block.len, block.offset) :
+				pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
+
+			if(ioRes != (ssize_t)block.len)
+				throwIOError(block, isRead, ioRes, errno);
+
+			block.ioUSec = elapsedUSecSince(ioStartT);
+
+			if(!isRead)
+				ioAccountBlock(batch, block, false, block.ioUSec + gpuShareUSec);
+		}
+
+		if(block.lastOfFile)
+			dirModeCloseFile();
+	}
+}
+
+/**
+ * Asynchronous storage stage on the raw kernel AIO ABI: the whole batch goes down with one
+ * io_submit (the reference submits one iocb per syscall, LocalWorker.cpp:1855).
+ */
+void Worker::ioSubmitAio(Batch& batch, bool isRead)
+{
+	const size_t numBlocks = batch.blocks.size();
+	size_t numIocbs = 0;
+
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		BlockRef& block = batch.blocks[i];
+
+		const int fd = resolveFD(block, isRead);
+
+		if(!block.len)
+			continue;
+
+		struct iocb& cb = batch.iocbs[numIocbs];
+		memset(&cb, 0, sizeof(cb) );
+		cb.aio_lio_opcode = isRead ? IOCB_CMD_PREAD : IOCB_CMD_PWRITE;
+		cb.aio_fildes = fd;
+		cb.aio_buf = (uint64_t)(uintptr_t)slotHostPtr(batch, i);
+		cb.aio_nbytes = block.len;
+		cb.aio_offset = block.offset;
+		cb.aio_data = ( (uint64_t)batch.index << 32) | i;
+
+		batch.iocbPtrs[numIocbs] = &cb;
+		block.submitT = Clock::now();
+		numIocbs++;
+	}
+
+	batch.numIOPending = (uint32_t)numIocbs;
+	batch.ioSubmitted = true;
+
+	size_t numSubmitted = 0;
+
+	while(numSubmitted < numIocbs)
+	{
+		long submitRes = syscall(SYS_io_submit, aioContext, (long)(numIocbs - numSubmitted),
+			&batch.iocbPtrs[numSubmitted] );
+
+		if(submitRes < 0)
+		{
+			if(errno == EAGAIN)
+			{ // queue full: reap something first
+				ioReapAio(true);
+				continue;
+			}
+
+			throw WorkerError(std::string("Async IO submission (io_submit) failed. ") +
+				"NumRequests: " + std::to_string(numIocbs - numSubmitted) + "; "
+				"SysErr: " + strerror(errno) );
+		}
+
+		numSubmitted += submitRes;
+	}
+}
+
+/* io_getevents + result checks of aioBlockSized (LocalWorker.cpp:1881-1932) */
+void Worker::ioReapAio(bool blockUntilEvent)
+{
+	struct io_event events[ELB_AIO_MAX_EVENTS];
+	struct timespec timeout;
+	timeout.tv_sec = blockUntilEvent ? ELB_AIO_MAX_WAIT_SEC : 0;
+	timeout.tv_nsec = 0;
+
+	long eventsRes = syscall(SYS_io_getevents, aioContext, (long)(blockUntilEvent ? 1 : 0),
+		(long)ELB_AIO_MAX_EVENTS, events, &timeout);
+
+	if(!eventsRes)
+	{ // timeout expired: that's ok, we only set it to check interruptions
+		checkInterruptionRequest();
+		return;
+	}
+
+	if(eventsRes < 0)
+	{
+		if(errno == EINTR)
+			return;
+
+		throw WorkerError(std::string("Getting async IO events (io_getevents) failed. ") +
+			"SysErr: " + strerror(errno) );
+	}
+
+	for(long eventIdx = 0; eventIdx < eventsRes; eventIdx++)
+	{
+		const struct io_event& event = events[eventIdx];
+		const uint32_t batchIdx = (uint32_t)(event.data >> 32);
+		const uint32_t blockIdx = (uint32_t)event.data;
+		Batch& batch = batches[batchIdx];
+		BlockRef& block = batch.blocks[blockIdx];
+		const struct iocb* cb = (const struct iocb*)(uintptr_t)event.obj;
+		const bool wasRead = (cb->aio_lio_opcode == IOCB_CMD_PREAD);
+
+		if(event.res2)
+			throw WorkerError(std::string("Async IO framework error. ") +
+				"res: " + std::to_string(event.res) + "; "
+				"res2: " + std::to_string(event.res2) + "; "
+				"IO size: " + std::to_string(cb->aio_nbytes) + "; "
+				"SysErr: " + strerror(-(int)event.res2) );
+
+		if(event.res != (int64_t)cb->aio_nbytes)
+			throwIOError(block, wasRead, (event.res < 0) ? -1 : (ssize_t)event.res,
+				(event.res < 0) ? -(int)event.res : 0);
+
+		block.ioUSec = elapsedUSecSince(block.submitT);
+		batch.numIOPending--;
+	}
+}
+
+void Worker::ioWaitAio(Batch& batch, bool isRead)
+{
+	if(!batch.ioSubmitted)
+		return;
+
+	while(batch.numIOPending)
+	{
+		checkInterruptionRequest();
+		ioReapAio(true);
+	}
+
+	batch.ioSubmitted = false;
+
+	const size_t numBlocks = batch.blocks.size();
+
+	if(!isRead)
+	{
+		const uint64_t gpuShareUSec = (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+
+		for(size_t i = 0; i < numBlocks; i++)
+			ioAccountBlock(batch, batch.blocks[i], false, batch.blocks[i].ioUSec + gpuShareUSec);
+	}
+
+	// dir mode: batches end at file boundaries, so the file can be closed now
+	if( (cfg.pathType == ELB_PATH_DIR) && !batch.blocks.empty() &&
+		batch.blocks.back().lastOfFile && (dirModeFD != -1) )
+		dirModeCloseFile();
+}
+
+} // namespace elb

@@ -1,0 +1,392 @@
+/*
+ * elbencho_b200 — C ABI of the Blackwell-native GPU I/O benchmark worker.
+ *
+ * This is the drop-in boundary for elbencho's LocalWorker hot path. The reference has no
+ * plugin/FFI mechanism (WorkerManager.cpp:163 hard-codes `new LocalWorker(...)`), so the entry
+ * points below mirror, one-to-one, what a thin C++ `Worker` subclass would bind:
+ *
+ *   kernel level  -> the BLOCK_MODIFIER slots of LocalWorker (source/workers/LocalWorker.h:44-74)
+ *   worker level  -> the abstract Worker interface (source/workers/Worker.h:20-226)
+ *   manager level -> WorkerManager (source/workers/WorkerManager.cpp:142-324)
+ *
+ * Every signature uses plain pointers and sizes only. `stream` arguments are `cudaStream_t`
+ * passed as `void*` (NULL = the legacy default stream). Device pointers are ordinary CUDA device
+ * addresses; no torch types cross this boundary.
+ *
+ * All entry points return 0 on success and a negative value on error unless stated otherwise;
+ * the error text is available through elb_last_error() (thread-local) or
+ * elb_worker_last_error()/elb_mgr_last_error() (WorkerException text of the reference, e.g. the
+ * byte-identical "Data verification failed. Offset: ..." message of LocalWorker.cpp:2174-2177).
+ */
+#ifndef ELBENCHO_B200_H_
+#define ELBENCHO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELB_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------
+ * Enums (values follow source/Common.h:142-179 so a shim can cast directly)
+ * ------------------------------------------------------------------------------------------- */
+
+enum elb_bench_phase
+{
+	ELB_PHASE_IDLE = 0,
+	ELB_PHASE_TERMINATE = 1,
+	ELB_PHASE_CREATEDIRS = 2,
+	ELB_PHASE_DELETEDIRS = 3,
+	ELB_PHASE_CREATEFILES = 4,
+	ELB_PHASE_DELETEFILES = 5,
+	ELB_PHASE_READFILES = 6,
+	ELB_PHASE_SYNC = 7,
+	ELB_PHASE_DROPCACHES = 8,
+	ELB_PHASE_STATFILES = 9,
+};
+
+enum elb_path_type
+{
+	ELB_PATH_DIR = 0,
+	ELB_PATH_FILE = 1,
+	ELB_PATH_BLOCKDEV = 2,
+};
+
+/* I/O engines of the per-block loop. SYNC = rwBlockSized semantics (LocalWorker.cpp:1669-1781),
+ * AIO = aioBlockSized semantics (:1795-2037) on raw kernel AIO (no libaio dependency). */
+enum elb_io_engine
+{
+	ELB_IOENGINE_AUTO = 0, /* SYNC when iodepth==1, else AIO (LocalWorker.cpp:1243-1244) */
+	ELB_IOENGINE_SYNC = 1,
+	ELB_IOENGINE_AIO = 2,
+};
+
+/* Random-fill generators for --blockvarpct (counter-based, position-keyed) */
+enum elb_rand_algo
+{
+	ELB_RANDALGO_SPLITMIX64 = 0, /* splitmix64 of (seed, block counter, word index); uniform u64 */
+};
+
+/* Histogram kinds for elb_worker_histogram (Worker.h:55-58) */
+enum elb_histo_kind
+{
+	ELB_HISTO_IOPS = 0,
+	ELB_HISTO_IOPS_READMIX = 1,
+	ELB_HISTO_ENTRIES = 2,
+	ELB_HISTO_ENTRIES_READMIX = 3,
+};
+
+#define ELB_LATHISTO_NUMBUCKETS 112 /* LatencyHistogram.h:14-18 */
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel level: on-GPU block modifiers / checkers (replace LocalWorker.cpp:2091-2277)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Result of an on-GPU integrity check. One per block descriptor.
+ * numMismatchBytes: number of bytes differing from the expected pattern (0 = block is good).
+ * firstMismatchIdx: index within the block of the first differing byte, ~0ULL if none.
+ * (expected/actual byte values follow from the closed form / one 1-byte read; the worker layer
+ * produces the reference's exception text from them.) */
+typedef struct elb_verify_result
+{
+	uint64_t numMismatchBytes;
+	uint64_t firstMismatchIdx;
+} elb_verify_result;
+
+/* One block of the in-flight window: device address, length, file offset, and the block counter
+ * that keys the random fill (ignored by pattern fill/verify). */
+typedef struct elb_block_desc
+{
+	void* devPtr;
+	uint64_t len;
+	uint64_t fileOffset;
+	uint64_t blockCounter;
+} elb_block_desc;
+
+/* Device-resident counter block of a worker (what the stats reduce sums across GPUs). */
+enum elb_dev_counter
+{
+	ELB_DEVCTR_VERIFY_MISMATCH_BYTES = 0,
+	ELB_DEVCTR_VERIFIED_BYTES = 1,
+	ELB_DEVCTR_FILLED_BYTES = 2,
+	ELB_DEVCTR_NUM = 8,
+};
+
+/* K1: buffer byte i <- byte ((fileOffset+i) % 8) of little-endian u64 (((fileOffset+i) & ~7) +
+ * salt). Replaces preWriteIntegrityCheckFillBuf (LocalWorker.cpp:2091-2128). Any alignment/len. */
+int elb_fill_pattern(void* devPtr, uint64_t len, uint64_t fileOffset, uint64_t salt,
+	void* stream);
+
+/* K2: compare device buffer with the pattern; *devOut (device memory, 16 bytes) receives the
+ * result. Replaces postReadIntegrityCheckVerifyBuf (LocalWorker.cpp:2137-2179). */
+int elb_verify_pattern(const void* devPtr, uint64_t len, uint64_t fileOffset, uint64_t salt,
+	elb_verify_result* devOut, void* stream);
+
+/* K3: first varFillLen = (len*pct)/100 bytes (rounded down to a multiple of 4 like the
+ * reference's GPU path, LocalWorker.cpp:2253-2256) random, remainder = one repeated u64.
+ * Replaces preWriteBufRandRefillCuda (:2236-2277: curandGenerate + host bufFill + H2D copy). */
+int elb_fill_random(void* devPtr, uint64_t len, unsigned pct, uint64_t seed,
+	uint64_t blockCounter, int randAlgo, void* stream);
+
+/* Batched forms: one launch over the whole in-flight window. `descs` must be readable by the
+ * device (device memory or pinned mapped host memory); `numDescs` blocks. `devResults` has one
+ * entry per descriptor. `devCounters` (may be NULL) points to ELB_DEVCTR_NUM u64 in device memory
+ * that the kernels accumulate into (device-resident stats block). */
+int elb_fill_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	uint64_t* devCounters, void* stream);
+int elb_verify_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	elb_verify_result* devResults, uint64_t* devCounters, void* stream);
+int elb_fill_random_batch(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
+	uint64_t seed, int randAlgo, uint64_t* devCounters, void* stream);
+/* As above, plus totalBytes = sum of the descriptor lengths (when the caller knows it) so that
+ * small windows launch a grid no larger than their tile count. 0 = unknown. */
+int elb_fill_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	uint64_t* devCounters, uint64_t totalBytes, void* stream);
+int elb_verify_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	elb_verify_result* devResults, uint64_t* devCounters, uint64_t totalBytes, void* stream);
+int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
+	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, void* stream);
+
+/* Number of kernel launches issued through this library since load (all threads). */
+uint64_t elb_num_kernel_launches(void);
+
+/* Thread-local text of the last error returned by any entry point on this thread. */
+const char* elb_last_error(void);
+
+/* ABI version of the loaded library (== ELB_ABI_VERSION). */
+int elb_abi_version(void);
+
+/* sizeof(elb_cfg) / sizeof(elb_phase_results) as compiled into the library (binding self-check) */
+uint32_t elb_cfg_struct_size(void);
+uint32_t elb_phase_results_struct_size(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Configuration (the ProgArgs subset that reaches the hot path; SURVEY.md §5 "Config / flags")
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct elb_cfg
+{
+	uint32_t structSize; /* = sizeof(elb_cfg), for ABI checking */
+
+	/* bench paths (ProgArgs benchPathsVec / benchPathType) */
+	const char* const* paths;
+	uint32_t numPaths;
+	int32_t pathType; /* enum elb_path_type */
+
+	/* -t / --rankoffset / numDataSetThreads */
+	uint32_t numThreads;
+	uint32_t rankOffset;
+	uint32_t numDataSetThreads; /* 0 = numThreads */
+
+	/* -b / -s / --iodepth / --direct */
+	uint64_t blockSize;
+	uint64_t fileSize;
+	uint32_t ioDepth;
+	int32_t useDirectIO;
+	int32_t ioEngine; /* enum elb_io_engine */
+
+	/* -n / -N / --dirsharing (dir mode) */
+	uint64_t numDirs;
+	uint64_t numFiles;
+	int32_t doDirSharing;
+
+	/* --trunc / --trunctosize / --preallocfile */
+	int32_t doTruncate;
+	int32_t doTruncToSize;
+	int32_t doPreallocFile;
+
+	/* --rand / --randamount / --norandalign / --randalgo / --backward / --strided */
+	int32_t useRandomOffsets;
+	int32_t useRandomUnaligned;
+	int32_t useExplicitRandOffsetAlgo; /* nonzero = user gave --randalgo => no full coverage */
+	int32_t doReverseSeqOffsets;
+	int32_t useStridedAccess;
+	uint64_t randomAmount; /* 0 = default (ProgArgs.cpp:1558-1561) */
+	uint64_t randOffsetSeed; /* 0 = self-seed (std::random_device) like the reference */
+
+	/* --verify <salt> / --verifydirect / --readinline */
+	uint64_t integrityCheckSalt;
+	int32_t doDirectVerify;
+	int32_t doReadInline;
+
+	/* --blockvarpct / --blockvaralgo (+ injected seed; 0 = self-seed) */
+	uint32_t blockVariancePercent;
+	int32_t blockVarianceAlgo; /* enum elb_rand_algo */
+	uint64_t blockVarianceSeed;
+
+	/* --rwmixpct */
+	uint32_t rwMixReadPercent;
+
+	/* --gpuids / --cufile / --gds / --gdsbufreg / --cuhostbufreg */
+	const int32_t* gpuIDs;
+	uint32_t numGPUIDs;
+	int32_t useCuFile;
+	int32_t useGDSBufReg;
+
+	/* pipeline tuning of the staged loop (new; 0 = defaults) */
+	uint32_t pipelineBatchBlocks; /* blocks per batched kernel launch / staged copy */
+	uint32_t pipelineNumBatches;  /* batches in flight (>= 2 for overlap) */
+
+	int32_t ignoreDelErrors;
+	int32_t runAsService; /* disables last-finisher stonewall trigger (Worker.cpp:41-43) */
+	int32_t verifyCollectAll; /* nonzero: do not stop at first bad block, count all mismatches */
+	int32_t reserved0;
+} elb_cfg;
+
+/* ---------------------------------------------------------------------------------------------
+ * Stats types (source/LiveOps.h:13-118, source/LiveLatency.h:12-89, LatencyHistogram.h:28-45)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct elb_liveops
+{
+	uint64_t numEntriesDone;
+	uint64_t numBytesDone;
+	uint64_t numIOPSDone;
+} elb_liveops;
+
+typedef struct elb_livelat
+{
+	uint64_t numAvgIOLatValues;
+	uint64_t avgIOLatMicroSecsSum;
+	uint64_t numAvgIOLatReadMixValues;
+	uint64_t avgIOLatReadMixMicroSecsSum;
+	uint64_t numAvgEntriesLatValues;
+	uint64_t avgEntriesLatMicroSecsSum;
+	uint64_t numAvgEntriesLatReadMixValues;
+	uint64_t avgEntriesLatReadMixMicrosSecsSum;
+} elb_livelat;
+
+typedef struct elb_histogram
+{
+	uint64_t buckets[ELB_LATHISTO_NUMBUCKETS];
+	uint64_t numStoredValues;
+	uint64_t numMicroSecTotal;
+	uint64_t minMicroSecLat; /* ~0 when empty */
+	uint64_t maxMicroSecLat;
+} elb_histogram;
+
+/* Aggregated result of one phase (what Statistics::generatePhaseResults computes,
+ * Statistics.cpp:1641-1764). */
+typedef struct elb_phase_results
+{
+	uint64_t firstFinishUSec; /* stonewall: fastest worker with work */
+	uint64_t lastFinishUSec;
+	elb_liveops opsTotal;          /* last done */
+	elb_liveops opsStoneWallTotal; /* first done */
+	elb_liveops opsPerSec;          /* getPerSecFromUSec(opsTotal, lastFinishUSec) */
+	elb_liveops opsStoneWallPerSec; /* getPerSecFromUSec(stonewall, firstFinishUSec) */
+	elb_liveops opsReadMixTotal;
+	elb_histogram iopsLatHisto;
+	elb_histogram entriesLatHisto;
+	uint64_t verifyMismatchBytes; /* device counter, summed over workers */
+	uint64_t verifiedBytes;
+	uint64_t filledBytes;
+	uint64_t numKernelLaunches;
+	uint64_t h2dBytes;
+	uint64_t d2hBytes;
+	uint64_t devKernelUSec; /* sum of event-timed kernel durations (fill/verify), microseconds */
+	uint32_t numWorkersDone;
+	uint32_t numWorkersDoneWithError;
+} elb_phase_results;
+
+/* ---------------------------------------------------------------------------------------------
+ * Worker level (mirrors Worker.h / LocalWorker.h)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct elb_worker elb_worker;
+typedef struct elb_mgr elb_mgr;
+
+/* Histogram helpers (LatencyHistogram.h:50-77, :140-159, operator+= :187-202) */
+void elb_histogram_reset(elb_histogram* h);
+void elb_histogram_add_latency(elb_histogram* h, uint64_t latencyMicroSec);
+void elb_histogram_merge(elb_histogram* dst, const elb_histogram* src);
+double elb_histogram_percentile(const elb_histogram* h, double percentage);
+/* UnitTk::getPerSecFromUSec (toolkits/UnitTk.h:48-56) */
+uint64_t elb_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec);
+
+/* ---------------------------------------------------------------------------------------------
+ * Offset plans (toolkits/offsetgen/OffsetGenerator.h:27-46 interface; one handle type for all
+ * six generators). Exposed so that a reference-side shim can reuse them and so that their
+ * sequences can be checked without a GPU. kind: 0 sequential, 1 reverse, 2 random unaligned,
+ * 3 random aligned, 4 strided, 5 random aligned full coverage. randState: xoshiro256** state
+ * (NULL = self-seed); lcgSeed/haveLCGSeed: start-state source of the full coverage permutation.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct elb_offset_plan elb_offset_plan;
+
+elb_offset_plan* elb_offset_plan_create(int kind, uint64_t amount, uint64_t rangeLen,
+	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads,
+	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed);
+void elb_offset_plan_destroy(elb_offset_plan* plan);
+void elb_offset_plan_restart(elb_offset_plan* plan); /* reset() */
+void elb_offset_plan_restart_range(elb_offset_plan* plan, uint64_t rangeLen,
+	uint64_t rangeOffset); /* reset(len, offset) */
+/* next block; the requested length counts as submitted. returns 0 when nothing is left. */
+int elb_offset_plan_next(elb_offset_plan* plan, uint64_t* outOffset, uint64_t* outLen);
+uint64_t elb_offset_plan_bytes_total(const elb_offset_plan* plan);
+uint64_t elb_offset_plan_bytes_left(const elb_offset_plan* plan);
+/* expand an injected 64-bit seed to the xoshiro256** state used for worker `rank` */
+void elb_expand_offset_seed(uint64_t seed, uint64_t rank, uint64_t outState[4]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Manager level (WorkerManager: owns the workers and their threads, one thread per worker)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Create workers (numThreads LocalWorker equivalents, ranks rankOffset..), allocate their rings on
+ * GPU gpuIDs[rank % numGPUIDs] (LocalWorker.cpp:1420-1429) and start their threads; returns after
+ * all workers finished preparation (WorkerManager.cpp:142-199). NULL on error (elb_last_error). */
+elb_mgr* elb_mgr_create(const elb_cfg* cfg);
+
+/* WorkerManager::startNextPhase (:291-324): reset stats, set phase + phaseStartT, wake workers. */
+int elb_mgr_start_phase(elb_mgr* m, int benchPhase);
+
+/* Wait up to timeoutMS for all workers to finish the phase (WorkerManager::waitForWorkersDone
+ * :245-267). Returns 1 when all are done, 0 on timeout, <0 if a worker ended with an error. */
+int elb_mgr_wait_done(elb_mgr* m, int timeoutMS);
+
+/* start + wait in one call. */
+int elb_mgr_run_phase(elb_mgr* m, int benchPhase);
+
+/* Statistics::getLiveOps (Statistics.cpp:1333-1345): sum over workers. out[0] = liveOps,
+ * out[1] = liveOpsReadMix. */
+int elb_mgr_live_ops(elb_mgr* m, elb_liveops out[2]);
+int elb_mgr_live_latency(elb_mgr* m, elb_livelat* out); /* add-and-reset */
+
+/* Phase results (valid after wait_done returned 1). */
+int elb_mgr_phase_results(elb_mgr* m, elb_phase_results* out);
+
+/* Expected totals of a phase (WorkerManager::getPhaseNumEntriesAndBytes, :333-487). */
+int elb_mgr_expected_totals(elb_mgr* m, int benchPhase, uint64_t* outEntries,
+	uint64_t* outBytes);
+
+/* Request friendly interruption of all workers (Worker::interruptExecution). */
+int elb_mgr_interrupt(elb_mgr* m);
+
+uint32_t elb_mgr_num_workers(elb_mgr* m);
+elb_worker* elb_mgr_worker(elb_mgr* m, uint32_t localIdx);
+const char* elb_mgr_last_error(elb_mgr* m);
+
+/* Terminate threads (BenchPhase_TERMINATE), run cleanup, free everything. */
+void elb_mgr_destroy(elb_mgr* m);
+
+/* Per-worker getters (may be called from any thread while the worker runs; Worker.h:83-226) */
+uint64_t elb_worker_rank(elb_worker* w);
+int elb_worker_gpu_id(elb_worker* w);
+int elb_worker_live_ops(elb_worker* w, elb_liveops out[2]);
+int elb_worker_stonewall_ops(elb_worker* w, elb_liveops out[2]);
+int elb_worker_histogram(elb_worker* w, int kind, elb_histogram* out);
+uint64_t elb_worker_elapsed_usec(elb_worker* w); /* 0 if none (no work / error) */
+int elb_worker_got_work(elb_worker* w);
+int elb_worker_dev_counters(elb_worker* w, uint64_t out[ELB_DEVCTR_NUM]); /* D2H snapshot */
+/* device address of the worker's counter block (ELB_DEVCTR_NUM u64) on its GPU — the payload of
+ * the NCCL stats reduce; never dereference on the host. */
+uint64_t* elb_worker_dev_counters_ptr(elb_worker* w);
+const char* elb_worker_last_error(elb_worker* w);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ELBENCHO_B200_H_ */

@@ -1,0 +1,110 @@
+"""Generate tests/golden/ref_vectors.json from the REFERENCE's own headers.
+
+Run in the build container (needs /root/reference and oracle/_ref/libelb_ref.so, built by
+`make -C oracle`):   python tests/golden/make_golden.py
+
+The vectors pin the oracle (and through it the product) to the reference's PRNG streams and offset
+generator sequences for injected states. The reference has no golden data of its own (SURVEY.md
+§4, §8c); what its tests pin is the closed-form --verify pattern, which is added here from the
+closed form itself (pure Python, independent of both the oracle and the product).
+"""
+import ctypes
+import hashlib
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO_ROOT)
+
+from tests import oracle_lib  # noqa: E402
+
+XOSHIRO_STATES = [[1, 2, 3, 4], [0x0123456789ABCDEF, 0xFEDCBA9876543210, 0xDEADBEEFCAFEBABE, 42]]
+GOLDEN_SEEDS = [12345, 0xFFFFFFFFFFFFFFF1]
+
+# (kind, numBytesTotal, len, offset, blockSize, numDataSetThreads, lcgSeed)
+OFFSETGEN_CASES = [
+    (0, 0, 10 * 1048576, 0, 1048576, 1, 0),
+    (0, 0, 10 * 1048576 + 123, 4096, 1048576, 1, 0),
+    (1, 0, 10 * 1048576, 0, 1048576, 1, 0),
+    (1, 0, 5 * 65536 + 1000, 65536, 65536, 1, 0),
+    (2, 40 * 4096, 1048576, 8192, 4096, 1, 0),
+    (2, 10 * 4096 + 77, 100000, 0, 4096, 1, 0),
+    (3, 64 * 4096, 16 * 1048576, 1048576, 4096, 1, 0),
+    (3, 20 * 65536 + 5, 65536 * 7, 0, 65536, 1, 0),
+    (4, 0, 8 * 4096, 3 * 4096, 4096, 4, 0),
+    (5, 16 * 4096, 16 * 4096, 0, 4096, 1, 7),
+    # (full coverage: one cycle only - the reference re-seeds later cycles from random_device)
+    (5, 13 * 4096, 13 * 4096, 26 * 4096, 4096, 1, 0xDEADBEEF),
+    (5, 1000 * 512, 1000 * 512, 512 * 3, 512, 1, 123456789),
+]
+
+
+def pattern_closed_form(length, file_offset, salt):
+    """byte x of the file = byte (x % 8) of little-endian u64 ((x & ~7) + salt) mod 2^64
+    (LocalWorker.cpp:2091-2128)."""
+    out = bytearray()
+    for x in range(file_offset, file_offset + length):
+        word = ((x & ~7) + salt) & 0xFFFFFFFFFFFFFFFF
+        out.append((word >> ((x % 8) * 8)) & 0xFF)
+    return bytes(out)
+
+
+def main():
+    ref = oracle_lib.load_ref()
+    if ref is None:
+        raise SystemExit("oracle/_ref/libelb_ref.so missing: run `make -C oracle` first")
+
+    vectors = {"generator": "tests/golden/make_golden.py", "reference": "breuner/elbencho @ v3.1-4"}
+
+    xo = []
+    for state in XOSHIRO_STATES:
+        algo = ref.ref_xoshiro256ss_create(oracle_lib.u64x4(state))
+        nexts = [ref.ref_randalgo_next(algo) for _ in range(16)]
+        buf = ctypes.create_string_buffer(37)
+        ref.ref_randalgo_fill_buf(algo, buf, 37)
+        ref.ref_randalgo_destroy(algo)
+        xo.append({"state": state, "next16": nexts, "then_fill37_hex": buf.raw.hex()})
+    vectors["xoshiro256ss"] = xo
+
+    gp = []
+    for seed in GOLDEN_SEEDS:
+        algo = ref.ref_goldenprime_create(seed, oracle_lib.u64x4(XOSHIRO_STATES[0]))
+        nexts = [ref.ref_randalgo_next(algo) for _ in range(8)]
+        length = 600000 + 5  # two full reseed chunks + tail with a partial word
+        buf = ctypes.create_string_buffer(length)
+        ref.ref_randalgo_fill_buf(algo, buf, length)
+        after = ref.ref_randalgo_next(algo)
+        ref.ref_randalgo_destroy(algo)
+        gp.append({"seed": seed, "seeder_state": XOSHIRO_STATES[0], "next8": nexts,
+                   "fill_len": length, "fill_sha256": hashlib.sha256(buf.raw).hexdigest(),
+                   "fill_first64_hex": buf.raw[:64].hex(), "fill_last16_hex": buf.raw[-16:].hex(),
+                   "next_after_fill": after})
+    vectors["goldenprime"] = gp
+
+    og = []
+    for case in OFFSETGEN_CASES:
+        kind, total, length, offset, block, threads, lcg = case
+        seq = oracle_lib.offsetgen_sequence(ref, "ref", kind, total, length, offset, block,
+                                            threads, XOSHIRO_STATES[1], lcg)
+        og.append({"kind": kind, "numBytesTotal": total, "len": length, "offset": offset,
+                   "blockSize": block, "numDataSetThreads": threads, "lcgSeed": lcg,
+                   "randState": XOSHIRO_STATES[1], "sequence": seq})
+    vectors["offsetgen"] = og
+
+    pat = []
+    for length, off, salt in [(16, 0, 1), (24, 5, 1), (7, 13, 0xFFFFFFFFFFFFFFFF), (40, 1048573, 42),
+                              (3, 6, 0x0102030405060708), (17, 0xFFFFFFFFFFFFFFF0 - 8, 99)]:
+        pat.append({"len": length, "fileOffset": off, "salt": salt,
+                    "hex": pattern_closed_form(length, off, salt).hex()})
+    vectors["pattern_closed_form"] = pat
+
+    out_path = os.path.join(HERE, "ref_vectors.json")
+    with open(out_path, "w") as f:
+        json.dump(vectors, f, indent=1)
+    print("wrote", out_path, os.path.getsize(out_path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -373,74 +373,214 @@ struct KernelArgs
 	unsigned long long* counters; // optional device counter block
 };
 
+/* number of tiles of a block; same rule as make_geom() */
+__device__ __forceinline__ uint64_t num_tiles_of(const elb_block_desc& desc)
+{
+	const uint64_t misalign = (uint64_t)(uintptr_t)desc.devPtr & (ELB_VEC_BYTES - 1);
+	uint64_t headLen = misalign ? (ELB_VEC_BYTES - misalign) : 0;
+	if(headLen > desc.len)
+		headLen = desc.len;
+
+	const uint64_t bodyLen = (desc.len - headLen) & ~(uint64_t)(ELB_VEC_BYTES - 1);
+	const uint64_t numTiles = (bodyLen + ELB_TILE_BYTES - 1) / ELB_TILE_BYTES;
+
+	return (!numTiles && desc.len) ? 1 : numTiles;
+}
+
+/* process tiles [tileBegin, tileEnd) of one block */
+template<int MODE>
+__device__ __forceinline__ void process_block_tiles(const KernelArgs& args,
+	const elb_block_desc& desc, uint32_t descIdx, const BlockGeom& g, uint64_t tileBegin,
+	uint64_t tileEnd)
+{
+	if(MODE == MODE_FILL_PATTERN)
+	{
+		PatternGen gen;
+		gen.fileOffset = desc.fileOffset;
+		gen.salt = args.salt;
+
+		if(gen.canUseFast(g.headLen) )
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				fill_tile<true>(g, gen, tileIdx);
+		else
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				fill_tile<false>(g, gen, tileIdx);
+	}
+	else if(MODE == MODE_VERIFY_PATTERN)
+	{
+		PatternGen gen;
+		gen.fileOffset = desc.fileOffset;
+		gen.salt = args.salt;
+
+		if(gen.canUseFast(g.headLen) )
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				verify_tile<true>(g, gen, tileIdx, &args.results[descIdx], args.counters);
+		else
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				verify_tile<false>(g, gen, tileIdx, &args.results[descIdx], args.counters);
+	}
+	else
+	{
+		RandomGen gen;
+		gen.blockKey = elb_rand_block_key(args.seed, desc.blockCounter);
+		gen.varFillLen = elb_rand_var_fill_len(desc.len, args.pct);
+		gen.remainderVal = elb_rand_remainder_val(gen.blockKey);
+
+		if(gen.canUseFast(g.headLen) )
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				fill_tile<true>(g, gen, tileIdx);
+		else
+			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+				fill_tile<false>(g, gen, tileIdx);
+	}
+}
+
+/* block-wide sum; result valid in all threads. sScratch: one slot per warp. */
+__device__ __forceinline__ uint64_t block_sum(uint64_t val, uint64_t* sScratch)
+{
+	for(int offset = 16; offset > 0; offset >>= 1)
+		val += __shfl_xor_sync(0xffffffffu, val, offset);
+
+	__syncthreads(); // protect sScratch from the previous use
+
+	if( !(threadIdx.x & 31) )
+		sScratch[threadIdx.x >> 5] = val;
+
+	__syncthreads();
+
+	uint64_t total = 0;
+
+	#pragma unroll
+	for(int warp = 0; warp < (ELB_THREADS / 32); warp++)
+		total += sScratch[warp];
+
+	return total;
+}
+
+/**
+ * One launch over the whole window. All tiles of all blocks form one sequence; CTA b takes the
+ * contiguous chunk [b*chunk, (b+1)*chunk) of it, so every CTA streams through consecutive
+ * addresses and touches only the few descriptors its chunk overlaps. Finding the chunk start
+ * needs the prefix sums of the per-block tile counts: the CTA computes them cooperatively
+ * (coalesced descriptor loads + a block scan per 256 descriptors), which costs a few
+ * microseconds per launch instead of a serial walk over all descriptors per CTA.
+ */
 template<int MODE>
 __global__ void __launch_bounds__(ELB_THREADS, 4)
 elb_blocks_kernel(const KernelArgs args)
 {
-	uint64_t tileBase = 0; // global index of the first tile of the current descriptor
+	__shared__ uint64_t sScratch[ELB_THREADS / 32];
+	__shared__ uint64_t sStartTile;
+	__shared__ uint32_t sStartDesc;
 
-	for(uint32_t descIdx = 0; descIdx < args.numDescs; descIdx++)
+	const uint32_t numDescs = args.numDescs;
+	const elb_block_desc* descs = args.descs;
+
+	// pass 1: total number of tiles
+	uint64_t myTiles = 0;
+
+	if(!descs)
+		myTiles = threadIdx.x ? 0 : num_tiles_of(args.inlineDesc);
+	else
+		for(uint32_t descIdx = threadIdx.x; descIdx < numDescs; descIdx += ELB_THREADS)
+			myTiles += num_tiles_of(descs[descIdx] );
+
+	const uint64_t totalTiles = block_sum(myTiles, sScratch);
+	const uint64_t chunkTiles = (totalTiles + gridDim.x - 1) / gridDim.x;
+	const uint64_t chunkBegin = (uint64_t)blockIdx.x * chunkTiles;
+
+	if(chunkBegin >= totalTiles)
+		return; // (uniform for the whole CTA)
+
+	const uint64_t chunkEnd = (chunkBegin + chunkTiles < totalTiles) ?
+		(chunkBegin + chunkTiles) : totalTiles;
+
+	// pass 2: locate the block that contains tile chunkBegin
+	uint32_t descIdx = 0;
+	uint64_t tileIdx = chunkBegin;
+
+	if(descs)
 	{
-		const elb_block_desc desc = args.descs ? args.descs[descIdx] : args.inlineDesc;
-		const BlockGeom g = make_geom(desc);
+		uint64_t segmentBase = 0; // tiles of all previous segments (uniform)
 
-		// first global tile of this descriptor owned by this CTA (tiles go round-robin over CTAs)
-		const uint64_t gridSize = gridDim.x;
-		const uint64_t baseMod = tileBase % gridSize;
-		uint64_t tileIdx = (blockIdx.x + gridSize - baseMod) % gridSize;
-
-		if(tileIdx < g.numTiles)
+		for(uint32_t segment = 0; segment < numDescs; segment += ELB_THREADS)
 		{
-			if(MODE == MODE_FILL_PATTERN)
-			{
-				PatternGen gen;
-				gen.fileOffset = desc.fileOffset;
-				gen.salt = args.salt;
+			const uint32_t myDesc = segment + threadIdx.x;
+			const uint64_t tiles = (myDesc < numDescs) ? num_tiles_of(descs[myDesc] ) : 0;
 
-				if(gen.canUseFast(g.headLen) )
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						fill_tile<true>(g, gen, tileIdx);
-				else
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						fill_tile<false>(g, gen, tileIdx);
-			}
-			else if(MODE == MODE_VERIFY_PATTERN)
+			// inclusive scan inside the warp
+			uint64_t inclusive = tiles;
+			for(int offset = 1; offset < 32; offset <<= 1)
 			{
-				PatternGen gen;
-				gen.fileOffset = desc.fileOffset;
-				gen.salt = args.salt;
-
-				if(gen.canUseFast(g.headLen) )
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						verify_tile<true>(g, gen, tileIdx, &args.results[descIdx], args.counters);
-				else
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						verify_tile<false>(g, gen, tileIdx, &args.results[descIdx],
-							args.counters);
+				const uint64_t other = __shfl_up_sync(0xffffffffu, inclusive, offset);
+				if( (threadIdx.x & 31) >= offset)
+					inclusive += other;
 			}
-			else
+
+			__syncthreads();
+
+			if( (threadIdx.x & 31) == 31)
+				sScratch[threadIdx.x >> 5] = inclusive;
+
+			__syncthreads();
+
+			uint64_t warpBase = 0;
+			uint64_t segmentTotal = 0;
+
+			#pragma unroll
+			for(int warp = 0; warp < (ELB_THREADS / 32); warp++)
 			{
-				RandomGen gen;
-				gen.blockKey = elb_rand_block_key(args.seed, desc.blockCounter);
-				gen.varFillLen = elb_rand_var_fill_len(desc.len, args.pct);
-				gen.remainderVal = elb_rand_remainder_val(gen.blockKey);
-
-				if(gen.canUseFast(g.headLen) )
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						fill_tile<true>(g, gen, tileIdx);
-				else
-					for( ; tileIdx < g.numTiles; tileIdx += gridSize)
-						fill_tile<false>(g, gen, tileIdx);
+				if(warp < (int)(threadIdx.x >> 5) )
+					warpBase += sScratch[warp];
+				segmentTotal += sScratch[warp];
 			}
+
+			const uint64_t exclusive = segmentBase + warpBase + inclusive - tiles;
+
+			if(tiles && (chunkBegin >= exclusive) && (chunkBegin < (exclusive + tiles) ) )
+			{
+				sStartDesc = myDesc;
+				sStartTile = chunkBegin - exclusive;
+			}
+
+			segmentBase += segmentTotal;
+
+			if(segmentBase > chunkBegin)
+				break; // found (uniform)
 		}
 
-		// device-resident stats: one atomic per block, by the CTA that owns the block's tile 0
-		if(args.counters && g.len && (baseMod == blockIdx.x) && !threadIdx.x)
-			atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
-				ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
-				(unsigned long long)g.len);
+		__syncthreads();
 
-		tileBase += g.numTiles;
+		descIdx = sStartDesc;
+		tileIdx = sStartTile;
+	}
+
+	// walk the chunk: consecutive tiles, block after block
+	uint64_t tilesLeft = chunkEnd - chunkBegin;
+
+	while(tilesLeft)
+	{
+		const elb_block_desc desc = descs ? descs[descIdx] : args.inlineDesc;
+		const BlockGeom g = make_geom(desc);
+
+		const uint64_t tileEnd = (g.numTiles - tileIdx < tilesLeft) ?
+			g.numTiles : (tileIdx + tilesLeft);
+
+		if(tileIdx < tileEnd)
+		{
+			process_block_tiles<MODE>(args, desc, descIdx, g, tileIdx, tileEnd);
+
+			// device-resident stats: one atomic per block, by the CTA that owns its first tile
+			if(args.counters && !tileIdx && !threadIdx.x)
+				atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
+					ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
+					(unsigned long long)g.len);
+
+			tilesLeft -= (tileEnd - tileIdx);
+		}
+
+		descIdx++;
+		tileIdx = 0;
 	}
 }
 

@@ -71,6 +71,10 @@ def parse_args():
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--batch-blocks", type=int, default=0)
     p.add_argument("--num-batches", type=int, default=0)
+    p.add_argument("--no-write-gate", action="store_true",
+                   help="do not queue buffered writers of one file in user space")
+    p.add_argument("--single-thread-sample-gib", type=float, default=4.0,
+                   help="size of the extra -t 1 comparison (GPU worker vs CPU LocalWorker); 0 = skip")
     return p.parse_args()
 
 
@@ -164,7 +168,7 @@ def bench_dir(args, rank):
 _CPU_THREADS_CACHE = {}
 
 
-def cpu_threads_default(args):
+def cpu_threads_default(args, nfiles=1):
     """Thread count of the CPU LocalWorker arm. The reference's throughput on a single shared file
     peaks at a moderate thread count (buffered writes serialise on the inode lock) and falls
     beyond it, so 'all the host threads it can use' is found by a short calibration."""
@@ -173,23 +177,25 @@ def cpu_threads_default(args):
     if "best" in _CPU_THREADS_CACHE:
         return _CPU_THREADS_CACHE["best"]
     nproc = os.cpu_count() or 1
-    candidates = sorted({t for t in (1, 4, 8, 16, 32, nproc) if t <= nproc})
+    candidates = sorted({t for t in (1, 4, 8, 16, 32, 64, nproc) if nfiles <= t <= nproc})
     block = int(args.block_mib * MiB)
-    size = max(block * nproc, 4 * GiB)
+    size = max(block * nproc, (4 * GiB) // nfiles)
     size -= size % block
-    path = os.path.join(bench_dir(args, 0), "cpu_calibrate.bin")
-    best, best_val, table = 1, 0.0, {}
+    paths = [os.path.join(bench_dir(args, 0), "cpu_calibrate_%d.bin" % i) for i in range(nfiles)]
+    best, best_val, table = candidates[0], 0.0, {}
     try:
         for threads in candidates:
-            if os.path.exists(path):
-                os.unlink(path)
-            res = run_cpu_localworker([path], threads, size, block, args.salt, args.direct)
+            for path in paths:
+                if os.path.exists(path):
+                    os.unlink(path)
+            res = run_cpu_localworker(paths, threads, size, block, args.salt, args.direct)
             table[threads] = round(res["gib_s"], 2)
             if res["gib_s"] > best_val:
                 best, best_val = threads, res["gib_s"]
     finally:
-        if os.path.exists(path):
-            os.unlink(path)
+        for path in paths:
+            if os.path.exists(path):
+                os.unlink(path)
     _CPU_THREADS_CACHE["best"] = best
     _CPU_THREADS_CACHE["table"] = table
     return best
@@ -247,29 +253,33 @@ def reference_arm(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0  # other ranks exit without work
-    threads = cpu_threads_default(args)
+    # the GPU arm's config at N GPUs is N files (rank r <-> file r): same file set here
+    nfiles = max(1, args.gpus)
+    threads = cpu_threads_default(args, nfiles)
     block = int(args.block_mib * MiB)
     step_size = int(args.ref_step_gib * GiB)
     step_size -= step_size % block
     workdir = bench_dir(args, 0)
-    path = os.path.join(workdir, "ref_arm.bin")
+    paths = [os.path.join(workdir, "ref_arm_%d.bin" % i) for i in range(nfiles)]
     times = []
     nbytes = 0
     try:
         for step in range(args.warmup + args.steps):
-            if os.path.exists(path):
-                os.unlink(path)
-            res = run_cpu_localworker([path], threads, step_size, block, args.salt, args.direct)
+            for path in paths:
+                if os.path.exists(path):
+                    os.unlink(path)
+            res = run_cpu_localworker(paths, threads, step_size, block, args.salt, args.direct)
             if step >= args.warmup:
                 times.append(res["usec"] / 1e6)
                 nbytes += res["bytes"]
     finally:
-        if os.path.exists(path):
-            os.unlink(path)
+        for path in paths:
+            if os.path.exists(path):
+                os.unlink(path)
     total = sum(times)
     value = (nbytes / GiB) / total if total else 0.0
-    sample = "%d steps x (write+read --verify of a %.1f GiB file, %d MiB blocks, -t %d) in %s" % (
-        args.steps, step_size / GiB, block // MiB, threads, args.dir)
+    sample = "%d steps x (write+read --verify of %d x %.1f GiB file(s), %d MiB blocks, -t %d) in %s" % (
+        args.steps, nfiles, step_size / GiB, block // MiB, threads, args.dir)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -277,7 +287,8 @@ def reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "seq 1 MiB write+read --verify, CPU LocalWorker (oracle port of "
                                "LocalWorker.cpp:1669-1781, 2091-2179)",
-                   "file_gib": step_size / GiB, "block_mib": args.block_mib, "threads": threads,
+                   "file_gib": step_size / GiB, "num_files": nfiles, "block_mib": args.block_mib,
+                   "threads": threads,
                    "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
                    "dir": args.dir, "direct": args.direct},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
@@ -286,7 +297,7 @@ def reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -429,7 +440,8 @@ def e2e_level(args, torch, device, rank, world):
                        file_size=file_size, integrity_check_salt=args.salt,
                        gpu_ids=[device.index], use_direct_io=args.direct,
                        pipeline_batch_blocks=args.batch_blocks,
-                       pipeline_num_batches=args.num_batches)
+                       pipeline_num_batches=args.num_batches,
+                       serialize_buffered_writes=not args.no_write_gate)
     out = {}
     with WorkerManager(cfg) as mgr:
         total_usec = 0
@@ -472,12 +484,62 @@ def e2e_level(args, torch, device, rank, world):
     }
 
 
+def single_thread_compare(args, device):
+    """The literal '-t 1' form of the config: one worker thread on either arm,
+    bounded sample. With one thread the reference serialises fill -> write and read -> verify on
+    the CPU, while the GPU worker overlaps its on-GPU work with the storage call."""
+    from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
+    block = int(args.block_mib * MiB)
+    size = int(args.single_thread_sample_gib * GiB)
+    size -= size % block
+    workdir = bench_dir(args, 0)
+    gpu_path = os.path.join(workdir, "single_gpu.bin")
+    cpu_path = os.path.join(workdir, "single_cpu.bin")
+    out = {"sample": "write+read --verify of a %.1f GiB file, 1 MiB blocks, -t 1" % (size / GiB)}
+    try:
+        total_usec = 0
+        with WorkerManager(WorkerConfig(paths=[gpu_path], num_threads=1, block_size=block,
+                                        file_size=size, integrity_check_salt=args.salt,
+                                        gpu_ids=[device.index], use_direct_io=args.direct)) as mgr:
+            for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
+                total_usec += mgr.run_phase(phase)["last_finish_usec"]
+        out["gpu_worker_gib_s"] = round((2 * size / GiB) / (total_usec / 1e6), 3)
+        res = run_cpu_localworker([cpu_path], 1, size, block, args.salt, args.direct)
+        out["cpu_localworker_gib_s"] = round(res["gib_s"], 3)
+        out["ratio"] = round(out["gpu_worker_gib_s"] / out["cpu_localworker_gib_s"], 2)
+    finally:
+        for path in (gpu_path, cpu_path):
+            if os.path.exists(path):
+                os.unlink(path)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # main
 # ------------------------------------------------------------------------------------------------
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver parses ONE JSON line from stdout; libraries (NCCL's version banner) also write
+    there. Keep the real stdout aside and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    protect_stdout()
 
     if args.impl == "reference":
         return reference_arm(args)
@@ -542,6 +604,11 @@ def main():
                "read_gib_s": round(res["phases"]["READFILES"]["bytes"] / GiB /
                                    (res["phases"]["READFILES"]["usec"] / 1e6), 3)}
 
+    single = None
+    if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_e2e and \
+            args.single_thread_sample_gib > 0:
+        single = single_thread_compare(args, device)
+
     if world > 1:
         dist.barrier(device_ids=[device.index])
         dist.destroy_process_group()
@@ -574,10 +641,11 @@ def main():
                                                "(2 x window bytes)",
             "l2": "inputs_larger_than_l2 (window %.1f GiB >> 126 MB L2)" % (window / GiB),
             "storage_dir": args.dir, "direct": args.direct,
+            "serialize_buffered_writes": not args.no_write_gate,
             "parallelism": "%d process(es) x %d worker threads, rank r <-> file r <-> GPU r" % (
                 world, args.threads),
         },
-        "gpu_launches": kern["launches"],
+        "gpu_launches": kern["launches"] * world,
         "roofline": {
             "bound": "hbm", "kernel": dom_name, "achieved": round(dom_gbs, 1), "peak": peak,
             "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": None,
@@ -620,7 +688,9 @@ def main():
                            "file serialise on the inode lock, so the write phase does not scale "
                            "with threads on either arm")
         line["storage_roofline"] = storage
-    print(json.dumps(line), flush=True)
+    if single:
+        line["single_thread"] = single
+    emit(line)
     return 0
 
 

@@ -69,7 +69,7 @@ class Cfg(ctypes.Structure):
         ("ignoreDelErrors", c_i32),
         ("runAsService", c_i32),
         ("verifyCollectAll", c_i32),
-        ("reserved0", c_i32),
+        ("serializeBufferedWrites", c_i32),
     ]
 
 

@@ -66,6 +66,7 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.ignoreDelErrors = cfg->ignoreDelErrors;
 	c.runAsService = cfg->runAsService;
 	c.verifyCollectAll = cfg->verifyCollectAll;
+	c.serializeBufferedWrites = cfg->serializeBufferedWrites;
 
 	for(uint32_t i = 0; i < cfg->numGPUIDs; i++)
 		c.gpuIDs.push_back(cfg->gpuIDs[i] );

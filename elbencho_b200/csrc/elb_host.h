@@ -502,6 +502,7 @@ struct Config
 	bool ignoreDelErrors{false};
 	bool runAsService{false};
 	bool verifyCollectAll{false};
+	bool serializeBufferedWrites{false};
 
 	/* @throw WorkerError on invalid combinations */
 	static Config fromABI(const elb_cfg* cfg);

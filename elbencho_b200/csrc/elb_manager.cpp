@@ -117,6 +117,7 @@ void Manager::prepareBenchPathFDs()
 		}
 
 		shared.pathFDs.push_back(fd);
+		shared.fileWriteGates.emplace_back(new std::mutex() );
 	}
 }
 

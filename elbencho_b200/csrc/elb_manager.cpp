@@ -119,10 +119,34 @@ void Manager::prepareBenchPathFDs()
 		shared.pathFDs.push_back(fd);
 		shared.fileWriteGates.emplace_back(new std::mutex() );
 	}
+
+	/* ProgArgs::prepareCuFileHandleDataVec (ProgArgs.cpp:1950-1990): driver open + one registered
+	   handle per file in file/bdev mode (dir mode registers per file in the worker) */
+	if(cfg.useCuFile)
+	{
+		try
+		{
+			CuFileApi::get().driverOpenOnce();
+
+			if(cfg.pathType != ELB_PATH_DIR)
+				for(size_t i = 0; i < shared.pathFDs.size(); i++)
+				{
+					shared.cuFileHandles.emplace_back(new CuFileHandle() );
+					shared.cuFileHandles.back()->registerFD(shared.pathFDs[i], cfg.paths[i] );
+				}
+		}
+		catch(...)
+		{
+			closeBenchPathFDs();
+			throw;
+		}
+	}
 }
 
 void Manager::closeBenchPathFDs()
 {
+	shared.cuFileHandles.clear(); // deregisters
+
 	for(int fd : shared.pathFDs)
 		close(fd);
 

@@ -605,9 +605,35 @@ void Worker::allocRings()
 
 		batch.iocbs.resize(batchBlocks);
 		batch.iocbPtrs.resize(batchBlocks);
+
+		if(cfg.useCuFile && useAio)
+		{ // one cuFile batch context per pipeline batch
+			CUfileError_t setupRes = CuFileApi::get().BatchIOSetUp(&batch.cuBatch, batchBlocks);
+
+			if(setupRes.err != CU_FILE_SUCCESS)
+				throw WorkerError("cuFile batch setup failed (cuFileBatchIOSetUp). "
+					"Batch size: " + std::to_string(batchBlocks) + "; "
+					"cuFile Error: " + CuFileApi::errorStr(setupRes) );
+
+			batch.cuBatchValid = true;
+			batch.cuParams.resize(batchBlocks);
+			batch.cuEvents.resize(batchBlocks);
+		}
 	}
 
-	if(useAio)
+	if(cfg.useCuFile && cfg.useGDSBufReg)
+	{ // register the whole device ring for DMA once (reference: per buffer, :1495-1509)
+		CUfileError_t registerRes = CuFileApi::get().BufRegister(devRing, ringBytes, 0);
+
+		if(registerRes.err != CU_FILE_SUCCESS)
+			throw WorkerError("GPU DMA buffer registration via cuFileBufRegister failed. "
+				"GPU ID: " + std::to_string(gpuID) + "; "
+				"cuFile Error: " + CuFileApi::errorStr(registerRes) );
+
+		devRingCuFileRegistered = true;
+	}
+
+	if(useAio && !cfg.useCuFile)
 	{ // initLibAio (LocalWorker.cpp:455-480) on the raw kernel ABI
 		aioContext = 0;
 		long setupRes = syscall(SYS_io_setup, (unsigned)numSlots, &aioContext);
@@ -634,8 +660,22 @@ void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
 
 	cudaSetDevice(gpuID);
 
+	if(devRingCuFileRegistered)
+	{ // reference: cuFileBufDeregister in cleanup (:1586-1596)
+		CuFileApi::get().BufDeregister(devRing);
+		devRingCuFileRegistered = false;
+	}
+
+	dirModeCuFileHandle.deregister();
+
 	for(Batch& batch : batches)
 	{
+		if(batch.cuBatchValid)
+		{
+			CuFileApi::get().BatchIODestroy(batch.cuBatch);
+			batch.cuBatchValid = false;
+		}
+
 		if(batch.stream)
 			cudaStreamDestroy(batch.stream);
 		if(batch.gpuStartEvent)
@@ -675,6 +715,8 @@ void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
  * in the kernel AIO context finish, so that the rings can be reused by the next phase */
 void Worker::abortInFlight()
 {
+	dirModeCuFileHandle.deregister();
+
 	if(dirModeFD != -1)
 	{
 		close(dirModeFD);
@@ -1176,7 +1218,7 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 			if(isRead)
 			{
 				if(useAio && batch->numIOPending)
-					ioReapAio(false);
+					ioPollAsync(*batch);
 
 				stageOneComplete = !batch->numIOPending;
 			}
@@ -1286,7 +1328,11 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 		numKernelLaunches++;
 	}
 
-	// staged copy to the pinned ring: one copy when the batch is a dense run of full slots
+	/* staged copy to the pinned ring: one copy when the batch is a dense run of full slots.
+	   (cuFile writes straight from the device ring: no host copy, LocalWorker.cpp:1249-1250) */
+	if(cfg.useCuFile)
+		; // nothing to stage
+	else
 	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
 		ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, 0), slotDevPtr(batch, 0),
 			batch.numBytes, cudaMemcpyDeviceToHost, batch.stream), "Async GPU to host copy");
@@ -1301,7 +1347,8 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 				"Async GPU to host copy");
 		}
 
-	numD2HBytes += batch.numBytes;
+	if(!cfg.useCuFile)
+		numD2HBytes += batch.numBytes;
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuDoneEvent, batch.stream), "CUDA event record");
 }
@@ -1318,6 +1365,9 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
+	if(cfg.useCuFile)
+		; // cuFile read straight into the device ring (LocalWorker.cpp:1231-1232)
+	else
 	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
 		ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, 0), slotHostPtr(batch, 0),
 			batch.numBytes, cudaMemcpyHostToDevice, batch.stream), "Async host to GPU copy");
@@ -1332,7 +1382,8 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 				"Async host to GPU copy");
 		}
 
-	numH2DBytes += batch.numBytes;
+	if(!cfg.useCuFile)
+		numH2DBytes += batch.numBytes;
 
 	batch.hadKernel = false;
 
@@ -1408,7 +1459,17 @@ void Worker::throwVerifyError(Batch& batch, size_t blockIdx)
 	const uint64_t badOffset = block.offset + firstIdx;
 
 	const unsigned expectedVal = elb_pattern_byte(badOffset, cfg.integrityCheckSalt);
-	const unsigned actualVal = (unsigned char)slotHostPtr(batch, blockIdx)[firstIdx];
+	unsigned actualVal;
+
+	if(!cfg.useCuFile)
+		actualVal = (unsigned char)slotHostPtr(batch, blockIdx)[firstIdx];
+	else
+	{ // the block never touched host memory: fetch the one bad byte
+		unsigned char actualByte = 0;
+		ELB_CUDA_CHECK(cudaMemcpy(&actualByte, slotDevPtr(batch, blockIdx) + firstIdx, 1,
+			cudaMemcpyDeviceToHost), "Copy of mismatching byte from GPU");
+		actualVal = actualByte;
+	}
 
 	throw WorkerError("Data verification failed. "
 		"Offset: " + std::to_string(badOffset) + "; "
@@ -1540,6 +1601,9 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 			"Path: " + dirModeCurrentPath + "; "
 			"SysErr: " + strerror(errno) );
 
+	if(cfg.useCuFile) // dirModeCuFileHandleReg (LocalWorker.cpp:3091)
+		dirModeCuFileHandle.registerFD(dirModeFD, dirModeCurrentPath);
+
 	if(!isRead)
 	{
 		if(cfg.doTruncToSize && (ftruncate(dirModeFD, cfg.fileSize) == -1) )
@@ -1563,6 +1627,8 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 /* close + entry accounting (LocalWorker.cpp:3185-3243) */
 void Worker::dirModeCloseFile()
 {
+	dirModeCuFileHandle.deregister(); // (LocalWorker.cpp:3185)
+
 	int closeRes = close(dirModeFD);
 	int closeErrno = errno;
 	int closedFD = dirModeFD;
@@ -1601,6 +1667,12 @@ int Worker::resolveFD(const BlockRef& block, bool isRead)
  */
 void Worker::ioRunSync(Batch& batch, bool isRead)
 {
+	if(cfg.useCuFile)
+	{
+		ioRunSyncCuFile(batch, isRead);
+		return;
+	}
+
 	const size_t numBlocks = batch.blocks.size();
 	const uint64_t gpuShareUSec = isRead ?
 		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
@@ -1653,6 +1725,12 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
  */
 void Worker::ioSubmitAio(Batch& batch, bool isRead)
 {
+	if(cfg.useCuFile)
+	{
+		ioSubmitCuFileBatch(batch, isRead);
+		return;
+	}
+
 	const size_t numBlocks = batch.blocks.size();
 	size_t numIocbs = 0;
 
@@ -1766,7 +1844,11 @@ void Worker::ioWaitAio(Batch& batch, bool isRead)
 	while(batch.numIOPending)
 	{
 		checkInterruptionRequest();
-		ioReapAio(true);
+
+		if(cfg.useCuFile)
+			ioReapCuFileBatch(batch, true);
+		else
+			ioReapAio(true);
 	}
 
 	batch.ioSubmitted = false;
@@ -1785,6 +1867,170 @@ void Worker::ioWaitAio(Batch& batch, bool isRead)
 	if( (cfg.pathType == ELB_PATH_DIR) && !batch.blocks.empty() &&
 		batch.blocks.back().lastOfFile && (dirModeFD != -1) )
 		dirModeCloseFile();
+}
+
+/* ---- cuFile / GDS storage stages ----------------------------------------------------------- */
+
+CUfileHandle_t Worker::resolveCuFileHandle(const BlockRef& block, bool isRead)
+{
+	if(cfg.pathType != ELB_PATH_DIR)
+		return shared->cuFileHandles[block.fileIdx]->get();
+
+	if(block.firstOfFile)
+		dirModeOpenFile(block, isRead);
+
+	return dirModeCuFileHandle.get();
+}
+
+/**
+ * Synchronous GDS stage: cuFileRead/cuFileWrite between the file and the block's slot of the
+ * device ring (reference wrappers LocalWorker.cpp:2600-2640, which always use buffer 0 at
+ * devPtr_offset 0; here the registered ring base plus the slot offset).
+ */
+void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
+{
+	CuFileApi& api = CuFileApi::get();
+	const size_t numBlocks = batch.blocks.size();
+	const uint64_t gpuShareUSec = isRead ?
+		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		BlockRef& block = batch.blocks[i];
+
+		checkInterruptionRequest();
+
+		CUfileHandle_t handle = resolveCuFileHandle(block, isRead);
+
+		if(block.len)
+		{
+			const off_t devOffset = (off_t)( (uint64_t)(batch.firstSlot + i) * slotStride);
+
+			Clock::time_point ioStartT = Clock::now();
+
+			ssize_t ioRes = isRead ?
+				api.Read(handle, devRing, block.len, block.offset, devOffset) :
+				api.Write(handle, devRing, block.len, block.offset, devOffset);
+
+			if(ioRes != (ssize_t)block.len)
+			{
+				if(ioRes < -1) // cuFile specific error code (not errno)
+					throw WorkerError(std::string(isRead ?
+							"cuFile read failed. " : "cuFile write failed. ") +
+						"Path: " + blockPathForLog(block) + "; "
+						"cuFile Error: " + CUFILE_ERRSTR( (int)-ioRes) );
+
+				throwIOError(block, isRead, ioRes, errno);
+			}
+
+			block.ioUSec = elapsedUSecSince(ioStartT);
+
+			if(!isRead)
+				ioAccountBlock(batch, block, false, block.ioUSec + gpuShareUSec);
+		}
+
+		if(block.lastOfFile)
+			dirModeCloseFile();
+	}
+}
+
+/**
+ * iodepth > 1 with GDS: the whole batch goes down with one cuFileBatchIOSubmit (new capability;
+ * the reference rejects --cufile with --iodepth > 1, ProgArgs.cpp:1312-1313).
+ */
+void Worker::ioSubmitCuFileBatch(Batch& batch, bool isRead)
+{
+	CuFileApi& api = CuFileApi::get();
+	const size_t numBlocks = batch.blocks.size();
+	unsigned numParams = 0;
+
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		BlockRef& block = batch.blocks[i];
+
+		CUfileHandle_t handle = resolveCuFileHandle(block, isRead);
+
+		if(!block.len)
+			continue;
+
+		CUfileIOParams_t& params = batch.cuParams[numParams];
+		memset(&params, 0, sizeof(params) );
+		params.mode = CUFILE_BATCH;
+		params.fh = handle;
+		params.opcode = isRead ? CUFILE_READ : CUFILE_WRITE;
+		params.u.batch.devPtr_base = devRing;
+		params.u.batch.devPtr_offset = (off_t)( (uint64_t)(batch.firstSlot + i) * slotStride);
+		params.u.batch.file_offset = block.offset;
+		params.u.batch.size = block.len;
+		params.cookie = (void*)(uintptr_t)i;
+
+		block.submitT = Clock::now();
+		numParams++;
+	}
+
+	batch.numIOPending = numParams;
+	batch.ioSubmitted = true;
+
+	if(!numParams)
+		return;
+
+	CUfileError_t submitRes = api.BatchIOSubmit(batch.cuBatch, numParams, batch.cuParams.data(), 0);
+
+	if(submitRes.err != CU_FILE_SUCCESS)
+	{
+		batch.numIOPending = 0;
+		throw WorkerError("cuFile batch submission failed (cuFileBatchIOSubmit). "
+			"NumRequests: " + std::to_string(numParams) + "; "
+			"cuFile Error: " + CuFileApi::errorStr(submitRes) );
+	}
+}
+
+void Worker::ioReapCuFileBatch(Batch& batch, bool blockUntilEvent)
+{
+	CuFileApi& api = CuFileApi::get();
+
+	unsigned numEvents = batch.numIOPending;
+	struct timespec timeout;
+	timeout.tv_sec = blockUntilEvent ? ELB_AIO_MAX_WAIT_SEC : 0;
+	timeout.tv_nsec = 0;
+
+	CUfileError_t statusRes = api.BatchIOGetStatus(batch.cuBatch, blockUntilEvent ? 1 : 0,
+		&numEvents, batch.cuEvents.data(), &timeout);
+
+	if(statusRes.err != CU_FILE_SUCCESS)
+		throw WorkerError("Getting cuFile batch status failed (cuFileBatchIOGetStatus). "
+			"NumPending: " + std::to_string(batch.numIOPending) + "; "
+			"cuFile Error: " + CuFileApi::errorStr(statusRes) );
+
+	for(unsigned eventIdx = 0; eventIdx < numEvents; eventIdx++)
+	{
+		const CUfileIOEvents_t& event = batch.cuEvents[eventIdx];
+		const size_t blockIdx = (size_t)(uintptr_t)event.cookie;
+		BlockRef& block = batch.blocks[blockIdx];
+
+		if( (event.status == CUFILE_WAITING) || (event.status == CUFILE_PENDING) )
+			continue; // not a completion
+
+		if( (event.status != CUFILE_COMPLETE) || (event.ret != block.len) )
+			throw WorkerError("cuFile batch I/O failed. "
+				"Path: " + blockPathForLog(block) + "; "
+				"Offset: " + std::to_string(block.offset) + "; "
+				"Status: " + std::to_string( (int)event.status) + "; "
+				"Result: " + std::to_string( (long long)event.ret) + "; "
+				"Expected: " + std::to_string(block.len) );
+
+		block.ioUSec = elapsedUSecSince(block.submitT);
+		batch.numIOPending--;
+	}
+}
+
+/* non-blocking progress check of the async engine for one batch */
+void Worker::ioPollAsync(Batch& batch)
+{
+	if(cfg.useCuFile)
+		ioReapCuFileBatch(batch, false);
+	else
+		ioReapAio(false);
 }
 
 } // namespace elb

@@ -33,6 +33,7 @@
 #include <thread>
 #include <vector>
 
+#include "elb_cufile.h"
 #include "elb_host.h"
 #include "elb_internal.h"
 
@@ -50,6 +51,7 @@ struct Shared
 	Config cfg;
 	std::vector<int> pathFDs; // ProgArgs::benchPathFDsVec (opened by the manager)
 	std::vector<std::unique_ptr<std::mutex> > fileWriteGates; // one per path (file mode)
+	std::vector<std::unique_ptr<CuFileHandle> > cuFileHandles; // file mode with --cufile
 
 	std::mutex mutex;
 	std::condition_variable condition;
@@ -111,6 +113,12 @@ struct Batch
 	std::vector<struct iocb*> iocbPtrs;
 	uint32_t numIOPending{0};
 	bool ioSubmitted{false};
+
+	// cuFile batch state (iodepth > 1 with --cufile)
+	CUfileBatchHandle_t cuBatch{NULL};
+	bool cuBatchValid{false};
+	std::vector<CUfileIOParams_t> cuParams;
+	std::vector<CUfileIOEvents_t> cuEvents;
 
 	uint64_t numBytes{0};
 	float gpuMilliSecs{0};
@@ -204,6 +212,10 @@ class Worker
 		aio_context_t aioContext{0};
 		bool aioInitialized{false};
 
+		// cuFile / GDS
+		CuFileHandle dirModeCuFileHandle; // dir mode: handle of the currently open file
+		bool devRingCuFileRegistered{false};
+
 		// accounting
 		std::atomic<uint64_t> numH2DBytes{0};
 		std::atomic<uint64_t> numD2HBytes{0};
@@ -243,6 +255,11 @@ class Worker
 		void ioSubmitAio(Batch& batch, bool isRead);
 		void ioWaitAio(Batch& batch, bool isRead);
 		void ioReapAio(bool blockUntilEvent);
+		void ioPollAsync(Batch& batch);
+		void ioRunSyncCuFile(Batch& batch, bool isRead);
+		void ioSubmitCuFileBatch(Batch& batch, bool isRead);
+		void ioReapCuFileBatch(Batch& batch, bool blockUntilEvent);
+		CUfileHandle_t resolveCuFileHandle(const BlockRef& block, bool isRead);
 		void ioAccountBlock(Batch& batch, BlockRef& block, bool isRead, uint64_t latencyUSec);
 		void throwVerifyError(Batch& batch, size_t blockIdx);
 		int resolveFD(const BlockRef& block, bool isRead);

@@ -70,6 +70,8 @@ class Cfg(ctypes.Structure):
         ("runAsService", c_i32),
         ("verifyCollectAll", c_i32),
         ("serializeBufferedWrites", c_i32),
+        ("numRWMixReadThreads", c_u32),
+        ("reserved1", c_u32),
     ]
 
 

@@ -67,6 +67,7 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.runAsService = cfg->runAsService;
 	c.verifyCollectAll = cfg->verifyCollectAll;
 	c.serializeBufferedWrites = cfg->serializeBufferedWrites;
+	c.numRWMixReadThreads = std::min(cfg->numRWMixReadThreads, cfg->numThreads); // :1088
 
 	for(uint32_t i = 0; i < cfg->numGPUIDs; i++)
 		c.gpuIDs.push_back(cfg->gpuIDs[i] );
@@ -99,11 +100,20 @@ Config Config::fromABI(const elb_cfg* cfg)
 	if(c.integrityCheckSalt && c.rwMixReadPercent) // :1414
 		throw WorkerError("Integrity check cannot be used together with rwmixpct.");
 
-	if(c.rwMixReadPercent)
-		throw WorkerError("--rwmixpct is not supported by the GPU worker yet.");
+	if(c.rwMixReadPercent && c.numRWMixReadThreads) // :1402-1404
+		throw WorkerError("Option \"--rwmixpct\" cannot be used together with \"--rwmixthr\"");
 
-	if(c.doDirectVerify || c.doReadInline)
-		throw WorkerError("--verifydirect/--readinline are not supported by the GPU worker yet.");
+	if(c.doDirectVerify && !c.integrityCheckSalt) // :1424-1426
+		throw WorkerError("Direct verification requires --verify and --write");
+
+	if(c.doDirectVerify && (c.ioDepth > 1) ) // :1428-1429
+		throw WorkerError("Direct verification cannot be used together with --iodepth");
+
+	if(c.doReadInline && (c.ioDepth > 1) ) // :1431-1432
+		throw WorkerError("Inline read cannot be used together with --iodepth");
+
+	if( (c.doDirectVerify || c.doReadInline) && c.rwMixReadPercent)
+		throw WorkerError("--verifydirect/--readinline cannot be used together with --rwmixpct");
 
 	if(c.integrityCheckSalt && c.blockVariancePercent) // :1161-1167: verify wins
 		c.blockVariancePercent = 0;

@@ -494,6 +494,7 @@ struct Config
 	int blockVarianceAlgo{ELB_RANDALGO_SPLITMIX64};
 	uint64_t blockVarianceSeed{0};
 	uint32_t rwMixReadPercent{0};
+	uint32_t numRWMixReadThreads{0};
 	std::vector<int> gpuIDs;
 	bool useCuFile{false};
 	bool useGDSBufReg{false};

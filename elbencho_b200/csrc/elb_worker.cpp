@@ -1061,7 +1061,13 @@ void Worker::anyModeDropCaches() // LocalWorker.cpp:7822-7854
 
 void Worker::rwPhase()
 {
-	const bool isRead = (benchPhase == ELB_PHASE_READFILES);
+	/* --rwmixthr: the first numRWMixReadThreads local workers read during the write phase
+	   (initThreadPhaseVars, LocalWorker.cpp:1028-1041) */
+	const uint64_t localRank = rank - cfg.rankOffset;
+	isRWMixReaderThread = (benchPhase == ELB_PHASE_CREATEFILES) &&
+		(localRank < cfg.numRWMixReadThreads);
+
+	const bool isRead = (benchPhase == ELB_PHASE_READFILES) || isRWMixReaderThread;
 
 	if(!cfg.blockSize || !gpuPrepared)
 	{ // zero-sized files: only dir mode has something to do (create/open empty files)
@@ -1111,7 +1117,7 @@ void Worker::rwPhase()
  *
  * @return false if the source had no more blocks (batch stays empty).
  */
-bool Worker::collectBatch(Batch& batch, BlockSource& source)
+bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead)
 {
 	batch.blocks.clear();
 	batch.numBytes = 0;
@@ -1127,6 +1133,14 @@ bool Worker::collectBatch(Batch& batch, BlockSource& source)
 
 		if(!source.next(block) )
 			break;
+
+		/* rwmix rule of rwBlockSized (LocalWorker.cpp:1708-1718): in a write phase block n of a
+		   worker is a read if (rank + numIOPSSubmitted) % 100 < rwmixpct */
+		const bool isRWMixPctRead = !isRead && cfg.rwMixReadPercent &&
+			( ( (rank + block.blockCounter) % 100) < cfg.rwMixReadPercent);
+
+		block.ioIsRead = isRead || isRWMixPctRead;
+		block.statsReadMix = isRWMixPctRead || isRWMixReaderThread;
 
 		batch.numBytes += block.len;
 		batch.blocks.push_back(block);
@@ -1183,7 +1197,7 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 		{
 			Batch* batch = freeBatches.front();
 
-			if(!collectBatch(*batch, source) )
+			if(!collectBatch(*batch, source, isRead) )
 				sourceExhausted = true;
 			else
 			{
@@ -1292,17 +1306,26 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 
 	batch.hadKernel = false;
 
-	if(doPatternFill || doRandFill)
-	{
-		for(size_t i = 0; i < numBlocks; i++)
-		{
-			const BlockRef& block = batch.blocks[i];
-			batch.hostDescs[i] = elb_block_desc{slotDevPtr(batch, i), block.len, block.offset,
-				(rank << 40) + block.blockCounter};
-		}
+	// blocks that rwmix turned into reads get no fill and no staging (LocalWorker.cpp:2213)
+	size_t numWriteBlocks = 0;
+	uint64_t numWriteBytes = 0;
 
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		const BlockRef& block = batch.blocks[i];
+
+		if(block.ioIsRead)
+			continue;
+
+		batch.hostDescs[numWriteBlocks++] = elb_block_desc{slotDevPtr(batch, i), block.len,
+			block.offset, (rank << 40) + block.blockCounter};
+		numWriteBytes += block.len;
+	}
+
+	if( (doPatternFill || doRandFill) && numWriteBlocks)
+	{
 		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
-			sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
+			sizeof(elb_block_desc) * numWriteBlocks, cudaMemcpyHostToDevice, batch.stream),
 			"Async copy of block descriptors");
 
 		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
@@ -1311,11 +1334,11 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 		int launchRes;
 
 		if(doPatternFill)
-			launchRes = elb_launch_fill_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
-				cfg.integrityCheckSalt, devCounters, batch.numBytes, batch.stream);
+			launchRes = elb_launch_fill_pattern(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
+				cfg.integrityCheckSalt, devCounters, numWriteBytes, batch.stream);
 		else
-			launchRes = elb_launch_fill_random(batch.devDescs, NULL, (uint32_t)numBlocks,
-				cfg.blockVariancePercent, blockVarianceSeed, devCounters, batch.numBytes,
+			launchRes = elb_launch_fill_random(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
+				cfg.blockVariancePercent, blockVarianceSeed, devCounters, numWriteBytes,
 				batch.stream);
 
 		if(launchRes)
@@ -1333,13 +1356,14 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 	if(cfg.useCuFile)
 		; // nothing to stage
 	else
-	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
+	if( (numWriteBlocks == numBlocks) && (slotStride == cfg.blockSize) &&
+		(batch.numBytes == (numBlocks * slotStride) ) )
 		ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, 0), slotDevPtr(batch, 0),
 			batch.numBytes, cudaMemcpyDeviceToHost, batch.stream), "Async GPU to host copy");
 	else
 		for(size_t i = 0; i < numBlocks; i++)
 		{
-			if(!batch.blocks[i].len)
+			if(!batch.blocks[i].len || batch.blocks[i].ioIsRead)
 				continue;
 
 			ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, i), slotDevPtr(batch, i),
@@ -1348,7 +1372,7 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 		}
 
 	if(!cfg.useCuFile)
-		numD2HBytes += batch.numBytes;
+		numD2HBytes += numWriteBytes;
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuDoneEvent, batch.stream), "CUDA event record");
 }
@@ -1500,27 +1524,66 @@ void Worker::retireReadBatch(Batch& batch)
 		}
 	}
 
-	const uint64_t gpuShareUSec = (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+	accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
+}
 
-	for(size_t i = 0; i < numBlocks; i++)
-		ioAccountBlock(batch, batch.blocks[i], true, batch.blocks[i].ioUSec + gpuShareUSec);
+/**
+ * --verifydirect (LocalWorker.cpp:1269-1281): the blocks of this batch were written and read back
+ * into their slots; check them on the GPU right away, then account (the check is part of the
+ * reported latency like in the reference).
+ */
+void Worker::verifyWrittenBatch(Batch& batch)
+{
+	const float fillMilliSecs = batch.gpuMilliSecs;
+
+	gpuLaunchReadStage(batch);
+	gpuWait(batch);
+
+	for(size_t i = 0; i < batch.blocks.size(); i++)
+	{
+		if(!batch.hostResults[i].numMismatchBytes)
+			continue;
+
+		batch.devResultsClean = false;
+
+		if(!cfg.verifyCollectAll)
+			throwVerifyError(batch, i);
+	}
+
+	accountBatch(batch, (uint64_t)( (fillMilliSecs + batch.gpuMilliSecs) * 1000) );
 }
 
 /* ---- storage stages ------------------------------------------------------------------------ */
 
-void Worker::ioAccountBlock(Batch& batch, BlockRef& block, bool isRead, uint64_t latencyUSec)
+/* per-block counters of rwBlockSized (LocalWorker.cpp:1755-1772) */
+void Worker::ioAccountBlock(BlockRef& block, uint64_t latencyUSec)
 {
-	(void)batch;
-	(void)isRead;
-
 	if(!block.len && (cfg.pathType == ELB_PATH_DIR) )
 		return; // empty file: no I/O happened
+
+	if(block.statsReadMix)
+	{ // rwmix read in a write phase
+		histogramAdd(iopsLatHistoReadMix, latencyUSec);
+		atomicLiveOpsReadMix.numBytesDone += block.len;
+		atomicLiveOpsReadMix.numIOPSDone++;
+		return;
+	}
 
 	histogramAdd(iopsLatHisto, latencyUSec);
 	liveLatNumIO++;
 	liveLatSumIO += latencyUSec;
 	atomicLiveOps.numBytesDone += block.len;
 	atomicLiveOps.numIOPSDone++;
+}
+
+/* account all blocks of a batch: latency = storage time + share of the batch's GPU time */
+void Worker::accountBatch(Batch& batch, uint64_t gpuUSecTotal)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const uint64_t gpuShareUSec = numBlocks ? (gpuUSecTotal / numBlocks) : 0;
+
+	for(size_t i = 0; i < numBlocks; i++)
+		ioAccountBlock(batch.blocks[i], batch.blocks[i].ioUSec + gpuShareUSec);
 }
 
 std::string Worker::blockPathForLog(const BlockRef& block) const
@@ -1643,6 +1706,13 @@ void Worker::dirModeCloseFile()
 
 	const uint64_t entryUSec = elapsedUSecSince(dirModeFileStartT);
 
+	if(isRWMixReaderThread)
+	{ // (LocalWorker.cpp:3233-3237)
+		histogramAdd(entriesLatHistoReadMix, entryUSec);
+		atomicLiveOpsReadMix.numEntriesDone++;
+		return;
+	}
+
 	histogramAdd(entriesLatHisto, entryUSec);
 	liveLatNumEntries++;
 	liveLatSumEntries += entryUSec;
@@ -1674,8 +1744,7 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 	}
 
 	const size_t numBlocks = batch.blocks.size();
-	const uint64_t gpuShareUSec = isRead ?
-		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+	const bool doReadBack = !isRead && (cfg.doDirectVerify || cfg.doReadInline);
 	const bool useWriteGate = !isRead && cfg.serializeBufferedWrites && !cfg.useDirectIO &&
 		(cfg.pathType != ELB_PATH_DIR);
 
@@ -1690,32 +1759,53 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 		if(block.len)
 		{
 			Clock::time_point ioStartT = Clock::now();
-
+			char* hostBuf = slotHostPtr(batch, i);
 			ssize_t ioRes;
 
-			if(isRead)
-				ioRes = pread(fd, slotHostPtr(batch, i), block.len, block.offset);
+			if(block.ioIsRead)
+				ioRes = pread(fd, hostBuf, block.len, block.offset);
 			else
 			if(useWriteGate)
 			{ // one buffered writer per file at a time (see elb_cfg::serializeBufferedWrites)
 				std::unique_lock<std::mutex> gate(*shared->fileWriteGates[block.fileIdx] );
 				ioStartT = Clock::now(); // storage time without the queueing
-				ioRes = pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
+				ioRes = pwrite(fd, hostBuf, block.len, block.offset);
 			}
 			else
-				ioRes = pwrite(fd, slotHostPtr(batch, i), block.len, block.offset);
+				ioRes = pwrite(fd, hostBuf, block.len, block.offset);
 
 			if(ioRes != (ssize_t)block.len)
-				throwIOError(block, isRead, ioRes, errno);
+				throwIOError(block, block.ioIsRead, ioRes, errno);
+
+			if(doReadBack)
+			{ // pwriteAndReadWrapper (LocalWorker.cpp:2533-2554): read the same range back
+				ioRes = pread(fd, hostBuf, block.len, block.offset);
+
+				if(ioRes != (ssize_t)block.len)
+					throwIOError(block, true, ioRes, errno);
+			}
 
 			block.ioUSec = elapsedUSecSince(ioStartT);
 
-			if(!isRead)
-				ioAccountBlock(batch, block, false, block.ioUSec + gpuShareUSec);
+			if(!isRead && block.ioIsRead)
+			{ // rwmix read in a write phase: the data goes to the GPU like any read (:1311-1312)
+				ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, i), hostBuf, block.len,
+					cudaMemcpyHostToDevice, batch.stream), "Async host to GPU copy");
+				numH2DBytes += block.len;
+			}
 		}
 
 		if(block.lastOfFile)
 			dirModeCloseFile();
+	}
+
+	// write phase accounting happens here; reads are accounted when their GPU stage retires
+	if(!isRead)
+	{
+		if(cfg.doDirectVerify)
+			verifyWrittenBatch(batch);
+		else
+			accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
 	}
 }
 
@@ -1745,7 +1835,7 @@ void Worker::ioSubmitAio(Batch& batch, bool isRead)
 
 		struct iocb& cb = batch.iocbs[numIocbs];
 		memset(&cb, 0, sizeof(cb) );
-		cb.aio_lio_opcode = isRead ? IOCB_CMD_PREAD : IOCB_CMD_PWRITE;
+		cb.aio_lio_opcode = block.ioIsRead ? IOCB_CMD_PREAD : IOCB_CMD_PWRITE;
 		cb.aio_fildes = fd;
 		cb.aio_buf = (uint64_t)(uintptr_t)slotHostPtr(batch, i);
 		cb.aio_nbytes = block.len;
@@ -1853,14 +1943,22 @@ void Worker::ioWaitAio(Batch& batch, bool isRead)
 
 	batch.ioSubmitted = false;
 
-	const size_t numBlocks = batch.blocks.size();
-
 	if(!isRead)
 	{
-		const uint64_t gpuShareUSec = (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+		if(!cfg.useCuFile)
+			for(size_t i = 0; i < batch.blocks.size(); i++)
+			{ // rwmix reads of a write phase go to the GPU like any read
+				const BlockRef& block = batch.blocks[i];
 
-		for(size_t i = 0; i < numBlocks; i++)
-			ioAccountBlock(batch, batch.blocks[i], false, batch.blocks[i].ioUSec + gpuShareUSec);
+				if(!block.ioIsRead || !block.len)
+					continue;
+
+				ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, i), slotHostPtr(batch, i),
+					block.len, cudaMemcpyHostToDevice, batch.stream), "Async host to GPU copy");
+				numH2DBytes += block.len;
+			}
+
+		accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
 	}
 
 	// dir mode: batches end at file boundaries, so the file can be closed now
@@ -1891,8 +1989,7 @@ void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
 {
 	CuFileApi& api = CuFileApi::get();
 	const size_t numBlocks = batch.blocks.size();
-	const uint64_t gpuShareUSec = isRead ?
-		0 : (uint64_t)( (batch.gpuMilliSecs * 1000) / numBlocks);
+	const bool doReadBack = !isRead && (cfg.doDirectVerify || cfg.doReadInline);
 
 	for(size_t i = 0; i < numBlocks; i++)
 	{
@@ -1908,29 +2005,38 @@ void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
 
 			Clock::time_point ioStartT = Clock::now();
 
-			ssize_t ioRes = isRead ?
+			ssize_t ioRes = block.ioIsRead ?
 				api.Read(handle, devRing, block.len, block.offset, devOffset) :
 				api.Write(handle, devRing, block.len, block.offset, devOffset);
+
+			// cuFileWriteAndReadWrapper (LocalWorker.cpp:2643-2670)
+			if( (ioRes == (ssize_t)block.len) && doReadBack)
+				ioRes = api.Read(handle, devRing, block.len, block.offset, devOffset);
 
 			if(ioRes != (ssize_t)block.len)
 			{
 				if(ioRes < -1) // cuFile specific error code (not errno)
-					throw WorkerError(std::string(isRead ?
+					throw WorkerError(std::string(block.ioIsRead ?
 							"cuFile read failed. " : "cuFile write failed. ") +
 						"Path: " + blockPathForLog(block) + "; "
 						"cuFile Error: " + CUFILE_ERRSTR( (int)-ioRes) );
 
-				throwIOError(block, isRead, ioRes, errno);
+				throwIOError(block, block.ioIsRead, ioRes, errno);
 			}
 
 			block.ioUSec = elapsedUSecSince(ioStartT);
-
-			if(!isRead)
-				ioAccountBlock(batch, block, false, block.ioUSec + gpuShareUSec);
 		}
 
 		if(block.lastOfFile)
 			dirModeCloseFile();
+	}
+
+	if(!isRead)
+	{
+		if(cfg.doDirectVerify)
+			verifyWrittenBatch(batch);
+		else
+			accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
 	}
 }
 
@@ -1957,7 +2063,7 @@ void Worker::ioSubmitCuFileBatch(Batch& batch, bool isRead)
 		memset(&params, 0, sizeof(params) );
 		params.mode = CUFILE_BATCH;
 		params.fh = handle;
-		params.opcode = isRead ? CUFILE_READ : CUFILE_WRITE;
+		params.opcode = block.ioIsRead ? CUFILE_READ : CUFILE_WRITE;
 		params.u.batch.devPtr_base = devRing;
 		params.u.batch.devPtr_offset = (off_t)( (uint64_t)(batch.firstSlot + i) * slotStride);
 		params.u.batch.file_offset = block.offset;

@@ -74,6 +74,8 @@ struct BlockRef
 	uint64_t fileIndex{0};    // dir mode
 	bool firstOfFile{false};  // dir mode: open the file before this block
 	bool lastOfFile{false};   // dir mode: close the file after this block
+	bool ioIsRead{false};     // direction of this block's storage call (rwmix: read in a write phase)
+	bool statsReadMix{false}; // account into the *ReadMix counters (Worker.h:52,56,58)
 	uint64_t blockCounter{0}; // keys the random fill
 	uint64_t ioUSec{0};       // measured storage time of this block
 	Clock::time_point submitT; // aio: time of submission
@@ -186,6 +188,7 @@ class Worker
 		std::string lastError;
 
 		int benchPhase{ELB_PHASE_IDLE};
+		bool isRWMixReaderThread{false}; // --rwmixthr reader in a write phase (LocalWorker.cpp:1028-1041)
 		uint64_t numIOPSSubmitted{0}; // never reset between phases (LocalWorker.h:121)
 
 		// rings + batches
@@ -246,7 +249,9 @@ class Worker
 
 		// the pipeline
 		void rwBlocksPipelined(BlockSource& source, bool isRead);
-		bool collectBatch(Batch& batch, BlockSource& source);
+		bool collectBatch(Batch& batch, BlockSource& source, bool isRead);
+		void verifyWrittenBatch(Batch& batch);
+		void accountBatch(Batch& batch, uint64_t gpuUSecTotal);
 		void gpuLaunchWriteStage(Batch& batch);
 		void gpuLaunchReadStage(Batch& batch);
 		void gpuWait(Batch& batch);
@@ -260,7 +265,7 @@ class Worker
 		void ioSubmitCuFileBatch(Batch& batch, bool isRead);
 		void ioReapCuFileBatch(Batch& batch, bool blockUntilEvent);
 		CUfileHandle_t resolveCuFileHandle(const BlockRef& block, bool isRead);
-		void ioAccountBlock(Batch& batch, BlockRef& block, bool isRead, uint64_t latencyUSec);
+		void ioAccountBlock(BlockRef& block, uint64_t latencyUSec);
 		void throwVerifyError(Batch& batch, size_t blockIdx);
 		int resolveFD(const BlockRef& block, bool isRead);
 		void dirModeOpenFile(const BlockRef& block, bool isRead);

@@ -85,6 +85,7 @@ class WorkerConfig:
     run_as_service: bool = False
     verify_collect_all: bool = False
     serialize_buffered_writes: bool = False
+    num_rwmix_read_threads: int = 0   # --rwmixthr
 
     def to_abi(self):
         """-> (Cfg, keepalive objects)"""
@@ -134,6 +135,7 @@ class WorkerConfig:
         cfg.runAsService = int(self.run_as_service)
         cfg.verifyCollectAll = int(self.verify_collect_all)
         cfg.serializeBufferedWrites = int(self.serialize_buffered_writes)
+        cfg.numRWMixReadThreads = self.num_rwmix_read_threads
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

@@ -238,6 +238,11 @@ typedef struct elb_cfg
 	 * the inode lock anyway; queueing in user space avoids the lock's spinning under contention
 	 * (measured on tmpfs: 3.2 -> 4.1 GiB/s at 16 writers). I/O sizes and order are unchanged. */
 	int32_t serializeBufferedWrites;
+
+	/* --rwmixthr: the first N local workers read (their share of the data set) during the write
+	 * phase; their stats go to the ReadMix counters (LocalWorker.cpp:1028-1041) */
+	uint32_t numRWMixReadThreads;
+	uint32_t reserved1;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

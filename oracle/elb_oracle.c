@@ -743,6 +743,7 @@ typedef struct orc_worker
 	uint64_t numIOPSSubmitted;
 	int currentFD; // fdVec[0] of sequential/dir mode
 	orc_goldenprime blockVarAlgo;
+	int isRWMixReader; // --rwmixthr reader in a write phase (workers/LocalWorker.cpp:1028-1041)
 	orc_worker_result* res;
 	elb_liveops stoneWallOps;
 	char errTmp[512];
@@ -853,7 +854,10 @@ static int64_t orc_rw_block_sized(orc_worker* w, const int* fdVec, size_t numFDs
 		}
 
 		if(isRead)
+		{ // this is a read, but could be a rwmix read thread (:1697-1706)
+			isRWMixRead = w->isRWMixReader;
 			rwRes = pread(fdVec[fileHandleIdx], w->ioBuf, currentBlockSize, currentOffset);
+		}
 		else
 		if(rwMixReadPercent && ( ( (w->rank + w->numIOPSSubmitted) % 100) < rwMixReadPercent) )
 		{ // :1708-1718
@@ -861,14 +865,20 @@ static int64_t orc_rw_block_sized(orc_worker* w, const int* fdVec, size_t numFDs
 			rwRes = pread(fdVec[fileHandleIdx], w->ioBuf, currentBlockSize, currentOffset);
 		}
 		else
+		{
 			rwRes = pwrite(fdVec[fileHandleIdx], w->ioBuf, currentBlockSize, currentOffset);
+
+			// pwriteAndReadWrapper for --verifydirect/--readinline (:2533-2554)
+			if( (rwRes > 0) && (cfg->doDirectVerify || cfg->doReadInline) )
+				rwRes = pread(fdVec[fileHandleIdx], w->ioBuf, rwRes, currentOffset);
+		}
 
 		if(rwRes <= 0)
 			return (rwRes < 0) ? rwRes :
 				(int64_t)(orc_offsetgen_bytes_total(gen) - orc_offsetgen_bytes_left(gen) );
 
-		if(isRead && cfg->integrityCheckSalt)
-		{ // funcPostReadBlockChecker (:1318-1319)
+		if( (isRead || (!isRWMixRead && cfg->doDirectVerify) ) && cfg->integrityCheckSalt)
+		{ // funcPostReadBlockChecker (:1318-1319; --verifydirect :1279-1280)
 			int verifyRes = orc_verify_pattern(w->ioBuf, currentBlockSize, currentOffset,
 				cfg->integrityCheckSalt, NULL, NULL, NULL, NULL, w->errTmp, sizeof(w->errTmp) );
 			if(verifyRes)
@@ -1195,6 +1205,12 @@ static void orc_dir_mode_iterate_files(orc_worker* w, int benchPhase)
 				}
 			}
 
+			if(w->isRWMixReader)
+			{ // (:3233-3237)
+				__atomic_fetch_add(&w->res->liveOpsReadMix.numEntriesDone, 1, __ATOMIC_RELAXED);
+				continue;
+			}
+
 			orc_histogram_add_latency(&w->res->entriesLatHisto, orc_elapsed_usec(&ioStartT) );
 			__atomic_fetch_add(&w->res->liveOps.numEntriesDone, 1, __ATOMIC_RELAXED);
 		}
@@ -1373,12 +1389,16 @@ static void* orc_worker_thread(void* arg)
 		case ELB_PHASE_CREATEFILES:
 		case ELB_PHASE_READFILES:
 		{
-			const int isRead = (benchPhase == ELB_PHASE_READFILES);
+			// initThreadPhaseVars (:1028-1041): rwmix reader threads read in the write phase
+			w->isRWMixReader = (benchPhase == ELB_PHASE_CREATEFILES) &&
+				( (w->rank - cfg->rankOffset) < cfg->numRWMixReadThreads);
 
-			orc_init_offset_gen(w, !isRead);
+			const int isRead = (benchPhase == ELB_PHASE_READFILES) || w->isRWMixReader;
+
+			orc_init_offset_gen(w, benchPhase == ELB_PHASE_CREATEFILES);
 
 			if(isDir)
-				orc_dir_mode_iterate_files(w, benchPhase);
+				orc_dir_mode_iterate_files(w, isRead ? ELB_PHASE_READFILES : benchPhase);
 			else
 			if(cfg->useRandomOffsets || cfg->useStridedAccess)
 				orc_file_mode_iterate_rand(w, isRead);

@@ -1,0 +1,162 @@
+"""GPU parity tests of the remaining loop variants: --rwmixpct, --rwmixthr,
+--verifydirect, --readinline, on the staged path and on the GDS path (mock cuFile)."""
+import os
+import shutil
+import tempfile
+
+import pytest
+
+from tests.test_cufile_gpu import MOCK_LIB  # noqa: F401  (sets ELB_CUFILE_LIB before first use)
+from elbencho_b200 import BenchPhase, PathType, WorkerConfig, WorkerError, WorkerManager
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+MiB = 1 << 20
+KiB = 1 << 10
+
+
+@pytest.fixture()
+def workdir(cuda_device):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    path = tempfile.mkdtemp(prefix="elb_var_", dir=base)
+    yield path
+    shutil.rmtree(path, ignore_errors=True)
+
+
+def prefill(path, size, salt):
+    with WorkerManager(WorkerConfig(paths=[path], block_size=MiB, file_size=size,
+                                    integrity_check_salt=salt)) as mgr:
+        mgr.run_phase(BenchPhase.CREATEFILES)
+
+
+@pytest.mark.parametrize("cufile", [False, True])
+def test_rwmixpct_decisions_counters_and_bytes(workdir, cufile):
+    size, block, threads, pct, seed = 8 * MiB, 64 * KiB, 2, 30, 777
+    gpath, cpath = os.path.join(workdir, "g"), os.path.join(workdir, "c")
+    prefill(gpath, size, 9)
+    shutil.copy(gpath, cpath)
+    common = dict(num_threads=threads, block_size=block, file_size=size, rwmix_read_percent=pct,
+                  block_variance_percent=100)
+    with WorkerManager(WorkerConfig(paths=[gpath], block_variance_seed=seed, use_cufile=cufile,
+                                    pipeline_batch_blocks=5, **common)) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        rc, ow, opr = oracle_lib.run_oracle_phase(WorkerConfig(paths=[cpath], **common),
+                                                  BenchPhase.CREATEFILES)
+        assert rc == 0
+        # same read/write decision per block: (rank + numIOPSSubmitted) % 100 < pct (:1708-1709)
+        assert res["ops_total"]["bytes"] == opr.opsTotal.numBytesDone
+        assert res["ops_total"]["iops"] == opr.opsTotal.numIOPSDone
+        assert res["ops_readmix_total"]["bytes"] == opr.opsReadMixTotal.numBytesDone
+        assert res["ops_readmix_total"]["iops"] == opr.opsReadMixTotal.numIOPSDone
+        assert res["ops_total"]["iops"] + res["ops_readmix_total"]["iops"] == size // block
+        assert 0 < res["ops_readmix_total"]["iops"] < size // block
+        for i, worker in enumerate(mgr.workers()):
+            ops, mix = worker.live_ops()
+            assert ops["iops"] == ow[i].liveOps.numIOPSDone
+            assert mix["iops"] == ow[i].liveOpsReadMix.numIOPSDone
+            assert worker.histogram(1)["num"] == mix["iops"]  # iopsLatHistoReadMix
+        # random refill only on write turns (:2213): filled bytes == written bytes
+        assert res["filled_bytes"] == res["ops_total"]["bytes"]
+    with open(gpath, "rb") as f:
+        data = f.read()
+    blocks_per_rank = (size // block) // threads
+    for blk in range(size // block):
+        rank, ctr = blk // blocks_per_rank, blk % blocks_per_rank
+        got = data[blk * block:(blk + 1) * block]
+        if (rank + ctr) % 100 < pct:
+            assert got == oracle_lib.fill_pattern(block, blk * block, 9), blk  # read turn: untouched
+        else:
+            assert got == oracle_lib.fill_random_ctr(block, 100, seed, (rank << 40) + ctr), blk
+
+
+def test_rwmixpct_async_engine(workdir):
+    size, block = 4 * MiB, 16 * KiB
+    gpath, cpath = os.path.join(workdir, "g"), os.path.join(workdir, "c")
+    prefill(gpath, size, 3)
+    shutil.copy(gpath, cpath)
+    common = dict(num_threads=2, block_size=block, file_size=size, rwmix_read_percent=50)
+    with WorkerManager(WorkerConfig(paths=[gpath], io_depth=8, **common)) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+    rc, ow, opr = oracle_lib.run_oracle_phase(WorkerConfig(paths=[cpath], **common),
+                                              BenchPhase.CREATEFILES)
+    assert rc == 0
+    assert res["ops_total"]["iops"] == opr.opsTotal.numIOPSDone
+    assert res["ops_readmix_total"]["iops"] == opr.opsReadMixTotal.numIOPSDone
+    assert res["h2d_bytes"] == res["ops_readmix_total"]["bytes"]
+
+
+@pytest.mark.parametrize("dirmode", [False, True])
+def test_rwmix_reader_threads(workdir, dirmode):
+    """--rwmixthr 1 of 3: rank 0 reads (and verifies) its share while ranks 1-2 write theirs"""
+    salt = 4
+    if dirmode:
+        gdir, cdir = os.path.join(workdir, "g"), os.path.join(workdir, "c")
+        os.mkdir(gdir)
+        os.mkdir(cdir)
+        common = dict(path_type=PathType.DIR, num_threads=3, num_dirs=1, num_files=2,
+                      block_size=32 * KiB, file_size=96 * KiB, integrity_check_salt=salt)
+        gpaths, cpaths = [gdir], [cdir]
+        prep = [BenchPhase.CREATEDIRS, BenchPhase.CREATEFILES]
+    else:
+        common = dict(num_threads=3, block_size=64 * KiB, file_size=6 * MiB,
+                      integrity_check_salt=salt)
+        gpaths, cpaths = [os.path.join(workdir, "g")], [os.path.join(workdir, "c")]
+        prep = [BenchPhase.CREATEFILES]
+    with WorkerManager(WorkerConfig(paths=gpaths, **common)) as mgr:
+        for phase in prep:
+            mgr.run_phase(phase)
+    for phase in prep:
+        assert oracle_lib.run_oracle_phase(WorkerConfig(paths=cpaths, **common), phase)[0] == 0
+    with WorkerManager(WorkerConfig(paths=gpaths, num_rwmix_read_threads=1, **common)) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        rc, ow, opr = oracle_lib.run_oracle_phase(
+            WorkerConfig(paths=cpaths, num_rwmix_read_threads=1, **common), BenchPhase.CREATEFILES)
+        assert rc == 0
+        for key, ref in (("ops_total", opr.opsTotal), ("ops_readmix_total", opr.opsReadMixTotal)):
+            assert res[key] == {"entries": ref.numEntriesDone, "bytes": ref.numBytesDone,
+                                "iops": ref.numIOPSDone}, key
+        assert res["ops_readmix_total"]["bytes"] > 0
+        # the reader thread verified what it read
+        assert res["verified_bytes"] == res["ops_readmix_total"]["bytes"]
+        assert res["filled_bytes"] == res["ops_total"]["bytes"]
+        reader_ops, reader_mix = mgr.worker(0).live_ops()
+        assert reader_ops["bytes"] == 0 and reader_mix["bytes"] == res["ops_readmix_total"]["bytes"]
+
+
+@pytest.mark.parametrize("cufile", [False, True])
+@pytest.mark.parametrize("option", ["verifydirect", "readinline"])
+def test_verifydirect_and_readinline(workdir, option, cufile):
+    size, block = 5 * MiB + (512 if not cufile else 0), 512 * KiB
+    gpath, cpath = os.path.join(workdir, "g"), os.path.join(workdir, "c")
+    common = dict(num_threads=2, block_size=block, file_size=size, integrity_check_salt=6,
+                  do_direct_verify=(option == "verifydirect"),
+                  do_read_inline=(option == "readinline"))
+    with WorkerManager(WorkerConfig(paths=[gpath], use_cufile=cufile, pipeline_batch_blocks=3,
+                                    **common)) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        rc, ow, opr = oracle_lib.run_oracle_phase(WorkerConfig(paths=[cpath], **common),
+                                                  BenchPhase.CREATEFILES)
+        assert rc == 0
+        assert res["ops_total"]["bytes"] == opr.opsTotal.numBytesDone == size
+        assert res["ops_total"]["iops"] == opr.opsTotal.numIOPSDone
+        assert res["iops_lat_histo"]["num"] == opr.iopsLatHisto.numStoredValues
+        if option == "verifydirect":
+            assert res["verified_bytes"] == size and res["verify_mismatch_bytes"] == 0
+            if not cufile:
+                assert res["h2d_bytes"] == size  # what was read back went to the GPU
+        else:
+            assert res["verified_bytes"] == 0
+    with open(gpath, "rb") as f1, open(cpath, "rb") as f2:
+        assert f1.read() == f2.read()
+
+
+def test_variant_option_validation():
+    with pytest.raises(WorkerError, match="Direct verification requires"):
+        WorkerManager(WorkerConfig(paths=["/tmp/x"], file_size=4096, do_direct_verify=True))
+    with pytest.raises(WorkerError, match="cannot be used together with --iodepth"):
+        WorkerManager(WorkerConfig(paths=["/tmp/x"], file_size=4096, do_read_inline=True,
+                                   io_depth=4))
+    with pytest.raises(WorkerError, match="rwmixthr"):
+        WorkerManager(WorkerConfig(paths=["/tmp/x"], file_size=4096, rwmix_read_percent=10,
+                                   num_rwmix_read_threads=1))

@@ -122,6 +122,13 @@ class PhaseResults(ctypes.Structure):
         ("devKernelUSec", c_u64),
         ("numWorkersDone", c_u32),
         ("numWorkersDoneWithError", c_u32),
+        ("opsStoneWallReadMixTotal", LiveOps),
+        ("opsReadMixPerSec", LiveOps),
+        ("opsStoneWallReadMixPerSec", LiveOps),
+        ("iopsLatHistoReadMix", Histogram),
+        ("entriesLatHistoReadMix", Histogram),
+        ("cpuUtilStoneWallPercent", c_u32),
+        ("cpuUtilPercent", c_u32),
     ]
 
 
@@ -173,6 +180,10 @@ SIGNATURES = {
     "elb_mgr_worker": (_VP, [_VP, c_u32]),
     "elb_mgr_last_error": (ctypes.c_char_p, [_VP]),
     "elb_mgr_destroy": (None, [_VP]),
+    "elb_cli_main": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p)]),
+    "elb_format_phase_results": (ctypes.c_int64, [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                                  ctypes.c_int, ctypes.POINTER(PhaseResults),
+                                                  ctypes.c_int, ctypes.c_char_p, c_u64]),
     "elb_worker_rank": (c_u64, [_VP]),
     "elb_worker_gpu_id": (ctypes.c_int, [_VP]),
     "elb_worker_live_ops": (ctypes.c_int, [_VP, ctypes.POINTER(LiveOps)]),

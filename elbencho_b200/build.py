@@ -21,7 +21,13 @@ SOURCES = [
     "elb_cufile.cpp",
     "elb_worker.cpp",
     "elb_manager.cpp",
+    "elb_cli.cpp",
+    "elb_stats.cpp",
+    "elb_coordinator.cpp",
+    "elb_service.cpp",
 ]
+
+CLI_PATH = os.path.join(PKG_DIR, "elbencho-b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -64,6 +70,13 @@ def build_native(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC_DIR)
+    # the command line executable: a main() that calls elb_cli_main of the library next to it
+    cli_cmd = ["g++", "-O2", "-std=c++17", "-I", INCLUDE_DIR, "-o", CLI_PATH,
+               os.path.join(CSRC_DIR, "elb_main.cpp"), "-L", PKG_DIR, "-lelbencho_b200",
+               "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cli_cmd))
+    subprocess.run(cli_cmd, check=True)
     return LIB_PATH
 
 

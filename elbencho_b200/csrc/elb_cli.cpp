@@ -1,0 +1,682 @@
+/*
+ * Command line parsing (see elb_cli.h). Option names, defaults, implicit values and checks follow
+ * source/ProgArgs.h:27-221 and source/ProgArgs.cpp:202-836 (definitions), :838-1003 (defaults),
+ * :1041-1195 (implicit values), :1229-1462 (checks).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <sstream>
+
+#include "elb_cli.h"
+
+namespace elb
+{
+
+enum OptKind { Opt_FLAG, Opt_U64, Opt_BYTES, Opt_STR };
+
+struct OptDef
+{
+	const char* longName;
+	char shortName; // 0 = none
+	OptKind kind;
+	const char* help;
+};
+
+/* (order = order of the help text) */
+static const OptDef optDefs[] =
+{
+	{"help", 'h', Opt_FLAG, "Print this help message."},
+	{"version", 0, Opt_FLAG, "Show version and included optional build features."},
+	// phases
+	{"mkdirs", 'd', Opt_FLAG, "Create directories. (Already existing dirs are not treated as error.)"},
+	{"write", 'w', Opt_FLAG, "Write files. Create them if they don't exist."},
+	{"read", 'r', Opt_FLAG, "Read files."},
+	{"stat", 0, Opt_FLAG, "Read file status attributes (file size, owner etc)."},
+	{"delfiles", 'F', Opt_FLAG, "Delete files."},
+	{"deldirs", 'D', Opt_FLAG, "Delete directories."},
+	{"sync", 0, Opt_FLAG, "Sync Linux kernel page cache to stable storage before/after each phase."},
+	{"dropcache", 0, Opt_FLAG, "Drop Linux file system page cache, dentry cache and inode cache "
+		"before/after each phase. Requires root privileges."},
+	// basic
+	{"threads", 't', Opt_U64, "Number of I/O worker threads. (Default: 1)"},
+	{"dirs", 'n', Opt_U64, "Number of directories per I/O worker thread. (Default: 1)"},
+	{"files", 'N', Opt_U64, "Number of files per thread per directory. (Default: 1)"},
+	{"size", 's', Opt_BYTES, "File size. (Default: 0)"},
+	{"block", 'b', Opt_BYTES, "Number of bytes to read/write in a single operation. (Default: 1M)"},
+	{"iodepth", 0, Opt_U64, "Depth of I/O queue per thread for asynchronous I/O. (Default: 1)"},
+	{"direct", 0, Opt_FLAG, "Use direct IO (O_DIRECT) to avoid file system buffering/caching."},
+	{"dirsharing", 0, Opt_FLAG, "All threads share the same dirs of rank 0."},
+	{"trunc", 0, Opt_FLAG, "Truncate files to 0 size when opening for writing."},
+	{"trunctosize", 0, Opt_FLAG, "Truncate files to given --size via ftruncate() before writing."},
+	{"preallocfile", 0, Opt_FLAG, "Preallocate file disk space on creation via posix_fallocate()."},
+	{"nodelerr", 0, Opt_FLAG, "Ignore not existing files/dirs in deletion phase."},
+	// offsets
+	{"rand", 0, Opt_FLAG, "Read/write at random offsets."},
+	{"randamount", 0, Opt_BYTES, "Number of bytes to write/read when using random offsets. "
+		"(Default: file size times number of files)"},
+	{"norandalign", 0, Opt_FLAG, "Do not align random offsets to block size."},
+	{"randalgo", 0, Opt_STR, "Random number algorithm for --rand. Giving one disables the full "
+		"coverage generator for random writes. Values: balanced_single (xoshiro256**)"},
+	{"randseed", 0, Opt_U64, "Seed for reproducible random offsets (0 = self-seed). [b200]"},
+	{"backward", 0, Opt_FLAG, "Do backwards sequential reads/writes."},
+	{"strided", 0, Opt_FLAG, "Use strided access pattern for files/blockdevs."},
+	// integrity / content
+	{"verify", 0, Opt_U64, "Enable data integrity check with the given salt (non-zero). Written "
+		"on the GPU in the write phase, checked on the GPU in the read phase."},
+	{"verifydirect", 0, Opt_FLAG, "Verify data integrity by reading each block directly after writing."},
+	{"readinline", 0, Opt_FLAG, "Read each block directly after writing it."},
+	{"blockvarpct", 0, Opt_U64, "Block variance percentage: how much of each written block is "
+		"refilled with random data on the GPU. (Default: 100; forced 0 with --verify)"},
+	{"blockvaralgo", 0, Opt_STR, "Random number algorithm for --blockvarpct. Values: balanced "
+		"(splitmix64, counter based)"},
+	{"blockvarseed", 0, Opt_U64, "Seed for reproducible block variance data (0 = self-seed). [b200]"},
+	{"rwmixpct", 0, Opt_U64, "Percentage of blocks that should be read in a write phase."},
+	{"rwmixthr", 0, Opt_U64, "Number of threads that should do reads in a write phase."},
+	// GPU
+	{"gpuids", 0, Opt_STR, "Comma-separated list of CUDA GPU IDs (also \"all\", \"[0-7]\", "
+		"\"0-7\") to use for the on-GPU block fill/verify. Mandatory."},
+	{"cufile", 0, Opt_FLAG, "Use cuFile API for reads/writes to/from GPU memory."},
+	{"gdsbufreg", 0, Opt_FLAG, "Register GPU buffers for GPUDirect Storage (GDS)."},
+	{"gds", 0, Opt_FLAG, "Use GPUDirect Storage: shortcut for --direct --cufile --gdsbufreg."},
+	{"batchblocks", 0, Opt_U64, "Blocks per pipeline batch (one kernel launch / staged copy). [b200]"},
+	{"numbatches", 0, Opt_U64, "Pipeline batches in flight per thread. [b200]"},
+	{"writegate", 0, Opt_FLAG, "Queue buffered writers of one file in user space. [b200]"},
+	// results
+	{"lat", 0, Opt_FLAG, "Show minimum, average and maximum latency for I/Os and entries."},
+	{"latpercent", 0, Opt_FLAG, "Show latency percentiles."},
+	{"latpercent9s", 0, Opt_U64, "Number of decimal nines to show in latency percentiles."},
+	{"lathisto", 0, Opt_FLAG, "Show latency histogram."},
+	{"allelapsed", 0, Opt_FLAG, "Show elapsed time to completion of each I/O worker thread."},
+	{"cpu", 0, Opt_FLAG, "Show CPU utilization in phase stats results."},
+	{"dirstats", 0, Opt_FLAG, "Show directory completion statistics in file write/read phase."},
+	{"nolive", 0, Opt_FLAG, "Disable live statistics."},
+	{"liveint", 0, Opt_U64, "Update interval for live statistics in milliseconds. (Default: 2000)"},
+	{"no0usecerr", 0, Opt_FLAG, "Do not warn if worker thread completion time is less than 1 usec."},
+	{"label", 0, Opt_STR, "Custom label to identify the benchmark run in result files."},
+	{"csvfile", 0, Opt_STR, "Path to file for end results in csv format (appended)."},
+	{"nocsvlabels", 0, Opt_FLAG, "Do not print headline with labels to csv file."},
+	{"jsonfile", 0, Opt_STR, "Path to file for end results in json format (appended)."},
+	{"resfile", 0, Opt_STR, "Path to file for human-readable end results (appended)."},
+	{"dryrun", 0, Opt_FLAG, "Don't run any benchmark phase, just print the number of expected "
+		"entries and dataset size per phase."},
+	{"iterations", 'i', Opt_U64, "Number of iterations to run the benchmark. (Default: 1)"},
+	{"phasedelay", 0, Opt_U64, "Delay between different phases in seconds. (Default: 0)"},
+	{"timelimit", 0, Opt_U64, "Time limit in seconds for each phase. (Default: 0 = off)"},
+	{"log", 0, Opt_U64, "Log level. (Default: 0; Verbose: 1; Debug: 2)"},
+	// distributed
+	{"hosts", 0, Opt_STR, "Comma-separated list of hosts in service mode for coordinated benchmark."},
+	{"service", 0, Opt_FLAG, "Run as service for distributed mode, waiting for requests from master."},
+	{"foreground", 0, Opt_FLAG, "When running as service, stay in foreground and don't detach."},
+	{"port", 0, Opt_U64, "TCP port of background service. (Default: 1611)"},
+	{"rankoffset", 0, Opt_U64, "Rank offset for worker threads. (Default: 0)"},
+	{"interrupt", 0, Opt_FLAG, "Interrupt current benchmark phase on given service mode hosts."},
+	{"quit", 0, Opt_FLAG, "Quit services on given service mode hosts."},
+};
+
+static const OptDef* findLongOpt(const std::string& name)
+{
+	for(const OptDef& def : optDefs)
+		if(name == def.longName)
+			return &def;
+
+	return NULL;
+}
+
+static const OptDef* findShortOpt(char name)
+{
+	for(const OptDef& def : optDefs)
+		if(def.shortName && (def.shortName == name) )
+			return &def;
+
+	return NULL;
+}
+
+/* UnitTk::numHumanToBytesBinary (toolkits/UnitTk.cpp:18-76) */
+uint64_t ProgArgs::numHumanToBytesBinary(const std::string& numHuman)
+{
+	if(numHuman.empty() )
+		throw ProgError("Unable to parse empty string");
+
+	if(numHuman.find(".") != std::string::npos)
+		throw ProgError("Unable to parse number string containing '.' character: " + numHuman);
+
+	if(numHuman.find(",") != std::string::npos)
+		throw ProgError("Unable to parse number string containing ',' character: " + numHuman);
+
+	if(numHuman.find("-") != std::string::npos)
+		throw ProgError("Unable to parse value: " + numHuman + ". "
+			"A positive number is required (e.g. \"4k\"). "
+			"Negative and range values are not supported.");
+
+	const uint64_t bytesRes = strtoull(numHuman.c_str(), NULL, 10);
+	const char lastChar = numHuman[numHuman.length() - 1];
+
+	if( (lastChar >= '0') && (lastChar <= '9') )
+		return bytesRes;
+
+	switch(toupper(lastChar) )
+	{
+		case 'K': return bytesRes * (1ULL << 10);
+		case 'M': return bytesRes * (1ULL << 20);
+		case 'G': return bytesRes * (1ULL << 30);
+		case 'T': return bytesRes * (1ULL << 40);
+		case 'P': return bytesRes * (1ULL << 50);
+		case 'E': return bytesRes * (1ULL << 60);
+		default:
+			throw ProgError("Unable to parse string for unit conversion: " + numHuman);
+	}
+}
+
+/**
+ * --gpuids: comma/space separated list, "all", square bracket ranges "[0-7]"
+ * (ProgArgs.cpp:2556-2570, TranslatorTk::splitAndExpandStr) and additionally bare ranges "0-7"
+ * (the reference's stoi would read that as GPU 0 only; BASELINE.json spells its configs this way).
+ * "all" expands to an empty vector here and is resolved against the device count by the caller.
+ */
+std::vector<int> ProgArgs::parseGPUIDs(const std::string& gpuIDsStr)
+{
+	std::vector<int> ids;
+	std::string normalized = gpuIDsStr;
+
+	std::replace(normalized.begin(), normalized.end(), ' ', ',');
+
+	std::stringstream listStream(normalized);
+	std::string element;
+
+	while(std::getline(listStream, element, ',') )
+	{
+		if(element.empty() )
+			continue;
+
+		if( (element.front() == '[') && (element.back() == ']') )
+			element = element.substr(1, element.size() - 2);
+
+		const size_t dashPos = element.find('-');
+
+		try
+		{
+			if(dashPos == std::string::npos)
+				ids.push_back(std::stoi(element) );
+			else
+			{
+				const int first = std::stoi(element.substr(0, dashPos) );
+				const int last = std::stoi(element.substr(dashPos + 1) );
+
+				if(last < first)
+					throw ProgError("Invalid GPU ID range: " + element);
+
+				for(int id = first; id <= last; id++)
+					ids.push_back(id);
+			}
+		}
+		catch(std::invalid_argument&)
+		{
+			throw ProgError("Invalid GPU ID: " + element);
+		}
+		catch(std::out_of_range&)
+		{
+			throw ProgError("Invalid GPU ID: " + element);
+		}
+	}
+
+	for(int id : ids)
+		if(id < 0)
+			throw ProgError("Invalid GPU ID: " + std::to_string(id) );
+
+	return ids;
+}
+
+ProgArgs::ProgArgs(int argc, char** argv)
+{
+	for(int i = 0; i < argc; i++)
+		progArgVec.push_back(argv[i] );
+
+	std::map<std::string, std::string> values; // long name -> raw value ("1" for flags)
+
+	for(int i = 1; i < argc; i++)
+	{
+		const std::string arg = argv[i];
+		const OptDef* def = NULL;
+		std::string inlineValue;
+		bool haveInlineValue = false;
+
+		if( (arg.size() > 2) && (arg[0] == '-') && (arg[1] == '-') )
+		{
+			std::string name = arg.substr(2);
+			const size_t eqPos = name.find('=');
+
+			if(eqPos != std::string::npos)
+			{
+				inlineValue = name.substr(eqPos + 1);
+				name = name.substr(0, eqPos);
+				haveInlineValue = true;
+			}
+
+			def = findLongOpt(name);
+
+			if(!def)
+				throw ProgError("unrecognised option '" + arg + "'");
+		}
+		else
+		if( (arg.size() >= 2) && (arg[0] == '-') && (arg != "--") )
+		{
+			def = findShortOpt(arg[1] );
+
+			if(!def)
+				throw ProgError("unrecognised option '" + arg + "'");
+
+			if(arg.size() > 2)
+			{ // "-t4" style or grouped flags "-wr"
+				if(def->kind == Opt_FLAG)
+				{
+					for(size_t c = 1; c < arg.size(); c++)
+					{
+						const OptDef* flagDef = findShortOpt(arg[c] );
+
+						if(!flagDef || (flagDef->kind != Opt_FLAG) )
+							throw ProgError("unrecognised option '" + arg + "'");
+
+						values[flagDef->longName] = "1";
+					}
+
+					continue;
+				}
+
+				inlineValue = arg.substr(2);
+				haveInlineValue = true;
+			}
+		}
+		else
+		{ // positional argument = benchmark path
+			benchPaths.push_back(arg);
+			continue;
+		}
+
+		if(def->kind == Opt_FLAG)
+		{
+			values[def->longName] = "1";
+			continue;
+		}
+
+		if(!haveInlineValue)
+		{
+			if( (i + 1) >= argc)
+				throw ProgError(std::string("the required argument for option '--") +
+					def->longName + "' is missing");
+
+			inlineValue = argv[++i];
+		}
+
+		values[def->longName] = inlineValue;
+	}
+
+	auto flag = [&](const char* name) { return values.count(name) != 0; };
+	auto num = [&](const char* name, uint64_t& target)
+	{
+		if(!values.count(name) )
+			return false;
+
+		const std::string& raw = values[name];
+		const OptDef* def = findLongOpt(name);
+
+		if(def->kind == Opt_BYTES)
+			target = numHumanToBytesBinary(raw);
+		else
+		{
+			char* endPtr = NULL;
+			target = strtoull(raw.c_str(), &endPtr, 10);
+
+			if(raw.empty() || (endPtr && *endPtr) )
+				throw ProgError(std::string("the argument ('") + raw + "') for option '--" +
+					name + "' is invalid");
+		}
+
+		return true;
+	};
+	auto str = [&](const char* name, std::string& target)
+	{
+		if(values.count(name) )
+			target = values[name];
+	};
+
+	printHelp = flag("help");
+	printVersion = flag("version");
+	runCreateDirsPhase = flag("mkdirs");
+	runCreateFilesPhase = flag("write");
+	runReadPhase = flag("read");
+	runStatFilesPhase = flag("stat");
+	runDeleteFilesPhase = flag("delfiles");
+	runDeleteDirsPhase = flag("deldirs");
+	runSyncPhase = flag("sync");
+	runDropCachesPhase = flag("dropcache");
+
+	num("threads", numThreads);
+	num("dirs", numDirs);
+	num("files", numFiles);
+	num("size", fileSize);
+	num("block", blockSize);
+	num("iodepth", ioDepth);
+	useDirectIO = flag("direct");
+	doDirSharing = flag("dirsharing");
+	doTruncate = flag("trunc");
+	doTruncToSize = flag("trunctosize");
+	doPreallocFile = flag("preallocfile");
+	ignoreDelErrors = flag("nodelerr");
+
+	useRandomOffsets = flag("rand");
+	num("randamount", randomAmount);
+	useRandomUnaligned = flag("norandalign");
+	str("randalgo", randOffsetAlgo);
+	num("randseed", randOffsetSeed);
+	doReverseSeqOffsets = flag("backward");
+	useStridedAccess = flag("strided");
+
+	num("verify", integrityCheckSalt);
+	doDirectVerify = flag("verifydirect");
+	doReadInline = flag("readinline");
+	hasUserSetBlockVariance = num("blockvarpct", blockVariancePercent);
+	str("blockvaralgo", blockVarianceAlgo);
+	num("blockvarseed", blockVarianceSeed);
+	hasUserSetRWMixPercent = num("rwmixpct", rwMixReadPercent);
+	hasUserSetRWMixReadThreads = num("rwmixthr", numRWMixReadThreads);
+
+	str("gpuids", gpuIDsStr);
+	useCuFile = flag("cufile");
+	useGDSBufReg = flag("gdsbufreg");
+	useGPUDirectStorage = flag("gds");
+	num("batchblocks", pipelineBatchBlocks);
+	num("numbatches", pipelineNumBatches);
+	serializeBufferedWrites = flag("writegate");
+
+	showLatency = flag("lat");
+	showLatencyPercentiles = flag("latpercent");
+	num("latpercent9s", numLatencyPercentile9s);
+	showLatencyHistogram = flag("lathisto");
+	showAllElapsed = flag("allelapsed");
+	showCPUUtilization = flag("cpu");
+	showDirStats = flag("dirstats");
+	disableLiveStats = flag("nolive");
+	num("liveint", liveStatsSleepMS);
+	ignore0USecErrors = flag("no0usecerr");
+	str("label", benchLabel);
+	str("csvfile", csvFilePath);
+	noCSVLabels = flag("nocsvlabels");
+	str("jsonfile", jsonFilePath);
+	str("resfile", resFilePath);
+	doDryRun = flag("dryrun");
+	num("iterations", iterations);
+	num("phasedelay", nextPhaseDelaySecs);
+	num("timelimit", timeLimitSecs);
+	num("log", logLevel);
+
+	str("hosts", hostsStr);
+	runAsService = flag("service");
+	runServiceInForeground = flag("foreground");
+	num("port", servicePort);
+	num("rankoffset", rankOffset);
+	interruptServices = flag("interrupt");
+	quitServices = flag("quit");
+
+	if(printHelp || printVersion)
+		return;
+
+	initImplicitValues();
+
+	if(runAsService)
+		return; // the master sends the rest later (ProgArgs.cpp:160-163)
+
+	checkArgs();
+}
+
+/* ProgArgs.cpp:1041-1195 */
+void ProgArgs::initImplicitValues()
+{
+	numRWMixReadThreads = std::min(numRWMixReadThreads, numThreads); // :1088
+
+	if(useGPUDirectStorage) // :1090-1095
+	{
+		useDirectIO = true;
+		useCuFile = true;
+		useGDSBufReg = true;
+	}
+
+	if(integrityCheckSalt && blockVariancePercent) // :1161-1167: verify forces blockvarpct 0
+		blockVariancePercent = 0;
+
+	if(!hostsStr.empty() )
+	{
+		std::stringstream hostsStream(hostsStr);
+		std::string host;
+
+		while(std::getline(hostsStream, host, ',') )
+			if(!host.empty() )
+				hosts.push_back(host);
+	}
+
+	if(!gpuIDsStr.empty() && (gpuIDsStr != "all") )
+		gpuIDs = parseGPUIDs(gpuIDsStr);
+}
+
+/* ProgArgs::findBenchPathType (ProgArgs.cpp:1750-1790) */
+void ProgArgs::detectBenchPathType()
+{
+	bool isFirst = true;
+
+	for(const std::string& path : benchPaths)
+	{
+		struct stat statBuf;
+		int pathType;
+
+		if(stat(path.c_str(), &statBuf) == -1)
+			pathType = ELB_PATH_FILE; // not existing yet: will be created as file
+		else
+		if(S_ISDIR(statBuf.st_mode) )
+			pathType = ELB_PATH_DIR;
+		else
+		if(S_ISBLK(statBuf.st_mode) )
+			pathType = ELB_PATH_BLOCKDEV;
+		else
+			pathType = ELB_PATH_FILE;
+
+		if(isFirst)
+			benchPathType = pathType;
+		else
+		if(pathType != benchPathType)
+			throw ProgError("Conflicting path type found. All benchmark paths need to have the "
+				"same type. "
+				"Path: " + path + "; "
+				"Path of different type: " + benchPaths[0] );
+
+		isFirst = false;
+	}
+}
+
+/* ProgArgs.cpp:1229-1462 (the checks that apply to the supported subset) */
+void ProgArgs::checkArgs()
+{
+	if(interruptServices || quitServices)
+	{
+		if(hosts.empty() )
+			throw ProgError("Service interruption/termination requires a hosts list.");
+
+		return;
+	}
+
+	if(benchPaths.empty() )
+		throw ProgError("Benchmark path missing.");
+
+	detectBenchPathType();
+
+	if(!numThreads)
+		throw ProgError("Number of threads may not be zero.");
+
+	if( (benchPathType == ELB_PATH_DIR) && !numFiles && (runCreateFilesPhase || runReadPhase) )
+		throw ProgError("Number of files may not be zero.");
+
+	if( (benchPathType != ELB_PATH_DIR) && (runCreateDirsPhase || runDeleteDirsPhase) )
+		throw ProgError("Directory create and delete options are only allowed if benchmark path "
+			"is a directory.");
+
+	if( (benchPathType == ELB_PATH_BLOCKDEV) && runDeleteFilesPhase)
+		throw ProgError("File delete option is not allowed if benchmark path is a block device.");
+
+	if(hosts.empty() && gpuIDsStr.empty() )
+		throw ProgError("This is the GPU worker build: option \"--gpuids\" is mandatory (the "
+			"on-GPU block fill/verify has no CPU fallback).");
+
+	if(useCuFile && (ioDepth > 1) && false) // reference :1312-1313 forbids this; supported here
+		throw ProgError("cuFile API cannot be used together with iodepth > 1");
+
+	if(hasUserSetRWMixPercent && hasUserSetRWMixReadThreads) // :1402-1404
+		throw ProgError("Option \"--rwmixpct\" cannot be used together with \"--rwmixthr\"");
+
+	if(rwMixReadPercent > 100)
+		throw ProgError("Option \"--rwmixpct\" must be in range 0..100");
+
+	if(integrityCheckSalt && rwMixReadPercent) // :1414-1416
+		throw ProgError("Option --rwmixpct cannot be used together with option \"--verify\"");
+
+	if(integrityCheckSalt && hasUserSetBlockVariance && blockVariancePercent &&
+		runCreateFilesPhase) // :1418-1420 (only reachable if the user gave a value, see :1161)
+		throw ProgError("Option \"--verify\" requires \"--blockvarpct 0\"");
+
+	if(integrityCheckSalt && runCreateFilesPhase && useRandomOffsets) // :1422-1424
+		throw ProgError("Integrity check writes are not supported in combination with random "
+			"offsets.");
+
+	if(doDirectVerify && (!integrityCheckSalt || !runCreateFilesPhase) ) // :1426-1428
+		throw ProgError("Direct verification requires --verify and --write");
+
+	if(doDirectVerify && (ioDepth > 1) ) // :1430-1431
+		throw ProgError("Direct verification cannot be used together with --iodepth");
+
+	if(doReadInline && (ioDepth > 1) ) // :1433-1434
+		throw ProgError("Inline read cannot be used together with --iodepth");
+
+	if(blockVariancePercent > 100)
+		throw ProgError("Block variance percent must be in range 0..100");
+
+	if(!blockVarianceAlgo.empty() && (blockVarianceAlgo != "balanced") &&
+		(blockVarianceAlgo != "fast") )
+		throw ProgError("Unknown block variance algorithm: " + blockVarianceAlgo);
+
+	if(!randOffsetAlgo.empty() && (randOffsetAlgo != "balanced_single") &&
+		(randOffsetAlgo != "balanced") && (randOffsetAlgo != "fast") )
+		throw ProgError("Unknown random offset algorithm: " + randOffsetAlgo);
+
+	if(!runCreateDirsPhase && !runCreateFilesPhase && !runReadPhase && !runStatFilesPhase &&
+		!runDeleteFilesPhase && !runDeleteDirsPhase && !runSyncPhase && !runDropCachesPhase &&
+		!doDryRun)
+		throw ProgError("No benchmark phase selected. Try \"--help\".");
+}
+
+void ProgArgs::toABIConfig(ABIConfig& out) const
+{
+	memset(&out.cfg, 0, sizeof(out.cfg) );
+
+	out.pathPtrs.clear();
+	for(const std::string& path : benchPaths)
+		out.pathPtrs.push_back(path.c_str() );
+
+	out.gpuIDs.assign(gpuIDs.begin(), gpuIDs.end() );
+
+	elb_cfg& cfg = out.cfg;
+	cfg.structSize = sizeof(elb_cfg);
+	cfg.paths = out.pathPtrs.data();
+	cfg.numPaths = (uint32_t)out.pathPtrs.size();
+	cfg.pathType = benchPathType;
+	cfg.numThreads = (uint32_t)numThreads;
+	cfg.rankOffset = (uint32_t)rankOffset;
+	cfg.numDataSetThreads = 0;
+	cfg.blockSize = blockSize;
+	cfg.fileSize = fileSize;
+	cfg.ioDepth = (uint32_t)ioDepth;
+	cfg.useDirectIO = useDirectIO;
+	cfg.ioEngine = ELB_IOENGINE_AUTO;
+	cfg.numDirs = numDirs;
+	cfg.numFiles = numFiles;
+	cfg.doDirSharing = doDirSharing;
+	cfg.doTruncate = doTruncate;
+	cfg.doTruncToSize = doTruncToSize;
+	cfg.doPreallocFile = doPreallocFile;
+	cfg.useRandomOffsets = useRandomOffsets;
+	cfg.useRandomUnaligned = useRandomUnaligned;
+	cfg.useExplicitRandOffsetAlgo = !randOffsetAlgo.empty();
+	cfg.doReverseSeqOffsets = doReverseSeqOffsets;
+	cfg.useStridedAccess = useStridedAccess;
+	cfg.randomAmount = randomAmount;
+	cfg.randOffsetSeed = randOffsetSeed;
+	cfg.integrityCheckSalt = integrityCheckSalt;
+	cfg.doDirectVerify = doDirectVerify;
+	cfg.doReadInline = doReadInline;
+	cfg.blockVariancePercent = (uint32_t)blockVariancePercent;
+	cfg.blockVarianceAlgo = ELB_RANDALGO_SPLITMIX64;
+	cfg.blockVarianceSeed = blockVarianceSeed;
+	cfg.rwMixReadPercent = (uint32_t)rwMixReadPercent;
+	cfg.gpuIDs = out.gpuIDs.data();
+	cfg.numGPUIDs = (uint32_t)out.gpuIDs.size();
+	cfg.useCuFile = useCuFile;
+	cfg.useGDSBufReg = useGDSBufReg;
+	cfg.pipelineBatchBlocks = (uint32_t)pipelineBatchBlocks;
+	cfg.pipelineNumBatches = (uint32_t)pipelineNumBatches;
+	cfg.ignoreDelErrors = ignoreDelErrors;
+	cfg.runAsService = runAsService;
+	cfg.verifyCollectAll = 0;
+	cfg.serializeBufferedWrites = serializeBufferedWrites;
+	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+}
+
+std::string ProgArgs::helpText()
+{
+	std::ostringstream out;
+
+	out << "elbencho-b200 - GPU storage benchmark worker for Blackwell (elbencho compatible)" <<
+		std::endl << std::endl;
+	out << "Usage: elbencho-b200 [OPTIONS] PATH [MORE_PATHS]" << std::endl << std::endl;
+	out << "PATH is a directory (dir mode: per-thread files), a file or a block device." <<
+		std::endl << std::endl;
+	out << "Options:" << std::endl;
+
+	for(const OptDef& def : optDefs)
+	{
+		std::string names = "  ";
+
+		if(def.shortName)
+			names += std::string("-") + def.shortName + " [ --" + def.longName + " ]";
+		else
+			names += std::string("--") + def.longName;
+
+		if(def.kind != Opt_FLAG)
+			names += " arg";
+
+		out << names;
+
+		if(names.size() < 28)
+			out << std::string(28 - names.size(), ' ');
+		else
+			out << std::endl << std::string(28, ' ');
+
+		out << def.help << std::endl;
+	}
+
+	out << std::endl;
+	out << "Examples:" << std::endl;
+	out << "  Sequentially write and read a 64 GiB file with integrity check on GPU 0:" <<
+		std::endl;
+	out << "    $ elbencho-b200 -w -r -t 1 -b 1M -s 64G --verify 1 --gpuids 0 /data/testfile" <<
+		std::endl;
+	out << "  4 KiB random reads at iodepth 64 through cuFile batches:" << std::endl;
+	out << "    $ elbencho-b200 -r -b 4K -s 64G --rand --iodepth 64 --gpuids 0 --gds /data/testfile" <<
+		std::endl;
+	out << "  128 threads on 8 GPUs, 64x128 files of 64 KiB per thread, write+read+verify:" <<
+		std::endl;
+	out << "    $ elbencho-b200 -d -w -r -t 128 -n 64 -N 128 -s 64K -b 64K --verify 1 "
+		"--gpuids 0-7 /data/dir" << std::endl;
+
+	return out.str();
+}
+
+} // namespace elb

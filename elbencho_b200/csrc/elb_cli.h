@@ -1,0 +1,175 @@
+/*
+ * Command line front end: the ProgArgs option subset that reaches the hot path, the coordinator's
+ * phase sequence and the statistics output formats of the reference ("next" rows f1/f2 of
+ * SURVEY.md §8): source/ProgArgs.{h,cpp}, source/Coordinator.cpp:298-374,
+ * source/Statistics.cpp:1546-2400, 2429-2723, 2809-2876.
+ *
+ * Dependency-free (the reference uses boost::program_options / property_tree / format).
+ */
+#ifndef ELB_CLI_H_
+#define ELB_CLI_H_
+
+#include <stdint.h>
+
+#include <map>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "elb_host.h"
+
+namespace elb
+{
+
+/* reference: ProgException (source/ProgException.h) */
+class ProgError : public std::runtime_error
+{
+	public:
+		explicit ProgError(const std::string& msg) : std::runtime_error(msg) {}
+};
+
+/* reference: ProgArgs (the subset of source/ProgArgs.h:27-221 that is supported) */
+class ProgArgs
+{
+	public:
+		ProgArgs(int argc, char** argv); // @throw ProgError
+
+		// phases (ProgArgs.h runCreateDirsPhase etc.)
+		bool runCreateDirsPhase{false};
+		bool runCreateFilesPhase{false};
+		bool runReadPhase{false};
+		bool runStatFilesPhase{false};
+		bool runDeleteFilesPhase{false};
+		bool runDeleteDirsPhase{false};
+		bool runSyncPhase{false};
+		bool runDropCachesPhase{false};
+
+		// hot path
+		std::vector<std::string> benchPaths;
+		int benchPathType{ELB_PATH_FILE};
+		uint64_t numThreads{1};
+		uint64_t rankOffset{0};
+		uint64_t blockSize{1024 * 1024};
+		uint64_t fileSize{0};
+		uint64_t numDirs{1};
+		uint64_t numFiles{1};
+		uint64_t ioDepth{1};
+		bool useDirectIO{false};
+		bool doDirSharing{false};
+		bool doTruncate{false};
+		bool doTruncToSize{false};
+		bool doPreallocFile{false};
+		bool useRandomOffsets{false};
+		bool useRandomUnaligned{false};
+		std::string randOffsetAlgo;
+		bool doReverseSeqOffsets{false};
+		bool useStridedAccess{false};
+		uint64_t randomAmount{0};
+		uint64_t randOffsetSeed{0};
+		uint64_t integrityCheckSalt{0};
+		bool doDirectVerify{false};
+		bool doReadInline{false};
+		uint64_t blockVariancePercent{100}; // default (ProgArgs.cpp:846)
+		bool hasUserSetBlockVariance{false};
+		std::string blockVarianceAlgo;
+		uint64_t blockVarianceSeed{0};
+		uint64_t rwMixReadPercent{0};
+		bool hasUserSetRWMixPercent{false};
+		uint64_t numRWMixReadThreads{0};
+		bool hasUserSetRWMixReadThreads{false};
+		std::vector<int> gpuIDs;
+		std::string gpuIDsStr;
+		bool useCuFile{false};
+		bool useGDSBufReg{false};
+		bool useGPUDirectStorage{false}; // --gds
+		bool ignoreDelErrors{false};
+		uint64_t pipelineBatchBlocks{0};
+		uint64_t pipelineNumBatches{0};
+		bool serializeBufferedWrites{false};
+
+		// output / run control
+		bool showLatency{false};
+		bool showLatencyPercentiles{false};
+		bool showLatencyHistogram{false};
+		uint64_t numLatencyPercentile9s{0};
+		bool showAllElapsed{false};
+		bool showCPUUtilization{false};
+		bool showDirStats{false};
+		bool disableLiveStats{false};
+		bool ignore0USecErrors{false};
+		bool noCSVLabels{false};
+		bool doDryRun{false};
+		uint64_t liveStatsSleepMS{2000};
+		uint64_t iterations{1};
+		uint64_t nextPhaseDelaySecs{0};
+		uint64_t timeLimitSecs{0};
+		uint64_t logLevel{0};
+		std::string benchLabel;
+		std::string csvFilePath;
+		std::string jsonFilePath;
+		std::string resFilePath;
+
+		// service mode
+		bool runAsService{false};
+		bool runServiceInForeground{false};
+		uint64_t servicePort{1611}; // ProgArgs.h:224
+		std::vector<std::string> hosts;
+		std::string hostsStr;
+		bool interruptServices{false};
+		bool quitServices{false};
+
+		bool printHelp{false};
+		bool printVersion{false};
+
+		std::vector<std::string> progArgVec; // original command line (for CSV/JSON "command")
+
+		/* fill the ABI config struct; the returned object owns the arrays cfg points to */
+		struct ABIConfig
+		{
+			elb_cfg cfg;
+			std::vector<const char*> pathPtrs;
+			std::vector<int32_t> gpuIDs;
+		};
+		void toABIConfig(ABIConfig& out) const;
+
+		static std::string helpText();
+		static uint64_t numHumanToBytesBinary(const std::string& numHuman); // UnitTk.cpp:18-76
+		static std::vector<int> parseGPUIDs(const std::string& gpuIDsStr); // ProgArgs.cpp:2556-2570
+
+	private:
+		void initImplicitValues(); // ProgArgs.cpp:1041-1195
+		void checkArgs();          // ProgArgs.cpp:1229-1462
+		void detectBenchPathType(); // ProgArgs.cpp findBenchPathType
+};
+
+/* Statistics output (reference source/Statistics.cpp) */
+namespace stats
+{
+	std::string elapsedMSToHumanStr(uint64_t elapsedMS); // UnitTk.cpp:180-204
+	std::string latencyUsToHumanStr(uint64_t numMicroSec); // UnitTk.cpp:90-150
+	std::string phaseName(int benchPhase, const ProgArgs& progArgs); // TranslatorTk.cpp:41-125
+	std::string phaseEntryType(int benchPhase, bool firstToUpper); // TranslatorTk.cpp:127-175
+	std::string histogramStr(const elb_histogram& histo); // LatencyHistogram.h:125-150
+	std::string percentileStr(const elb_histogram& histo, double percentage);
+
+	void printPhaseResultsTableHeader(std::ostream& out); // Statistics.cpp:1546-1562
+	void printPhaseResults(const ProgArgs& progArgs, int benchPhase,
+		const elb_phase_results& res, const std::vector<uint64_t>& elapsedUSecVec,
+		std::ostream& out); // Statistics.cpp:1771-2140
+	void csvLabelsAndValues(const ProgArgs& progArgs, int benchPhase,
+		const elb_phase_results& res, const std::string& isoDate,
+		std::vector<std::string>& outLabels, std::vector<std::string>& outValues); // :2151-2323
+	std::string phaseResultsJSON(const ProgArgs& progArgs, int benchPhase,
+		const elb_phase_results& res, uint64_t phaseID, const std::string& isoStartDate); // :2429-2723
+	void printDryRunPhaseInfo(const ProgArgs& progArgs, int benchPhase, uint64_t entriesPerThread,
+		uint64_t bytesPerThread, std::ostream& out); // :2850-2876
+}
+
+/* expected entries/bytes per worker (WorkerManager::getPhaseNumEntriesAndBytes, :333-487) */
+void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
+	uint64_t& outBytes);
+
+} // namespace elb
+
+#endif /* ELB_CLI_H_ */

@@ -5,8 +5,30 @@
  */
 #include "elb_host.h"
 
+#include <fstream>
+
 namespace elb
 {
+
+void CPUUtil::update()
+{
+	std::ifstream procStatStream("/proc/stat");
+	procStatStream.ignore(5, ' '); // skip the "cpu" prefix
+
+	std::vector<uint64_t> cpuTimes;
+	for(uint64_t cpuTime; procStatStream >> cpuTime; cpuTimes.push_back(cpuTime) );
+
+	lastIdle = currentIdle;
+	lastTotal = currentTotal;
+
+	if(cpuTimes.size() < 4)
+		return; // no usable /proc/stat: utilisation stays 0
+
+	currentIdle = cpuTimes[3] + ( (cpuTimes.size() > 4) ? cpuTimes[4] : 0);
+	currentTotal = 0;
+	for(uint64_t cpuTime : cpuTimes)
+		currentTotal += cpuTime;
+}
 
 Config Config::fromABI(const elb_cfg* cfg)
 {

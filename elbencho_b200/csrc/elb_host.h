@@ -429,6 +429,25 @@ inline uint64_t perSecFromUSec(uint64_t totalValue, uint64_t elapsedUSec) // Uni
 	return (uint64_t)(totalValue * (numUSecsPerSec / elapsedUSec) );
 }
 
+/* ---- CPU utilisation between two update() calls (source/CPUUtil.cpp:31-75: first line of
+ * /proc/stat, idle = idle + iowait) ---- */
+class CPUUtil
+{
+	public:
+		void update();
+
+		unsigned getCPUUtilPercent() const
+		{
+			const uint64_t totalDiff = currentTotal - lastTotal;
+			const uint64_t idleDiff = currentIdle - lastIdle;
+
+			return totalDiff ? (unsigned)( (100.0 * (totalDiff - idleDiff) ) / totalDiff) : 0;
+		}
+
+	private:
+		uint64_t lastIdle{0}, lastTotal{0}, currentIdle{0}, currentTotal{0};
+};
+
 /* ---- live counters (source/LiveOps.h:86-115) ---- */
 struct AtomicLiveOps
 {

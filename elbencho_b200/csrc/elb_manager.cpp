@@ -9,6 +9,7 @@
 #include <sys/types.h>
 #include <unistd.h>
 
+#include "elb_cli.h"
 #include "elb_worker.h"
 
 #define ELB_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
@@ -203,6 +204,10 @@ void Manager::startNextPhase(int benchPhase)
 	shared.firstErrorMsg.clear();
 	shared.currentBenchPhase = benchPhase;
 	shared.currentBenchSeq++;
+	shared.cpuUtilFirstDone.update(); // WorkerManager.cpp:307-308
+	shared.cpuUtilLastDone.update();
+	shared.cpuUtilFirstDonePercent = 0;
+	shared.cpuUtilLastDonePercent = 0;
 	shared.phaseStartT = Clock::now();
 
 	shared.condition.notify_all();
@@ -263,6 +268,8 @@ void Manager::getPhaseResults(elb_phase_results& out)
 	memset(&out, 0, sizeof(out) );
 	histogramReset(out.iopsLatHisto);
 	histogramReset(out.entriesLatHisto);
+	histogramReset(out.iopsLatHistoReadMix);
+	histogramReset(out.entriesLatHistoReadMix);
 
 	uint64_t firstFinishUSec = ~0ULL;
 	uint64_t lastFinishUSec = 0;
@@ -280,8 +287,11 @@ void Manager::getPhaseResults(elb_phase_results& out)
 		liveOpsAdd(out.opsTotal, worker->getLiveOps() );
 		liveOpsAdd(out.opsReadMixTotal, worker->getLiveOpsReadMix() );
 		liveOpsAdd(out.opsStoneWallTotal, worker->getStoneWallOps() );
+		liveOpsAdd(out.opsStoneWallReadMixTotal, worker->getStoneWallOpsReadMix() );
 		histogramMerge(out.iopsLatHisto, worker->getIOPSLatHisto() );
 		histogramMerge(out.entriesLatHisto, worker->getEntriesLatHisto() );
+		histogramMerge(out.iopsLatHistoReadMix, worker->getIOPSLatHistoReadMix() );
+		histogramMerge(out.entriesLatHistoReadMix, worker->getEntriesLatHistoReadMix() );
 
 		uint64_t devCounters[ELB_DEVCTR_NUM];
 		if(!worker->snapshotDevCounters(devCounters) )
@@ -308,6 +318,30 @@ void Manager::getPhaseResults(elb_phase_results& out)
 		out.opsPerSec.numIOPSDone = perSecFromUSec(out.opsTotal.numIOPSDone, out.lastFinishUSec);
 	}
 
+	// rwmix read side (Statistics.cpp:1725-1745)
+	if(out.lastFinishUSec && out.opsReadMixTotal.numIOPSDone)
+	{
+		out.opsReadMixPerSec.numEntriesDone =
+			perSecFromUSec(out.opsReadMixTotal.numEntriesDone, out.lastFinishUSec);
+		out.opsReadMixPerSec.numBytesDone =
+			perSecFromUSec(out.opsReadMixTotal.numBytesDone, out.lastFinishUSec);
+		out.opsReadMixPerSec.numIOPSDone =
+			perSecFromUSec(out.opsReadMixTotal.numIOPSDone, out.lastFinishUSec);
+	}
+
+	if(out.firstFinishUSec && out.opsReadMixTotal.numIOPSDone)
+	{
+		out.opsStoneWallReadMixPerSec.numEntriesDone =
+			perSecFromUSec(out.opsStoneWallReadMixTotal.numEntriesDone, out.firstFinishUSec);
+		out.opsStoneWallReadMixPerSec.numBytesDone =
+			perSecFromUSec(out.opsStoneWallReadMixTotal.numBytesDone, out.firstFinishUSec);
+		out.opsStoneWallReadMixPerSec.numIOPSDone =
+			perSecFromUSec(out.opsStoneWallReadMixTotal.numIOPSDone, out.firstFinishUSec);
+	}
+
+	out.cpuUtilStoneWallPercent = shared.cpuUtilFirstDonePercent;
+	out.cpuUtilPercent = shared.cpuUtilLastDonePercent;
+
 	if(out.firstFinishUSec)
 	{
 		out.opsStoneWallPerSec.numEntriesDone =
@@ -323,12 +357,12 @@ void Manager::getPhaseResults(elb_phase_results& out)
 	out.numWorkersDoneWithError = (uint32_t)shared.numWorkersDoneWithError;
 }
 
-/* getPhaseNumEntriesAndBytes (WorkerManager.cpp:333-487), summed over this manager's workers */
-void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& outBytes)
+/* getPhaseNumEntriesAndBytes (WorkerManager.cpp:333-487): expected totals per worker */
+void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
+	uint64_t& outBytes)
 {
-	const Config& cfg = shared.cfg;
-	uint64_t entriesPerWorker = 0;
-	uint64_t bytesPerWorker = 0;
+	outEntries = 0;
+	outBytes = 0;
 
 	if(cfg.pathType == ELB_PATH_DIR)
 	{
@@ -338,18 +372,18 @@ void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& 
 		{
 			case ELB_PHASE_CREATEDIRS:
 			case ELB_PHASE_DELETEDIRS:
-				entriesPerWorker = cfg.numDirs;
+				outEntries = cfg.numDirs;
 				break;
 
 			case ELB_PHASE_CREATEFILES:
 			case ELB_PHASE_READFILES:
-				entriesPerWorker = numDirs * cfg.numFiles;
-				bytesPerWorker = entriesPerWorker * cfg.fileSize;
+				outEntries = numDirs * cfg.numFiles;
+				outBytes = outEntries * cfg.fileSize;
 				break;
 
 			case ELB_PHASE_DELETEFILES:
 			case ELB_PHASE_STATFILES:
-				entriesPerWorker = numDirs * cfg.numFiles;
+				outEntries = numDirs * cfg.numFiles;
 				break;
 
 			default:
@@ -358,16 +392,24 @@ void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& 
 	}
 	else
 	{
-		entriesPerWorker = cfg.paths.size();
+		outEntries = cfg.paths.size();
 
 		if( (benchPhase == ELB_PHASE_CREATEFILES) || (benchPhase == ELB_PHASE_READFILES) )
-			bytesPerWorker = cfg.useRandomOffsets ?
+			outBytes = cfg.useRandomOffsets ?
 				(cfg.randomAmount / cfg.numDataSetThreads) :
-				( (entriesPerWorker * cfg.fileSize) / cfg.numDataSetThreads);
+				( (outEntries * cfg.fileSize) / cfg.numDataSetThreads);
 	}
+}
 
-	outEntries = entriesPerWorker * cfg.numThreads;
-	outBytes = bytesPerWorker * cfg.numThreads;
+/* summed over this manager's workers */
+void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& outBytes)
+{
+	uint64_t entriesPerWorker, bytesPerWorker;
+
+	expectedPerWorker(shared.cfg, benchPhase, entriesPerWorker, bytesPerWorker);
+
+	outEntries = entriesPerWorker * shared.cfg.numThreads;
+	outBytes = bytesPerWorker * shared.cfg.numThreads;
 }
 
 } // namespace elb

@@ -353,8 +353,19 @@ void Worker::incNumWorkersDone() // Worker.cpp:33-55
 	shared->numWorkersDone++;
 
 	if(triggerStoneWall)
+	{
+		shared->cpuUtilFirstDone.update();
+		shared->cpuUtilFirstDonePercent = shared->cpuUtilFirstDone.getCPUUtilPercent();
+
 		for(Worker* worker : shared->workers)
 			worker->createStoneWallStats();
+	}
+
+	if(shared->numWorkersDone == numWorkersTotal)
+	{
+		shared->cpuUtilLastDone.update();
+		shared->cpuUtilLastDonePercent = shared->cpuUtilLastDone.getCPUUtilPercent();
+	}
 
 	shared->condition.notify_all();
 }
@@ -365,6 +376,12 @@ void Worker::incNumWorkersDoneWithError() // WorkersSharedData.cpp:36-44
 
 	shared->numWorkersDone++;
 	shared->numWorkersDoneWithError++;
+
+	if(shared->numWorkersDone == shared->workers.size() )
+	{
+		shared->cpuUtilLastDone.update();
+		shared->cpuUtilLastDonePercent = shared->cpuUtilLastDone.getCPUUtilPercent();
+	}
 
 	if(shared->firstErrorMsg.empty() )
 		shared->firstErrorMsg = getLastError();

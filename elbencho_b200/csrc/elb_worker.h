@@ -62,6 +62,12 @@ struct Shared
 	size_t numWorkersDoneWithError{0};
 	std::vector<Worker*> workers;
 	std::string firstErrorMsg;
+
+	// WorkersSharedData::cpuUtilFirstDone/LastDone (WorkersSharedData.cpp:19-30)
+	CPUUtil cpuUtilFirstDone;
+	CPUUtil cpuUtilLastDone;
+	unsigned cpuUtilFirstDonePercent{0};
+	unsigned cpuUtilLastDonePercent{0};
 };
 
 /* one block of the in-flight window */

@@ -284,6 +284,13 @@ class WorkerManager:
             "dev_kernel_usec": res.devKernelUSec,
             "num_workers_done": res.numWorkersDone,
             "num_workers_done_with_error": res.numWorkersDoneWithError,
+            "ops_stonewall_readmix_total": res.opsStoneWallReadMixTotal.as_dict(),
+            "ops_readmix_per_sec": res.opsReadMixPerSec.as_dict(),
+            "ops_stonewall_readmix_per_sec": res.opsStoneWallReadMixPerSec.as_dict(),
+            "iops_lat_histo_readmix": histogram_to_dict(res.iopsLatHistoReadMix),
+            "entries_lat_histo_readmix": histogram_to_dict(res.entriesLatHistoReadMix),
+            "cpu_util_stonewall_percent": res.cpuUtilStoneWallPercent,
+            "cpu_util_percent": res.cpuUtilPercent,
         }
 
     def expected_totals(self, phase: int):

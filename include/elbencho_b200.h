@@ -299,6 +299,16 @@ typedef struct elb_phase_results
 	uint64_t devKernelUSec; /* sum of event-timed kernel durations (fill/verify), microseconds */
 	uint32_t numWorkersDone;
 	uint32_t numWorkersDoneWithError;
+	/* rwmix read side (Statistics.h PhaseResults: ops*ReadMix, *LatHistoReadMix) */
+	elb_liveops opsStoneWallReadMixTotal;
+	elb_liveops opsReadMixPerSec;
+	elb_liveops opsStoneWallReadMixPerSec;
+	elb_histogram iopsLatHistoReadMix;
+	elb_histogram entriesLatHistoReadMix;
+	/* CPU utilisation of this process' host between phase start and first/last finisher
+	 * (CPUUtil.cpp; /proc/stat delta), percent */
+	uint32_t cpuUtilStoneWallPercent;
+	uint32_t cpuUtilPercent;
 } elb_phase_results;
 
 /* ---------------------------------------------------------------------------------------------
@@ -379,6 +389,19 @@ const char* elb_mgr_last_error(elb_mgr* m);
 
 /* Terminate threads (BenchPhase_TERMINATE), run cleanup, free everything. */
 void elb_mgr_destroy(elb_mgr* m);
+
+/* ---------------------------------------------------------------------------------------------
+ * Command line front end: the reference's main() (source/Main.cpp:13-68) for the supported option
+ * subset, incl. --service / --hosts distributed mode. Returns the process exit code.
+ * ------------------------------------------------------------------------------------------- */
+int elb_cli_main(int argc, char** argv);
+
+/* Render phase results the way the reference prints/stores them, for the options of the given
+ * command line: format 0 = console table rows (Statistics.cpp:1771-2140), 1 = CSV labels line +
+ * values line (:2151-2323), 2 = JSON document (:2429-2723). Writes a NUL-terminated string into
+ * outBuf (truncated to outBufLen) and returns the full length, or -1 on error (elb_last_error). */
+int64_t elb_format_phase_results(int argc, char** argv, int benchPhase,
+	const elb_phase_results* results, int format, char* outBuf, uint64_t outBufLen);
 
 /* Per-worker getters (may be called from any thread while the worker runs; Worker.h:83-226) */
 uint64_t elb_worker_rank(elb_worker* w);

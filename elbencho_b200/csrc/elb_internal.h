@@ -28,6 +28,7 @@ int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc*
 int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
 	uint64_t totalBytesHint, cudaStream_t stream);
+int elb_kernels_warmup();
 uint64_t elb_get_num_kernel_launches();
 
 #endif /* ELB_INTERNAL_H_ */

@@ -768,6 +768,13 @@ int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* in
 	return launchBlocksKernel<MODE_FILL_RANDOM>(args, totalBytesHint, stream);
 }
 
+/* query launch geometry of the current device now (so that no attribute/occupancy query happens
+ * later inside a stream capture) */
+int elb_kernels_warmup()
+{
+	return getDeviceLaunchInfo() ? 0 : -1;
+}
+
 uint64_t elb_get_num_kernel_launches()
 {
 	return gNumKernelLaunches.load(std::memory_order_relaxed);

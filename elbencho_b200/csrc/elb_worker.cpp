@@ -21,7 +21,7 @@
 #define ELB_AIO_MAX_EVENTS 64
 #define ELB_AIO_MAX_WAIT_SEC 5     /* LocalWorker.cpp:60 */
 #define ELB_DEFAULT_BATCH_BYTES (16ULL * 1024 * 1024)
-#define ELB_MAX_BATCH_BLOCKS 256
+#define ELB_MAX_BATCH_BLOCKS 2048
 #define ELB_SLOT_ALIGN 4096
 
 #define ELB_CUDA_CHECK(call, what) \
@@ -559,17 +559,17 @@ void Worker::allocRings()
 
 	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
 
+	/* a batch is the unit of one GPU stage (one kernel launch + one staged copy), independent of
+	   the storage queue depth: ~16 MiB so that launch and copy overheads vanish even for 4 KiB
+	   blocks */
 	if(cfg.pipelineBatchBlocks)
 		batchBlocks = cfg.pipelineBatchBlocks;
-	else
-	if(useAio)
-		batchBlocks = std::max(1u, (cfg.ioDepth + 1) / 2); // two batches in I/O flight = iodepth
 	else
 		batchBlocks = (uint32_t)std::max( (uint64_t)1, (uint64_t)(ELB_DEFAULT_BATCH_BYTES / slotStride) );
 
 	batchBlocks = std::min(batchBlocks, (uint32_t)ELB_MAX_BATCH_BLOCKS);
 
-	numBatches = cfg.pipelineNumBatches ? cfg.pipelineNumBatches : (useAio ? 3 : 2);
+	numBatches = cfg.pipelineNumBatches ? cfg.pipelineNumBatches : 2;
 
 	const uint64_t numSlots = (uint64_t)batchBlocks * numBatches;
 	const uint64_t ringBytes = numSlots * slotStride;
@@ -593,6 +593,9 @@ void Worker::allocRings()
 
 	ELB_CUDA_CHECK(cudaMemcpy(devRing, hostRing, ringBytes, cudaMemcpyHostToDevice),
 		"Initialization of GPU I/O ring");
+
+	if(elb_kernels_warmup() )
+		throw WorkerError(std::string("GPU kernel setup failed. ") + elb_last_error() );
 
 	batches.resize(numBatches);
 
@@ -625,16 +628,16 @@ void Worker::allocRings()
 
 		if(cfg.useCuFile && useAio)
 		{ // one cuFile batch context per pipeline batch
-			CUfileError_t setupRes = CuFileApi::get().BatchIOSetUp(&batch.cuBatch, batchBlocks);
+			CUfileError_t setupRes = CuFileApi::get().BatchIOSetUp(&batch.cuBatch, cfg.ioDepth);
 
 			if(setupRes.err != CU_FILE_SUCCESS)
 				throw WorkerError("cuFile batch setup failed (cuFileBatchIOSetUp). "
-					"Batch size: " + std::to_string(batchBlocks) + "; "
+					"Batch size: " + std::to_string(cfg.ioDepth) + "; "
 					"cuFile Error: " + CuFileApi::errorStr(setupRes) );
 
 			batch.cuBatchValid = true;
-			batch.cuParams.resize(batchBlocks);
-			batch.cuEvents.resize(batchBlocks);
+			batch.cuParams.resize(cfg.ioDepth);
+			batch.cuEvents.resize(cfg.ioDepth);
 		}
 	}
 
@@ -653,7 +656,7 @@ void Worker::allocRings()
 	if(useAio && !cfg.useCuFile)
 	{ // initLibAio (LocalWorker.cpp:455-480) on the raw kernel ABI
 		aioContext = 0;
-		long setupRes = syscall(SYS_io_setup, (unsigned)numSlots, &aioContext);
+		long setupRes = syscall(SYS_io_setup, (unsigned)cfg.ioDepth, &aioContext);
 		if(setupRes == -1)
 			throw WorkerError(std::string("Initializing async IO (io_setup) failed. ") +
 				"SysErr: " + strerror(errno) );
@@ -693,6 +696,10 @@ void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
 			batch.cuBatchValid = false;
 		}
 
+		if(batch.readGraphExec)
+			cudaGraphExecDestroy(batch.readGraphExec);
+		if(batch.writeGraphExec)
+			cudaGraphExecDestroy(batch.writeGraphExec);
 		if(batch.stream)
 			cudaStreamDestroy(batch.stream);
 		if(batch.gpuStartEvent)
@@ -757,8 +764,7 @@ void Worker::abortInFlight()
 	{ // io_destroy waits for all in-flight requests
 		syscall(SYS_io_destroy, aioContext);
 		aioContext = 0;
-		aioInitialized = (syscall(SYS_io_setup, (unsigned)(batchBlocks * numBatches),
-			&aioContext) != -1);
+		aioInitialized = (syscall(SYS_io_setup, (unsigned)cfg.ioDepth, &aioContext) != -1);
 	}
 }
 
@@ -1174,16 +1180,14 @@ bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead)
  * (LocalWorker.cpp:1669-2037).
  *
  * Two stage queues. Write: stage 1 = GPU (fill + staged D2H), stage 2 = storage writes.
- * Read: stage 1 = storage reads, stage 2 = GPU (staged H2D + verify). A new batch is started
- * whenever a batch is free; the oldest stage-1 batch moves on as soon as its stage-1 work is
- * complete, or is waited for when two batches are queued behind each other or nothing new can be
- * started; stage-2 batches are retired when no free batch is left or nothing else is to do.
+ * Read: stage 1 = storage reads, stage 2 = GPU (staged H2D + verify). GPU stages are
+ * asynchronous (stream work / one CUDA graph launch per batch); storage stages run on this
+ * thread: synchronous calls, or the async engines that keep --iodepth requests in flight while
+ * the batch is processed. A new batch is started whenever one is free, so the GPU works on one
+ * batch while this thread does the storage I/O of another.
  */
 void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 {
-	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
-	const bool dirModeAio = useAio && (cfg.pathType == ELB_PATH_DIR);
-
 	std::deque<Batch*> freeBatches;
 	std::deque<Batch*> stageOneQueue;
 	std::deque<Batch*> stageTwoQueue;
@@ -1221,16 +1225,7 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 				freeBatches.pop_front();
 
 				if(isRead)
-				{
-					if(!useAio)
-						ioRunSync(*batch, true);
-					else
-					{
-						ioSubmitAio(*batch, true);
-						if(dirModeAio)
-							ioWaitAio(*batch, true);
-					}
-				}
+					ioRun(*batch, true);
 				else
 					gpuLaunchWriteStage(*batch);
 
@@ -1244,41 +1239,23 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 		if(!stageOneQueue.empty() )
 		{
 			Batch* batch = stageOneQueue.front();
-			bool stageOneComplete;
 
-			if(isRead)
-			{
-				if(useAio && batch->numIOPending)
-					ioPollAsync(*batch);
-
-				stageOneComplete = !batch->numIOPending;
-			}
-			else
-				stageOneComplete = (cudaEventQuery(batch->gpuDoneEvent) == cudaSuccess);
+			/* reads: the storage stage is complete when ioRun returns, so the GPU stage follows
+			   immediately. writes: go on to the storage stage when the fill is done, or when a
+			   second batch is already queued behind it / nothing new can be started. */
+			const bool stageOneComplete = isRead ||
+				(cudaEventQuery(batch->gpuDoneEvent) == cudaSuccess);
 
 			if(stageOneComplete || (stageOneQueue.size() >= 2) || !canStartNew)
 			{
 				stageOneQueue.pop_front();
 
 				if(isRead)
-				{
-					if(useAio)
-						ioWaitAio(*batch, true);
-
 					gpuLaunchReadStage(*batch);
-				}
 				else
 				{
 					gpuWait(*batch);
-
-					if(!useAio)
-						ioRunSync(*batch, false);
-					else
-					{
-						ioSubmitAio(*batch, false);
-						if(dirModeAio)
-							ioWaitAio(*batch, false);
-					}
+					ioRun(*batch, false);
 				}
 
 				stageTwoQueue.push_back(batch);
@@ -1294,9 +1271,6 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 
 			if(isRead)
 				retireReadBatch(*batch);
-			else
-			if(useAio)
-				ioWaitAio(*batch, false);
 
 			freeBatches.push_back(batch);
 		}
@@ -1306,28 +1280,35 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 	}
 }
 
+/* storage stage of one batch through the configured engine; complete on return */
+void Worker::ioRun(Batch& batch, bool isRead)
+{
+	const bool useAsyncEngine = (cfg.ioEngine == ELB_IOENGINE_AIO);
+
+	if(cfg.useCuFile)
+	{
+		if(useAsyncEngine)
+			ioRunCuFileBatch(batch, isRead);
+		else
+			ioRunSyncCuFile(batch, isRead);
+	}
+	else
+	if(useAsyncEngine)
+		ioRunAio(batch, isRead);
+	else
+		ioRunSync(batch, isRead);
+}
+
 /* ---- GPU stages ---------------------------------------------------------------------------- */
 
-/**
- * Write phase GPU stage = policy of initPhaseFunctionPointers (LocalWorker.cpp:1249-1265):
- * pattern fill if salt != 0, else random refill if blockvarpct, else nothing; then the block goes
- * to the host for the storage write (cudaMemcpyGPUToHost, :1249-1250).
- */
-void Worker::gpuLaunchWriteStage(Batch& batch)
+/* fill the pinned descriptor mirror for the write stage; returns the number of blocks to fill */
+size_t Worker::fillWriteDescs(Batch& batch, uint64_t& outNumWriteBytes)
 {
-	const size_t numBlocks = batch.blocks.size();
-	const bool doPatternFill = (cfg.integrityCheckSalt != 0);
-	const bool doRandFill = !doPatternFill && cfg.blockVariancePercent;
-
-	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
-
-	batch.hadKernel = false;
+	size_t numWriteBlocks = 0;
+	outNumWriteBytes = 0;
 
 	// blocks that rwmix turned into reads get no fill and no staging (LocalWorker.cpp:2213)
-	size_t numWriteBlocks = 0;
-	uint64_t numWriteBytes = 0;
-
-	for(size_t i = 0; i < numBlocks; i++)
+	for(size_t i = 0; i < batch.blocks.size(); i++)
 	{
 		const BlockRef& block = batch.blocks[i];
 
@@ -1336,8 +1317,64 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 
 		batch.hostDescs[numWriteBlocks++] = elb_block_desc{slotDevPtr(batch, i), block.len,
 			block.offset, (rank << 40) + block.blockCounter};
-		numWriteBytes += block.len;
+		outNumWriteBytes += block.len;
 	}
+
+	return numWriteBlocks;
+}
+
+/* a full batch of full-size blocks in a dense run of slots: its GPU stage has fixed pointers and
+ * sizes and can be replayed from a CUDA graph */
+bool Worker::isStandardShapedBatch(const Batch& batch) const
+{
+	return (batch.blocks.size() == batchBlocks) && (slotStride == cfg.blockSize) &&
+		(batch.numBytes == ( (uint64_t)batchBlocks * slotStride) );
+}
+
+cudaGraphExec_t Worker::captureBatchGraph(Batch& batch, bool isRead)
+{
+	cudaGraph_t graph = NULL;
+	cudaGraphExec_t graphExec = NULL;
+
+	ELB_CUDA_CHECK(cudaStreamBeginCapture(batch.stream, cudaStreamCaptureModeThreadLocal),
+		"CUDA stream capture begin");
+
+	try
+	{
+		if(isRead)
+			enqueueReadWork(batch, false);
+		else
+			enqueueWriteWork(batch, batchBlocks, batch.numBytes, false);
+	}
+	catch(...)
+	{
+		cudaStreamEndCapture(batch.stream, &graph); // leave capture mode
+		if(graph)
+			cudaGraphDestroy(graph);
+		throw;
+	}
+
+	ELB_CUDA_CHECK(cudaStreamEndCapture(batch.stream, &graph), "CUDA stream capture end");
+
+	cudaError_t instantiateRes = cudaGraphInstantiate(&graphExec, graph, 0);
+	cudaGraphDestroy(graph);
+
+	ELB_CUDA_CHECK(instantiateRes, "CUDA graph instantiation");
+
+	return graphExec;
+}
+
+/**
+ * Stream work of the write stage = policy of initPhaseFunctionPointers (LocalWorker.cpp:
+ * 1249-1265): pattern fill if salt != 0, else random refill if blockvarpct, else nothing; then the
+ * blocks go to the host for the storage write (cudaMemcpyGPUToHost, :1249-1250).
+ */
+void Worker::enqueueWriteWork(Batch& batch, size_t numWriteBlocks, uint64_t numWriteBytes,
+	bool timeKernel)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const bool doPatternFill = (cfg.integrityCheckSalt != 0);
+	const bool doRandFill = !doPatternFill && cfg.blockVariancePercent;
 
 	if( (doPatternFill || doRandFill) && numWriteBlocks)
 	{
@@ -1345,8 +1382,9 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 			sizeof(elb_block_desc) * numWriteBlocks, cudaMemcpyHostToDevice, batch.stream),
 			"Async copy of block descriptors");
 
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
-			"CUDA event record");
+		if(timeKernel)
+			ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+				"CUDA event record");
 
 		int launchRes;
 
@@ -1361,11 +1399,12 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 		if(launchRes)
 			throw WorkerError(std::string("GPU block fill failed. ") + elb_last_error() );
 
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
-			"CUDA event record");
-
-		batch.hadKernel = true;
-		numKernelLaunches++;
+		if(timeKernel)
+		{
+			ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+				"CUDA event record");
+			batch.hadKernel = true;
+		}
 	}
 
 	/* staged copy to the pinned ring: one copy when the batch is a dense run of full slots.
@@ -1387,6 +1426,30 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 				batch.blocks[i].len, cudaMemcpyDeviceToHost, batch.stream),
 				"Async GPU to host copy");
 		}
+}
+
+void Worker::gpuLaunchWriteStage(Batch& batch)
+{
+	uint64_t numWriteBytes;
+	const size_t numWriteBlocks = fillWriteDescs(batch, numWriteBytes);
+	const bool haveKernel = (cfg.integrityCheckSalt || cfg.blockVariancePercent) && numWriteBlocks;
+
+	batch.hadKernel = false;
+
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
+
+	if(isStandardShapedBatch(batch) && (numWriteBlocks == batchBlocks) )
+	{
+		if(!batch.writeGraphExec)
+			batch.writeGraphExec = captureBatchGraph(batch, false);
+
+		ELB_CUDA_CHECK(cudaGraphLaunch(batch.writeGraphExec, batch.stream), "CUDA graph launch");
+	}
+	else
+		enqueueWriteWork(batch, numWriteBlocks, numWriteBytes, true);
+
+	if(haveKernel)
+		numKernelLaunches++;
 
 	if(!cfg.useCuFile)
 		numD2HBytes += numWriteBytes;
@@ -1395,16 +1458,14 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 }
 
 /**
- * Read phase GPU stage (LocalWorker.cpp:1311-1319): host -> GPU copy of what was read, then the
- * integrity check on the GPU (the reference verifies on the CPU); only the 16-byte results come
- * back.
+ * Stream work of the read stage (LocalWorker.cpp:1311-1319): host -> GPU copy of what was read,
+ * then the integrity check on the GPU (the reference verifies on the CPU); only the 16-byte
+ * results come back. Expects the pinned descriptor mirror to be filled and devResults clean.
  */
-void Worker::gpuLaunchReadStage(Batch& batch)
+void Worker::enqueueReadWork(Batch& batch, bool timeKernel)
 {
 	const size_t numBlocks = batch.blocks.size();
 	const bool doVerify = (cfg.integrityCheckSalt != 0);
-
-	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
 	if(cfg.useCuFile)
 		; // cuFile read straight into the device ring (LocalWorker.cpp:1231-1232)
@@ -1423,13 +1484,42 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 				"Async host to GPU copy");
 		}
 
-	if(!cfg.useCuFile)
-		numH2DBytes += batch.numBytes;
+	if(!doVerify)
+		return;
+
+	ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
+		sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
+		"Async copy of block descriptors");
+
+	if(timeKernel)
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+			"CUDA event record");
+
+	if(elb_launch_verify_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
+		cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes,
+		false /*initResults*/, batch.stream) )
+		throw WorkerError(std::string("GPU block verification failed. ") + elb_last_error() );
+
+	if(timeKernel)
+	{
+		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+			"CUDA event record");
+		batch.hadKernel = true;
+	}
+
+	ELB_CUDA_CHECK(cudaMemcpyAsync(batch.hostResults, batch.devResults,
+		sizeof(elb_verify_result) * numBlocks, cudaMemcpyDeviceToHost, batch.stream),
+		"Async copy of verify results");
+}
+
+void Worker::gpuLaunchReadStage(Batch& batch)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const bool doVerify = (cfg.integrityCheckSalt != 0);
 
 	batch.hadKernel = false;
 
 	if(doVerify)
-	{
 		for(size_t i = 0; i < numBlocks; i++)
 		{
 			const BlockRef& block = batch.blocks[i];
@@ -1437,42 +1527,32 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 				block.blockCounter};
 		}
 
-		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
-			sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
-			"Async copy of block descriptors");
+	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
-		const bool initResults = !batch.devResultsClean;
+	if(doVerify && !batch.devResultsClean)
+	{ // (all batchBlocks entries, so that later launches with more blocks stay valid)
+		if(elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream) )
+			throw WorkerError(std::string("GPU verify init failed. ") + elb_last_error() );
 
-		if(initResults)
-		{
-			/* (all batchBlocks entries, so that later launches with more blocks stay valid) */
-			if(elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream) )
-				throw WorkerError(std::string("GPU verify init failed. ") + elb_last_error() );
-
-			numKernelLaunches++;
-		}
-
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
-			"CUDA event record");
-
-		if(elb_launch_verify_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
-			cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes,
-			false /*initResults*/, batch.stream) )
-			throw WorkerError(std::string("GPU block verification failed. ") +
-				elb_last_error() );
-
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
-			"CUDA event record");
-
-		batch.hadKernel = true;
 		numKernelLaunches++;
-
-		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.hostResults, batch.devResults,
-			sizeof(elb_verify_result) * numBlocks, cudaMemcpyDeviceToHost, batch.stream),
-			"Async copy of verify results");
-
 		batch.devResultsClean = true; // until a mismatch shows up at retire time
 	}
+
+	if(isStandardShapedBatch(batch) )
+	{
+		if(!batch.readGraphExec)
+			batch.readGraphExec = captureBatchGraph(batch, true);
+
+		ELB_CUDA_CHECK(cudaGraphLaunch(batch.readGraphExec, batch.stream), "CUDA graph launch");
+	}
+	else
+		enqueueReadWork(batch, true);
+
+	if(doVerify)
+		numKernelLaunches++;
+
+	if(!cfg.useCuFile)
+		numH2DBytes += batch.numBytes;
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuDoneEvent, batch.stream), "CUDA event record");
 }
@@ -1754,12 +1834,6 @@ int Worker::resolveFD(const BlockRef& block, bool isRead)
  */
 void Worker::ioRunSync(Batch& batch, bool isRead)
 {
-	if(cfg.useCuFile)
-	{
-		ioRunSyncCuFile(batch, isRead);
-		return;
-	}
-
 	const size_t numBlocks = batch.blocks.size();
 	const bool doReadBack = !isRead && (cfg.doDirectVerify || cfg.doReadInline);
 	const bool useWriteGate = !isRead && cfg.serializeBufferedWrites && !cfg.useDirectIO &&
@@ -1827,17 +1901,14 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 }
 
 /**
- * Asynchronous storage stage on the raw kernel AIO ABI: the whole batch goes down with one
- * io_submit (the reference submits one iocb per syscall, LocalWorker.cpp:1855).
+ * Asynchronous storage stage on the raw kernel AIO ABI (io_submit/io_getevents syscalls; the
+ * reference uses libaio and submits one iocb per syscall, LocalWorker.cpp:1855). --iodepth
+ * requests are kept in flight while the batch is worked off: completions are reaped in groups
+ * and as many new requests are submitted with one io_submit; result checks follow
+ * aioBlockSized (:1881-1932). The batch is complete on return.
  */
-void Worker::ioSubmitAio(Batch& batch, bool isRead)
+void Worker::ioRunAio(Batch& batch, bool isRead)
 {
-	if(cfg.useCuFile)
-	{
-		ioSubmitCuFileBatch(batch, isRead);
-		return;
-	}
-
 	const size_t numBlocks = batch.blocks.size();
 	size_t numIocbs = 0;
 
@@ -1857,113 +1928,92 @@ void Worker::ioSubmitAio(Batch& batch, bool isRead)
 		cb.aio_buf = (uint64_t)(uintptr_t)slotHostPtr(batch, i);
 		cb.aio_nbytes = block.len;
 		cb.aio_offset = block.offset;
-		cb.aio_data = ( (uint64_t)batch.index << 32) | i;
+		cb.aio_data = i;
 
 		batch.iocbPtrs[numIocbs] = &cb;
-		block.submitT = Clock::now();
 		numIocbs++;
 	}
 
-	batch.numIOPending = (uint32_t)numIocbs;
-	batch.ioSubmitted = true;
-
 	size_t numSubmitted = 0;
+	size_t numCompleted = 0;
+	struct io_event events[ELB_AIO_MAX_EVENTS];
 
-	while(numSubmitted < numIocbs)
+	while(numCompleted < numIocbs)
 	{
-		long submitRes = syscall(SYS_io_submit, aioContext, (long)(numIocbs - numSubmitted),
-			&batch.iocbPtrs[numSubmitted] );
+		checkInterruptionRequest();
 
-		if(submitRes < 0)
+		// top up to --iodepth requests in flight
+		const size_t numInFlight = numSubmitted - numCompleted;
+
+		if( (numSubmitted < numIocbs) && (numInFlight < cfg.ioDepth) )
 		{
-			if(errno == EAGAIN)
-			{ // queue full: reap something first
-				ioReapAio(true);
-				continue;
-			}
+			const size_t numToSubmit = std::min(numIocbs - numSubmitted,
+				(size_t)cfg.ioDepth - numInFlight);
+			const Clock::time_point submitT = Clock::now();
 
-			throw WorkerError(std::string("Async IO submission (io_submit) failed. ") +
-				"NumRequests: " + std::to_string(numIocbs - numSubmitted) + "; "
+			for(size_t k = 0; k < numToSubmit; k++)
+				batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].submitT = submitT;
+
+			long submitRes = syscall(SYS_io_submit, aioContext, (long)numToSubmit,
+				&batch.iocbPtrs[numSubmitted] );
+
+			if(submitRes < 0)
+			{
+				if( (errno != EAGAIN) || !numInFlight)
+					throw WorkerError(std::string("Async IO submission (io_submit) failed. ") +
+						"NumRequests: " + std::to_string(numToSubmit) + "; "
+						"SysErr: " + strerror(errno) );
+			}
+			else
+				numSubmitted += submitRes;
+		}
+
+		struct timespec timeout;
+		timeout.tv_sec = ELB_AIO_MAX_WAIT_SEC;
+		timeout.tv_nsec = 0;
+
+		long eventsRes = syscall(SYS_io_getevents, aioContext, 1L, (long)ELB_AIO_MAX_EVENTS,
+			events, &timeout);
+
+		if(!eventsRes)
+			continue; // timeout expired: only set to check interruptions
+
+		if(eventsRes < 0)
+		{
+			if(errno == EINTR)
+				continue;
+
+			throw WorkerError(std::string("Getting async IO events (io_getevents) failed. ") +
+				"NumPending: " + std::to_string(numSubmitted - numCompleted) + "; "
 				"SysErr: " + strerror(errno) );
 		}
 
-		numSubmitted += submitRes;
+		for(long eventIdx = 0; eventIdx < eventsRes; eventIdx++)
+		{
+			const struct io_event& event = events[eventIdx];
+			BlockRef& block = batch.blocks[event.data];
+			const struct iocb* cb = (const struct iocb*)(uintptr_t)event.obj;
+
+			if(event.res2)
+				throw WorkerError(std::string("Async IO framework error. ") +
+					"res: " + std::to_string(event.res) + "; "
+					"res2: " + std::to_string(event.res2) + "; "
+					"IO size: " + std::to_string(cb->aio_nbytes) + "; "
+					"SysErr: " + strerror(-(int)event.res2) );
+
+			if(event.res != (int64_t)cb->aio_nbytes)
+				throwIOError(block, block.ioIsRead, (event.res < 0) ? -1 : (ssize_t)event.res,
+					(event.res < 0) ? -(int)event.res : 0);
+
+			block.ioUSec = elapsedUSecSince(block.submitT);
+			numCompleted++;
+		}
 	}
-}
-
-/* io_getevents + result checks of aioBlockSized (LocalWorker.cpp:1881-1932) */
-void Worker::ioReapAio(bool blockUntilEvent)
-{
-	struct io_event events[ELB_AIO_MAX_EVENTS];
-	struct timespec timeout;
-	timeout.tv_sec = blockUntilEvent ? ELB_AIO_MAX_WAIT_SEC : 0;
-	timeout.tv_nsec = 0;
-
-	long eventsRes = syscall(SYS_io_getevents, aioContext, (long)(blockUntilEvent ? 1 : 0),
-		(long)ELB_AIO_MAX_EVENTS, events, &timeout);
-
-	if(!eventsRes)
-	{ // timeout expired: that's ok, we only set it to check interruptions
-		checkInterruptionRequest();
-		return;
-	}
-
-	if(eventsRes < 0)
-	{
-		if(errno == EINTR)
-			return;
-
-		throw WorkerError(std::string("Getting async IO events (io_getevents) failed. ") +
-			"SysErr: " + strerror(errno) );
-	}
-
-	for(long eventIdx = 0; eventIdx < eventsRes; eventIdx++)
-	{
-		const struct io_event& event = events[eventIdx];
-		const uint32_t batchIdx = (uint32_t)(event.data >> 32);
-		const uint32_t blockIdx = (uint32_t)event.data;
-		Batch& batch = batches[batchIdx];
-		BlockRef& block = batch.blocks[blockIdx];
-		const struct iocb* cb = (const struct iocb*)(uintptr_t)event.obj;
-		const bool wasRead = (cb->aio_lio_opcode == IOCB_CMD_PREAD);
-
-		if(event.res2)
-			throw WorkerError(std::string("Async IO framework error. ") +
-				"res: " + std::to_string(event.res) + "; "
-				"res2: " + std::to_string(event.res2) + "; "
-				"IO size: " + std::to_string(cb->aio_nbytes) + "; "
-				"SysErr: " + strerror(-(int)event.res2) );
-
-		if(event.res != (int64_t)cb->aio_nbytes)
-			throwIOError(block, wasRead, (event.res < 0) ? -1 : (ssize_t)event.res,
-				(event.res < 0) ? -(int)event.res : 0);
-
-		block.ioUSec = elapsedUSecSince(block.submitT);
-		batch.numIOPending--;
-	}
-}
-
-void Worker::ioWaitAio(Batch& batch, bool isRead)
-{
-	if(!batch.ioSubmitted)
-		return;
-
-	while(batch.numIOPending)
-	{
-		checkInterruptionRequest();
-
-		if(cfg.useCuFile)
-			ioReapCuFileBatch(batch, true);
-		else
-			ioReapAio(true);
-	}
-
-	batch.ioSubmitted = false;
 
 	if(!isRead)
 	{
 		if(!cfg.useCuFile)
-			for(size_t i = 0; i < batch.blocks.size(); i++)
+			for(size_t i = 0; i < numBlocks; i++)
 			{ // rwmix reads of a write phase go to the GPU like any read
 				const BlockRef& block = batch.blocks[i];
 
@@ -2058,102 +2108,108 @@ void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
 }
 
 /**
- * iodepth > 1 with GDS: the whole batch goes down with one cuFileBatchIOSubmit (new capability;
- * the reference rejects --cufile with --iodepth > 1, ProgArgs.cpp:1312-1313).
+ * iodepth > 1 with GDS through the cuFile batch API (new capability; the reference rejects
+ * --cufile with --iodepth > 1, ProgArgs.cpp:1312-1313): the batch is worked off in groups of
+ * --iodepth requests, one cuFileBatchIOSubmit each. Complete on return.
  */
-void Worker::ioSubmitCuFileBatch(Batch& batch, bool isRead)
+void Worker::ioRunCuFileBatch(Batch& batch, bool isRead)
 {
 	CuFileApi& api = CuFileApi::get();
 	const size_t numBlocks = batch.blocks.size();
-	unsigned numParams = 0;
+	std::vector<size_t> blockIdxVec; // blocks with I/O, in order
 
 	for(size_t i = 0; i < numBlocks; i++)
 	{
-		BlockRef& block = batch.blocks[i];
+		resolveCuFileHandle(batch.blocks[i], isRead); // (opens the dir mode file)
 
-		CUfileHandle_t handle = resolveCuFileHandle(block, isRead);
-
-		if(!block.len)
-			continue;
-
-		CUfileIOParams_t& params = batch.cuParams[numParams];
-		memset(&params, 0, sizeof(params) );
-		params.mode = CUFILE_BATCH;
-		params.fh = handle;
-		params.opcode = block.ioIsRead ? CUFILE_READ : CUFILE_WRITE;
-		params.u.batch.devPtr_base = devRing;
-		params.u.batch.devPtr_offset = (off_t)( (uint64_t)(batch.firstSlot + i) * slotStride);
-		params.u.batch.file_offset = block.offset;
-		params.u.batch.size = block.len;
-		params.cookie = (void*)(uintptr_t)i;
-
-		block.submitT = Clock::now();
-		numParams++;
+		if(batch.blocks[i].len)
+			blockIdxVec.push_back(i);
 	}
 
-	batch.numIOPending = numParams;
-	batch.ioSubmitted = true;
-
-	if(!numParams)
-		return;
-
-	CUfileError_t submitRes = api.BatchIOSubmit(batch.cuBatch, numParams, batch.cuParams.data(), 0);
-
-	if(submitRes.err != CU_FILE_SUCCESS)
+	for(size_t groupStart = 0; groupStart < blockIdxVec.size(); groupStart += cfg.ioDepth)
 	{
-		batch.numIOPending = 0;
-		throw WorkerError("cuFile batch submission failed (cuFileBatchIOSubmit). "
-			"NumRequests: " + std::to_string(numParams) + "; "
-			"cuFile Error: " + CuFileApi::errorStr(submitRes) );
+		checkInterruptionRequest();
+
+		const unsigned groupLen = (unsigned)std::min( (size_t)cfg.ioDepth,
+			blockIdxVec.size() - groupStart);
+		const Clock::time_point submitT = Clock::now();
+
+		for(unsigned k = 0; k < groupLen; k++)
+		{
+			const size_t blockIdx = blockIdxVec[groupStart + k];
+			BlockRef& block = batch.blocks[blockIdx];
+
+			CUfileIOParams_t& params = batch.cuParams[k];
+			memset(&params, 0, sizeof(params) );
+			params.mode = CUFILE_BATCH;
+			params.fh = (cfg.pathType != ELB_PATH_DIR) ?
+				shared->cuFileHandles[block.fileIdx]->get() : dirModeCuFileHandle.get();
+			params.opcode = block.ioIsRead ? CUFILE_READ : CUFILE_WRITE;
+			params.u.batch.devPtr_base = devRing;
+			params.u.batch.devPtr_offset =
+				(off_t)( (uint64_t)(batch.firstSlot + blockIdx) * slotStride);
+			params.u.batch.file_offset = block.offset;
+			params.u.batch.size = block.len;
+			params.cookie = (void*)(uintptr_t)blockIdx;
+
+			block.submitT = submitT;
+		}
+
+		CUfileError_t submitRes = api.BatchIOSubmit(batch.cuBatch, groupLen,
+			batch.cuParams.data(), 0);
+
+		if(submitRes.err != CU_FILE_SUCCESS)
+			throw WorkerError("cuFile batch submission failed (cuFileBatchIOSubmit). "
+				"NumRequests: " + std::to_string(groupLen) + "; "
+				"cuFile Error: " + CuFileApi::errorStr(submitRes) );
+
+		unsigned numPending = groupLen;
+
+		while(numPending)
+		{
+			checkInterruptionRequest();
+
+			unsigned numEvents = numPending;
+			struct timespec timeout;
+			timeout.tv_sec = ELB_AIO_MAX_WAIT_SEC;
+			timeout.tv_nsec = 0;
+
+			CUfileError_t statusRes = api.BatchIOGetStatus(batch.cuBatch, 1, &numEvents,
+				batch.cuEvents.data(), &timeout);
+
+			if(statusRes.err != CU_FILE_SUCCESS)
+				throw WorkerError("Getting cuFile batch status failed (cuFileBatchIOGetStatus). "
+					"NumPending: " + std::to_string(numPending) + "; "
+					"cuFile Error: " + CuFileApi::errorStr(statusRes) );
+
+			for(unsigned eventIdx = 0; eventIdx < numEvents; eventIdx++)
+			{
+				const CUfileIOEvents_t& event = batch.cuEvents[eventIdx];
+				BlockRef& block = batch.blocks[ (size_t)(uintptr_t)event.cookie];
+
+				if( (event.status == CUFILE_WAITING) || (event.status == CUFILE_PENDING) )
+					continue; // not a completion
+
+				if( (event.status != CUFILE_COMPLETE) || (event.ret != block.len) )
+					throw WorkerError("cuFile batch I/O failed. "
+						"Path: " + blockPathForLog(block) + "; "
+						"Offset: " + std::to_string(block.offset) + "; "
+						"Status: " + std::to_string( (int)event.status) + "; "
+						"Result: " + std::to_string( (long long)event.ret) + "; "
+						"Expected: " + std::to_string(block.len) );
+
+				block.ioUSec = elapsedUSecSince(block.submitT);
+				numPending--;
+			}
+		}
 	}
-}
 
-void Worker::ioReapCuFileBatch(Batch& batch, bool blockUntilEvent)
-{
-	CuFileApi& api = CuFileApi::get();
+	if(!isRead)
+		accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
 
-	unsigned numEvents = batch.numIOPending;
-	struct timespec timeout;
-	timeout.tv_sec = blockUntilEvent ? ELB_AIO_MAX_WAIT_SEC : 0;
-	timeout.tv_nsec = 0;
-
-	CUfileError_t statusRes = api.BatchIOGetStatus(batch.cuBatch, blockUntilEvent ? 1 : 0,
-		&numEvents, batch.cuEvents.data(), &timeout);
-
-	if(statusRes.err != CU_FILE_SUCCESS)
-		throw WorkerError("Getting cuFile batch status failed (cuFileBatchIOGetStatus). "
-			"NumPending: " + std::to_string(batch.numIOPending) + "; "
-			"cuFile Error: " + CuFileApi::errorStr(statusRes) );
-
-	for(unsigned eventIdx = 0; eventIdx < numEvents; eventIdx++)
-	{
-		const CUfileIOEvents_t& event = batch.cuEvents[eventIdx];
-		const size_t blockIdx = (size_t)(uintptr_t)event.cookie;
-		BlockRef& block = batch.blocks[blockIdx];
-
-		if( (event.status == CUFILE_WAITING) || (event.status == CUFILE_PENDING) )
-			continue; // not a completion
-
-		if( (event.status != CUFILE_COMPLETE) || (event.ret != block.len) )
-			throw WorkerError("cuFile batch I/O failed. "
-				"Path: " + blockPathForLog(block) + "; "
-				"Offset: " + std::to_string(block.offset) + "; "
-				"Status: " + std::to_string( (int)event.status) + "; "
-				"Result: " + std::to_string( (long long)event.ret) + "; "
-				"Expected: " + std::to_string(block.len) );
-
-		block.ioUSec = elapsedUSecSince(block.submitT);
-		batch.numIOPending--;
-	}
-}
-
-/* non-blocking progress check of the async engine for one batch */
-void Worker::ioPollAsync(Batch& batch)
-{
-	if(cfg.useCuFile)
-		ioReapCuFileBatch(batch, false);
-	else
-		ioReapAio(false);
+	if( (cfg.pathType == ELB_PATH_DIR) && !batch.blocks.empty() &&
+		batch.blocks.back().lastOfFile && (dirModeFD != -1) )
+		dirModeCloseFile();
 }
 
 } // namespace elb

@@ -130,6 +130,11 @@ struct Batch
 
 	uint64_t numBytes{0};
 	float gpuMilliSecs{0};
+
+	/* CUDA graphs of the GPU stage for full, dense batches (fixed pointers and sizes): one
+	 * cudaGraphLaunch instead of 4-6 stream calls per batch */
+	cudaGraphExec_t readGraphExec{NULL};
+	cudaGraphExec_t writeGraphExec{NULL};
 };
 
 class Worker
@@ -260,16 +265,19 @@ class Worker
 		void accountBatch(Batch& batch, uint64_t gpuUSecTotal);
 		void gpuLaunchWriteStage(Batch& batch);
 		void gpuLaunchReadStage(Batch& batch);
+		size_t fillWriteDescs(Batch& batch, uint64_t& outNumWriteBytes);
+		void enqueueWriteWork(Batch& batch, size_t numWriteBlocks, uint64_t numWriteBytes,
+			bool timeKernel);
+		void enqueueReadWork(Batch& batch, bool timeKernel);
+		bool isStandardShapedBatch(const Batch& batch) const;
+		cudaGraphExec_t captureBatchGraph(Batch& batch, bool isRead);
 		void gpuWait(Batch& batch);
 		void retireReadBatch(Batch& batch);
+		void ioRun(Batch& batch, bool isRead);
 		void ioRunSync(Batch& batch, bool isRead);
-		void ioSubmitAio(Batch& batch, bool isRead);
-		void ioWaitAio(Batch& batch, bool isRead);
-		void ioReapAio(bool blockUntilEvent);
-		void ioPollAsync(Batch& batch);
+		void ioRunAio(Batch& batch, bool isRead);
 		void ioRunSyncCuFile(Batch& batch, bool isRead);
-		void ioSubmitCuFileBatch(Batch& batch, bool isRead);
-		void ioReapCuFileBatch(Batch& batch, bool blockUntilEvent);
+		void ioRunCuFileBatch(Batch& batch, bool isRead);
 		CUfileHandle_t resolveCuFileHandle(const BlockRef& block, bool isRead);
 		void ioAccountBlock(BlockRef& block, uint64_t latencyUSec);
 		void throwVerifyError(Batch& batch, size_t blockIdx);

@@ -123,7 +123,7 @@ def test_cufile_batch_iodepth_random_reads(workdir, mock):
         assert r["verify_mismatch_bytes"] == 0 and r["verified_bytes"] == size
         st = mock.stats()
         assert st["batch_ops"] == size // block and st["read"] == 0
-        assert st["batch_submit"] == (size // block) // (depth // 2)  # batches of iodepth/2 blocks
+        assert st["batch_submit"] == (size // block) // depth  # groups of --iodepth requests
         # random writes through the batch API too (full coverage), then verify again
         w = mgr.run_phase(BenchPhase.CREATEFILES)
         assert w["ops_total"]["bytes"] == size

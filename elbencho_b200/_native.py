@@ -92,6 +92,16 @@ class LiveLat(ctypes.Structure):
     ]
 
 
+class LiveSnapshot(ctypes.Structure):
+    _fields_ = [
+        ("ops", LiveOps), ("opsReadMix", LiveOps), ("lat", LiveLat),
+        ("numWorkersDone", c_u64), ("numWorkersTotal", c_u64),
+        ("devCounters", c_u64 * DEVCTR_NUM),
+        ("numGPUs", ctypes.c_uint32), ("reducedWithNccl", ctypes.c_int32),
+        ("gatheredOnDevice", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
 class Histogram(ctypes.Structure):
     _fields_ = [
         ("buckets", c_u64 * LATHISTO_NUMBUCKETS),
@@ -172,6 +182,8 @@ SIGNATURES = {
     "elb_mgr_run_phase": (ctypes.c_int, [_VP, ctypes.c_int]),
     "elb_mgr_live_ops": (ctypes.c_int, [_VP, ctypes.POINTER(LiveOps)]),
     "elb_mgr_live_latency": (ctypes.c_int, [_VP, ctypes.POINTER(LiveLat)]),
+    "elb_mgr_live_snapshot": (ctypes.c_int, [_VP, ctypes.POINTER(LiveSnapshot)]),
+    "elb_mgr_live_reduce_info": (ctypes.c_char_p, [_VP]),
     "elb_mgr_phase_results": (ctypes.c_int, [_VP, ctypes.POINTER(PhaseResults)]),
     "elb_mgr_expected_totals": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.POINTER(c_u64),
                                                 ctypes.POINTER(c_u64)]),

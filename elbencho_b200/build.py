@@ -21,6 +21,7 @@ SOURCES = [
     "elb_cufile.cpp",
     "elb_worker.cpp",
     "elb_manager.cpp",
+    "elb_statsreduce.cu",
     "elb_cli.cpp",
     "elb_stats.cpp",
     "elb_coordinator.cpp",

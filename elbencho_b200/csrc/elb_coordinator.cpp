@@ -297,7 +297,9 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 
 	liveCpuUtil.update();
 
-	const bool showLive = !progArgs.disableLiveStats && isatty(STDOUT_FILENO);
+	const bool showLive = !progArgs.disableLiveStats &&
+		(isatty(STDOUT_FILENO) || getenv("ELB_FORCE_LIVESTATS") );
+	const bool useLiveReduce = (manager->getNumGPUs() >= 2);
 
 	for( ; ; )
 	{
@@ -328,11 +330,19 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 		elb_liveops liveOps[2] = {};
 		size_t numWorkersDone;
 
-		for(const std::unique_ptr<Worker>& worker : manager->workers)
-		{
-			liveOpsAdd(liveOps[0], worker->getLiveOps() );
-			liveOpsAdd(liveOps[1], worker->getLiveOpsReadMix() );
+		if(useLiveReduce)
+		{ // workers on several GPUs: per-GPU partial sums, reduced over NVLink by NCCL
+			elb_live_snapshot snapshot;
+			manager->getLiveSnapshot(snapshot);
+			liveOps[0] = snapshot.ops;
+			liveOps[1] = snapshot.opsReadMix;
 		}
+		else
+			for(const std::unique_ptr<Worker>& worker : manager->workers)
+			{
+				liveOpsAdd(liveOps[0], worker->getLiveOps() );
+				liveOpsAdd(liveOps[1], worker->getLiveOpsReadMix() );
+			}
 
 		{
 			std::unique_lock<std::mutex> lock(manager->shared.mutex);

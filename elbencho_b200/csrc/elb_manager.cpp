@@ -3,6 +3,7 @@
  * worker/manager level declared in include/elbencho_b200.h.
  */
 #include <errno.h>
+#include <algorithm>
 #include <fcntl.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -10,6 +11,7 @@
 #include <unistd.h>
 
 #include "elb_cli.h"
+#include "elb_statsreduce.h"
 #include "elb_worker.h"
 
 #define ELB_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
@@ -58,6 +60,8 @@ Manager::Manager(const elb_cfg* abiCfg)
 
 Manager::~Manager()
 {
+	liveStatsReducer.reset(); // (refers to the workers and their device counter blocks)
+
 	// BenchPhase_TERMINATE tells workers to self-terminate (Common.h:145)
 	if(!threads.empty() )
 	{
@@ -75,6 +79,37 @@ Manager::~Manager()
 	}
 
 	closeBenchPathFDs();
+}
+
+void Manager::getLiveSnapshot(elb_live_snapshot& out)
+{
+	std::unique_lock<std::mutex> lock(liveStatsReducerMutex);
+
+	if(!liveStatsReducer)
+		liveStatsReducer.reset(new LiveStatsReducer(*this) );
+
+	liveStatsReducer->snapshot(out);
+}
+
+size_t Manager::getNumGPUs() const
+{
+	std::vector<int> gpuIDs;
+
+	for(const std::unique_ptr<Worker>& worker : workers)
+		if(std::find(gpuIDs.begin(), gpuIDs.end(), worker->getGPUID() ) == gpuIDs.end() )
+			gpuIDs.push_back(worker->getGPUID() );
+
+	return gpuIDs.size();
+}
+
+std::string Manager::getLiveReduceInfo()
+{
+	std::unique_lock<std::mutex> lock(liveStatsReducerMutex);
+
+	if(!liveStatsReducer)
+		liveStatsReducer.reset(new LiveStatsReducer(*this) );
+
+	return liveStatsReducer->getNcclNote();
 }
 
 /* ProgArgs::prepareBenchPathFDsVec (ProgArgs.cpp:1859-1935) */
@@ -422,6 +457,7 @@ struct elb_mgr
 {
 	elb::Manager* impl;
 	std::string lastError;
+	std::string liveReduceInfo;
 };
 
 /* elb_worker handles are the Worker objects themselves */
@@ -629,6 +665,18 @@ int elb_mgr_live_latency(elb_mgr* m, elb_livelat* out)
 		worker->getAndResetLiveLatency(*out);
 
 	return 0;
+}
+
+int elb_mgr_live_snapshot(elb_mgr* m, elb_live_snapshot* out)
+{
+	m->impl->getLiveSnapshot(*out);
+	return 0;
+}
+
+const char* elb_mgr_live_reduce_info(elb_mgr* m)
+{
+	m->liveReduceInfo = m->impl->getLiveReduceInfo();
+	return m->liveReduceInfo.c_str();
 }
 
 int elb_mgr_phase_results(elb_mgr* m, elb_phase_results* out)

@@ -756,7 +756,8 @@ class Service
 		HttpResponse handleInterruptPhase(const HttpRequest& request);
 		void resetManager();
 		void collectErrHistory();
-		void putCommonStats(JsonTree& tree, bool isFinal);
+		void putCommonStats(JsonTree& tree, bool isFinal,
+			const elb_live_snapshot* liveSnapshot = NULL);
 };
 
 void Service::resetManager()
@@ -811,7 +812,7 @@ static void histogramFromTree(const JsonTree& tree, const std::string& prefix, e
 }
 
 /* common part of /status and /benchresult (Statistics.cpp:1350-1405, 2728-2804) */
-void Service::putCommonStats(JsonTree& tree, bool isFinal)
+void Service::putCommonStats(JsonTree& tree, bool isFinal, const elb_live_snapshot* liveSnapshot)
 {
 	elb_liveops liveOps[2] = {};
 	size_t numWorkersDone = 0, numWorkersDoneWithError = 0;
@@ -819,11 +820,17 @@ void Service::putCommonStats(JsonTree& tree, bool isFinal)
 
 	if(manager)
 	{
-		for(const std::unique_ptr<Worker>& worker : manager->workers)
+		if(liveSnapshot)
 		{
-			liveOpsAdd(liveOps[0], worker->getLiveOps() );
-			liveOpsAdd(liveOps[1], worker->getLiveOpsReadMix() );
+			liveOps[0] = liveSnapshot->ops;
+			liveOps[1] = liveSnapshot->opsReadMix;
 		}
+		else
+			for(const std::unique_ptr<Worker>& worker : manager->workers)
+			{
+				liveOpsAdd(liveOps[0], worker->getLiveOps() );
+				liveOpsAdd(liveOps[1], worker->getLiveOpsReadMix() );
+			}
 
 		std::unique_lock<std::mutex> lock(manager->shared.mutex);
 		numWorkersDoneWithError = manager->shared.numWorkersDoneWithError;
@@ -860,7 +867,15 @@ HttpResponse Service::handleStatus()
 	JsonTree tree;
 	HttpResponse response;
 
-	putCommonStats(tree, false);
+	/* workers on several GPUs: per-GPU partial sums reduced over NVLink by NCCL
+	   (LiveStatsReducer); final results always come from the exact per-worker values */
+	elb_live_snapshot liveSnapshot;
+	const bool useLiveReduce = manager && (manager->getNumGPUs() >= 2);
+
+	if(useLiveReduce)
+		manager->getLiveSnapshot(liveSnapshot);
+
+	putCommonStats(tree, false, useLiveReduce ? &liveSnapshot : NULL);
 
 	liveCpuUtil.update();
 	tree.put("CPUUtil", liveCpuUtil.getCPUUtilPercent() );
@@ -868,6 +883,9 @@ HttpResponse Service::handleStatus()
 		Clock::now() - phaseStartT).count() );
 
 	elb_livelat liveLat = {};
+	if(useLiveReduce)
+		liveLat = liveSnapshot.lat;
+	else
 	if(manager)
 		for(const std::unique_ptr<Worker>& worker : manager->workers)
 			worker->getAndResetLiveLatency(liveLat);

@@ -554,6 +554,8 @@ void Worker::allocRings()
 	if(!cfg.blockSize)
 		return; // nothing to do here (LocalWorker.cpp:1364-1365)
 
+	std::shared_lock<std::shared_timed_mutex> allocLock(shared->gpuAllocMutex);
+
 	// slots are aligned for O_DIRECT; full-size slots make a batch one contiguous staged copy
 	slotStride = ( (cfg.blockSize + ELB_SLOT_ALIGN - 1) / ELB_SLOT_ALIGN) * ELB_SLOT_ALIGN;
 
@@ -669,6 +671,8 @@ void Worker::allocRings()
 
 void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
 {
+	std::shared_lock<std::shared_timed_mutex> allocLock(shared->gpuAllocMutex);
+
 	if(aioInitialized)
 	{
 		syscall(SYS_io_destroy, aioContext);
@@ -1335,6 +1339,8 @@ cudaGraphExec_t Worker::captureBatchGraph(Batch& batch, bool isRead)
 {
 	cudaGraph_t graph = NULL;
 	cudaGraphExec_t graphExec = NULL;
+
+	std::shared_lock<std::shared_timed_mutex> allocLock(shared->gpuAllocMutex);
 
 	ELB_CUDA_CHECK(cudaStreamBeginCapture(batch.stream, cudaStreamCaptureModeThreadLocal),
 		"CUDA stream capture begin");

@@ -29,6 +29,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,6 +63,12 @@ struct Shared
 	size_t numWorkersDoneWithError{0};
 	std::vector<Worker*> workers;
 	std::string firstErrorMsg;
+
+	/* workers hold this shared while they allocate / free device memory or instantiate graphs;
+	   the live stats reducer holds it exclusively while its collective is in flight, because a
+	   device-synchronising call on one GPU in the middle of a multi-GPU NCCL launch of the same
+	   process can deadlock */
+	std::shared_timed_mutex gpuAllocMutex;
 
 	// WorkersSharedData::cpuUtilFirstDone/LastDone (WorkersSharedData.cpp:19-30)
 	CPUUtil cpuUtilFirstDone;
@@ -154,6 +161,7 @@ class Worker
 		elb_liveops getStoneWallOpsReadMix() const { return stoneWallOpsReadMix; }
 		bool getStoneWallTriggered() const { return stoneWallTriggered; }
 		bool getWorkerGotPhaseWork() const { return workerGotPhaseWork; }
+		bool isPhaseFinished() const { return phaseFinished; }
 		uint64_t getElapsedUSec() const { return elapsedUSec; }
 		const elb_histogram& getIOPSLatHisto() const { return iopsLatHisto; }
 		const elb_histogram& getIOPSLatHistoReadMix() const { return iopsLatHistoReadMix; }
@@ -294,11 +302,19 @@ class Worker
 };
 
 /* WorkerManager (reference source/workers/WorkerManager.cpp) */
+class LiveStatsReducer;
+
 class Manager
 {
 	public:
 		explicit Manager(const elb_cfg* abiCfg);
 		~Manager();
+
+		/* sum of the live counters over all workers and GPUs (NCCL reduce for >= 2 GPUs);
+		   consumes the live latency counters */
+		void getLiveSnapshot(elb_live_snapshot& out);
+		std::string getLiveReduceInfo();
+		size_t getNumGPUs() const; // distinct GPUs of the workers
 
 		void startNextPhase(int benchPhase);
 		int waitForWorkersDone(int timeoutMS); // 1 done, 0 timeout, <0 error
@@ -317,6 +333,8 @@ class Manager
 		void prepareFilesForPhase(int benchPhase);
 		void closeBenchPathFDs();
 		bool pathFDsOpenedForWrite{false};
+		std::unique_ptr<LiveStatsReducer> liveStatsReducer; // created on first use
+		std::mutex liveStatsReducerMutex;
 };
 
 } // namespace elb

@@ -11,7 +11,8 @@ import enum
 from typing import List, Optional, Sequence
 
 from . import _native
-from ._native import Cfg, Histogram, LiveLat, LiveOps, PhaseResults, DEVCTR_NUM
+from ._native import (Cfg, Histogram, LiveLat, LiveOps, LiveSnapshot, PhaseResults,
+                      DEVCTR_NUM)
 
 
 class BenchPhase(enum.IntEnum):
@@ -257,6 +258,25 @@ class WorkerManager:
         lat = LiveLat()
         self._lib.elb_mgr_live_latency(self._h, ctypes.byref(lat))
         return {name: getattr(lat, name) for name, _ in LiveLat._fields_}
+
+    def live_snapshot(self):
+        """All live counters at once, summed over the manager's GPUs: per-GPU partial sums
+        (host counters + device-resident kernel counters gathered by a kernel) reduced to the
+        first GPU with one grouped ncclReduce when there are >= 2 GPUs. Consumes the live
+        latency counters (reference: Statistics.cpp:414-470 sums on the host)."""
+        snap = LiveSnapshot()
+        self._lib.elb_mgr_live_snapshot(self._h, ctypes.byref(snap))
+        return {
+            "ops": snap.ops.as_dict(), "ops_readmix": snap.opsReadMix.as_dict(),
+            "lat": {name: getattr(snap.lat, name) for name, _ in LiveLat._fields_},
+            "num_workers_done": snap.numWorkersDone, "num_workers_total": snap.numWorkersTotal,
+            "dev_counters": list(snap.devCounters), "num_gpus": snap.numGPUs,
+            "reduced_with_nccl": bool(snap.reducedWithNccl),
+            "gathered_on_device": bool(snap.gatheredOnDevice),
+        }
+
+    def live_reduce_info(self) -> str:
+        return self._lib.elb_mgr_live_reduce_info(self._h).decode()
 
     def phase_results_raw(self) -> PhaseResults:
         res = PhaseResults()

@@ -268,6 +268,24 @@ typedef struct elb_livelat
 	uint64_t avgEntriesLatReadMixMicrosSecsSum;
 } elb_livelat;
 
+/* Sum of the live counters over all workers and GPUs of a manager. With two or more GPUs the
+ * per-GPU partial sums (host counters staged to the GPU + the device-resident kernel counters of
+ * that GPU's workers) are reduced to the first GPU with one grouped ncclReduce over NVLink; the
+ * reference does this sum on the host (source/Statistics.cpp:414-470, :2728-2804). */
+typedef struct elb_live_snapshot
+{
+	elb_liveops ops;
+	elb_liveops opsReadMix;
+	elb_livelat lat;          /* consumed: add-and-reset like LiveLatency::getAndResetAll */
+	uint64_t numWorkersDone;
+	uint64_t numWorkersTotal;
+	uint64_t devCounters[ELB_DEVCTR_NUM]; /* verify mismatch / verified / filled bytes so far */
+	uint32_t numGPUs;
+	int32_t reducedWithNccl;  /* 1: summed by ncclReduce; 0: single GPU or NCCL unavailable */
+	int32_t gatheredOnDevice; /* 1: device counters read by the gather kernel (no per-worker D2H) */
+	int32_t reserved;
+} elb_live_snapshot;
+
 typedef struct elb_histogram
 {
 	uint64_t buckets[ELB_LATHISTO_NUMBUCKETS];
@@ -372,6 +390,10 @@ int elb_mgr_run_phase(elb_mgr* m, int benchPhase);
  * out[1] = liveOpsReadMix. */
 int elb_mgr_live_ops(elb_mgr* m, elb_liveops out[2]);
 int elb_mgr_live_latency(elb_mgr* m, elb_livelat* out); /* add-and-reset */
+/* all live counters at once, reduced across the manager's GPUs (NCCL for >= 2 GPUs) */
+int elb_mgr_live_snapshot(elb_mgr* m, elb_live_snapshot* out);
+/* one line describing how elb_mgr_live_snapshot reduces ("NCCL 22703, 2 GPUs, root GPU 0") */
+const char* elb_mgr_live_reduce_info(elb_mgr* m);
 
 /* Phase results (valid after wait_done returned 1). */
 int elb_mgr_phase_results(elb_mgr* m, elb_phase_results* out);

@@ -139,6 +139,8 @@ class PhaseResults(ctypes.Structure):
         ("entriesLatHistoReadMix", Histogram),
         ("cpuUtilStoneWallPercent", c_u32),
         ("cpuUtilPercent", c_u32),
+        ("statsReducedWithNccl", c_u32),
+        ("reserved2", c_u32),
     ]
 
 

@@ -477,6 +477,11 @@ int Coordinator::main() // Coordinator.cpp:31-142
 
 		manager.reset(new Manager(&abiConfig.cfg) );
 
+		/* workers on several GPUs: create the NCCL communicators of the statistics reduce now,
+		   while the workers are idle (and before any result output) */
+		if(manager->getNumGPUs() >= 2)
+			manager->getLiveReduceInfo();
+
 		// the normalised values are what results files report (e.g. block size reduced to file size)
 		progArgs.blockSize = manager->shared.cfg.blockSize;
 		progArgs.fileSize = manager->shared.cfg.fileSize;

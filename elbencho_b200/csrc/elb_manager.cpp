@@ -309,6 +309,36 @@ void Manager::getPhaseResults(elb_phase_results& out)
 	uint64_t firstFinishUSec = ~0ULL;
 	uint64_t lastFinishUSec = 0;
 
+	/* workers on several GPUs: histograms and the device counter blocks are merged per GPU and
+	   reduced to the first GPU by NCCL (sum / min / max); everything else is per-thread host
+	   state (elapsed times, stonewall snapshots) and stays a host loop */
+	bool reducedWithNccl = false;
+
+	if(getNumGPUs() >= 2)
+	{
+		elb_histogram histos[4];
+		uint64_t devCounters[ELB_DEVCTR_NUM];
+
+		std::unique_lock<std::mutex> lock(liveStatsReducerMutex);
+
+		if(!liveStatsReducer)
+			liveStatsReducer.reset(new LiveStatsReducer(*this) );
+
+		reducedWithNccl = liveStatsReducer->reducePhaseEnd(histos, devCounters);
+
+		if(reducedWithNccl)
+		{
+			out.iopsLatHisto = histos[0];
+			out.iopsLatHistoReadMix = histos[1];
+			out.entriesLatHisto = histos[2];
+			out.entriesLatHistoReadMix = histos[3];
+			out.verifyMismatchBytes = devCounters[ELB_DEVCTR_VERIFY_MISMATCH_BYTES];
+			out.verifiedBytes = devCounters[ELB_DEVCTR_VERIFIED_BYTES];
+			out.filledBytes = devCounters[ELB_DEVCTR_FILLED_BYTES];
+			out.statsReducedWithNccl = 1;
+		}
+	}
+
 	for(const std::unique_ptr<Worker>& worker : workers)
 	{
 		const uint64_t elapsedUSec = worker->getElapsedUSec();
@@ -323,6 +353,14 @@ void Manager::getPhaseResults(elb_phase_results& out)
 		liveOpsAdd(out.opsReadMixTotal, worker->getLiveOpsReadMix() );
 		liveOpsAdd(out.opsStoneWallTotal, worker->getStoneWallOps() );
 		liveOpsAdd(out.opsStoneWallReadMixTotal, worker->getStoneWallOpsReadMix() );
+		out.numKernelLaunches += worker->getNumKernelLaunches();
+		out.h2dBytes += worker->getNumH2DBytes();
+		out.d2hBytes += worker->getNumD2HBytes();
+		out.devKernelUSec += worker->getDevKernelUSec();
+
+		if(reducedWithNccl)
+			continue;
+
 		histogramMerge(out.iopsLatHisto, worker->getIOPSLatHisto() );
 		histogramMerge(out.entriesLatHisto, worker->getEntriesLatHisto() );
 		histogramMerge(out.iopsLatHistoReadMix, worker->getIOPSLatHistoReadMix() );
@@ -335,11 +373,6 @@ void Manager::getPhaseResults(elb_phase_results& out)
 			out.verifiedBytes += devCounters[ELB_DEVCTR_VERIFIED_BYTES];
 			out.filledBytes += devCounters[ELB_DEVCTR_FILLED_BYTES];
 		}
-
-		out.numKernelLaunches += worker->getNumKernelLaunches();
-		out.h2dBytes += worker->getNumH2DBytes();
-		out.d2hBytes += worker->getNumD2HBytes();
-		out.devKernelUSec += worker->getDevKernelUSec();
 	}
 
 	out.firstFinishUSec = (firstFinishUSec == ~0ULL) ? 0 : firstFinishUSec;

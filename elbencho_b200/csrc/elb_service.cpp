@@ -1129,6 +1129,11 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 
 		manager.reset(new Manager(&abiConfig.cfg) );
 
+		/* workers on several GPUs: create the NCCL communicators of the statistics reduce now,
+		   while the workers are idle (and before any result output) */
+		if(manager->getNumGPUs() >= 2)
+			manager->getLiveReduceInfo();
+
 		// normalised values go back to the master (ProgArgs::getBenchPathInfoTree :3986-3994)
 		args.blockSize = manager->shared.cfg.blockSize;
 		args.fileSize = manager->shared.cfg.fileSize;

@@ -30,6 +30,8 @@ namespace
 const int NCCL_SUCCESS = 0;
 const int NCCL_DATATYPE_UINT64 = 5;
 const int NCCL_REDOP_SUM = 0;
+const int NCCL_REDOP_MAX = 2;
+const int NCCL_REDOP_MIN = 3;
 
 struct NcclApi
 {
@@ -191,6 +193,7 @@ LiveStatsReducer::LiveStatsReducer(Manager& manager) : manager(manager)
 	{
 		const size_t ptrBytes = sizeof(uint64_t*) * gpu.workers.size();
 		const size_t slabBytes = sizeof(uint64_t) * LiveSlot_NUM;
+		const size_t histoBytes = sizeof(uint64_t) * HistoSlot_NUM;
 
 		deviceStateOK = deviceStateOK && (gpu.gpuID >= 0) &&
 			(cudaSetDevice(gpu.gpuID) == cudaSuccess) &&
@@ -203,6 +206,10 @@ LiveStatsReducer::LiveStatsReducer(Manager& manager) : manager(manager)
 			(cudaHostAlloc( (void**)&gpu.hostRecv, slabBytes, cudaHostAllocDefault) ==
 				cudaSuccess) &&
 			(cudaHostAlloc( (void**)&gpu.hostCtrPtrs, ptrBytes, cudaHostAllocDefault) ==
+				cudaSuccess) &&
+			(cudaMalloc( (void**)&gpu.devHistoSend, histoBytes) == cudaSuccess) &&
+			(cudaMalloc( (void**)&gpu.devHistoRecv, histoBytes) == cudaSuccess) &&
+			(cudaHostAlloc( (void**)&gpu.hostHisto, histoBytes, cudaHostAllocDefault) ==
 				cudaSuccess) &&
 			(cudaMemset(gpu.devRecv, 0, slabBytes) == cudaSuccess);
 
@@ -275,10 +282,17 @@ void LiveStatsReducer::releaseDeviceState()
 			cudaFreeHost(gpu.hostRecv);
 		if(gpu.hostCtrPtrs)
 			cudaFreeHost(gpu.hostCtrPtrs);
+		if(gpu.devHistoSend)
+			cudaFree(gpu.devHistoSend);
+		if(gpu.devHistoRecv)
+			cudaFree(gpu.devHistoRecv);
+		if(gpu.hostHisto)
+			cudaFreeHost(gpu.hostHisto);
 
 		gpu.stream = NULL;
 		gpu.devSend = gpu.devRecv = gpu.hostSend = gpu.hostRecv = NULL;
 		gpu.devCtrPtrs = gpu.hostCtrPtrs = NULL;
+		gpu.devHistoSend = gpu.devHistoRecv = gpu.hostHisto = NULL;
 	}
 
 	if(oldDev >= 0)
@@ -474,6 +488,155 @@ bool LiveStatsReducer::snapshotDevice(uint64_t* outSlots, bool& outUsedNccl)
 		cudaSetDevice(oldDev);
 
 	return launchOK;
+}
+
+/* Phase end: per GPU, the host merges the histograms of that GPU's workers into the slab (they
+ * are plain per-thread structures, LatencyHistogram.h), the gather kernel adds the workers'
+ * device counter blocks, then sum / min / max regions are reduced to the first GPU in one group.
+ * Empty histograms carry min = ~0 and max = 0, the neutral elements of ncclMin / ncclMax. */
+bool LiveStatsReducer::reducePhaseEnd(elb_histogram outHistos[4],
+	uint64_t outDevCounters[ELB_DEVCTR_NUM] )
+{
+	std::unique_lock<std::mutex> lock(mutex);
+
+	if(!deviceReady || !ncclReady || ncclBroken)
+		return false;
+
+	const unsigned timeoutMS = 10000;
+	const size_t histoBytes = sizeof(uint64_t) * HistoSlot_NUM;
+	NcclApi& api = ncclApi();
+
+	std::unique_lock<std::shared_timed_mutex> allocLock(manager.shared.gpuAllocMutex);
+
+	int oldDev = -1;
+	cudaGetDevice(&oldDev);
+
+	bool launchOK = true;
+
+	for(PerGPU& gpu : gpus)
+	{
+		elb_histogram merged[HistoSlot_NUMHISTOS];
+
+		for(elb_histogram& histo : merged)
+			histogramReset(histo);
+
+		for(size_t i = 0; i < gpu.workers.size(); i++)
+		{
+			const Worker* worker = gpu.workers[i];
+
+			histogramMerge(merged[0], worker->getIOPSLatHisto() );
+			histogramMerge(merged[1], worker->getIOPSLatHistoReadMix() );
+			histogramMerge(merged[2], worker->getEntriesLatHisto() );
+			histogramMerge(merged[3], worker->getEntriesLatHistoReadMix() );
+
+			gpu.hostCtrPtrs[i] = worker->getDevCountersPtr();
+		}
+
+		memset(gpu.hostHisto, 0, histoBytes);
+
+		for(unsigned histoIdx = 0; histoIdx < HistoSlot_NUMHISTOS; histoIdx++)
+		{
+			uint64_t* words = &gpu.hostHisto[HistoSlot_SUM + histoIdx * HistoSlot_WORDS_PER_HISTO];
+
+			memcpy(words, merged[histoIdx].buckets, sizeof(merged[histoIdx].buckets) );
+			words[ELB_LATHISTO_NUMBUCKETS] = merged[histoIdx].numStoredValues;
+			words[ELB_LATHISTO_NUMBUCKETS + 1] = merged[histoIdx].numMicroSecTotal;
+			gpu.hostHisto[HistoSlot_MIN + histoIdx] = merged[histoIdx].minMicroSecLat;
+			gpu.hostHisto[HistoSlot_MAX + histoIdx] = merged[histoIdx].maxMicroSecLat;
+		}
+
+		launchOK = launchOK && (cudaSetDevice(gpu.gpuID) == cudaSuccess) &&
+			(cudaMemcpyAsync(gpu.devHistoSend, gpu.hostHisto, histoBytes, cudaMemcpyHostToDevice,
+				gpu.stream) == cudaSuccess) &&
+			(cudaMemcpyAsync(gpu.devCtrPtrs, gpu.hostCtrPtrs,
+				sizeof(uint64_t*) * gpu.workers.size(), cudaMemcpyHostToDevice, gpu.stream) ==
+				cudaSuccess);
+
+		if(!launchOK)
+			break;
+
+		elb_stats_gather_kernel<<<1, 32, 0, gpu.stream>>>(gpu.devHistoSend + HistoSlot_DEVCTR,
+			gpu.devCtrPtrs, (uint32_t)gpu.workers.size() );
+
+		launchOK = (cudaGetLastError() == cudaSuccess);
+	}
+
+	if(launchOK)
+	{
+		int ncclRes = api.groupStart();
+
+		for(size_t i = 0; (i < gpus.size() ) && (ncclRes == NCCL_SUCCESS); i++)
+		{
+			PerGPU& gpu = gpus[i];
+
+			cudaSetDevice(gpu.gpuID);
+
+			ncclRes = api.reduce(gpu.devHistoSend + HistoSlot_SUM, gpu.devHistoRecv + HistoSlot_SUM,
+				HistoSlot_MIN - HistoSlot_SUM, NCCL_DATATYPE_UINT64, NCCL_REDOP_SUM, 0, gpu.comm,
+				gpu.stream);
+
+			if(ncclRes == NCCL_SUCCESS)
+				ncclRes = api.reduce(gpu.devHistoSend + HistoSlot_MIN,
+					gpu.devHistoRecv + HistoSlot_MIN, HistoSlot_NUMHISTOS, NCCL_DATATYPE_UINT64,
+					NCCL_REDOP_MIN, 0, gpu.comm, gpu.stream);
+
+			if(ncclRes == NCCL_SUCCESS)
+				ncclRes = api.reduce(gpu.devHistoSend + HistoSlot_MAX,
+					gpu.devHistoRecv + HistoSlot_MAX, HistoSlot_NUMHISTOS, NCCL_DATATYPE_UINT64,
+					NCCL_REDOP_MAX, 0, gpu.comm, gpu.stream);
+		}
+
+		int groupEndRes = api.groupEnd();
+
+		launchOK = (ncclRes == NCCL_SUCCESS) && (groupEndRes == NCCL_SUCCESS);
+
+		if(!launchOK)
+			ncclNote = std::string("ncclReduce (phase end) failed (") + api.getErrorString(
+				(ncclRes != NCCL_SUCCESS) ? ncclRes : groupEndRes) + ")";
+	}
+
+	if(launchOK)
+	{
+		cudaSetDevice(gpus[0].gpuID);
+
+		launchOK = (cudaMemcpyAsync(gpus[0].hostHisto, gpus[0].devHistoRecv, histoBytes,
+			cudaMemcpyDeviceToHost, gpus[0].stream) == cudaSuccess);
+
+		for(PerGPU& gpu : gpus)
+			launchOK = launchOK && waitForStream(gpu.stream, timeoutMS);
+
+		if(!launchOK)
+			ncclNote = "NCCL phase end reduce did not complete in time";
+	}
+
+	if(oldDev >= 0)
+		cudaSetDevice(oldDev);
+
+	if(!launchOK)
+	{
+		ncclBroken = true;
+		std::cerr << "NOTE: " << ncclNote << "; statistics are summed on the host" << std::endl;
+		return false;
+	}
+
+	const uint64_t* result = gpus[0].hostHisto;
+
+	for(unsigned histoIdx = 0; histoIdx < HistoSlot_NUMHISTOS; histoIdx++)
+	{
+		const uint64_t* words = &result[HistoSlot_SUM + histoIdx * HistoSlot_WORDS_PER_HISTO];
+		elb_histogram& histo = outHistos[histoIdx];
+
+		memcpy(histo.buckets, words, sizeof(histo.buckets) );
+		histo.numStoredValues = words[ELB_LATHISTO_NUMBUCKETS];
+		histo.numMicroSecTotal = words[ELB_LATHISTO_NUMBUCKETS + 1];
+		histo.minMicroSecLat = result[HistoSlot_MIN + histoIdx];
+		histo.maxMicroSecLat = result[HistoSlot_MAX + histoIdx];
+	}
+
+	for(unsigned i = 0; i < ELB_DEVCTR_NUM; i++)
+		outDevCounters[i] = result[HistoSlot_DEVCTR + i];
+
+	return true;
 }
 
 /* no usable device state: everything on the host (the live latency counters were possibly

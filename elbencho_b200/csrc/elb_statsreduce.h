@@ -44,6 +44,19 @@ enum LiveSlot
 	LiveSlot_NUM = LiveSlot_DEVCTR + ELB_DEVCTR_NUM,
 };
 
+/* phase-end slab: the 4 latency histograms of a phase (IOPS, IOPS read-mix, entries, entries
+ * read-mix; LatencyHistogram.h:28-45) as three regions, reduced with sum, min and max */
+enum HistoSlot
+{
+	HistoSlot_NUMHISTOS = 4,
+	HistoSlot_WORDS_PER_HISTO = ELB_LATHISTO_NUMBUCKETS + 2, // buckets, numStored, numMicroSecTotal
+	HistoSlot_SUM = 0,
+	HistoSlot_DEVCTR = HistoSlot_SUM + HistoSlot_NUMHISTOS * HistoSlot_WORDS_PER_HISTO,
+	HistoSlot_MIN = HistoSlot_DEVCTR + ELB_DEVCTR_NUM, // end of the sum region
+	HistoSlot_MAX = HistoSlot_MIN + HistoSlot_NUMHISTOS,
+	HistoSlot_NUM = HistoSlot_MAX + HistoSlot_NUMHISTOS,
+};
+
 class LiveStatsReducer
 {
 	public:
@@ -54,7 +67,12 @@ class LiveStatsReducer
 		   (add-and-reset, like LiveLatency::getAndResetAll of the reference) */
 		void snapshot(elb_live_snapshot& out);
 
-		bool usesNccl() const { return ncclReady; }
+		/* phase end (all workers done): merged histograms [iops, iopsReadMix, entries,
+		   entriesReadMix] and the summed device counter blocks, through ncclReduce sum / min / max
+		   (SURVEY.md §8e). @return false if NCCL is not in use (caller merges on the host) */
+		bool reducePhaseEnd(elb_histogram outHistos[4], uint64_t outDevCounters[ELB_DEVCTR_NUM] );
+
+		bool usesNccl() const { return ncclReady && !ncclBroken; }
 		const std::string& getNcclNote() const { return ncclNote; }
 
 	private:
@@ -68,6 +86,9 @@ class LiveStatsReducer
 			uint64_t** devCtrPtrs{NULL};   // device array of the workers' counter block addresses
 			uint64_t* hostSend{NULL};      // pinned, LiveSlot_NUM
 			uint64_t* hostRecv{NULL};      // pinned, LiveSlot_NUM
+			uint64_t* devHistoSend{NULL};  // HistoSlot_NUM
+			uint64_t* devHistoRecv{NULL};  // HistoSlot_NUM
+			uint64_t* hostHisto{NULL};     // pinned, HistoSlot_NUM (send staging; recv on the root)
 			uint64_t** hostCtrPtrs{NULL};  // pinned
 			void* comm{NULL};              // ncclComm_t
 		};

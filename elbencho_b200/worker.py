@@ -311,6 +311,7 @@ class WorkerManager:
             "entries_lat_histo_readmix": histogram_to_dict(res.entriesLatHistoReadMix),
             "cpu_util_stonewall_percent": res.cpuUtilStoneWallPercent,
             "cpu_util_percent": res.cpuUtilPercent,
+            "stats_reduced_with_nccl": bool(res.statsReducedWithNccl),
         }
 
     def expected_totals(self, phase: int):

@@ -327,6 +327,10 @@ typedef struct elb_phase_results
 	 * (CPUUtil.cpp; /proc/stat delta), percent */
 	uint32_t cpuUtilStoneWallPercent;
 	uint32_t cpuUtilPercent;
+	/* 1: workers span >= 2 GPUs and the histograms + device counter blocks above were merged by
+	 * ncclReduce sum / min / max to the first GPU; 0: merged on the host */
+	uint32_t statsReducedWithNccl;
+	uint32_t reserved2;
 } elb_phase_results;
 
 /* ---------------------------------------------------------------------------------------------

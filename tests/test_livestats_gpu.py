@@ -51,6 +51,32 @@ def check_snapshot_equals_workers(mgr, snap):
     assert snap["num_workers_done"] == len(mgr.workers())
 
 
+def merged_worker_histogram(mgr, kind):
+    """LatencyHistogram::operator+= over the workers (LatencyHistogram.h:187-202)"""
+    out = {"buckets": None, "num": 0, "sum_usec": 0, "min_usec": (1 << 64) - 1, "max_usec": 0}
+    for worker in mgr.workers():
+        histo = worker.histogram(kind)
+        out["buckets"] = histo["buckets"] if out["buckets"] is None else \
+            [a + b for a, b in zip(out["buckets"], histo["buckets"])]
+        out["num"] += histo["num"]
+        out["sum_usec"] += histo["sum_usec"]
+        out["min_usec"] = min(out["min_usec"], histo["min_usec"])
+        out["max_usec"] = max(out["max_usec"], histo["max_usec"])
+    return out
+
+
+def check_phase_results_reduced_with_nccl(mgr, res, num_bytes_key, num_bytes):
+    assert res["stats_reduced_with_nccl"]
+    assert res["iops_lat_histo"] == merged_worker_histogram(mgr, 0)
+    assert res["iops_lat_histo_readmix"] == merged_worker_histogram(mgr, 1)
+    assert res["entries_lat_histo"] == merged_worker_histogram(mgr, 2)
+    assert res["entries_lat_histo_readmix"] == merged_worker_histogram(mgr, 3)
+    assert res["iops_lat_histo"]["num"] == res["ops_total"]["iops"] > 0
+    assert res["iops_lat_histo"]["min_usec"] <= res["iops_lat_histo"]["max_usec"]
+    assert res[num_bytes_key] == num_bytes
+    assert res["verify_mismatch_bytes"] == 0
+
+
 def run_with_polling(mgr, phase):
     """start the phase, poll the snapshot from a second thread until done"""
     seen = []
@@ -151,6 +177,8 @@ def test_multi_gpu_snapshot_reduced_with_nccl(workdir, threads_per_gpu):
         assert snap["ops"]["bytes"] == expected_bytes
         assert snap["dev_counters"][DEVCTR_FILLED] == expected_bytes
         assert all(item["reduced_with_nccl"] for item in seen)
+        check_phase_results_reduced_with_nccl(mgr, mgr.phase_results(), "filled_bytes",
+                                              expected_bytes)
         prev = 0
         for item in seen:
             assert prev <= item["ops"]["bytes"] <= expected_bytes
@@ -162,6 +190,8 @@ def test_multi_gpu_snapshot_reduced_with_nccl(workdir, threads_per_gpu):
         assert snap["dev_counters"][DEVCTR_VERIFIED] == expected_bytes
         assert snap["dev_counters"][DEVCTR_MISMATCH] == 0
         assert snap["reduced_with_nccl"]
+        check_phase_results_reduced_with_nccl(mgr, mgr.phase_results(), "verified_bytes",
+                                              expected_bytes)
 
 
 def test_cli_live_line_over_all_gpus(workdir):

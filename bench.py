@@ -406,6 +406,24 @@ def barrier(torch, device):
 # end-to-end measurement through the worker ABI
 # ------------------------------------------------------------------------------------------------
 
+def fit_file_size_to_storage(args, torch, device, rank, world):
+    """world files of --file-gib must fit into --dir (tmpfs pages are RAM): if they do not, all
+    ranks agree on a smaller per-GPU file and the JSON line says so."""
+    args.file_gib_requested = args.file_gib
+    if args.skip_e2e:
+        return
+    os.makedirs(args.dir, exist_ok=True)
+    stat = os.statvfs(args.dir)
+    free_gib = stat.f_bavail * stat.f_frsize / GiB
+    fit = torch.tensor([free_gib], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(fit, op=dist.ReduceOp.MIN)
+    usable_gib = float(fit.item()) * 0.8 / world  # leave room for warm-up and baseline files
+    if args.file_gib > usable_gib:
+        args.file_gib = max(1.0, float(int(usable_gib)))
+
+
 def e2e_level(args, torch, device, rank, world):
     from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
     from elbencho_b200 import distributed as elbdist
@@ -565,6 +583,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
 
+    fit_file_size_to_storage(args, torch, device, rank, world)
+
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
 
     kern = kernel_level(args, torch, device, rank)
@@ -636,7 +656,8 @@ def main():
             "workload": "BASELINE configs[1]: single %.0f GiB file per GPU, %g MiB blocks, seq "
                         "write+read, --gpuids, cudaMemcpyAsync staging, --verify %d" % (
                             args.file_gib, args.block_mib, args.salt),
-            "file_gib": args.file_gib, "block_mib": args.block_mib, "threads_per_gpu": args.threads,
+            "file_gib": args.file_gib, "file_gib_requested": args.file_gib_requested,
+            "block_mib": args.block_mib, "threads_per_gpu": args.threads,
             "window_gib": window / GiB, "step": "K1 fill + K2 verify over the HBM-resident window "
                                                "(2 x window bytes)",
             "l2": "inputs_larger_than_l2 (window %.1f GiB >> 126 MB L2)" % (window / GiB),

@@ -71,7 +71,7 @@ class Cfg(ctypes.Structure):
         ("verifyCollectAll", c_i32),
         ("serializeBufferedWrites", c_i32),
         ("numRWMixReadThreads", c_u32),
-        ("reserved1", c_u32),
+        ("randOffsetAlgo", ctypes.c_int32),
     ]
 
 
@@ -171,6 +171,12 @@ SIGNATURES = {
     "elb_per_sec_from_usec": (c_u64, [c_u64, c_u64]),
     "elb_offset_plan_create": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
                                      ctypes.POINTER(c_u64), c_u64, ctypes.c_int]),
+    "elb_offset_plan_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
+                                          ctypes.c_int, ctypes.POINTER(c_u64), c_u64,
+                                          ctypes.c_int]),
+    "elb_rand_algo_create": (_VP, [ctypes.c_int, ctypes.POINTER(c_u64)]),
+    "elb_rand_algo_next": (c_u64, [_VP]),
+    "elb_rand_algo_destroy": (None, [_VP]),
     "elb_offset_plan_destroy": (None, [_VP]),
     "elb_offset_plan_restart": (None, [_VP]),
     "elb_offset_plan_restart_range": (None, [_VP, c_u64, c_u64]),

@@ -11,6 +11,7 @@
 #include <sstream>
 
 #include "elb_cli.h"
+#include "elb_host.h"
 
 namespace elb
 {
@@ -59,7 +60,8 @@ static const OptDef optDefs[] =
 		"(Default: file size times number of files)"},
 	{"norandalign", 0, Opt_FLAG, "Do not align random offsets to block size."},
 	{"randalgo", 0, Opt_STR, "Random number algorithm for --rand. Giving one disables the full "
-		"coverage generator for random writes. Values: balanced_single (xoshiro256**)"},
+		"coverage generator for random writes. Values: fast, balanced, balanced_single (default), "
+		"strong"},
 	{"randseed", 0, Opt_U64, "Seed for reproducible random offsets (0 = self-seed). [b200]"},
 	{"backward", 0, Opt_FLAG, "Do backwards sequential reads/writes."},
 	{"strided", 0, Opt_FLAG, "Use strided access pattern for files/blockdevs."},
@@ -70,8 +72,8 @@ static const OptDef optDefs[] =
 	{"readinline", 0, Opt_FLAG, "Read each block directly after writing it."},
 	{"blockvarpct", 0, Opt_U64, "Block variance percentage: how much of each written block is "
 		"refilled with random data on the GPU. (Default: 100; forced 0 with --verify)"},
-	{"blockvaralgo", 0, Opt_STR, "Random number algorithm for --blockvarpct. Values: balanced "
-		"(splitmix64, counter based)"},
+	{"blockvaralgo", 0, Opt_STR, "Random number algorithm for --blockvarpct. Values: fast, balanced, "
+		"balanced_single, strong (all map to the counter based GPU generator)"},
 	{"blockvarseed", 0, Opt_U64, "Seed for reproducible block variance data (0 = self-seed). [b200]"},
 	{"rwmixpct", 0, Opt_U64, "Percentage of blocks that should be read in a write phase."},
 	{"rwmixthr", 0, Opt_U64, "Number of threads that should do reads in a write phase."},
@@ -559,13 +561,14 @@ void ProgArgs::checkArgs()
 	if(blockVariancePercent > 100)
 		throw ProgError("Block variance percent must be in range 0..100");
 
-	if(!blockVarianceAlgo.empty() && (blockVarianceAlgo != "balanced") &&
-		(blockVarianceAlgo != "fast") )
-		throw ProgError("Unknown block variance algorithm: " + blockVarianceAlgo);
+	/* names of RandAlgoSelectorTk.h:10-13. The block variance bytes are generated on the GPU by
+	   one counter-based generator whatever the name says, like the reference's GPU refill always
+	   uses cuRAND (LocalWorker.cpp:2236-2277) */
+	if(!blockVarianceAlgo.empty() && (RandAlgo::algoFromString(blockVarianceAlgo) < 0) )
+		throw ProgError("Invalid random algo: " + blockVarianceAlgo); // RandAlgoSelectorTk.cpp:54
 
-	if(!randOffsetAlgo.empty() && (randOffsetAlgo != "balanced_single") &&
-		(randOffsetAlgo != "balanced") && (randOffsetAlgo != "fast") )
-		throw ProgError("Unknown random offset algorithm: " + randOffsetAlgo);
+	if(!randOffsetAlgo.empty() && (RandAlgo::algoFromString(randOffsetAlgo) < 0) )
+		throw ProgError("Invalid random algo: " + randOffsetAlgo);
 
 	if(!runCreateDirsPhase && !runCreateFilesPhase && !runReadPhase && !runStatFilesPhase &&
 		!runDeleteFilesPhase && !runDeleteDirsPhase && !runSyncPhase && !runDropCachesPhase &&
@@ -627,6 +630,8 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	cfg.randOffsetAlgo = randOffsetAlgo.empty() ?
+		ELB_OFFSETALGO_XOSHIRO256SS : RandAlgo::algoFromString(randOffsetAlgo);
 }
 
 std::string ProgArgs::helpText()

@@ -74,6 +74,7 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.useStridedAccess = cfg->useStridedAccess;
 	c.randomAmount = cfg->randomAmount;
 	c.randOffsetSeed = cfg->randOffsetSeed;
+	c.randOffsetAlgo = cfg->randOffsetAlgo;
 	c.integrityCheckSalt = cfg->integrityCheckSalt;
 	c.doDirectVerify = cfg->doDirectVerify;
 	c.doReadInline = cfg->doReadInline;
@@ -114,6 +115,9 @@ Config Config::fromABI(const elb_cfg* cfg)
 
 	if(c.rwMixReadPercent > 100)
 		throw WorkerError("RWMix read percent must be in range 0..100.");
+
+	if( (c.randOffsetAlgo < ELB_OFFSETALGO_XOSHIRO256SS) || (c.randOffsetAlgo > ELB_OFFSETALGO_MT19937) )
+		throw WorkerError("Invalid random offset algorithm: " + std::to_string(c.randOffsetAlgo) );
 
 	if(c.blockVarianceAlgo != ELB_RANDALGO_SPLITMIX64)
 		throw WorkerError("Unknown block variance algorithm: " +

@@ -43,11 +43,32 @@ class WorkerInterrupted : public std::runtime_error
 			std::runtime_error("Received friendly request to interrupt execution.") {}
 };
 
-/* ---- PRNG for random offsets: xoshiro256** (toolkits/random/RandAlgoXoshiro256ss.h:76-91),
+/* ---- PRNGs for random offsets (--randalgo; toolkits/random/RandAlgoInterface.h:14-32,
+ * RandAlgoSelectorTk.cpp:17-53). Only next() is on the GPU worker's path: block contents are
+ * generated on the GPU. ---- */
+class RandAlgo
+{
+	public:
+		virtual ~RandAlgo() {}
+		virtual uint64_t next() = 0;
+
+		/* value in [minVal, maxVal] by plain modulo like RandAlgoRange.h:50-54 */
+		uint64_t nextInRange(uint64_t minVal, uint64_t maxVal)
+		{
+			return minVal + (next() % (maxVal - minVal + 1) );
+		}
+
+		/* @state injected state words (NULL = self-seed from std::random_device like the
+		 *    reference): xoshiro variants take 4 words, golden prime and mt19937 take word 0 */
+		static std::unique_ptr<RandAlgo> create(int algo, const uint64_t state[4]);
+		static int algoFromString(const std::string& algoString); // -1 if unknown
+};
+
+/* ---- xoshiro256** (toolkits/random/RandAlgoXoshiro256ss.h:76-91),
  * the reference's default "balanced_single" offset algorithm (LocalWorker.cpp:1135-1136).
  * Seeded either from std::random_device like the reference (:22-29) or from an injected 64-bit
  * seed expanded through splitmix64 (for reproducible runs/tests). ---- */
-class Xoshiro256ss
+class Xoshiro256ss : public RandAlgo
 {
 	public:
 		Xoshiro256ss()
@@ -84,7 +105,7 @@ class Xoshiro256ss
 			}
 		}
 
-		uint64_t next()
+		uint64_t next() override
 		{
 			const uint64_t result = rotl(state[1] * 5, 7) * 9;
 			const uint64_t shifted = state[1] << 17;
@@ -99,12 +120,6 @@ class Xoshiro256ss
 			return result;
 		}
 
-		/* value in [minVal, maxVal] by plain modulo like RandAlgoRange.h:50-54 */
-		uint64_t nextInRange(uint64_t minVal, uint64_t maxVal)
-		{
-			return minVal + (next() % (maxVal - minVal + 1) );
-		}
-
 		const uint64_t* getState() const { return state; }
 
 	private:
@@ -112,6 +127,126 @@ class Xoshiro256ss
 
 		static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k) ); }
 };
+
+/* "fast": multiply by one of four golden primes and drop 3 bits
+ * (RandAlgoGoldenPrime.h:16-17, 37-42, 128-134). The reference reseeds this generator from a
+ * xoshiro256** only inside fillBuf() (:60-84); the offset generators call next() only, so the
+ * stream is a pure function of the start state. */
+class GoldenPrimeRand : public RandAlgo
+{
+	public:
+		GoldenPrimeRand()
+		{
+			Xoshiro256ss seeder;
+			init(seeder.next() );
+		}
+
+		explicit GoldenPrimeRand(uint64_t seed) { init(seed); }
+
+		uint64_t next() override
+		{
+			static const uint64_t primes[4] = { 0x9e37fffffffc0001ULL, 0x9e3779b97f4a7c15ULL,
+				0xbf58476d1ce4e5b9ULL, 0x94d049bb133111ebULL };
+
+			state *= primes[primeIdx];
+			state >>= 3;
+
+			return state;
+		}
+
+	private:
+		uint64_t state;
+		unsigned primeIdx;
+
+		void init(uint64_t seed)
+		{
+			state = seed;
+			primeIdx = (unsigned)(seed % 4);
+		}
+};
+
+/* "balanced": one lane of xoshiro256++ (RandAlgoXoshiro256ppSIMD.h:100-135 with Nway 1 on lane 0,
+ * which is what next() of the 4-way SIMD class advances) */
+class Xoshiro256pp : public RandAlgo
+{
+	public:
+		Xoshiro256pp()
+		{
+			std::random_device randDev;
+			for(uint64_t& word : state)
+				word = ( (uint64_t)randDev() << 32) | (uint32_t)randDev();
+		}
+
+		explicit Xoshiro256pp(const uint64_t initState[4])
+		{
+			std::memcpy(state, initState, sizeof(state) );
+		}
+
+		uint64_t next() override
+		{
+			const uint64_t sum = state[0] + state[3];
+			const uint64_t result = ( (sum << 23) | (sum >> 41) ) + state[0];
+			const uint64_t shifted = state[1] << 17;
+
+			state[2] ^= state[0];
+			state[3] ^= state[1];
+			state[1] ^= state[2];
+			state[0] ^= state[3];
+			state[2] ^= shifted;
+			state[3] = (state[3] << 45) | (state[3] >> 19);
+
+			return result;
+		}
+
+	private:
+		uint64_t state[4];
+};
+
+/* "strong": 64-bit Mersenne Twister of the standard library (RandAlgoMT19937.h:22, 62-65) */
+class MT19937Rand : public RandAlgo
+{
+	public:
+		MT19937Rand() : randGen(std::random_device()() ) {}
+		explicit MT19937Rand(uint64_t seed) : randGen(seed) {}
+
+		uint64_t next() override { return randGen(); }
+
+	private:
+		std::mt19937_64 randGen;
+};
+
+inline std::unique_ptr<RandAlgo> RandAlgo::create(int algo, const uint64_t state[4])
+{
+	switch(algo)
+	{
+		case ELB_OFFSETALGO_XOSHIRO256SS:
+			return std::unique_ptr<RandAlgo>(state ? new Xoshiro256ss(state) : new Xoshiro256ss() );
+		case ELB_OFFSETALGO_GOLDENPRIME:
+			return std::unique_ptr<RandAlgo>(
+				state ? new GoldenPrimeRand(state[0] ) : new GoldenPrimeRand() );
+		case ELB_OFFSETALGO_XOSHIRO256PP:
+			return std::unique_ptr<RandAlgo>(state ? new Xoshiro256pp(state) : new Xoshiro256pp() );
+		case ELB_OFFSETALGO_MT19937:
+			return std::unique_ptr<RandAlgo>(state ? new MT19937Rand(state[0] ) : new MT19937Rand() );
+		default:
+			throw WorkerError("Invalid random offset algorithm: " + std::to_string(algo) );
+	}
+}
+
+/* names of RandAlgoSelectorTk.h:10-13 */
+inline int RandAlgo::algoFromString(const std::string& algoString)
+{
+	if(algoString == "balanced_single")
+		return ELB_OFFSETALGO_XOSHIRO256SS;
+	if(algoString == "fast")
+		return ELB_OFFSETALGO_GOLDENPRIME;
+	if(algoString == "balanced")
+		return ELB_OFFSETALGO_XOSHIRO256PP;
+	if(algoString == "strong")
+		return ELB_OFFSETALGO_MT19937;
+
+	return -1;
+}
 
 /* ---- Offset plans (toolkits/offsetgen/OffsetGenerator.h, OffsetGenRandomAlignedFullCoverageV2.h)
  *
@@ -138,7 +273,7 @@ class OffsetPlan
 		 *    (the reference uses std::random_device for every cycle, FullCoverageV2.h:93,158).
 		 */
 		OffsetPlan(Kind kind, uint64_t amount, uint64_t rangeLen, uint64_t rangeOffset,
-			uint64_t blockSize, uint64_t numDataSetThreads, Xoshiro256ss* randAlgo,
+			uint64_t blockSize, uint64_t numDataSetThreads, RandAlgo* randAlgo,
 			uint64_t lcgSeed, bool haveLCGSeed) :
 			kind(kind), blockSize(blockSize), numDataSetThreads(numDataSetThreads),
 			randAlgo(randAlgo), lcgSeedState(lcgSeed), haveLCGSeed(haveLCGSeed)
@@ -241,7 +376,7 @@ class OffsetPlan
 		const Kind kind;
 		const uint64_t blockSize;
 		const uint64_t numDataSetThreads;
-		Xoshiro256ss* randAlgo;
+		RandAlgo* randAlgo;
 
 		uint64_t numBytesTotal{0};
 		uint64_t numBytesLeft{0};
@@ -506,6 +641,7 @@ struct Config
 	bool useStridedAccess{false};
 	uint64_t randomAmount{0};
 	uint64_t randOffsetSeed{0};
+	int randOffsetAlgo{ELB_OFFSETALGO_XOSHIRO256SS};
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

@@ -540,12 +540,44 @@ uint32_t elb_phase_results_struct_size(void)
 
 struct elb_offset_plan_impl
 {
-	std::unique_ptr<elb::Xoshiro256ss> randAlgo;
+	std::unique_ptr<elb::RandAlgo> randAlgo;
 	std::unique_ptr<elb::OffsetPlan> plan;
 };
 
+elb_rand_algo_handle* elb_rand_algo_create(int randAlgo, const uint64_t state[4])
+{
+	try
+	{
+		return reinterpret_cast<elb_rand_algo_handle*>(
+			elb::RandAlgo::create(randAlgo, state).release() );
+	}
+	catch(const std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return NULL;
+	}
+}
+
+uint64_t elb_rand_algo_next(elb_rand_algo_handle* algo)
+{
+	return reinterpret_cast<elb::RandAlgo*>(algo)->next();
+}
+
+void elb_rand_algo_destroy(elb_rand_algo_handle* algo)
+{
+	delete reinterpret_cast<elb::RandAlgo*>(algo);
+}
+
 elb_offset_plan* elb_offset_plan_create(int kind, uint64_t amount, uint64_t rangeLen,
 	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads,
+	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed)
+{
+	return elb_offset_plan_create_algo(kind, amount, rangeLen, rangeOffset, blockSize,
+		numDataSetThreads, ELB_OFFSETALGO_XOSHIRO256SS, randState, lcgSeed, haveLCGSeed);
+}
+
+elb_offset_plan* elb_offset_plan_create_algo(int kind, uint64_t amount, uint64_t rangeLen,
+	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads, int randAlgo,
 	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed)
 {
 	if( (kind < elb::OffsetPlan::Kind_SEQUENTIAL) || (kind > elb::OffsetPlan::Kind_FULL_COVERAGE) )
@@ -554,12 +586,21 @@ elb_offset_plan* elb_offset_plan_create(int kind, uint64_t amount, uint64_t rang
 		return NULL;
 	}
 
+	std::unique_ptr<elb::RandAlgo> algoObj;
+
+	try
+	{
+		algoObj = elb::RandAlgo::create(randAlgo, randState);
+	}
+	catch(const std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return NULL;
+	}
+
 	elb_offset_plan_impl* impl = new elb_offset_plan_impl();
 
-	if(randState)
-		impl->randAlgo.reset(new elb::Xoshiro256ss(randState) );
-	else
-		impl->randAlgo.reset(new elb::Xoshiro256ss() );
+	impl->randAlgo = std::move(algoObj);
 
 	impl->plan.reset(new elb::OffsetPlan( (elb::OffsetPlan::Kind)kind, amount, rangeLen,
 		rangeOffset, blockSize, numDataSetThreads, impl->randAlgo.get(), lcgSeed,

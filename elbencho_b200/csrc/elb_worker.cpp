@@ -534,9 +534,13 @@ void Worker::preparePhase()
 
 	// injected seeds make runs reproducible; 0 = self-seed like the reference
 	if(cfg.randOffsetSeed)
-		randOffsetAlgo.reset(new Xoshiro256ss(Xoshiro256ss::fromSeed(cfg.randOffsetSeed, rank) ) );
+	{
+		uint64_t expanded[4];
+		Xoshiro256ss::expandSeed(cfg.randOffsetSeed, rank, expanded);
+		randOffsetAlgo = RandAlgo::create(cfg.randOffsetAlgo, expanded);
+	}
 	else
-		randOffsetAlgo.reset(new Xoshiro256ss() );
+		randOffsetAlgo = RandAlgo::create(cfg.randOffsetAlgo, NULL);
 
 	if(cfg.blockVarianceSeed)
 		blockVarianceSeed = cfg.blockVarianceSeed;
@@ -806,7 +810,7 @@ void Worker::initPhaseOffsetPlan()
 		lcgSeed = expanded[0] ^ expanded[1];
 
 		// every phase restarts the offset stream from the injected seed
-		randOffsetAlgo.reset(new Xoshiro256ss(expanded) );
+		randOffsetAlgo = RandAlgo::create(cfg.randOffsetAlgo, expanded);
 	}
 
 	OffsetPlan::Kind kind;

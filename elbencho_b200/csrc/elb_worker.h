@@ -221,7 +221,7 @@ class Worker
 		bool gpuPrepared{false};
 
 		// offsets
-		std::unique_ptr<Xoshiro256ss> randOffsetAlgo;
+		std::unique_ptr<RandAlgo> randOffsetAlgo; // --randalgo
 		std::unique_ptr<OffsetPlan> offsetPlan;
 		uint64_t blockVarianceSeed{0};
 

@@ -40,6 +40,14 @@ class IOEngine(enum.IntEnum):
     AIO = 2
 
 
+class OffsetRandAlgo(enum.IntEnum):
+    """--randalgo (RandAlgoSelectorTk.h:10-25)"""
+    BALANCED_SINGLE = 0  # xoshiro256**, the default
+    FAST = 1             # golden prime
+    BALANCED = 2         # xoshiro256++ (lane 0 of the reference's SIMD class)
+    STRONG = 3           # mt19937_64
+
+
 class WorkerError(RuntimeError):
     """Text of the reference's WorkerException for the failed worker."""
 
@@ -70,6 +78,7 @@ class WorkerConfig:
     use_strided_access: bool = False  # --strided
     random_amount: int = 0            # --randamount
     rand_offset_seed: int = 0         # injected seed (0 = self-seed like the reference)
+    rand_offset_algo: int = 0         # --randalgo (OffsetRandAlgo)
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -137,6 +146,7 @@ class WorkerConfig:
         cfg.verifyCollectAll = int(self.verify_collect_all)
         cfg.serializeBufferedWrites = int(self.serialize_buffered_writes)
         cfg.numRWMixReadThreads = self.num_rwmix_read_threads
+        cfg.randOffsetAlgo = int(self.rand_offset_algo)
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

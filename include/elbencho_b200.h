@@ -70,6 +70,16 @@ enum elb_rand_algo
 	ELB_RANDALGO_SPLITMIX64 = 0, /* splitmix64 of (seed, block counter, word index); uniform u64 */
 };
 
+/* Generators of random offsets for --rand (--randalgo; toolkits/random/RandAlgoSelectorTk.h:10-25).
+ * All four streams are bit-identical to the reference's classes for the same injected state. */
+enum elb_offset_rand_algo
+{
+	ELB_OFFSETALGO_XOSHIRO256SS = 0, /* "balanced_single", the default (LocalWorker.cpp:1135-1136) */
+	ELB_OFFSETALGO_GOLDENPRIME = 1,  /* "fast" */
+	ELB_OFFSETALGO_XOSHIRO256PP = 2, /* "balanced": lane 0 of the reference's 4-way SIMD class */
+	ELB_OFFSETALGO_MT19937 = 3,      /* "strong": std::mt19937_64 */
+};
+
 /* Histogram kinds for elb_worker_histogram (Worker.h:55-58) */
 enum elb_histo_kind
 {
@@ -242,7 +252,7 @@ typedef struct elb_cfg
 	/* --rwmixthr: the first N local workers read (their share of the data set) during the write
 	 * phase; their stats go to the ReadMix counters (LocalWorker.cpp:1028-1041) */
 	uint32_t numRWMixReadThreads;
-	uint32_t reserved1;
+	int32_t randOffsetAlgo; /* enum elb_offset_rand_algo (--randalgo) */
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------
@@ -360,6 +370,17 @@ typedef struct elb_offset_plan elb_offset_plan;
 elb_offset_plan* elb_offset_plan_create(int kind, uint64_t amount, uint64_t rangeLen,
 	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads,
 	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed);
+/* same with an explicit generator (enum elb_offset_rand_algo); randState: 4 words for the
+ * xoshiro variants, word 0 = seed for golden prime and mt19937 (NULL = self-seed) */
+elb_offset_plan* elb_offset_plan_create_algo(int kind, uint64_t amount, uint64_t rangeLen,
+	uint64_t rangeOffset, uint64_t blockSize, uint64_t numDataSetThreads, int randAlgo,
+	const uint64_t randState[4], uint64_t lcgSeed, int haveLCGSeed);
+
+/* The offset PRNGs on their own (RandAlgoInterface::next, toolkits/random/RandAlgoInterface.h:27) */
+typedef struct elb_rand_algo_handle elb_rand_algo_handle;
+elb_rand_algo_handle* elb_rand_algo_create(int randAlgo, const uint64_t state[4]);
+uint64_t elb_rand_algo_next(elb_rand_algo_handle* algo);
+void elb_rand_algo_destroy(elb_rand_algo_handle* algo);
 void elb_offset_plan_destroy(elb_offset_plan* plan);
 void elb_offset_plan_restart(elb_offset_plan* plan); /* reset() */
 void elb_offset_plan_restart_range(elb_offset_plan* plan, uint64_t rangeLen,

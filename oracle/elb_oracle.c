@@ -338,6 +338,125 @@ void orc_fill_random_ctr(char* buf, uint64_t bufLen, unsigned pct, uint64_t seed
  * Offset generators (toolkits/offsetgen/OffsetGenerator.h, OffsetGenRandomAlignedFullCoverageV2.h)
  * ========================================================================================== */
 
+/* ---- xoshiro256++, one lane (RandAlgoXoshiro256ppSIMD.h:100-135 with NwayInternal 1) ---- */
+uint64_t orc_xoshiro256pp_next(orc_xoshiro256pp* st)
+{
+	const uint64_t x = st->s[0] + st->s[3];
+	const uint64_t result = ( (x << 23) | (x >> 41) ) + st->s[0];
+	const uint64_t t = st->s[1] << 17;
+
+	st->s[2] ^= st->s[0];
+	st->s[3] ^= st->s[1];
+	st->s[1] ^= st->s[2];
+	st->s[0] ^= st->s[3];
+	st->s[2] ^= t;
+	st->s[3] = (st->s[3] << 45) | (st->s[3] >> 19);
+
+	return result;
+}
+
+/* ---- std::mt19937_64 as the C++ standard defines it ([rand.predef]: w 64, n 312, m 156, r 31,
+ * a 0xb5026f5aa96619e9, u 29, d 0x5555555555555555, s 17, b 0x71d67fffeda60000, t 37,
+ * c 0xfff7eee000000000, l 43, f 6364136223846793005), what RandAlgoMT19937.h:22 instantiates ---- */
+void orc_mt19937_64_seed(orc_mt19937_64* st, uint64_t seed)
+{
+	st->mt[0] = seed;
+
+	for(unsigned i = 1; i < 312; i++)
+		st->mt[i] = 6364136223846793005ULL * (st->mt[i - 1] ^ (st->mt[i - 1] >> 62) ) + i;
+
+	st->idx = 312;
+}
+
+uint64_t orc_mt19937_64_next(orc_mt19937_64* st)
+{
+	if(st->idx >= 312)
+	{ // regenerate the whole state block
+		const uint64_t upperMask = 0xFFFFFFFF80000000ULL; // upper w-r bits
+		const uint64_t lowerMask = 0x000000007FFFFFFFULL; // lower r bits
+
+		for(unsigned i = 0; i < 312; i++)
+		{
+			const uint64_t y = (st->mt[i] & upperMask) | (st->mt[ (i + 1) % 312] & lowerMask);
+			uint64_t next = st->mt[ (i + 156) % 312] ^ (y >> 1);
+
+			if(y & 1)
+				next ^= 0xB5026F5AA96619E9ULL;
+
+			st->mt[i] = next;
+		}
+
+		st->idx = 0;
+	}
+
+	uint64_t z = st->mt[st->idx++];
+
+	z ^= (z >> 29) & 0x5555555555555555ULL;
+	z ^= (z << 17) & 0x71D67FFFEDA60000ULL;
+	z ^= (z << 37) & 0xFFF7EEE000000000ULL;
+	z ^= (z >> 43);
+
+	return z;
+}
+
+/* ---- RandAlgoSelectorTk::stringToAlgo (RandAlgoSelectorTk.cpp:37-53) with injected state ---- */
+int orc_randalgo_init(orc_randalgo* st, int algo, const uint64_t state[4])
+{
+	static const uint64_t zeroState[4] = {0, 0, 0, 0};
+
+	if(!state)
+		state = zeroState;
+
+	st->algo = algo;
+
+	switch(algo)
+	{
+		case ELB_OFFSETALGO_XOSHIRO256SS:
+			memcpy(st->u.xoshiroSS.s, state, sizeof(st->u.xoshiroSS.s) );
+			return 0;
+		case ELB_OFFSETALGO_GOLDENPRIME:
+			orc_goldenprime_init(&st->u.goldenPrime, state[0], state);
+			return 0;
+		case ELB_OFFSETALGO_XOSHIRO256PP:
+			memcpy(st->u.xoshiroPP.s, state, sizeof(st->u.xoshiroPP.s) );
+			return 0;
+		case ELB_OFFSETALGO_MT19937:
+			orc_mt19937_64_seed(&st->u.mt, state[0] );
+			return 0;
+		default:
+			return -1;
+	}
+}
+
+uint64_t orc_randalgo_next(orc_randalgo* st)
+{
+	switch(st->algo)
+	{
+		case ELB_OFFSETALGO_GOLDENPRIME: return orc_goldenprime_next(&st->u.goldenPrime);
+		case ELB_OFFSETALGO_XOSHIRO256PP: return orc_xoshiro256pp_next(&st->u.xoshiroPP);
+		case ELB_OFFSETALGO_MT19937: return orc_mt19937_64_next(&st->u.mt);
+		default: return orc_xoshiro256ss_next(&st->u.xoshiroSS);
+	}
+}
+
+orc_randalgo* orc_randalgo_create(int algo, const uint64_t state[4])
+{
+	orc_randalgo* st = (orc_randalgo*)calloc(1, sizeof(*st) );
+
+	if(st && orc_randalgo_init(st, algo, state) )
+	{
+		free(st);
+		return NULL;
+	}
+
+	return st;
+}
+
+void orc_randalgo_destroy(orc_randalgo* st)
+{
+	free(st);
+}
+
 struct orc_offsetgen
 {
 	int kind;
@@ -348,7 +467,7 @@ struct orc_offsetgen
 	uint64_t blockSize;
 	uint64_t numDataSetThreads; // strided
 	// RandAlgoRange (toolkits/random/RandAlgoRange.h:14-56)
-	orc_xoshiro256ss rand;
+	orc_randalgo rand;
 	uint64_t rangeStart;
 	uint64_t rangeLengthPlusOne;
 	// CoveringRandomGenerator (OffsetGenRandomAlignedFullCoverageV2.h:9-203)
@@ -358,7 +477,7 @@ struct orc_offsetgen
 
 static uint64_t orc_range_next(orc_offsetgen* g) // RandAlgoRange.h:50-54
 {
-	return (orc_xoshiro256ss_next(&g->rand) % g->rangeLengthPlusOne) + g->rangeStart;
+	return (orc_randalgo_next(&g->rand) % g->rangeLengthPlusOne) + g->rangeStart;
 }
 
 static void orc_range_reset(orc_offsetgen* g, uint64_t min, uint64_t max) // RandAlgoRange.h:40-48
@@ -519,6 +638,14 @@ orc_offsetgen* orc_offsetgen_create(int kind, uint64_t numBytesTotal, uint64_t l
 	uint64_t offset, uint64_t blockSize, uint64_t numDataSetThreads,
 	const uint64_t randState[4], uint64_t lcgSeed)
 {
+	return orc_offsetgen_create_algo(kind, numBytesTotal, len, offset, blockSize,
+		numDataSetThreads, ELB_OFFSETALGO_XOSHIRO256SS, randState, lcgSeed);
+}
+
+orc_offsetgen* orc_offsetgen_create_algo(int kind, uint64_t numBytesTotal, uint64_t len,
+	uint64_t offset, uint64_t blockSize, uint64_t numDataSetThreads, int randAlgo,
+	const uint64_t randState[4], uint64_t lcgSeed)
+{
 	orc_offsetgen* g = (orc_offsetgen*)calloc(1, sizeof(*g) );
 	if(!g)
 		return NULL;
@@ -528,8 +655,11 @@ orc_offsetgen* orc_offsetgen_create(int kind, uint64_t numBytesTotal, uint64_t l
 	g->numDataSetThreads = numDataSetThreads;
 	g->covNextSeed = lcgSeed;
 
-	if(randState)
-		memcpy(g->rand.s, randState, sizeof(g->rand.s) );
+	if(orc_randalgo_init(&g->rand, randAlgo, randState) )
+	{
+		free(g);
+		return NULL;
+	}
 
 	switch(kind)
 	{
@@ -1038,12 +1168,13 @@ static void orc_init_offset_gen(orc_worker* w, int isWritePhase)
 				blockSize * w->rank, blockSize, numDataSetThreads, randState, lcgSeed);
 		else
 		if(cfg->useRandomUnaligned)
-			w->offsetGen = orc_offsetgen_create(ORC_OFFGEN_RANDOM, randomAmount, rangeLen,
-				rangeOffset, blockSize, numDataSetThreads, randState, lcgSeed);
+			w->offsetGen = orc_offsetgen_create_algo(ORC_OFFGEN_RANDOM, randomAmount, rangeLen,
+				rangeOffset, blockSize, numDataSetThreads, cfg->randOffsetAlgo, randState, lcgSeed);
 		else
 		if(cfg->useExplicitRandOffsetAlgo || !isWritePhase)
-			w->offsetGen = orc_offsetgen_create(ORC_OFFGEN_RANDOM_ALIGNED, randomAmount, rangeLen,
-				rangeOffset, blockSize, numDataSetThreads, randState, lcgSeed);
+			w->offsetGen = orc_offsetgen_create_algo(ORC_OFFGEN_RANDOM_ALIGNED, randomAmount,
+				rangeLen, rangeOffset, blockSize, numDataSetThreads, cfg->randOffsetAlgo, randState,
+				lcgSeed);
 		else
 			w->offsetGen = orc_offsetgen_create(ORC_OFFGEN_RANDOM_ALIGNED_FULLCOV, randomAmount,
 				rangeLen, rangeOffset, blockSize, numDataSetThreads, randState, lcgSeed);

@@ -66,12 +66,42 @@ enum orc_offsetgen_kind
 	ORC_OFFGEN_RANDOM_ALIGNED_FULLCOV = 5,
 };
 
+/* ---- the four --randalgo generators behind one next() (RandAlgoSelectorTk.cpp:37-53);
+ * algo values = enum elb_offset_rand_algo. state: 4 words for the xoshiro variants, word 0 = seed
+ * for golden prime (its seeder is never consulted by next() ) and for mt19937_64. ---- */
+typedef struct orc_xoshiro256pp { uint64_t s[4]; } orc_xoshiro256pp; /* lane 0 of the SIMD class */
+uint64_t orc_xoshiro256pp_next(orc_xoshiro256pp* st);
+
+typedef struct orc_mt19937_64 { uint64_t mt[312]; unsigned idx; } orc_mt19937_64;
+void orc_mt19937_64_seed(orc_mt19937_64* st, uint64_t seed);
+uint64_t orc_mt19937_64_next(orc_mt19937_64* st);
+
+typedef struct orc_randalgo
+{
+	int algo;
+	union
+	{
+		orc_xoshiro256ss xoshiroSS;
+		orc_goldenprime goldenPrime;
+		orc_xoshiro256pp xoshiroPP;
+		orc_mt19937_64 mt;
+	} u;
+} orc_randalgo;
+
+int orc_randalgo_init(orc_randalgo* st, int algo, const uint64_t state[4]); /* 0 ok, -1 bad algo */
+uint64_t orc_randalgo_next(orc_randalgo* st);
+orc_randalgo* orc_randalgo_create(int algo, const uint64_t state[4]); /* heap, for ctypes */
+void orc_randalgo_destroy(orc_randalgo* st);
+
 typedef struct orc_offsetgen orc_offsetgen;
 
 /* randState: xoshiro256** state for RANDOM/RANDOM_ALIGNED; lcgSeed: initial LCG state for FULLCOV
  * (the reference takes both from std::random_device) */
 orc_offsetgen* orc_offsetgen_create(int kind, uint64_t numBytesTotal, uint64_t len,
 	uint64_t offset, uint64_t blockSize, uint64_t numDataSetThreads,
+	const uint64_t randState[4], uint64_t lcgSeed);
+orc_offsetgen* orc_offsetgen_create_algo(int kind, uint64_t numBytesTotal, uint64_t len,
+	uint64_t offset, uint64_t blockSize, uint64_t numDataSetThreads, int randAlgo,
 	const uint64_t randState[4], uint64_t lcgSeed);
 void orc_offsetgen_destroy(orc_offsetgen* g);
 void orc_offsetgen_reset(orc_offsetgen* g);

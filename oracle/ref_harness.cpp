@@ -44,6 +44,38 @@ void* ref_goldenprime_create(uint64_t seed, const uint64_t seederState[4])
 	return algo;
 }
 
+/* algo values = enum elb_offset_rand_algo; the object is what RandAlgoSelectorTk::stringToAlgo
+ * returns for "balanced_single" / "fast" / "balanced" / "strong", with an injected state */
+void* ref_randalgo_create(int algoType, const uint64_t state[4])
+{
+	switch(algoType)
+	{
+		case 0:
+			return ref_xoshiro256ss_create(state);
+
+		case 1:
+			return ref_goldenprime_create(state[0], state);
+
+		case 2:
+		{ // (the selector instantiates the default template argument, RandAlgoSelectorTk.cpp:49)
+			RandAlgoXoshiro256ppSIMD<>* algo = new RandAlgoXoshiro256ppSIMD<>();
+			for(int i = 0; i < 4; i++)
+				algo->state.s[i][0] = state[i]; // next() advances lane 0 only
+			return algo;
+		}
+
+		case 3:
+		{
+			RandAlgoMT19937* algo = new RandAlgoMT19937();
+			algo->randGen.seed(state[0] );
+			return algo;
+		}
+
+		default:
+			return NULL;
+	}
+}
+
 uint64_t ref_randalgo_next(void* algo)
 {
 	return ( (RandAlgoInterface*)algo)->next();
@@ -63,20 +95,38 @@ void ref_randalgo_destroy(void* algo)
 
 struct RefOffsetGen
 {
-	std::unique_ptr<RandAlgoXoshiro256ss> randAlgo;
+	std::unique_ptr<RandAlgoInterface> randAlgo;
 	std::unique_ptr<OffsetGenerator> gen;
 };
+
+void* ref_offsetgen_create_algo(int kind, uint64_t numBytesTotal, uint64_t len, uint64_t offset,
+	uint64_t blockSize, uint64_t numDataSetThreads, int algoType, const uint64_t randState[4],
+	uint64_t lcgState);
 
 /* kind values = enum orc_offsetgen_kind of oracle/elb_oracle.h */
 void* ref_offsetgen_create(int kind, uint64_t numBytesTotal, uint64_t len, uint64_t offset,
 	uint64_t blockSize, uint64_t numDataSetThreads, const uint64_t randState[4],
 	uint64_t lcgState)
 {
-	RefOffsetGen* ref = new RefOffsetGen();
-	ref->randAlgo.reset(new RandAlgoXoshiro256ss() );
+	return ref_offsetgen_create_algo(kind, numBytesTotal, len, offset, blockSize,
+		numDataSetThreads, 0, randState, lcgState);
+}
 
-	if(randState)
-		memcpy(ref->randAlgo->state.s, randState, sizeof(ref->randAlgo->state.s) );
+void* ref_offsetgen_create_algo(int kind, uint64_t numBytesTotal, uint64_t len, uint64_t offset,
+	uint64_t blockSize, uint64_t numDataSetThreads, int algoType, const uint64_t randState[4],
+	uint64_t lcgState)
+{
+	static const uint64_t zeroState[4] = {0, 0, 0, 0};
+
+	RefOffsetGen* ref = new RefOffsetGen();
+	ref->randAlgo.reset( (RandAlgoInterface*)ref_randalgo_create(algoType,
+		randState ? randState : zeroState) );
+
+	if(!ref->randAlgo)
+	{
+		delete ref;
+		return NULL;
+	}
 
 	switch(kind)
 	{

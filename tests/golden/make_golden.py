@@ -41,6 +41,12 @@ OFFSETGEN_CASES = [
 ]
 
 
+OFFSETGEN_ALGO_CASES = [
+    (2, 40 * 4096, 1048576, 8192, 4096, 1, 0),
+    (3, 64 * 4096, 16 * 1048576, 1048576, 4096, 1, 0),
+]
+
+
 def pattern_closed_form(length, file_offset, salt):
     """byte x of the file = byte (x % 8) of little-endian u64 ((x & ~7) + salt) mod 2^64
     (LocalWorker.cpp:2091-2128)."""
@@ -82,6 +88,31 @@ def main():
                    "fill_first64_hex": buf.raw[:64].hex(), "fill_last16_hex": buf.raw[-16:].hex(),
                    "next_after_fill": after})
     vectors["goldenprime"] = gp
+
+    # the four --randalgo generators behind RandAlgoInterface::next(), injected state
+    # (algo ids = enum elb_offset_rand_algo: 0 balanced_single, 1 fast, 2 balanced, 3 strong)
+    ra = []
+    for algo_id in (0, 1, 2, 3):
+        for state in XOSHIRO_STATES:
+            algo = ref.ref_randalgo_create(algo_id, oracle_lib.u64x4(state))
+            nexts = [ref.ref_randalgo_next(algo) for _ in range(700)]  # mt19937_64: > 2 x 312
+            ref.ref_randalgo_destroy(algo)
+            digest = hashlib.sha256(b"".join(v.to_bytes(8, "little") for v in nexts)).hexdigest()
+            ra.append({"algo": algo_id, "state": state, "next8": nexts[:8],
+                       "next700_sha256": digest, "last": nexts[-1]})
+    vectors["randalgo"] = ra
+
+    # random offset generators driven by each non-default algorithm
+    oa = []
+    for algo_id in (1, 2, 3):
+        for case in OFFSETGEN_ALGO_CASES:
+            kind, total, length, offset, block, threads, lcg = case
+            seq = oracle_lib.offsetgen_sequence(ref, "ref", kind, total, length, offset, block,
+                                                threads, XOSHIRO_STATES[1], lcg, rand_algo=algo_id)
+            oa.append({"algo": algo_id, "kind": kind, "numBytesTotal": total, "len": length,
+                       "offset": offset, "blockSize": block, "numDataSetThreads": threads,
+                       "lcgSeed": lcg, "randState": XOSHIRO_STATES[1], "sequence": seq})
+    vectors["offsetgen_randalgo"] = oa
 
     og = []
     for case in OFFSETGEN_CASES:

@@ -79,6 +79,11 @@ def load_oracle():
         "orc_fill_random_ctr": (None, [_VP, c_u64, ctypes.c_uint, c_u64, c_u64]),
         "orc_offsetgen_create": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64, u64p,
                                         c_u64]),
+        "orc_offsetgen_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
+                                             ctypes.c_int, u64p, c_u64]),
+        "orc_randalgo_create": (_VP, [ctypes.c_int, u64p]),
+        "orc_randalgo_next": (c_u64, [_VP]),
+        "orc_randalgo_destroy": (None, [_VP]),
         "orc_offsetgen_destroy": (None, [_VP]),
         "orc_offsetgen_reset": (None, [_VP]),
         "orc_offsetgen_reset_range": (None, [_VP, c_u64, c_u64]),
@@ -129,6 +134,9 @@ def load_ref():
         "ref_randalgo_destroy": (None, [_VP]),
         "ref_offsetgen_create": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64, u64p,
                                         c_u64]),
+        "ref_offsetgen_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
+                                             ctypes.c_int, u64p, c_u64]),
+        "ref_randalgo_create": (_VP, [ctypes.c_int, u64p]),
         "ref_offsetgen_destroy": (None, [_VP]),
         "ref_offsetgen_reset": (None, [_VP]),
         "ref_offsetgen_reset_range": (None, [_VP, c_u64, c_u64]),
@@ -182,13 +190,13 @@ def fill_random_ctr(length, pct, seed, block_counter):
 
 
 def offsetgen_sequence(lib, prefix, kind, num_bytes_total, length, offset, block_size,
-                       num_dataset_threads, rand_state, lcg_seed, max_steps=100000):
+                       num_dataset_threads, rand_state, lcg_seed, max_steps=100000, rand_algo=0):
     """Drive an offset generator the way rwBlockSized does (getNextOffset, getNextBlockSize,
-    addBytesSubmitted(blockSize)) -> list of (offset, len)."""
-    create = getattr(lib, prefix + "_offsetgen_create")
+    addBytesSubmitted(blockSize)) -> list of (offset, len). rand_algo: enum elb_offset_rand_algo."""
+    create = getattr(lib, prefix + "_offsetgen_create_algo")
     state = u64x4(rand_state) if rand_state is not None else None
-    gen = create(kind, num_bytes_total, length, offset, block_size, num_dataset_threads, state,
-                 lcg_seed)
+    gen = create(kind, num_bytes_total, length, offset, block_size, num_dataset_threads,
+                 rand_algo, state, lcg_seed)
     assert gen
     if prefix == "ref" and kind == OFFGEN_FULLCOV:
         # the reference takes random_device()() (32 bit) % m as start state

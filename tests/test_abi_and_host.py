@@ -88,6 +88,41 @@ def test_offset_plans_match_reference_golden(native):
         assert [list(x) for x in seq] == vec["sequence"], vec
 
 
+def test_rand_algos_match_reference_golden(native):
+    """--randalgo fast / balanced / balanced_single / strong: RandAlgoInterface::next() streams"""
+    with open(GOLDEN_PATH) as f:
+        golden = json.load(f)
+    import hashlib
+    for vec in golden["randalgo"]:
+        st = (ctypes.c_uint64 * 4)(*vec["state"])
+        algo = native.elb_rand_algo_create(vec["algo"], st)
+        assert algo
+        nexts = [native.elb_rand_algo_next(algo) for _ in range(700)]
+        native.elb_rand_algo_destroy(algo)
+        assert nexts[:8] == vec["next8"], vec["algo"]
+        digest = hashlib.sha256(b"".join(v.to_bytes(8, "little") for v in nexts)).hexdigest()
+        assert digest == vec["next700_sha256"], vec["algo"]
+    assert not native.elb_rand_algo_create(9, (ctypes.c_uint64 * 4)(1, 2, 3, 4))
+
+
+def test_offset_plans_with_rand_algos_match_reference_golden(native):
+    with open(GOLDEN_PATH) as f:
+        golden = json.load(f)
+    for vec in golden["offsetgen_randalgo"]:
+        st = (ctypes.c_uint64 * 4)(*vec["randState"])
+        plan = native.elb_offset_plan_create_algo(
+            vec["kind"], vec["numBytesTotal"], vec["len"], vec["offset"], vec["blockSize"],
+            vec["numDataSetThreads"], vec["algo"], st, vec["lcgSeed"], 1)
+        assert plan
+        out = []
+        off = ctypes.c_uint64()
+        length = ctypes.c_uint64()
+        while native.elb_offset_plan_next(plan, ctypes.byref(off), ctypes.byref(length)):
+            out.append([off.value, length.value])
+        native.elb_offset_plan_destroy(plan)
+        assert out == vec["sequence"], (vec["algo"], vec["kind"])
+
+
 def test_offset_plans_match_oracle_random_cases(native, oracle):
     rng = random.Random(4321)
     for _ in range(150):

@@ -57,6 +57,14 @@ def test_dryrun_counters_of_baseline_configs(args, entries, total_bytes):
             assert lines[4].startswith("* Bytes total:        %d |" % total_bytes)
 
 
+@pytest.mark.parametrize("algo", ["fast", "balanced", "balanced_single", "strong"])
+def test_rand_algo_names_of_the_reference_are_accepted(algo):
+    # RandAlgoSelectorTk.h:10-13
+    res = run_cli("--dryrun", "-r", "-b", "4K", "-s", "1G", "--rand", "--randalgo", algo,
+                  "--blockvaralgo", algo, "--gpuids", "0", "/tmp/elb_dry")
+    assert res.returncode == 0, res.stderr
+
+
 def test_config3_random_read_iops_via_dryrun():
     # C3: 64 GiB / 4 KiB random reads -> randamount defaults to the file size (ProgArgs.cpp:1558)
     res = run_cli("--dryrun", "-r", "-b", "4K", "-s", "64G", "--rand", "--iodepth", "64",
@@ -82,6 +90,10 @@ def test_config3_random_read_iops_via_dryrun():
     (["-w", "-d", "-s", "1g", "--gpuids", "0", "/tmp/elb_not_a_dir.bin"],
      "only allowed if benchmark path is a directory"),
     (["-w", "-s", "1g", "--gpuids", "0"], "Benchmark path missing."),
+    (["-r", "-s", "1g", "--gpuids", "0", "--rand", "--randalgo", "quick", "/tmp/x"],
+     "Invalid random algo: quick"),
+    (["-w", "-s", "1g", "--gpuids", "0", "--blockvarpct", "50", "--blockvaralgo", "best",
+      "/tmp/x"], "Invalid random algo: best"),
 ])
 def test_validation_messages(args, message):
     res = run_cli(*args)

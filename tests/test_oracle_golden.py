@@ -113,6 +113,62 @@ def test_goldenprime_survey_known_answer(oracle):
     assert oracle.orc_goldenprime_next(ctypes.byref(st)) == 0x099e3ccb3809e8f7
 
 
+def test_randalgo_golden(oracle, golden):
+    """the four --randalgo generators (RandAlgoSelectorTk.cpp:37-53) for injected states"""
+    assert {vec["algo"] for vec in golden["randalgo"]} == {0, 1, 2, 3}
+    for vec in golden["randalgo"]:
+        algo = oracle.orc_randalgo_create(vec["algo"], oracle_lib.u64x4(vec["state"]))
+        assert algo
+        nexts = [oracle.orc_randalgo_next(algo) for _ in range(700)]
+        oracle.orc_randalgo_destroy(algo)
+        assert nexts[:8] == vec["next8"], vec["algo"]
+        assert nexts[-1] == vec["last"]
+        digest = hashlib.sha256(b"".join(v.to_bytes(8, "little") for v in nexts)).hexdigest()
+        assert digest == vec["next700_sha256"], vec["algo"]
+
+
+def test_randalgo_mt19937_64_known_answer(oracle):
+    # C++ standard [rand.predef]: the 10000th invocation of a default-constructed mt19937_64
+    # (seed 5489) produces 9981545732273789042
+    algo = oracle.orc_randalgo_create(3, oracle_lib.u64x4([5489, 0, 0, 0]))
+    val = 0
+    for _ in range(10000):
+        val = oracle.orc_randalgo_next(algo)
+    oracle.orc_randalgo_destroy(algo)
+    assert val == 9981545732273789042
+
+
+def test_randalgo_invalid(oracle):
+    assert not oracle.orc_randalgo_create(4, oracle_lib.u64x4([1, 2, 3, 4]))
+
+
+def test_offsetgen_randalgo_golden(oracle, golden):
+    assert golden["offsetgen_randalgo"]
+    for vec in golden["offsetgen_randalgo"]:
+        seq = oracle_lib.offsetgen_sequence(
+            oracle, "orc", vec["kind"], vec["numBytesTotal"], vec["len"], vec["offset"],
+            vec["blockSize"], vec["numDataSetThreads"], vec["randState"], vec["lcgSeed"],
+            rand_algo=vec["algo"])
+        assert [list(x) for x in seq] == vec["sequence"], (vec["algo"], vec["kind"])
+
+
+def test_randalgo_live_vs_reference_headers(oracle, ref):
+    rng = random.Random(99)
+    for algo_id in (0, 1, 2, 3):
+        for _ in range(5):
+            state = [rng.getrandbits(64) for _ in range(4)]
+            a = oracle.orc_randalgo_create(algo_id, oracle_lib.u64x4(state))
+            b = ref.ref_randalgo_create(algo_id, oracle_lib.u64x4(state))
+            assert [oracle.orc_randalgo_next(a) for _ in range(1000)] == \
+                [ref.ref_randalgo_next(b) for _ in range(1000)], algo_id
+            oracle.orc_randalgo_destroy(a)
+            ref.ref_randalgo_destroy(b)
+            for kind in (2, 3):
+                args = (kind, 50 * 4096 + 5, 1 << 20, 8192, 4096, 1, state, 0)
+                assert oracle_lib.offsetgen_sequence(oracle, "orc", *args, rand_algo=algo_id) == \
+                    oracle_lib.offsetgen_sequence(ref, "ref", *args, rand_algo=algo_id)
+
+
 def test_offsetgen_golden(oracle, golden):
     for vec in golden["offsetgen"]:
         seq = oracle_lib.offsetgen_sequence(

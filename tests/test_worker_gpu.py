@@ -169,6 +169,13 @@ def test_file_mode_random_full_coverage_write_then_random_read(workdir):
     dict(use_random_offsets=True, use_random_unaligned=True, rand_offset_seed=9,
          random_amount=3 * MiB),
     dict(use_random_offsets=True, use_explicit_rand_offset_algo=True, rand_offset_seed=10),
+    # --randalgo fast / balanced / strong (RandAlgoSelectorTk.h:10-13)
+    dict(use_random_offsets=True, use_explicit_rand_offset_algo=True, rand_offset_seed=11,
+         rand_offset_algo=1),
+    dict(use_random_offsets=True, use_explicit_rand_offset_algo=True, rand_offset_seed=12,
+         rand_offset_algo=2),
+    dict(use_random_offsets=True, use_random_unaligned=True, rand_offset_seed=13,
+         random_amount=2 * MiB, rand_offset_algo=3),
 ])
 def test_file_mode_offset_variants(workdir, extra):
     size, block, threads = 1 * MiB + 4096 * 3, 4 * KiB * 3, 2

@@ -338,12 +338,13 @@ def kernel_level(args, torch, device, rank):
         if timed_idx is not None:
             fill_events[timed_idx][0].record(stream)
         kernels.fill_pattern_batch(descs.data_ptr(), nblocks, args.salt, counters.data_ptr(),
-                                   handle, total_bytes=window)
+                                   handle, total_bytes=window, max_block_len=block)
         if timed_idx is not None:
             fill_events[timed_idx][1].record(stream)
             verify_events[timed_idx][0].record(stream)
         kernels.verify_pattern_batch(descs.data_ptr(), nblocks, args.salt, results.data_ptr(),
-                                     counters.data_ptr(), handle, total_bytes=window)
+                                     counters.data_ptr(), handle, total_bytes=window,
+                                     max_block_len=block)
         if timed_idx is not None:
             verify_events[timed_idx][1].record(stream)
 
@@ -380,7 +381,7 @@ def kernel_level(args, torch, device, rank):
         a, b = ev(), ev()
         a.record(stream)
         kernels.fill_random_batch(rand_descs.data_ptr(), nblocks, 100, 12345, 0, handle,
-                                  total_bytes=window)
+                                  total_bytes=window, max_block_len=block)
         b.record(stream)
         if i >= 3:
             rnd_events.append((a, b))
@@ -643,9 +644,9 @@ def main():
     rand_gbs = window / (kern["rand_ms_avg"] * 1e-3) / 1e9
     # dominant kernel = the one that takes the larger share of a step
     if kern["verify_ms_avg"] >= kern["fill_ms_avg"]:
-        dom_name, dom_gbs = "elb_blocks_kernel<VERIFY_PATTERN> (K2)", verify_gbs
+        dom_name, dom_gbs = "elb_blocks_tiled_kernel<VERIFY_PATTERN> (K2)", verify_gbs
     else:
-        dom_name, dom_gbs = "elb_blocks_kernel<FILL_PATTERN> (K1)", fill_gbs
+        dom_name, dom_gbs = "elb_blocks_tiled_kernel<FILL_PATTERN> (K1)", fill_gbs
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world,

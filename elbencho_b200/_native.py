@@ -155,10 +155,11 @@ SIGNATURES = {
     "elb_verify_pattern_batch": (ctypes.c_int, [_VP, c_u32, c_u64, _VP, _VP, _VP]),
     "elb_fill_random_batch": (ctypes.c_int, [_VP, c_u32, ctypes.c_uint, c_u64, ctypes.c_int,
                                               _VP, _VP]),
-    "elb_fill_pattern_batch_sized": (ctypes.c_int, [_VP, c_u32, c_u64, _VP, c_u64, _VP]),
-    "elb_verify_pattern_batch_sized": (ctypes.c_int, [_VP, c_u32, c_u64, _VP, _VP, c_u64, _VP]),
+    "elb_fill_pattern_batch_sized": (ctypes.c_int, [_VP, c_u32, c_u64, _VP, c_u64, c_u64, _VP]),
+    "elb_verify_pattern_batch_sized": (ctypes.c_int, [_VP, c_u32, c_u64, _VP, _VP, c_u64, c_u64,
+                                                      _VP]),
     "elb_fill_random_batch_sized": (ctypes.c_int, [_VP, c_u32, ctypes.c_uint, c_u64,
-                                                    ctypes.c_int, _VP, c_u64, _VP]),
+                                                    ctypes.c_int, _VP, c_u64, c_u64, _VP]),
     "elb_num_kernel_launches": (c_u64, []),
     "elb_last_error": (ctypes.c_char_p, []),
     "elb_abi_version": (ctypes.c_int, []),

@@ -61,7 +61,7 @@ int elb_fill_pattern(void* devPtr, uint64_t len, uint64_t fileOffset, uint64_t s
 
 	elb_block_desc desc{devPtr, len, fileOffset, 0};
 
-	return elb_launch_fill_pattern(NULL, &desc, 1, salt, NULL, len, (cudaStream_t)stream);
+	return elb_launch_fill_pattern(NULL, &desc, 1, salt, NULL, len, len, (cudaStream_t)stream);
 }
 
 int elb_verify_pattern(const void* devPtr, uint64_t len, uint64_t fileOffset, uint64_t salt,
@@ -84,7 +84,7 @@ int elb_verify_pattern(const void* devPtr, uint64_t len, uint64_t fileOffset, ui
 
 	elb_block_desc desc{const_cast<void*>(devPtr), len, fileOffset, 0};
 
-	return elb_launch_verify_pattern(NULL, &desc, 1, salt, devOut, NULL, len,
+	return elb_launch_verify_pattern(NULL, &desc, 1, salt, devOut, NULL, len, len,
 		true /*initResults*/, (cudaStream_t)stream);
 }
 
@@ -105,11 +105,12 @@ int elb_fill_random(void* devPtr, uint64_t len, unsigned pct, uint64_t seed,
 
 	elb_block_desc desc{devPtr, len, 0, blockCounter};
 
-	return elb_launch_fill_random(NULL, &desc, 1, pct, seed, NULL, len, (cudaStream_t)stream);
+	return elb_launch_fill_random(NULL, &desc, 1, pct, seed, NULL, len, len,
+		(cudaStream_t)stream);
 }
 
 int elb_fill_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
-	uint64_t* devCounters, uint64_t totalBytes, void* stream)
+	uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen, void* stream)
 {
 	if(numDescs && !descs)
 	{
@@ -118,12 +119,12 @@ int elb_fill_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs,
 	}
 
 	return elb_launch_fill_pattern(descs, NULL, numDescs, salt, devCounters, totalBytes,
-		(cudaStream_t)stream);
+		maxBlockLen, (cudaStream_t)stream);
 }
 
 int elb_verify_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs,
 	uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters, uint64_t totalBytes,
-	void* stream)
+	uint64_t maxBlockLen, void* stream)
 {
 	if(numDescs && (!descs || !devResults) )
 	{
@@ -132,11 +133,12 @@ int elb_verify_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDesc
 	}
 
 	return elb_launch_verify_pattern(descs, NULL, numDescs, salt, devResults, devCounters,
-		totalBytes, true /*initResults*/, (cudaStream_t)stream);
+		totalBytes, maxBlockLen, true /*initResults*/, (cudaStream_t)stream);
 }
 
 int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
-	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, void* stream)
+	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream)
 {
 	if(checkRandArgs(pct, randAlgo) )
 		return -1;
@@ -148,26 +150,26 @@ int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, 
 	}
 
 	return elb_launch_fill_random(descs, NULL, numDescs, pct, seed, devCounters, totalBytes,
-		(cudaStream_t)stream);
+		maxBlockLen, (cudaStream_t)stream);
 }
 
 int elb_fill_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
 	uint64_t* devCounters, void* stream)
 {
-	return elb_fill_pattern_batch_sized(descs, numDescs, salt, devCounters, 0, stream);
+	return elb_fill_pattern_batch_sized(descs, numDescs, salt, devCounters, 0, 0, stream);
 }
 
 int elb_verify_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
 	elb_verify_result* devResults, uint64_t* devCounters, void* stream)
 {
-	return elb_verify_pattern_batch_sized(descs, numDescs, salt, devResults, devCounters, 0,
+	return elb_verify_pattern_batch_sized(descs, numDescs, salt, devResults, devCounters, 0, 0,
 		stream);
 }
 
 int elb_fill_random_batch(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
 	uint64_t seed, int randAlgo, uint64_t* devCounters, void* stream)
 {
-	return elb_fill_random_batch_sized(descs, numDescs, pct, seed, randAlgo, devCounters, 0,
+	return elb_fill_random_batch_sized(descs, numDescs, pct, seed, randAlgo, devCounters, 0, 0,
 		stream);
 }
 

@@ -15,19 +15,20 @@
 
 void elb_set_last_error(const std::string& msg);
 
-// kernel launchers (elb_kernels.cu). totalBytesHint only sizes the grid (0 = full grid).
+// kernel launchers (elb_kernels.cu). totalBytesHint / maxBlockLenHint (0 = unknown) only pick the
+// launch shape: both known and (nearly) uniform blocks -> hardware-scheduled tiled kernel.
 // (descs == NULL => single block passed by value through inlineDesc, numDescs must be 1)
 int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, uint64_t* devCounters, uint64_t totalBytesHint,
-	cudaStream_t stream);
+	uint64_t maxBlockLenHint, cudaStream_t stream);
 int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
 	cudaStream_t stream);
 int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters,
-	uint64_t totalBytesHint, bool initResults, cudaStream_t stream);
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, bool initResults, cudaStream_t stream);
 int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
-	uint64_t totalBytesHint, cudaStream_t stream);
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, cudaStream_t stream);
 int elb_kernels_warmup();
 uint64_t elb_get_num_kernel_launches();
 

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -584,6 +585,42 @@ elb_blocks_kernel(const KernelArgs args)
 	}
 }
 
+/**
+ * Hardware-scheduled form for windows whose blocks are (nearly) all the same size: a 1-D grid of
+ * numDescs x ctasPerBlock short-lived CTAs, CTA i works on tile (i % ctasPerBlock) of block
+ * (i / ctasPerBlock) and exits. No prefix scan, and - the point - the block scheduler hands out
+ * tiles dynamically: SMs that get more bandwidth (smaller GPCs, nearer memory partitions) take
+ * more tiles, and the set of addresses in flight is a compact window that moves through the
+ * buffer. A static partition (the persistent kernel above) ends when the slowest SM is done;
+ * measured write-only: 6.2 TB/s static vs 7.5 TB/s dynamic (profiles/, fill_variants2).
+ * CTAs past the end of a shorter block exit immediately.
+ */
+template<int MODE>
+__global__ void __launch_bounds__(ELB_THREADS, 4)
+elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
+	const uint32_t tilesPerCTA)
+{
+	const uint32_t descIdx = blockIdx.x / ctasPerBlock;
+	const uint64_t tileIdx = (uint64_t)(blockIdx.x - descIdx * ctasPerBlock) * tilesPerCTA;
+
+	const elb_block_desc desc = args.descs ? args.descs[descIdx] : args.inlineDesc;
+	const BlockGeom g = make_geom(desc);
+
+	if(tileIdx >= g.numTiles)
+		return; // (uniform for the whole CTA)
+
+	const uint64_t tileEnd = (tileIdx + tilesPerCTA < g.numTiles) ?
+		(tileIdx + tilesPerCTA) : g.numTiles;
+
+	process_block_tiles<MODE>(args, desc, descIdx, g, tileIdx, tileEnd);
+
+	// device-resident stats: one atomic per block, by the CTA that owns its first tile
+	if(args.counters && !tileIdx && !threadIdx.x)
+		atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
+			ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
+			(unsigned long long)g.len);
+}
+
 __global__ void elb_verify_init_kernel(elb_verify_result* results, uint32_t numDescs)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,6 +647,9 @@ struct DeviceLaunchInfo
 {
 	int numSMs{0};
 	int ctasPerSM[3]{0, 0, 0};
+	/* 32 KiB tiles per CTA of the hardware-scheduled kernel; 0 = always use the persistent
+	   kernel for this mode. Tuning knob: ELB_TILES_PER_CTA="fill,verify,random". */
+	uint32_t tilesPerCTA[3]{1, 2, 8}; // measured best on B200 (profiles/: sweep_tiles)
 };
 
 static DeviceLaunchInfo gDevInfo[ELB_MAX_DEVICES];
@@ -641,6 +681,15 @@ static const DeviceLaunchInfo* getDeviceLaunchInfo()
 		gDevInfo[dev].ctasPerSM[MODE_FILL_PATTERN] = queryOccupancy<MODE_FILL_PATTERN>();
 		gDevInfo[dev].ctasPerSM[MODE_VERIFY_PATTERN] = queryOccupancy<MODE_VERIFY_PATTERN>();
 		gDevInfo[dev].ctasPerSM[MODE_FILL_RANDOM] = queryOccupancy<MODE_FILL_RANDOM>();
+
+		const char* tilesEnv = getenv("ELB_TILES_PER_CTA");
+		if(tilesEnv)
+		{
+			unsigned vals[3];
+			if(sscanf(tilesEnv, "%u,%u,%u", &vals[0], &vals[1], &vals[2]) == 3)
+				for(int mode = 0; mode < 3; mode++)
+					gDevInfo[dev].tilesPerCTA[mode] = vals[mode];
+		}
 	});
 
 	if(gDevInfo[dev].numSMs <= 0)
@@ -669,10 +718,13 @@ static int checkLaunch(const char* what)
 /**
  * @totalBytesHint upper bound of bytes covered by the launch (used only to size the grid);
  *    0 = unknown (launch a full persistent grid).
+ * @maxBlockLenHint upper bound of the length of any block of the launch; 0 = unknown. With both
+ *    hints and blocks of (nearly) uniform size the hardware-scheduled tiled kernel is used,
+ *    otherwise (ragged windows: many CTAs would find nothing to do) the persistent one.
  */
 template<int MODE>
 static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
-	cudaStream_t stream)
+	uint64_t maxBlockLenHint, cudaStream_t stream)
 {
 	if(!args.numDescs)
 		return 0;
@@ -680,6 +732,26 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 	const DeviceLaunchInfo* devInfo = getDeviceLaunchInfo();
 	if(!devInfo)
 		return -1;
+
+	const uint32_t tilesPerCTA = devInfo->tilesPerCTA[MODE];
+
+	if(maxBlockLenHint && totalBytesHint && tilesPerCTA)
+	{
+		const uint64_t ctaBytes = (uint64_t)ELB_TILE_BYTES * tilesPerCTA;
+		const uint64_t ctasPerBlock = (maxBlockLenHint + ctaBytes - 1) / ctaBytes;
+		const uint64_t numCTAs = ctasPerBlock * args.numDescs;
+		const uint64_t neededCTAs = (totalBytesHint + ctaBytes - 1) / ctaBytes + args.numDescs;
+
+		if( (numCTAs <= 0x7fffffffULL) && (numCTAs <= (2 * neededCTAs + 1024) ) )
+		{
+			elb_blocks_tiled_kernel<MODE><<<(unsigned)numCTAs, ELB_THREADS, 0, stream>>>(args,
+				(uint32_t)ctasPerBlock, tilesPerCTA);
+			gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
+
+			return checkLaunch( (MODE == MODE_FILL_PATTERN) ? "fill_pattern" :
+				(MODE == MODE_VERIFY_PATTERN) ? "verify_pattern" : "fill_random");
+		}
+	}
 
 	// grid: a multiple of the SM count, never more CTAs than tiles
 	uint64_t gridSize = (uint64_t)devInfo->numSMs * devInfo->ctasPerSM[MODE];
@@ -701,7 +773,7 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 
 int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, uint64_t* devCounters, uint64_t totalBytesHint,
-	cudaStream_t stream)
+	uint64_t maxBlockLenHint, cudaStream_t stream)
 {
 	KernelArgs args{};
 	args.descs = descs;
@@ -711,7 +783,7 @@ int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* i
 	args.salt = salt;
 	args.counters = (unsigned long long*)devCounters;
 
-	return launchBlocksKernel<MODE_FILL_PATTERN>(args, totalBytesHint, stream);
+	return launchBlocksKernel<MODE_FILL_PATTERN>(args, totalBytesHint, maxBlockLenHint, stream);
 }
 
 int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
@@ -732,7 +804,7 @@ int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
  */
 int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters,
-	uint64_t totalBytesHint, bool initResults, cudaStream_t stream)
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, bool initResults, cudaStream_t stream)
 {
 	if(!numDescs)
 		return 0;
@@ -749,12 +821,12 @@ int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc*
 	args.results = devResults;
 	args.counters = (unsigned long long*)devCounters;
 
-	return launchBlocksKernel<MODE_VERIFY_PATTERN>(args, totalBytesHint, stream);
+	return launchBlocksKernel<MODE_VERIFY_PATTERN>(args, totalBytesHint, maxBlockLenHint, stream);
 }
 
 int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
-	uint64_t totalBytesHint, cudaStream_t stream)
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, cudaStream_t stream)
 {
 	KernelArgs args{};
 	args.descs = descs;
@@ -765,7 +837,7 @@ int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* in
 	args.pct = pct;
 	args.counters = (unsigned long long*)devCounters;
 
-	return launchBlocksKernel<MODE_FILL_RANDOM>(args, totalBytesHint, stream);
+	return launchBlocksKernel<MODE_FILL_RANDOM>(args, totalBytesHint, maxBlockLenHint, stream);
 }
 
 /* query launch geometry of the current device now (so that no attribute/occupancy query happens

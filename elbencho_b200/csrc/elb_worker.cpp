@@ -1339,6 +1339,19 @@ bool Worker::isStandardShapedBatch(const Batch& batch) const
 		(batch.numBytes == ( (uint64_t)batchBlocks * slotStride) );
 }
 
+/* debugging knob: ELB_NO_CUDA_GRAPHS=1 enqueues the GPU stage call by call instead of replaying
+ * the per-batch graph (same kernels, same copies) */
+static bool useCudaGraphs()
+{
+	static const bool enabled = []()
+	{
+		const char* env = getenv("ELB_NO_CUDA_GRAPHS");
+		return !(env && env[0] && (env[0] != '0') );
+	}();
+
+	return enabled;
+}
+
 cudaGraphExec_t Worker::captureBatchGraph(Batch& batch, bool isRead)
 {
 	cudaGraph_t graph = NULL;
@@ -1400,11 +1413,11 @@ void Worker::enqueueWriteWork(Batch& batch, size_t numWriteBlocks, uint64_t numW
 
 		if(doPatternFill)
 			launchRes = elb_launch_fill_pattern(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
-				cfg.integrityCheckSalt, devCounters, numWriteBytes, batch.stream);
+				cfg.integrityCheckSalt, devCounters, numWriteBytes, cfg.blockSize, batch.stream);
 		else
 			launchRes = elb_launch_fill_random(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
 				cfg.blockVariancePercent, blockVarianceSeed, devCounters, numWriteBytes,
-				batch.stream);
+				cfg.blockSize, batch.stream);
 
 		if(launchRes)
 			throw WorkerError(std::string("GPU block fill failed. ") + elb_last_error() );
@@ -1448,7 +1461,7 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
-	if(isStandardShapedBatch(batch) && (numWriteBlocks == batchBlocks) )
+	if(useCudaGraphs() && isStandardShapedBatch(batch) && (numWriteBlocks == batchBlocks) )
 	{
 		if(!batch.writeGraphExec)
 			batch.writeGraphExec = captureBatchGraph(batch, false);
@@ -1506,7 +1519,7 @@ void Worker::enqueueReadWork(Batch& batch, bool timeKernel)
 			"CUDA event record");
 
 	if(elb_launch_verify_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
-		cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes,
+		cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes, cfg.blockSize,
 		false /*initResults*/, batch.stream) )
 		throw WorkerError(std::string("GPU block verification failed. ") + elb_last_error() );
 
@@ -1548,7 +1561,7 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 		batch.devResultsClean = true; // until a mismatch shows up at retire time
 	}
 
-	if(isStandardShapedBatch(batch) )
+	if(useCudaGraphs() && isStandardShapedBatch(batch) )
 	{
 		if(!batch.readGraphExec)
 			batch.readGraphExec = captureBatchGraph(batch, true);

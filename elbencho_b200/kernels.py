@@ -48,25 +48,30 @@ def fill_random(dev_ptr, length, pct, seed, block_counter, stream=0, algo=RANDAL
 
 
 def fill_pattern_batch(dev_descs_ptr, num_descs, salt, dev_counters_ptr=0, stream=0,
-                       total_bytes=0):
+                       total_bytes=0, max_block_len=0):
+    """total_bytes / max_block_len: size hints (0 = unknown) that pick the launch shape: both
+    given and (nearly) uniform blocks -> hardware-scheduled tiles, else a persistent grid."""
     _check(_native.load().elb_fill_pattern_batch_sized(dev_descs_ptr, num_descs, salt,
                                                        dev_counters_ptr or None, total_bytes,
-                                                       stream), "elb_fill_pattern_batch")
+                                                       max_block_len, stream),
+           "elb_fill_pattern_batch")
 
 
 def verify_pattern_batch(dev_descs_ptr, num_descs, salt, dev_results_ptr, dev_counters_ptr=0,
-                         stream=0, total_bytes=0):
+                         stream=0, total_bytes=0, max_block_len=0):
     _check(_native.load().elb_verify_pattern_batch_sized(dev_descs_ptr, num_descs, salt,
                                                          dev_results_ptr,
                                                          dev_counters_ptr or None, total_bytes,
-                                                         stream), "elb_verify_pattern_batch")
+                                                         max_block_len, stream),
+           "elb_verify_pattern_batch")
 
 
 def fill_random_batch(dev_descs_ptr, num_descs, pct, seed, dev_counters_ptr=0, stream=0,
-                      total_bytes=0, algo=RANDALGO_SPLITMIX64):
+                      total_bytes=0, algo=RANDALGO_SPLITMIX64, max_block_len=0):
     _check(_native.load().elb_fill_random_batch_sized(dev_descs_ptr, num_descs, pct, seed, algo,
                                                       dev_counters_ptr or None, total_bytes,
-                                                      stream), "elb_fill_random_batch")
+                                                      max_block_len, stream),
+           "elb_fill_random_batch")
 
 
 def num_kernel_launches():

@@ -151,14 +151,19 @@ int elb_verify_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uin
 	elb_verify_result* devResults, uint64_t* devCounters, void* stream);
 int elb_fill_random_batch(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
 	uint64_t seed, int randAlgo, uint64_t* devCounters, void* stream);
-/* As above, plus totalBytes = sum of the descriptor lengths (when the caller knows it) so that
- * small windows launch a grid no larger than their tile count. 0 = unknown. */
+/* As above, plus two size hints (0 = unknown) that only pick the launch shape: totalBytes = sum
+ * of the descriptor lengths, maxBlockLen = upper bound of any descriptor's length (the block
+ * size). With both, windows of (nearly) equally sized blocks run as a grid of short-lived CTAs,
+ * one 32 KiB tile each, handed out dynamically by the hardware block scheduler; ragged or
+ * unknown windows run on a persistent grid that partitions all tiles statically. */
 int elb_fill_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
-	uint64_t* devCounters, uint64_t totalBytes, void* stream);
+	uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen, void* stream);
 int elb_verify_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
-	elb_verify_result* devResults, uint64_t* devCounters, uint64_t totalBytes, void* stream);
+	elb_verify_result* devResults, uint64_t* devCounters, uint64_t totalBytes,
+	uint64_t maxBlockLen, void* stream);
 int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
-	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, void* stream);
+	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream);
 
 /* Number of kernel launches issued through this library since load (all threads). */
 uint64_t elb_num_kernel_launches(void);

@@ -166,8 +166,12 @@ def make_batch(cuda_device, blocks):
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(cuda_device)
 
 
-def test_batched_window_ragged_blocks(cuda_device):
-    """one launch over a ragged window: different lengths, offsets, alignments, empty blocks"""
+@pytest.mark.parametrize("max_block_len", [0, 1 << 20, 1 << 26])
+def test_batched_window_ragged_blocks(cuda_device, max_block_len):
+    """one launch over a ragged window: different lengths, offsets, alignments, empty blocks.
+    max_block_len 0: persistent grid with static tile partition; 1 MiB: hardware-scheduled tiles
+    (CTAs past the end of shorter blocks exit); 64 MiB: bound so loose that the launcher falls
+    back to the persistent grid"""
     rng = random.Random(77)
     lens = [1 << 20, 4096, 0, 65536 + 3, 1, (1 << 20) - 32, 777, 32768 * 3, 5, 1 << 16]
     arena = dev_bytes(sum(lens) + 64 * len(lens), cuda_device)
@@ -183,7 +187,7 @@ def test_batched_window_ragged_blocks(cuda_device):
     salt = 0xABCDEF0123456789
 
     kernels.fill_pattern_batch(descs.data_ptr(), len(blocks), salt, counters.data_ptr(),
-                               stream_handle(), total_bytes=sum(lens))
+                               stream_handle(), total_bytes=sum(lens), max_block_len=max_block_len)
     torch.cuda.synchronize()
     host = to_bytes(arena)
     base = arena.data_ptr()
@@ -193,7 +197,8 @@ def test_batched_window_ragged_blocks(cuda_device):
 
     # verify: clean
     kernels.verify_pattern_batch(descs.data_ptr(), len(blocks), salt, results.data_ptr(),
-                                 counters.data_ptr(), stream_handle(), total_bytes=sum(lens))
+                                 counters.data_ptr(), stream_handle(), total_bytes=sum(lens),
+                                 max_block_len=max_block_len)
     torch.cuda.synchronize()
     assert read_result(results) == [(0, 0xFFFFFFFFFFFFFFFF)] * len(blocks)
     ctr = counters.cpu().tolist()
@@ -207,7 +212,8 @@ def test_batched_window_ragged_blocks(cuda_device):
         for p in positions:
             arena[ptr - base + p] ^= 0x5A
     kernels.verify_pattern_batch(descs.data_ptr(), len(blocks), salt, results.data_ptr(),
-                                 counters.data_ptr(), stream_handle())
+                                 counters.data_ptr(), stream_handle(), total_bytes=sum(lens),
+                                 max_block_len=max_block_len)
     torch.cuda.synchronize()
     got = read_result(results)
     for idx in range(len(blocks)):
@@ -219,7 +225,7 @@ def test_batched_window_ragged_blocks(cuda_device):
 
     # random fill over the same ragged window
     kernels.fill_random_batch(descs.data_ptr(), len(blocks), 60, 999, 0, stream_handle(),
-                              total_bytes=sum(lens))
+                              total_bytes=sum(lens), max_block_len=max_block_len)
     torch.cuda.synchronize()
     host = to_bytes(arena)
     for ptr, length, _, ctr_val in blocks:
@@ -238,7 +244,7 @@ def test_large_window_round_trip_properties(cuda_device):
     wblocks = [(arena.data_ptr() + i * block, block, i * block, i) for i in range(nblocks)]
     wdescs = make_batch(cuda_device, wblocks)
     kernels.fill_pattern_batch(wdescs.data_ptr(), nblocks, salt, 0, stream_handle(),
-                               total_bytes=block * nblocks)
+                               total_bytes=block * nblocks, max_block_len=block)
     # read back with 128 KiB blocks
     rblock = 128 << 10
     rn = block * nblocks // rblock
@@ -247,7 +253,8 @@ def test_large_window_round_trip_properties(cuda_device):
     results = torch.zeros(2 * rn, dtype=torch.int64, device=cuda_device)
     counters = torch.zeros(kernels.DEVCTR_NUM, dtype=torch.int64, device=cuda_device)
     kernels.verify_pattern_batch(rdescs.data_ptr(), rn, salt, results.data_ptr(),
-                                 counters.data_ptr(), stream_handle(), total_bytes=block * nblocks)
+                                 counters.data_ptr(), stream_handle(), total_bytes=block * nblocks,
+                                 max_block_len=rblock)
     torch.cuda.synchronize()
     assert int(results.view(-1, 2)[:, 0].sum()) == 0
     assert counters.cpu().tolist()[kernels.DEVCTR_VERIFIED_BYTES] == block * nblocks

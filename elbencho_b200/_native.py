@@ -72,6 +72,10 @@ class Cfg(ctypes.Structure):
         ("serializeBufferedWrites", c_i32),
         ("numRWMixReadThreads", c_u32),
         ("randOffsetAlgo", ctypes.c_int32),
+        ("limitReadBps", c_u64),
+        ("limitWriteBps", c_u64),
+        ("doInfiniteIOLoop", ctypes.c_int32),
+        ("reserved3", ctypes.c_int32),
     ]
 
 

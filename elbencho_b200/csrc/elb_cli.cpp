@@ -80,6 +80,11 @@ static const OptDef optDefs[] =
 	// GPU
 	{"gpuids", 0, Opt_STR, "Comma-separated list of CUDA GPU IDs (also \"all\", \"[0-7]\", "
 		"\"0-7\") to use for the on-GPU block fill/verify. Mandatory."},
+	{"cuhostbufreg", 0, Opt_FLAG, "Pin host memory buffers and register with CUDA for faster "
+		"transfer to/from GPU memory. (Always on: the host rings are cudaHostAlloc memory.)"},
+	{"nodiocheck", 0, Opt_FLAG, "Don't check direct IO alignment and sanity."},
+	{"nopathexp", 0, Opt_FLAG, "Disable expansion of number lists and ranges in square brackets "
+		"for given paths. (Always on: paths are taken literally.)"},
 	{"cufile", 0, Opt_FLAG, "Use cuFile API for reads/writes to/from GPU memory."},
 	{"gdsbufreg", 0, Opt_FLAG, "Register GPU buffers for GPUDirect Storage (GDS)."},
 	{"gds", 0, Opt_FLAG, "Use GPUDirect Storage: shortcut for --direct --cufile --gdsbufreg."},
@@ -95,6 +100,11 @@ static const OptDef optDefs[] =
 	{"cpu", 0, Opt_FLAG, "Show CPU utilization in phase stats results."},
 	{"dirstats", 0, Opt_FLAG, "Show directory completion statistics in file write/read phase."},
 	{"nolive", 0, Opt_FLAG, "Disable live statistics."},
+	{"live1", 0, Opt_FLAG, "Use brief live statistics format, i.e. a single line instead of full "
+		"screen stats. (Always on: this implementation has no full screen live stats.)"},
+	{"live1n", 0, Opt_FLAG, "Brief live statistics where every update is a new line."},
+	{"livecsv", 0, Opt_STR, "Path to file for live statistics in CSV format ('stdout' for console). "
+		"One line per --liveint interval with the aggregate of all local workers."},
 	{"liveint", 0, Opt_U64, "Update interval for live statistics in milliseconds. (Default: 2000)"},
 	{"no0usecerr", 0, Opt_FLAG, "Do not warn if worker thread completion time is less than 1 usec."},
 	{"label", 0, Opt_STR, "Custom label to identify the benchmark run in result files."},
@@ -105,11 +115,30 @@ static const OptDef optDefs[] =
 	{"dryrun", 0, Opt_FLAG, "Don't run any benchmark phase, just print the number of expected "
 		"entries and dataset size per phase."},
 	{"iterations", 'i', Opt_U64, "Number of iterations to run the benchmark. (Default: 1)"},
+	{"infloop", 0, Opt_FLAG, "Let I/O threads run in an infinite repeat loop, i.e. each thread "
+		"individually restarts its work from the beginning when it reaches the end of its "
+		"workload. Terminate this via ctrl+c or by using \"--timelimit\"."},
+	{"limitread", 0, Opt_BYTES, "Per-thread read limit in bytes per second. (Default: 0 = off)"},
+	{"limitwrite", 0, Opt_BYTES, "Per-thread write limit in bytes per second. (Default: 0 = off)"},
+	{"start", 0, Opt_U64, "Start time of first benchmark in UTC seconds since the epoch, to "
+		"synchronize the start of benchmarks on different hosts."},
+	{"configfile", 'c', Opt_STR, "Path to benchmark configuration file. All command line options "
+		"starting with double dashes can be used as \"OPTIONNAME=VALUE\" in the config file."},
 	{"phasedelay", 0, Opt_U64, "Delay between different phases in seconds. (Default: 0)"},
 	{"timelimit", 0, Opt_U64, "Time limit in seconds for each phase. (Default: 0 = off)"},
 	{"log", 0, Opt_U64, "Log level. (Default: 0; Verbose: 1; Debug: 2)"},
 	// distributed
 	{"hosts", 0, Opt_STR, "Comma-separated list of hosts in service mode for coordinated benchmark."},
+	{"hostsfile", 0, Opt_STR, "Path to file containing line-separated service hosts to use for "
+		"benchmark. Lines starting with \"#\" will be ignored. (Format: hostname[:port])"},
+	{"numhosts", 0, Opt_STR, "Number of hosts to use from given hosts list or hosts file. "
+		"(Default: use all given hosts)"},
+	{"gpuperservice", 0, Opt_FLAG, "Assign GPUs round robin to service instances (one GPU of the "
+		"--gpuids list per service) instead of round robin to the threads of each service."},
+	{"svcwait", 0, Opt_U64, "Number of seconds to wait for the services to become reachable. "
+		"(Default: 5)"},
+	{"datasetthreads", 0, Opt_U64, "Total number of threads that share the data set when several "
+		"independent instances each work on their --rankoffset share. (Default: --threads)"},
 	{"service", 0, Opt_FLAG, "Run as service for distributed mode, waiting for requests from master."},
 	{"foreground", 0, Opt_FLAG, "When running as service, stay in foreground and don't detach."},
 	{"port", 0, Opt_U64, "TCP port of background service. (Default: 1611)"},
@@ -315,6 +344,83 @@ ProgArgs::ProgArgs(int argc, char** argv)
 		values[def->longName] = inlineValue;
 	}
 
+	/* --configfile: "OPTIONNAME=VALUE" lines like boost::program_options' config file parser
+	   (ProgArgs.cpp:1012-1030); the command line wins; "path=..." lines add benchmark paths */
+	if(values.count("configfile") )
+	{
+		const std::string configPath = values["configfile"];
+		FILE* configFile = fopen(configPath.c_str(), "r");
+
+		if(!configFile)
+			throw ProgError("Unable to read config file. Path: " + configPath);
+
+		char lineBuf[4096];
+		std::vector<std::string> configPaths;
+
+		while(fgets(lineBuf, sizeof(lineBuf), configFile) )
+		{
+			std::string line = lineBuf;
+			const size_t commentPos = line.find('#');
+
+			if(commentPos != std::string::npos)
+				line = line.substr(0, commentPos);
+
+			auto trim = [](std::string& text)
+			{
+				const char* blanks = " \t\r\n";
+				const size_t first = text.find_first_not_of(blanks);
+				const size_t last = text.find_last_not_of(blanks);
+				text = (first == std::string::npos) ? "" : text.substr(first, last - first + 1);
+			};
+
+			trim(line);
+
+			if(line.empty() )
+				continue;
+
+			const size_t eqPos = line.find('=');
+			std::string key = (eqPos == std::string::npos) ? line : line.substr(0, eqPos);
+			std::string value = (eqPos == std::string::npos) ? "" : line.substr(eqPos + 1);
+
+			trim(key);
+			trim(value);
+
+			if(key == "path")
+			{
+				configPaths.push_back(value);
+				continue;
+			}
+
+			const OptDef* def = findLongOpt(key);
+
+			if(!def)
+			{
+				fclose(configFile);
+				throw ProgError("unrecognised option '" + key + "'");
+			}
+
+			if(values.count(key) )
+				continue; // given on the command line
+
+			if(def->kind == Opt_FLAG)
+			{
+				std::string lower = value;
+				std::transform(lower.begin(), lower.end(), lower.begin(), ::tolower);
+
+				if(lower.empty() || (lower == "1") || (lower == "true") || (lower == "yes") ||
+					(lower == "on") )
+					values[key] = "1";
+			}
+			else
+				values[key] = value;
+		}
+
+		fclose(configFile);
+
+		if(benchPaths.empty() )
+			benchPaths = configPaths;
+	}
+
 	auto flag = [&](const char* name) { return values.count(name) != 0; };
 	auto num = [&](const char* name, uint64_t& target)
 	{
@@ -414,7 +520,28 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("timelimit", timeLimitSecs);
 	num("log", logLevel);
 
+	doInfiniteIOLoop = flag("infloop");
+	num("limitread", limitReadBps);
+	num("limitwrite", limitWriteBps);
+	num("start", startTime);
+	num("datasetthreads", numDataSetThreads);
+	useBriefLiveStatsNewLine = flag("live1n");
+	str("livecsv", liveCSVFilePath);
+	str("configfile", configFilePath);
+
 	str("hosts", hostsStr);
+	str("hostsfile", hostsFilePath);
+	if(values.count("numhosts") )
+	{
+		char* endPtr = NULL;
+		numHosts = strtoll(values["numhosts"].c_str(), &endPtr, 10);
+
+		if(values["numhosts"].empty() || (endPtr && *endPtr) )
+			throw ProgError("the argument ('" + values["numhosts"] + "') for option "
+				"'--numhosts' is invalid");
+	}
+	assignGPUPerService = flag("gpuperservice");
+	num("svcwait", svcReadyWaitSec);
 	runAsService = flag("service");
 	runServiceInForeground = flag("foreground");
 	num("port", servicePort);
@@ -448,18 +575,86 @@ void ProgArgs::initImplicitValues()
 	if(integrityCheckSalt && blockVariancePercent) // :1161-1167: verify forces blockvarpct 0
 		blockVariancePercent = 0;
 
-	if(!hostsStr.empty() )
-	{
-		std::stringstream hostsStream(hostsStr);
-		std::string host;
-
-		while(std::getline(hostsStream, host, ',') )
-			if(!host.empty() )
-				hosts.push_back(host);
-	}
+	parseHosts();
 
 	if(!gpuIDsStr.empty() && (gpuIDsStr != "all") )
 		gpuIDs = parseGPUIDs(gpuIDsStr);
+}
+
+/* ProgArgs::parseHosts (ProgArgs.cpp:2221-2340): hosts string + hosts file, delimiters ", \n\r",
+ * duplicates are an error, --numhosts cuts the list (0 = run locally). (The default port is
+ * applied by the HTTP client, square bracket ranges are not expanded here.) */
+void ProgArgs::parseHosts()
+{
+	if(!numHosts)
+	{ // user explicitly selected zero hosts: ignore any given hosts list or hosts file
+		hostsStr.clear();
+		hostsFilePath.clear();
+		return;
+	}
+
+	if(hostsStr.empty() && hostsFilePath.empty() )
+		return;
+
+	std::string allHostsStr = hostsStr;
+
+	if(!hostsFilePath.empty() )
+	{
+		FILE* hostsFile = fopen(hostsFilePath.c_str(), "r");
+
+		if(!hostsFile)
+			throw ProgError("Unable to read hosts file. Path: " + hostsFilePath);
+
+		char lineBuf[1024];
+
+		allHostsStr += " ";
+
+		while(fgets(lineBuf, sizeof(lineBuf), hostsFile) )
+		{
+			if(lineBuf[0] == '#')
+				continue; // comment line
+
+			allHostsStr += std::string(lineBuf) + ",";
+		}
+
+		fclose(hostsFile);
+	}
+
+	std::string host;
+
+	auto flushHost = [&]()
+	{
+		if(!host.empty() )
+			hosts.push_back(host);
+
+		host.clear();
+	};
+
+	for(const char c : allHostsStr)
+	{
+		if( (c == ',') || (c == ' ') || (c == '\n') || (c == '\r') || (c == '\t') )
+			flushHost();
+		else
+			host += c;
+	}
+
+	flushHost();
+
+	if(hosts.empty() )
+		throw ProgError("Hosts defined, but parsing resulted in an empty list. Given list: \"" +
+			allHostsStr + "\"");
+
+	std::vector<std::string> sortedHosts(hosts);
+	std::sort(sortedHosts.begin(), sortedHosts.end() );
+	const size_t numUnique = std::unique(sortedHosts.begin(), sortedHosts.end() ) -
+		sortedHosts.begin();
+
+	if(numUnique != hosts.size() )
+		throw ProgError("List of hosts contains duplicates. Number of duplicates: " +
+			std::to_string(hosts.size() - numUnique) );
+
+	if( (numHosts != -1) && (hosts.size() > (uint64_t)numHosts) )
+		hosts.resize(numHosts);
 }
 
 /* ProgArgs::findBenchPathType (ProgArgs.cpp:1750-1790) */
@@ -593,7 +788,7 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.pathType = benchPathType;
 	cfg.numThreads = (uint32_t)numThreads;
 	cfg.rankOffset = (uint32_t)rankOffset;
-	cfg.numDataSetThreads = 0;
+	cfg.numDataSetThreads = (uint32_t)numDataSetThreads;
 	cfg.blockSize = blockSize;
 	cfg.fileSize = fileSize;
 	cfg.ioDepth = (uint32_t)ioDepth;
@@ -630,6 +825,9 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	cfg.limitReadBps = limitReadBps;
+	cfg.limitWriteBps = limitWriteBps;
+	cfg.doInfiniteIOLoop = doInfiniteIOLoop;
 	cfg.randOffsetAlgo = randOffsetAlgo.empty() ?
 		ELB_OFFSETALGO_XOSHIRO256SS : RandAlgo::algoFromString(randOffsetAlgo);
 }

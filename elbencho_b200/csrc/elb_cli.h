@@ -87,6 +87,10 @@ class ProgArgs
 		uint64_t pipelineBatchBlocks{0};
 		uint64_t pipelineNumBatches{0};
 		bool serializeBufferedWrites{false};
+		bool doInfiniteIOLoop{false};   // --infloop
+		uint64_t limitReadBps{0};       // --limitread (per thread)
+		uint64_t limitWriteBps{0};      // --limitwrite
+		uint64_t numDataSetThreads{0};  // --datasetthreads (0 = numThreads)
 
 		// output / run control
 		bool showLatency{false};
@@ -105,6 +109,10 @@ class ProgArgs
 		uint64_t nextPhaseDelaySecs{0};
 		uint64_t timeLimitSecs{0};
 		uint64_t logLevel{0};
+		uint64_t startTime{0};          // --start (UTC seconds since the epoch)
+		bool useBriefLiveStatsNewLine{false}; // --live1n
+		std::string liveCSVFilePath;    // --livecsv
+		std::string configFilePath;     // --configfile
 		std::string benchLabel;
 		std::string csvFilePath;
 		std::string jsonFilePath;
@@ -116,6 +124,10 @@ class ProgArgs
 		uint64_t servicePort{1611}; // ProgArgs.h:224
 		std::vector<std::string> hosts;
 		std::string hostsStr;
+		std::string hostsFilePath;      // --hostsfile
+		int64_t numHosts{-1};           // --numhosts (-1 = all)
+		bool assignGPUPerService{false}; // --gpuperservice
+		uint64_t svcReadyWaitSec{5};    // --svcwait (ProgArgs.cpp:967)
 		bool interruptServices{false};
 		bool quitServices{false};
 
@@ -141,6 +153,7 @@ class ProgArgs
 		void initImplicitValues(); // ProgArgs.cpp:1041-1195
 		void checkArgs();          // ProgArgs.cpp:1229-1462
 		void detectBenchPathType(); // ProgArgs.cpp findBenchPathType
+		void parseHosts();          // ProgArgs.cpp:2221-2340
 };
 
 /* Statistics output (reference source/Statistics.cpp) */
@@ -165,6 +178,9 @@ namespace stats
 	void printDryRunPhaseInfo(const ProgArgs& progArgs, int benchPhase, uint64_t entriesPerThread,
 		uint64_t bytesPerThread, std::ostream& out); // :2850-2876
 }
+
+/* Coordinator::waitForUserDefinedStartTime (Coordinator.cpp:149-158) */
+void waitForUserDefinedStartTime(const ProgArgs& progArgs);
 
 /* expected entries/bytes per worker (WorkerManager::getPhaseNumEntriesAndBytes, :333-487) */
 void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,

@@ -75,6 +75,9 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.randomAmount = cfg->randomAmount;
 	c.randOffsetSeed = cfg->randOffsetSeed;
 	c.randOffsetAlgo = cfg->randOffsetAlgo;
+	c.limitReadBps = cfg->limitReadBps;
+	c.limitWriteBps = cfg->limitWriteBps;
+	c.doInfiniteIOLoop = (cfg->doInfiniteIOLoop != 0);
 	c.integrityCheckSalt = cfg->integrityCheckSalt;
 	c.doDirectVerify = cfg->doDirectVerify;
 	c.doReadInline = cfg->doReadInline;

@@ -9,6 +9,7 @@
  */
 #include <signal.h>
 #include <sys/ioctl.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -88,6 +89,11 @@ class Coordinator
 		void runBenchmarks();
 		void runBenchmarkPhase(int benchPhase);
 		void runSyncAndDropCaches();
+		bool liveCSVHeaderPrinted{false};
+		void printLiveStatsCSV(int benchPhase, const elb_liveops liveOps[2],
+			const elb_liveops oldLiveOps[2], const elb_livelat& liveLat, uint64_t intervalUSec,
+			size_t numWorkersDone, uint64_t expectedEntries, uint64_t expectedBytes,
+			uint64_t elapsedMS);
 		void printLiveStatsLine(int benchPhase, const elb_liveops liveOps[2],
 			const elb_liveops oldLiveOps[2], uint64_t intervalUSec, size_t numWorkersDone,
 			uint64_t elapsedSec);
@@ -196,6 +202,83 @@ void Coordinator::printLiveStatsLine(int benchPhase, const elb_liveops liveOps[2
 	std::cout << lineStr << std::flush;
 }
 
+/* Statistics::prepLiveCSVFile + printLiveStatsCSV (:2944-3113): one "Total" line per interval
+ * (plus a "Read" line in rwmix phases) with the aggregate of all local workers */
+void Coordinator::printLiveStatsCSV(int benchPhase, const elb_liveops liveOps[2],
+	const elb_liveops oldLiveOps[2], const elb_livelat& liveLat, uint64_t intervalUSec,
+	size_t numWorkersDone, uint64_t expectedEntries, uint64_t expectedBytes, uint64_t elapsedMS)
+{
+	const bool toStdout = (progArgs.liveCSVFilePath == "stdout");
+	std::ofstream fileStream;
+	bool printHeaders = toStdout ? !liveCSVHeaderPrinted : false;
+
+	if(!toStdout)
+	{
+		struct stat statBuf;
+		printHeaders = (stat(progArgs.liveCSVFilePath.c_str(), &statBuf) != 0) ||
+			!statBuf.st_size;
+
+		fileStream.open(progArgs.liveCSVFilePath, std::ofstream::app);
+
+		if(!fileStream)
+			throw ProgError("Unable to open live stats csv file: " + progArgs.liveCSVFilePath);
+	}
+
+	std::ostream& out = toStdout ? std::cout : fileStream;
+
+	if(printHeaders)
+		out << "ISO Date,Label,Phase,RuntimeMS,Rank,MixType,Done%,DoneBytes,MiB/s,IOPS,Entries,"
+			"Entries/s,Lat Ent us,Lat IO us,Active,CPU,Service," << std::endl;
+
+	liveCSVHeaderPrinted = true;
+
+	const bool isRWMixPhase = (liveOps[1].numBytesDone || liveOps[1].numEntriesDone);
+	const bool isDirMode = (progArgs.benchPathType == ELB_PATH_DIR);
+	const std::string isoDate = isoDateNow(true);
+	const std::string phaseName = stats::phaseName(benchPhase, progArgs);
+	std::string label = progArgs.benchLabel;
+	std::replace(label.begin(), label.end(), ',', ' ');
+
+	liveCpuUtil.update();
+
+	auto perSec = [&](uint64_t newVal, uint64_t oldVal)
+		{ return intervalUSec ? perSecFromUSec(newVal - oldVal, intervalUSec) : 0; };
+	auto percentDone = [&](const elb_liveops& ops)
+	{
+		uint64_t percent = 0;
+
+		if(expectedBytes)
+			percent = (100 * ops.numBytesDone) / expectedBytes;
+		else
+		if(expectedEntries)
+			percent = (100 * ops.numEntriesDone) / expectedEntries;
+
+		return std::min(percent, (uint64_t)100);
+	};
+	auto avg = [](uint64_t sum, uint64_t num) { return num ? (sum / num) : 0; };
+
+	for(int mixIdx = 0; mixIdx < (isRWMixPhase ? 2 : 1); mixIdx++)
+	{
+		const elb_liveops& ops = liveOps[mixIdx];
+		const elb_liveops& oldOps = oldLiveOps[mixIdx];
+
+		out << isoDate << "," << label << "," << phaseName << "," << elapsedMS << "," <<
+			"Total" << "," << (isRWMixPhase ? (mixIdx ? "Read" : "Write") : "") << "," <<
+			percentDone(ops) << "," << ops.numBytesDone << "," <<
+			(perSec(ops.numBytesDone, oldOps.numBytesDone) / (1024 * 1024) ) << "," <<
+			perSec(ops.numIOPSDone, oldOps.numIOPSDone) << "," <<
+			(isDirMode ? ops.numEntriesDone : 0) << "," <<
+			(isDirMode ? perSec(ops.numEntriesDone, oldOps.numEntriesDone) : 0) << "," <<
+			(mixIdx ? avg(liveLat.avgEntriesLatReadMixMicrosSecsSum,
+				liveLat.numAvgEntriesLatReadMixValues) :
+				avg(liveLat.avgEntriesLatMicroSecsSum, liveLat.numAvgEntriesLatValues) ) << "," <<
+			(mixIdx ? avg(liveLat.avgIOLatReadMixMicroSecsSum, liveLat.numAvgIOLatReadMixValues) :
+				avg(liveLat.avgIOLatMicroSecsSum, liveLat.numAvgIOLatValues) ) << "," <<
+			(manager->workers.size() - numWorkersDone) << "," <<
+			liveCpuUtil.getCPUUtilPercent() << "," << "" << "," << std::endl;
+	}
+}
+
 /* Statistics::printPhaseResults (:1568-1632): console + optional txt/csv/json files */
 void Coordinator::printPhaseResultsEverywhere(int benchPhase, const std::string& isoStartDate)
 {
@@ -297,9 +380,14 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 
 	liveCpuUtil.update();
 
-	const bool showLive = !progArgs.disableLiveStats &&
+	const bool showLiveLine = !progArgs.disableLiveStats &&
 		(isatty(STDOUT_FILENO) || getenv("ELB_FORCE_LIVESTATS") );
+	const bool writeLiveCSV = !progArgs.liveCSVFilePath.empty();
+	const bool showLive = showLiveLine || writeLiveCSV;
 	const bool useLiveReduce = (manager->getNumGPUs() >= 2);
+
+	uint64_t expectedEntries = 0, expectedBytes = 0; // of all local workers, for "Done%"
+	manager->getExpectedTotals(benchPhase, expectedEntries, expectedBytes);
 
 	for( ; ; )
 	{
@@ -328,6 +416,7 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 			continue;
 
 		elb_liveops liveOps[2] = {};
+		elb_livelat liveLat = {};
 		size_t numWorkersDone;
 
 		if(useLiveReduce)
@@ -336,12 +425,16 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 			manager->getLiveSnapshot(snapshot);
 			liveOps[0] = snapshot.ops;
 			liveOps[1] = snapshot.opsReadMix;
+			liveLat = snapshot.lat;
 		}
 		else
 			for(const std::unique_ptr<Worker>& worker : manager->workers)
 			{
 				liveOpsAdd(liveOps[0], worker->getLiveOps() );
 				liveOpsAdd(liveOps[1], worker->getLiveOpsReadMix() );
+
+				if(writeLiveCSV)
+					worker->getAndResetLiveLatency(liveLat);
 			}
 
 		{
@@ -353,10 +446,22 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 		const uint64_t intervalUSec =
 			std::chrono::duration_cast<std::chrono::microseconds>(nowT - lastLiveT).count();
 
-		printLiveStatsLine(benchPhase, liveOps, oldLiveOps, intervalUSec, numWorkersDone,
-			elapsedSec);
+		if(writeLiveCSV)
+			printLiveStatsCSV(benchPhase, liveOps, oldLiveOps, liveLat, intervalUSec,
+				numWorkersDone, expectedEntries, expectedBytes,
+				std::chrono::duration_cast<std::chrono::milliseconds>(nowT - phaseStartT).count() );
 
-		printedLiveLine = true;
+		if(showLiveLine)
+		{
+			printLiveStatsLine(benchPhase, liveOps, oldLiveOps, intervalUSec, numWorkersDone,
+				elapsedSec);
+
+			if(progArgs.useBriefLiveStatsNewLine)
+				std::cout << std::endl; // --live1n
+			else
+				printedLiveLine = true;
+		}
+
 		oldLiveOps[0] = liveOps[0];
 		oldLiveOps[1] = liveOps[1];
 		lastLiveT = nowT;
@@ -388,6 +493,22 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 		std::vector<uint64_t> elapsedUSecVec(1, res.lastFinishUSec);
 		stats::printPhaseResults(progArgs, benchPhase, res, elapsedUSecVec, std::cout);
 	}
+}
+
+void waitForUserDefinedStartTime(const ProgArgs& progArgs) // Coordinator.cpp:149-158
+{
+	if(!progArgs.startTime)
+		return;
+
+	if(time(NULL) > (time_t)progArgs.startTime)
+		throw ProgError("Defined start time has already passed. Aborting.");
+
+	if(!progArgs.disableLiveStats)
+		std::cout << "Waiting for start time: " << (progArgs.startTime - time(NULL) ) << "s" <<
+			std::endl;
+
+	while(time(NULL) < (time_t)progArgs.startTime)
+		usleep(1000);
 }
 
 void Coordinator::runSyncAndDropCaches() // Coordinator.cpp:380-413
@@ -491,6 +612,8 @@ int Coordinator::main() // Coordinator.cpp:31-142
 		sigAction.sa_handler = interruptSignalHandler;
 		sigaction(SIGINT, &sigAction, NULL);
 		sigaction(SIGTERM, &sigAction, NULL);
+
+		waitForUserDefinedStartTime(progArgs);
 
 		runBenchmarks();
 

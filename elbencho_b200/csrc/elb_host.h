@@ -14,6 +14,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -247,6 +249,52 @@ inline int RandAlgo::algoFromString(const std::string& algoString)
 
 	return -1;
 }
+
+/* ---- per-thread rate limit (toolkits/RateLimiter.h:13-66): budget per second; the block that
+ * would exceed it sleeps until the second is over ---- */
+class RateLimiter
+{
+	public:
+		void initStart(uint64_t newLimitPerSec)
+		{
+			limitPerSec = newLimitPerSec;
+			numDoneThisSec = 0;
+			startT = std::chrono::steady_clock::now();
+		}
+
+		bool isEnabled() const { return limitPerSec != 0; }
+
+		/* @return true if the caller had to sleep */
+		bool wait(uint64_t nextSize)
+		{
+			const std::chrono::steady_clock::time_point nowT = std::chrono::steady_clock::now();
+			const int64_t elapsedUSec =
+				std::chrono::duration_cast<std::chrono::microseconds>(nowT - startT).count();
+
+			if(elapsedUSec >= 1000000)
+			{ // a second went by without exceeding the limit
+				numDoneThisSec = nextSize;
+				startT = std::chrono::steady_clock::now();
+				return false;
+			}
+
+			if( (numDoneThisSec + nextSize) > limitPerSec)
+			{
+				std::this_thread::sleep_until(startT + std::chrono::microseconds(1000000) );
+				numDoneThisSec = nextSize;
+				startT = std::chrono::steady_clock::now();
+				return true;
+			}
+
+			numDoneThisSec += nextSize;
+			return false;
+		}
+
+	private:
+		uint64_t limitPerSec{0};
+		uint64_t numDoneThisSec{0};
+		std::chrono::steady_clock::time_point startT;
+};
 
 /* ---- Offset plans (toolkits/offsetgen/OffsetGenerator.h, OffsetGenRandomAlignedFullCoverageV2.h)
  *
@@ -642,6 +690,9 @@ struct Config
 	uint64_t randomAmount{0};
 	uint64_t randOffsetSeed{0};
 	int randOffsetAlgo{ELB_OFFSETALGO_XOSHIRO256SS};
+	uint64_t limitReadBps{0};
+	uint64_t limitWriteBps{0};
+	bool doInfiniteIOLoop{false};
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

@@ -1020,6 +1020,9 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.gpuIDsStr = recvTree.getStr("gpuids", "");
 		args.ignoreDelErrors = recvTree.getBool("nodelerr", false);
 		args.integrityCheckSalt = recvTree.getU64("verify", 0);
+		args.doInfiniteIOLoop = recvTree.getBool("infloop", false);
+		args.limitReadBps = recvTree.getU64("limitread", 0);
+		args.limitWriteBps = recvTree.getU64("limitwrite", 0);
 		args.ioDepth = recvTree.getU64("iodepth", 1);
 		args.numDirs = recvTree.getU64("dirs", 1);
 		args.numFiles = recvTree.getU64("files", 1);
@@ -1650,11 +1653,11 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("hdfs", false);
 	tree.putBool("no0usecerr", args.ignore0USecErrors);
 	tree.putBool("nodelerr", args.ignoreDelErrors);
-	tree.putBool("infloop", false);
+	tree.putBool("infloop", args.doInfiniteIOLoop);
 	tree.put("verify", args.integrityCheckSalt);
 	tree.put("iodepth", args.ioDepth);
-	tree.put("limitread", (uint64_t)0);
-	tree.put("limitwrite", (uint64_t)0);
+	tree.put("limitread", args.limitReadBps);
+	tree.put("limitwrite", args.limitWriteBps);
 	tree.put("madv", (uint64_t)0);
 	tree.putBool("mmap", false);
 	tree.putBool("netbench", false);
@@ -1716,7 +1719,13 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	// dynamically calculated values for service hosts (:3845-3861)
 	tree.put("rankoffset", args.rankOffset + (serviceRank * args.numThreads) );
 	tree.put("treefile", "");
-	tree.put("gpuids", args.gpuIDsStr);
+	if(!args.assignGPUPerService || args.gpuIDs.empty() )
+		tree.put("gpuids", args.gpuIDsStr);
+	else
+	{ // --gpuperservice: one GPU of the list per service instance (ProgArgs.cpp:3852-3859)
+		const size_t gpuIndex = serviceRank % args.gpuIDs.size();
+		tree.put("gpuids", std::to_string(args.gpuIDs[gpuIndex] ) );
+	}
 
 	// extensions of this build
 	tree.put("b200_randseed", args.randOffsetSeed);
@@ -1746,6 +1755,7 @@ class Master
 		void runPhase(int benchPhase);
 		void runSyncAndDropCaches();
 		void interruptAll(bool quit);
+		void waitForServicesReady();
 };
 
 void Master::initHosts()
@@ -2140,13 +2150,58 @@ void Master::runSyncAndDropCaches()
 		runPhase(ELB_PHASE_DROPCACHES);
 }
 
+/* Coordinator::waitForServicesReady (Coordinator.cpp:160-230): GET /status on every service until
+ * all answer or --svcwait seconds are over */
+void Master::waitForServicesReady()
+{
+	if(!progArgs.svcReadyWaitSec)
+		return;
+
+	const Clock::time_point endWaitT =
+		Clock::now() + std::chrono::seconds(progArgs.svcReadyWaitSec);
+
+	for( ; ; )
+	{
+		std::string notReadyServiceHost;
+
+		for(const RemoteHost& remote : hosts)
+		{
+			try
+			{
+				HttpResponse response = httpRequest(remote.host, remote.port, "GET", "/status", "",
+					(int)progArgs.svcReadyWaitSec);
+
+				if(response.statusCode == 200)
+					continue;
+			}
+			catch(std::exception& e) { }
+
+			notReadyServiceHost = remote.host + ":" + std::to_string(remote.port);
+			break;
+		}
+
+		if(notReadyServiceHost.empty() )
+			return;
+
+		if(Clock::now() >= endWaitT)
+			throw ProgError("Timed out waiting for services to become ready. "
+				"Unreachable service: " + notReadyServiceHost);
+
+		usleep(1000 * 1000);
+	}
+}
+
 int Master::run()
 {
 	initHosts();
 
 	try
 	{
+		waitForServicesReady();
+
 		prepareRemotePhases();
+
+		waitForUserDefinedStartTime(progArgs);
 
 		struct BenchPhaseConfig { int benchPhase; bool runPhase; };
 

@@ -436,6 +436,13 @@ void Worker::run() // LocalWorker.cpp:177-396
 				benchPhase = shared->currentBenchPhase;
 			}
 
+			/* --infloop: restart the own share of the phase until interrupted
+			   (LocalWorker.cpp:196-364; sync and dropcache phases run once) */
+			bool doInfiniteIOLoop = cfg.doInfiniteIOLoop;
+
+			do
+			{
+
 			switch(benchPhase)
 			{
 				case ELB_PHASE_TERMINATE:
@@ -475,16 +482,22 @@ void Worker::run() // LocalWorker.cpp:177-396
 
 				case ELB_PHASE_SYNC:
 					anyModeSync();
+					doInfiniteIOLoop = false;
 					break;
 
 				case ELB_PHASE_DROPCACHES:
 					anyModeDropCaches();
+					doInfiniteIOLoop = false;
 					break;
 
 				default:
 					throw WorkerError("Unknown/invalid next phase type: " +
 						std::to_string(benchPhase) );
 			}
+
+			checkInterruptionRequest(); // for infinite loop workers with no work
+
+			} while(doInfiniteIOLoop && workerGotPhaseWork);
 
 			finishPhase();
 		}
@@ -1116,6 +1129,9 @@ void Worker::rwPhase()
 			"GPU counter block reset");
 
 	initPhaseOffsetPlan();
+
+	// plain per-thread rate limit (LocalWorker.cpp:1293-1299 write side, 1331-1337 read side)
+	rateLimiter.initStart(isRead ? cfg.limitReadBps : cfg.limitWriteBps);
 
 	if(cfg.pathType == ELB_PATH_DIR)
 	{
@@ -1872,6 +1888,9 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 
 		if(block.len)
 		{
+			if(rateLimiter.isEnabled() )
+				rateLimiter.wait(block.len); // --limitread/--limitwrite (LocalWorker.cpp:1689)
+
 			Clock::time_point ioStartT = Clock::now();
 			char* hostBuf = slotHostPtr(batch, i);
 			ssize_t ioRes;
@@ -1973,6 +1992,10 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 			const size_t numToSubmit = std::min(numIocbs - numSubmitted,
 				(size_t)cfg.ioDepth - numInFlight);
 			const Clock::time_point submitT = Clock::now();
+
+			if(rateLimiter.isEnabled() ) // (LocalWorker.cpp:1842, 2003)
+				for(size_t k = 0; k < numToSubmit; k++)
+					rateLimiter.wait(batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].len);
 
 			for(size_t k = 0; k < numToSubmit; k++)
 				batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].submitT = submitT;
@@ -2089,6 +2112,9 @@ void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
 
 		CUfileHandle_t handle = resolveCuFileHandle(block, isRead);
 
+		if(block.len && rateLimiter.isEnabled() )
+			rateLimiter.wait(block.len);
+
 		if(block.len)
 		{
 			const off_t devOffset = (off_t)( (uint64_t)(batch.firstSlot + i) * slotStride);
@@ -2161,6 +2187,9 @@ void Worker::ioRunCuFileBatch(Batch& batch, bool isRead)
 		{
 			const size_t blockIdx = blockIdxVec[groupStart + k];
 			BlockRef& block = batch.blocks[blockIdx];
+
+			if(rateLimiter.isEnabled() )
+				rateLimiter.wait(block.len);
 
 			CUfileIOParams_t& params = batch.cuParams[k];
 			memset(&params, 0, sizeof(params) );

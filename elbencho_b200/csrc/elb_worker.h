@@ -222,6 +222,7 @@ class Worker
 
 		// offsets
 		std::unique_ptr<RandAlgo> randOffsetAlgo; // --randalgo
+		RateLimiter rateLimiter; // --limitread / --limitwrite
 		std::unique_ptr<OffsetPlan> offsetPlan;
 		uint64_t blockVarianceSeed{0};
 

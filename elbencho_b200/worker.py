@@ -79,6 +79,9 @@ class WorkerConfig:
     random_amount: int = 0            # --randamount
     rand_offset_seed: int = 0         # injected seed (0 = self-seed like the reference)
     rand_offset_algo: int = 0         # --randalgo (OffsetRandAlgo)
+    limit_read_bps: int = 0           # --limitread (per thread, 0 = unlimited)
+    limit_write_bps: int = 0          # --limitwrite
+    do_infinite_io_loop: bool = False  # --infloop
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -147,6 +150,9 @@ class WorkerConfig:
         cfg.serializeBufferedWrites = int(self.serialize_buffered_writes)
         cfg.numRWMixReadThreads = self.num_rwmix_read_threads
         cfg.randOffsetAlgo = int(self.rand_offset_algo)
+        cfg.limitReadBps = self.limit_read_bps
+        cfg.limitWriteBps = self.limit_write_bps
+        cfg.doInfiniteIOLoop = int(self.do_infinite_io_loop)
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

@@ -258,6 +258,15 @@ typedef struct elb_cfg
 	 * phase; their stats go to the ReadMix counters (LocalWorker.cpp:1028-1041) */
 	uint32_t numRWMixReadThreads;
 	int32_t randOffsetAlgo; /* enum elb_offset_rand_algo (--randalgo) */
+
+	/* --limitread / --limitwrite: per-thread bytes per second, 0 = unlimited (RateLimiter.h:13-66,
+	 * LocalWorker.cpp:1293-1299, 1331-1337); applied per block before its storage call */
+	uint64_t limitReadBps;
+	uint64_t limitWriteBps;
+	/* --infloop: every worker restarts its share of the phase when it reaches the end, until
+	 * interrupted or until the time limit (LocalWorker.cpp:196-364) */
+	int32_t doInfiniteIOLoop;
+	int32_t reserved3;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ from elbencho_b200.build import CLI_PATH
 from elbencho_b200._native import PhaseResults
 
 GiB = 1 << 30
+MiB = 1 << 20
 
 
 def run_cli(*args, timeout=60):
@@ -62,6 +63,53 @@ def test_rand_algo_names_of_the_reference_are_accepted(algo):
     # RandAlgoSelectorTk.h:10-13
     res = run_cli("--dryrun", "-r", "-b", "4K", "-s", "1G", "--rand", "--randalgo", algo,
                   "--blockvaralgo", algo, "--gpuids", "0", "/tmp/elb_dry")
+    assert res.returncode == 0, res.stderr
+
+
+def test_config_file_options_and_paths(tmp_path):
+    """--configfile: OPTIONNAME=VALUE lines, command line wins, path= lines (ProgArgs.cpp:1012-1030)"""
+    cfg = tmp_path / "bench.conf"
+    cfg.write_text("# comment\nwrite=1\nread = true\nblock=4K\nsize=1M\nthreads=2\n"
+                   "gpuids=0\nverify=0\npath=/tmp/elb_dry_cfg\n")
+    res = run_cli("--dryrun", "-c", str(cfg), "-t", "4")
+    assert res.returncode == 0, res.stderr
+    assert "WRITE" in res.stdout and "READ" in res.stdout
+    # 1 MiB file / 4 threads (command line wins over threads=2)
+    assert "* Bytes per thread:   %d |" % (MiB // 4) in res.stdout
+    cfg.write_text("nosuchoption=1\n")
+    res = run_cli("--dryrun", "-c", str(cfg), "-w", "--gpuids", "0", "/tmp/x")
+    assert res.returncode == 1 and "unrecognised option 'nosuchoption'" in res.stderr
+    res = run_cli("--dryrun", "-c", str(tmp_path / "missing.conf"), "-w", "--gpuids", "0", "/tmp/x")
+    assert res.returncode == 1 and "Unable to read config file" in res.stderr
+
+
+def test_hosts_file_numhosts_and_duplicates(tmp_path):
+    """ProgArgs::parseHosts (ProgArgs.cpp:2221-2340)"""
+    hosts = tmp_path / "hosts.txt"
+    hosts.write_text("# services\nnode1:1611\nnode2\n")
+    # --numhosts 0: ignore all hosts and run locally (here: dry run)
+    res = run_cli("--dryrun", "-w", "-s", "1M", "--gpuids", "0", "--hostsfile", str(hosts),
+                  "--numhosts", "0", "/tmp/elb_dry")
+    assert res.returncode == 0, res.stderr
+    res = run_cli("-w", "-s", "1M", "--gpuids", "0", "--hosts", "node1,node1", "/tmp/elb_dry")
+    assert res.returncode == 1 and "List of hosts contains duplicates" in res.stderr
+    res = run_cli("-w", "-s", "1M", "--gpuids", "0", "--hostsfile", str(tmp_path / "none"),
+                  "/tmp/elb_dry")
+    assert res.returncode == 1 and "Unable to read hosts file" in res.stderr
+    # unreachable services: --svcwait bounds the wait (Coordinator.cpp:160-230)
+    res = run_cli("-w", "-s", "1M", "--gpuids", "0", "--hosts", "127.0.0.1:1", "--svcwait", "1",
+                  "/tmp/elb_dry", timeout=30)
+    assert res.returncode == 1
+    assert "Timed out waiting for services to become ready. Unreachable service: 127.0.0.1:1" \
+        in res.stderr
+
+
+def test_new_run_control_options_parse():
+    res = run_cli("--dryrun", "-w", "-r", "-s", "1M", "--gpuids", "0", "--infloop", "--timelimit",
+                  "1", "--limitread", "10M", "--limitwrite", "1G", "--live1", "--live1n",
+                  "--cuhostbufreg", "--nodiocheck", "--nopathexp", "--datasetthreads", "4",
+                  "--rankoffset", "1", "--start", "0", "--livecsv", "/tmp/elb_live.csv",
+                  "/tmp/elb_dry")
     assert res.returncode == 0, res.stderr
 
 

@@ -179,3 +179,68 @@ def test_distributed_mode_two_services_on_localhost(workdir):
         for svc in services:
             if svc.poll() is None:
                 svc.kill()
+
+
+def test_rate_limit_infloop_livecsv_and_start_time(workdir):
+    """run control options of the reference: --limitwrite (RateLimiter.h), --infloop +
+    --timelimit (LocalWorker.cpp:196-364), --livecsv (Statistics.cpp:2944-3113), --start"""
+    path = os.path.join(workdir, "ctl.bin")
+    # 2 threads x 8 MiB at 4 MiB/s per thread: the second half of each share has to wait one second
+    t0 = time.time()
+    res = run_cli("-w", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--limitwrite", "4M",
+                  "--nolive", path)
+    elapsed = time.time() - t0
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert elapsed >= 1.0
+    assert int(table_value(res.stdout, "WRITE", "Total MiB")) == 16
+    assert int(table_value(res.stdout, "WRITE", "Throughput MiB/s")) <= 16
+
+    # infinite loop over a small file, stopped by the time limit: more bytes than the file holds
+    live_csv = os.path.join(workdir, "live.csv")
+    res = run_cli("-r", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--infloop",
+                  "--timelimit", "2", "--liveint", "200", "--livecsv", live_csv, path, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert int(table_value(res.stdout, "READ", "Total MiB")) > 16
+    with open(live_csv) as f:
+        lines = f.read().splitlines()
+    assert lines[0].startswith("ISO Date,Label,Phase,RuntimeMS,Rank,MixType,Done%,DoneBytes,MiB/s,")
+    assert len(lines[0].split(",")) == 18  # 17 columns + trailing comma
+    rows = [line.split(",") for line in lines[1:]]
+    assert len(rows) >= 3
+    assert all(row[2] == "READ" and row[4] == "Total" and len(row) == 18 for row in rows)
+    done_bytes = [int(row[7]) for row in rows]
+    assert done_bytes == sorted(done_bytes) and done_bytes[-1] > 0
+    assert all(int(row[14]) == 2 for row in rows[:2])  # both threads active
+
+    # a start time in the past is an error (Coordinator.cpp:151-152), one 2 s ahead is waited for
+    res = run_cli("-r", "-b", "1M", "-s", "16M", "--gpuids", "0", "--start", "1000", path)
+    assert res.returncode == 1 and "Defined start time has already passed" in res.stderr
+    start = int(time.time()) + 2
+    res = run_cli("-r", "-b", "1M", "-s", "16M", "--gpuids", "0", "--nolive", "--start",
+                  str(start), path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert time.time() >= start
+
+
+def test_gpu_per_service_assignment(workdir):
+    """--gpuperservice: service i gets GPU gpuids[i % n] (ProgArgs.cpp:3852-3859)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ports = [free_port(), free_port()]
+    services = [subprocess.Popen([CLI_PATH, "--service", "--foreground", "--port", str(p)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE) for p in ports]
+    try:
+        path = os.path.join(workdir, "gps.bin")
+        hosts = ",".join("127.0.0.1:%d" % p for p in ports)
+        res = run_cli("-w", "-r", "-t", "2", "-b", "1M", "-s", "32M", "--verify", "1", "--gpuids",
+                      "0,1", "--gpuperservice", "--hosts", hosts, "--svcwait", "20", path)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert int(table_value(res.stdout, "READ", "Total MiB")) == 32
+    finally:
+        run_cli("--quit", "--hosts", hosts)
+        for svc in services:
+            try:
+                svc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                svc.kill()

@@ -1,0 +1,50 @@
+"""Turn the raw page of an `ncu --set full` capture of the three block kernels into
+profiles/ncu_traffic.json, which bench.py reads for `roofline.traffic` (DRAM bytes per launch).
+
+    ncu -i gpurun_out/prof_blocks_kernels_4g.ncu-rep --page raw --csv > raw.csv
+    python scripts/ncu_traffic.py raw.csv <window_bytes> profiles/<copy of raw.csv>
+"""
+import csv
+import json
+import os
+import sys
+
+UNIT_FACTORS = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
+                "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
+MODES = {"<0>": "K1_fill_pattern", "<1>": "K2_verify_pattern", "<2>": "K3_fill_random_pct100"}
+
+
+def main():
+    raw_path, window_bytes, source = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    rows = list(csv.reader(open(raw_path)))
+    header, units = rows[0], rows[1]
+    col = {name: i for i, name in enumerate(header)}
+
+    def value(row, name):
+        return float(row[col[name]].replace(",", "")) * UNIT_FACTORS.get(units[col[name]], 1)
+
+    kernels = {}
+    for row in rows[2:]:
+        name = row[col["Kernel Name"]]
+        key = next((val for tag, val in MODES.items() if tag in name), None)
+        if key is None or key in kernels:
+            continue
+        kernels[key] = {
+            "kernel": name.split("(")[0].replace("void ", ""),
+            "dram_bytes_read": int(value(row, "dram__bytes_read.sum")),
+            "dram_bytes_write": int(value(row, "dram__bytes_write.sum")),
+            "duration_us": round(value(row, "gpu__time_duration.sum"), 2),
+            "registers_per_thread": int(value(row, "launch__registers_per_thread")),
+        }
+    out = {"window_bytes": window_bytes, "source": source,
+           "tool": "ncu --set full --clock-control none (one launch per kernel)",
+           "kernels": kernels}
+    out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                            "profiles", "ncu_traffic.json")
+    with open(out_path, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -75,7 +75,7 @@ class Cfg(ctypes.Structure):
         ("limitReadBps", c_u64),
         ("limitWriteBps", c_u64),
         ("doInfiniteIOLoop", ctypes.c_int32),
-        ("reserved3", ctypes.c_int32),
+        ("rwMixThreadsReadPercent", c_u32),
     ]
 
 

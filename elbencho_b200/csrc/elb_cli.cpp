@@ -78,6 +78,9 @@ static const OptDef optDefs[] =
 	{"rwmixpct", 0, Opt_U64, "Percentage of blocks that should be read in a write phase."},
 	{"rwmixthr", 0, Opt_U64, "Number of threads that should do reads in a write phase."},
 	// GPU
+	{"rwmixthrpct", 0, Opt_U64, "Percentage of bytes that the --rwmixthr reader threads should "
+		"read out of all bytes of a write phase (rate balancing between readers and writers; "
+		"typically used with --infloop and --timelimit). (Default: 0 = no balancing)"},
 	{"gpuids", 0, Opt_STR, "Comma-separated list of CUDA GPU IDs (also \"all\", \"[0-7]\", "
 		"\"0-7\") to use for the on-GPU block fill/verify. Mandatory."},
 	{"cuhostbufreg", 0, Opt_FLAG, "Pin host memory buffers and register with CUDA for faster "
@@ -490,6 +493,7 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("blockvarseed", blockVarianceSeed);
 	hasUserSetRWMixPercent = num("rwmixpct", rwMixReadPercent);
 	hasUserSetRWMixReadThreads = num("rwmixthr", numRWMixReadThreads);
+	num("rwmixthrpct", rwMixThreadsReadPercent);
 
 	str("gpuids", gpuIDsStr);
 	useCuFile = flag("cufile");
@@ -756,6 +760,13 @@ void ProgArgs::checkArgs()
 	if(blockVariancePercent > 100)
 		throw ProgError("Block variance percent must be in range 0..100");
 
+	if(rwMixThreadsReadPercent > 100)
+		throw ProgError("Read percentage of rwmix threads must be in range 0..100");
+
+	if(rwMixThreadsReadPercent && (limitReadBps || limitWriteBps) ) // ProgArgs.cpp:1406-1408
+		throw ProgError("Option \"--rwmixthrpct\" cannot be used together with "
+			"\"--limitread\" or \"--limitwrite\"");
+
 	/* names of RandAlgoSelectorTk.h:10-13. The block variance bytes are generated on the GPU by
 	   one counter-based generator whatever the name says, like the reference's GPU refill always
 	   uses cuRAND (LocalWorker.cpp:2236-2277) */
@@ -825,6 +836,7 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	cfg.rwMixThreadsReadPercent = (uint32_t)rwMixThreadsReadPercent;
 	cfg.limitReadBps = limitReadBps;
 	cfg.limitWriteBps = limitWriteBps;
 	cfg.doInfiniteIOLoop = doInfiniteIOLoop;

@@ -78,6 +78,7 @@ class ProgArgs
 		bool hasUserSetRWMixPercent{false};
 		uint64_t numRWMixReadThreads{0};
 		bool hasUserSetRWMixReadThreads{false};
+		uint64_t rwMixThreadsReadPercent{0}; // --rwmixthrpct
 		std::vector<int> gpuIDs;
 		std::string gpuIDsStr;
 		bool useCuFile{false};

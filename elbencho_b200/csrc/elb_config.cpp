@@ -78,6 +78,14 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.limitReadBps = cfg->limitReadBps;
 	c.limitWriteBps = cfg->limitWriteBps;
 	c.doInfiniteIOLoop = (cfg->doInfiniteIOLoop != 0);
+	c.rwMixThreadsReadPercent = cfg->rwMixThreadsReadPercent;
+
+	if(c.rwMixThreadsReadPercent > 100)
+		throw WorkerError("Read percentage of rwmix threads must be in range 0..100");
+
+	if(c.rwMixThreadsReadPercent && (c.limitReadBps || c.limitWriteBps) ) // ProgArgs.cpp:1406
+		throw WorkerError("Option \"--rwmixthrpct\" cannot be used together with "
+			"\"--limitread\" or \"--limitwrite\"");
 	c.integrityCheckSalt = cfg->integrityCheckSalt;
 	c.doDirectVerify = cfg->doDirectVerify;
 	c.doReadInline = cfg->doReadInline;

@@ -16,6 +16,8 @@
 #include <atomic>
 #include <chrono>
 #include <thread>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -294,6 +296,107 @@ class RateLimiter
 		uint64_t limitPerSec{0};
 		uint64_t numDoneThisSec{0};
 		std::chrono::steady_clock::time_point startT;
+};
+
+/* ---- --rwmixthrpct: balance the bytes of the reader threads of a write phase against the bytes
+ * of its writer threads (toolkits/RateLimiterRWMixThreads.h:22-197). One instance per manager
+ * (the reference keeps the counters in static members). A thread of one group may proceed while
+ * its group's share of all bytes, counting a head room of one block per thread of the other
+ * group, is at most the configured percentage; otherwise it naps 20 ms at a time and wakes the
+ * other group. ---- */
+class RWMixThreadsBalancer
+{
+	public:
+		void initStart(unsigned newReadRatioPercent, unsigned newNumReaderThreads,
+			unsigned newNumWriterThreads, uint64_t newMaxBlockSize)
+		{
+			readRatioPercent = newReadRatioPercent;
+			numReaderThreads = newNumReaderThreads;
+			numWriterThreads = newNumWriterThreads;
+			maxBlockSize = newMaxBlockSize;
+			numBytesRead = 0;
+			numBytesWrite = 0;
+		}
+
+		bool isEnabled() const { return readRatioPercent != 0; }
+
+		/* @throw WorkerInterrupted, WorkerError (after 600 s of waiting) */
+		bool waitRead(uint64_t nextBlockSize, const std::atomic_bool& isInterruptionRequested)
+		{
+			return wait(true, nextBlockSize, isInterruptionRequested);
+		}
+
+		bool waitWrite(uint64_t nextBlockSize, const std::atomic_bool& isInterruptionRequested)
+		{
+			return wait(false, nextBlockSize, isInterruptionRequested);
+		}
+
+	private:
+		unsigned readRatioPercent{0};
+		unsigned numReaderThreads{0};
+		unsigned numWriterThreads{0};
+		uint64_t maxBlockSize{0};
+
+		std::atomic<uint64_t> numBytesRead{0};
+		std::atomic<uint64_t> numBytesWrite{0};
+		std::condition_variable readWaitCondition;
+		std::condition_variable writeWaitCondition;
+		std::mutex readWaitMutex;  // (protects nothing, condition variables need one)
+		std::mutex writeWaitMutex;
+
+		bool wait(bool isReader, uint64_t nextBlockSize,
+			const std::atomic_bool& isInterruptionRequested)
+		{
+			const unsigned maxWaitTimeoutSecs = 600;
+			const unsigned sleepMS = 20;
+			const std::chrono::steady_clock::time_point waitStartT =
+				std::chrono::steady_clock::now();
+			bool hadToWait = false;
+
+			std::atomic<uint64_t>& ownBytes = isReader ? numBytesRead : numBytesWrite;
+			std::atomic<uint64_t>& otherBytes = isReader ? numBytesWrite : numBytesRead;
+			const uint64_t headRoomBytes =
+				maxBlockSize * (isReader ? numWriterThreads : numReaderThreads);
+			const unsigned ownPercent = isReader ? readRatioPercent : (100 - readRatioPercent);
+			std::condition_variable& ownCondition =
+				isReader ? readWaitCondition : writeWaitCondition;
+			std::condition_variable& otherCondition =
+				isReader ? writeWaitCondition : readWaitCondition;
+			std::mutex& ownMutex = isReader ? readWaitMutex : writeWaitMutex;
+
+			for( ; ; )
+			{
+				const uint64_t otherWithHeadroom = otherBytes + headRoomBytes;
+				const uint64_t numBytesAllowed = ( (otherWithHeadroom + ownBytes) * ownPercent) / 100;
+
+				if(ownBytes <= numBytesAllowed)
+				{
+					ownCondition.notify_all();
+					ownBytes += nextBlockSize;
+					return hadToWait;
+				}
+
+				hadToWait = true;
+
+				if(isInterruptionRequested)
+					throw WorkerInterrupted();
+
+				const int64_t elapsedSecs = std::chrono::duration_cast<std::chrono::seconds>(
+					std::chrono::steady_clock::now() - waitStartT).count();
+
+				if(elapsedSecs >= maxWaitTimeoutSecs)
+					throw WorkerError(std::string("Max wait time exceeded for rate balanced ") +
+						(isReader ? "reader. Your read ratio might be too high so that the readers" :
+							"writer. Your read ratio might be too low so that the writers") +
+						" starve over a long time or you might have forgotten to add --infloop. "
+						"Max wait time in secs: " + std::to_string(maxWaitTimeoutSecs) );
+
+				otherCondition.notify_all();
+
+				std::unique_lock<std::mutex> lock(ownMutex);
+				ownCondition.wait_for(lock, std::chrono::milliseconds(sleepMS) );
+			}
+		}
 };
 
 /* ---- Offset plans (toolkits/offsetgen/OffsetGenerator.h, OffsetGenRandomAlignedFullCoverageV2.h)
@@ -693,6 +796,7 @@ struct Config
 	uint64_t limitReadBps{0};
 	uint64_t limitWriteBps{0};
 	bool doInfiniteIOLoop{false};
+	unsigned rwMixThreadsReadPercent{0}; // --rwmixthrpct
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

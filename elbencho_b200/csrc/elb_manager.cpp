@@ -245,6 +245,13 @@ void Manager::startNextPhase(int benchPhase)
 	shared.cpuUtilLastDonePercent = 0;
 	shared.phaseStartT = Clock::now();
 
+	// --rwmixthrpct (LocalWorker.cpp:1284-1290): fresh byte counters for every phase
+	shared.rwMixThreadsBalancer.initStart(
+		(benchPhase == ELB_PHASE_CREATEFILES) && shared.cfg.numRWMixReadThreads ?
+			shared.cfg.rwMixThreadsReadPercent : 0,
+		shared.cfg.numRWMixReadThreads, shared.cfg.numThreads - shared.cfg.numRWMixReadThreads,
+		shared.cfg.blockSize);
+
 	shared.condition.notify_all();
 }
 

@@ -1028,6 +1028,7 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.numFiles = recvTree.getU64("files", 1);
 		args.numRWMixReadThreads = recvTree.getU64("rwmixthr", 0);
 		args.hasUserSetRWMixReadThreads = (args.numRWMixReadThreads != 0);
+		args.rwMixThreadsReadPercent = recvTree.getU64("rwmixthrpct", 0);
 		args.numThreads = recvTree.getU64("threads", 1);
 		args.randOffsetAlgo = recvTree.getStr("randalgo", "");
 		args.randomAmount = recvTree.getU64("randamount", 0);
@@ -1683,7 +1684,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("backward", args.doReverseSeqOffsets);
 	tree.put("rwmixpct", args.rwMixReadPercent);
 	tree.put("rwmixthr", args.numRWMixReadThreads);
-	tree.put("rwmixthrpct", (uint64_t)0);
+	tree.put("rwmixthrpct", args.rwMixThreadsReadPercent);
 
 	// S3 keys: neutral values
 	const char* s3EmptyStrings[] = {"s3key", "s3secret", "s3aclgrantee", "s3aclgtype",

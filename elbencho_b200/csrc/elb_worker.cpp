@@ -1103,6 +1103,20 @@ void Worker::anyModeDropCaches() // LocalWorker.cpp:7822-7854
  * Read/write phases
  * ============================================================================================ */
 
+void Worker::rateLimitNextBlock(uint64_t len)
+{
+	if(useRWMixThreadsBalancer)
+	{
+		if(isRWMixReaderThread)
+			shared->rwMixThreadsBalancer.waitRead(len, isInterruptionRequested);
+		else
+			shared->rwMixThreadsBalancer.waitWrite(len, isInterruptionRequested);
+	}
+	else
+	if(rateLimiter.isEnabled() )
+		rateLimiter.wait(len);
+}
+
 void Worker::rwPhase()
 {
 	/* --rwmixthr: the first numRWMixReadThreads local workers read during the write phase
@@ -1130,8 +1144,12 @@ void Worker::rwPhase()
 
 	initPhaseOffsetPlan();
 
-	// plain per-thread rate limit (LocalWorker.cpp:1293-1299 write side, 1331-1337 read side)
-	rateLimiter.initStart(isRead ? cfg.limitReadBps : cfg.limitWriteBps);
+	/* rate balancer between the reader and writer threads of a write phase, else the plain
+	   per-thread limit (LocalWorker.cpp:1284-1299 write side, 1322-1337 read side) */
+	useRWMixThreadsBalancer = (benchPhase == ELB_PHASE_CREATEFILES) && cfg.numRWMixReadThreads &&
+		cfg.rwMixThreadsReadPercent;
+	rateLimiter.initStart(useRWMixThreadsBalancer ? 0 :
+		(isRead ? cfg.limitReadBps : cfg.limitWriteBps) );
 
 	if(cfg.pathType == ELB_PATH_DIR)
 	{
@@ -1888,8 +1906,7 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 
 		if(block.len)
 		{
-			if(rateLimiter.isEnabled() )
-				rateLimiter.wait(block.len); // --limitread/--limitwrite (LocalWorker.cpp:1689)
+			rateLimitNextBlock(block.len); // (LocalWorker.cpp:1689)
 
 			Clock::time_point ioStartT = Clock::now();
 			char* hostBuf = slotHostPtr(batch, i);
@@ -1993,9 +2010,8 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 				(size_t)cfg.ioDepth - numInFlight);
 			const Clock::time_point submitT = Clock::now();
 
-			if(rateLimiter.isEnabled() ) // (LocalWorker.cpp:1842, 2003)
-				for(size_t k = 0; k < numToSubmit; k++)
-					rateLimiter.wait(batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].len);
+			for(size_t k = 0; k < numToSubmit; k++) // (LocalWorker.cpp:1842, 2003)
+				rateLimitNextBlock(batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].len);
 
 			for(size_t k = 0; k < numToSubmit; k++)
 				batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].submitT = submitT;
@@ -2112,8 +2128,8 @@ void Worker::ioRunSyncCuFile(Batch& batch, bool isRead)
 
 		CUfileHandle_t handle = resolveCuFileHandle(block, isRead);
 
-		if(block.len && rateLimiter.isEnabled() )
-			rateLimiter.wait(block.len);
+		if(block.len)
+			rateLimitNextBlock(block.len);
 
 		if(block.len)
 		{
@@ -2188,8 +2204,7 @@ void Worker::ioRunCuFileBatch(Batch& batch, bool isRead)
 			const size_t blockIdx = blockIdxVec[groupStart + k];
 			BlockRef& block = batch.blocks[blockIdx];
 
-			if(rateLimiter.isEnabled() )
-				rateLimiter.wait(block.len);
+			rateLimitNextBlock(block.len);
 
 			CUfileIOParams_t& params = batch.cuParams[k];
 			memset(&params, 0, sizeof(params) );

@@ -64,6 +64,8 @@ struct Shared
 	std::vector<Worker*> workers;
 	std::string firstErrorMsg;
 
+	RWMixThreadsBalancer rwMixThreadsBalancer; // --rwmixthrpct (reset by the manager per phase)
+
 	/* workers hold this shared while they allocate / free device memory or instantiate graphs;
 	   the live stats reducer holds it exclusively while its collective is in flight, because a
 	   device-synchronising call on one GPU in the middle of a multi-GPU NCCL launch of the same
@@ -223,6 +225,8 @@ class Worker
 		// offsets
 		std::unique_ptr<RandAlgo> randOffsetAlgo; // --randalgo
 		RateLimiter rateLimiter; // --limitread / --limitwrite
+		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase
+		void rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)
 		std::unique_ptr<OffsetPlan> offsetPlan;
 		uint64_t blockVarianceSeed{0};
 

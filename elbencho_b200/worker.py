@@ -82,6 +82,7 @@ class WorkerConfig:
     limit_read_bps: int = 0           # --limitread (per thread, 0 = unlimited)
     limit_write_bps: int = 0          # --limitwrite
     do_infinite_io_loop: bool = False  # --infloop
+    rwmix_threads_read_percent: int = 0  # --rwmixthrpct
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -153,6 +154,7 @@ class WorkerConfig:
         cfg.limitReadBps = self.limit_read_bps
         cfg.limitWriteBps = self.limit_write_bps
         cfg.doInfiniteIOLoop = int(self.do_infinite_io_loop)
+        cfg.rwMixThreadsReadPercent = self.rwmix_threads_read_percent
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

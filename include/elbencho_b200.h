@@ -266,7 +266,9 @@ typedef struct elb_cfg
 	/* --infloop: every worker restarts its share of the phase when it reaches the end, until
 	 * interrupted or until the time limit (LocalWorker.cpp:196-364) */
 	int32_t doInfiniteIOLoop;
-	int32_t reserved3;
+	/* --rwmixthrpct: with --rwmixthr, keep the bytes of the reader threads at this percentage
+	 * of all bytes of the write phase (RateLimiterRWMixThreads.h:22-197); 0 = no balancing */
+	uint32_t rwMixThreadsReadPercent;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

@@ -138,6 +138,9 @@ def test_config3_random_read_iops_via_dryrun():
     (["-w", "-d", "-s", "1g", "--gpuids", "0", "/tmp/elb_not_a_dir.bin"],
      "only allowed if benchmark path is a directory"),
     (["-w", "-s", "1g", "--gpuids", "0"], "Benchmark path missing."),
+    (["-w", "-s", "1g", "-t", "2", "--gpuids", "0", "--rwmixthr", "1", "--rwmixthrpct", "40",
+      "--limitwrite", "1M", "/tmp/x"],
+     'Option "--rwmixthrpct" cannot be used together with "--limitread" or "--limitwrite"'),
     (["-r", "-s", "1g", "--gpuids", "0", "--rand", "--randalgo", "quick", "/tmp/x"],
      "Invalid random algo: quick"),
     (["-w", "-s", "1g", "--gpuids", "0", "--blockvarpct", "50", "--blockvaralgo", "best",

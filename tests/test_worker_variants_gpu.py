@@ -160,3 +160,38 @@ def test_variant_option_validation():
     with pytest.raises(WorkerError, match="rwmixthr"):
         WorkerManager(WorkerConfig(paths=["/tmp/x"], file_size=4096, rwmix_read_percent=10,
                                    num_rwmix_read_threads=1))
+
+
+def test_rwmixthrpct_balances_reader_and_writer_bytes(workdir):
+    """--rwmixthr 2 --rwmixthrpct 30 --infloop: the reader threads' share of all bytes of the write
+    phase stays near 30 % (RateLimiterRWMixThreads.h:22-197), although unthrottled reads would be
+    several times faster than writes on this storage"""
+    import time
+    size, block, threads, pct = 64 * MiB, 256 * KiB, 4, 30
+    path = os.path.join(workdir, "bal.bin")
+    prefill(path, size, 0)
+    cfg = WorkerConfig(paths=[path], num_threads=threads, block_size=block, file_size=size,
+                       num_rwmix_read_threads=2, rwmix_threads_read_percent=pct,
+                       do_infinite_io_loop=True, block_variance_percent=100)
+    with WorkerManager(cfg) as mgr:
+        mgr.start_phase(BenchPhase.CREATEFILES)
+        time.sleep(2.0)
+        mgr.interrupt()
+        try:
+            mgr.wait_done(-1)
+        except WorkerError:
+            pass
+        res = mgr.phase_results()
+    read_bytes = res["ops_readmix_total"]["bytes"]
+    write_bytes = res["ops_total"]["bytes"]
+    assert read_bytes > size and write_bytes > size  # both groups looped several times
+    share = 100.0 * read_bytes / (read_bytes + write_bytes)
+    assert pct - 5 <= share <= pct + 5, share
+
+
+def test_rwmixthrpct_rejects_rate_limits(workdir):
+    cfg = WorkerConfig(paths=[os.path.join(workdir, "x")], num_threads=2, block_size=MiB,
+                       file_size=4 * MiB, num_rwmix_read_threads=1, rwmix_threads_read_percent=50,
+                       limit_read_bps=1 << 20)
+    with pytest.raises(WorkerError, match="cannot be used together"):
+        WorkerManager(cfg)

@@ -76,6 +76,12 @@ class Cfg(ctypes.Structure):
         ("limitWriteBps", c_u64),
         ("doInfiniteIOLoop", ctypes.c_int32),
         ("rwMixThreadsReadPercent", c_u32),
+        ("treeFilePath", ctypes.c_char_p),
+        ("treeRoundUpSize", c_u64),
+        ("fileShareSize", c_u64),
+        ("useCustomTreeRandomize", ctypes.c_int32),
+        ("reserved4", ctypes.c_int32),
+        ("treeRandomizeSeed", c_u64),
     ]
 
 
@@ -179,6 +185,9 @@ SIGNATURES = {
     "elb_offset_plan_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
                                           ctypes.c_int, ctypes.POINTER(c_u64), c_u64,
                                           ctypes.c_int]),
+    "elb_custom_tree_worker_list": (ctypes.c_int64, [ctypes.c_char_p, c_u64, c_u64, c_u64, c_u64,
+                                                     c_u64, ctypes.c_int, ctypes.c_char_p, c_u64]),
+    "elb_custom_tree_scan": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_char_p]),
     "elb_rand_algo_create": (_VP, [ctypes.c_int, ctypes.POINTER(c_u64)]),
     "elb_rand_algo_next": (c_u64, [_VP]),
     "elb_rand_algo_destroy": (None, [_VP]),

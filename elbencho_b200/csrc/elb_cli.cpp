@@ -118,6 +118,18 @@ static const OptDef optDefs[] =
 	{"dryrun", 0, Opt_FLAG, "Don't run any benchmark phase, just print the number of expected "
 		"entries and dataset size per phase."},
 	{"iterations", 'i', Opt_U64, "Number of iterations to run the benchmark. (Default: 1)"},
+	{"treefile", 0, Opt_STR, "The path to a treefile containing a list of dirs and filenames to "
+		"use. This is called \"custom tree mode\" and enables testing with files of different "
+		"size. The benchmark path must be a directory. Lines: \"d <relative_path>\" and "
+		"\"f <size_in_bytes> <relative_path>\"."},
+	{"treescan", 0, Opt_STR, "Path to a directory to scan: its dirs and files are written to the "
+		"file given by --treefile (default: elbencho-treescan.txt) for use in custom tree mode."},
+	{"treerand", 0, Opt_FLAG, "In custom tree mode: randomize file order. (Default: order by "
+		"file size.)"},
+	{"treeroundup", 0, Opt_BYTES, "When loading a treefile, round up all contained file sizes to "
+		"a multiple of the given size. (Default: 0 = no rounding)"},
+	{"sharesize", 0, Opt_BYTES, "In custom tree mode, this defines the file size as of which "
+		"files are no longer exclusively assigned to a thread. (Default: 0 = 32 x blocksize)"},
 	{"infloop", 0, Opt_FLAG, "Let I/O threads run in an infinite repeat loop, i.e. each thread "
 		"individually restarts its work from the beginning when it reaches the end of its "
 		"workload. Terminate this via ctrl+c or by using \"--timelimit\"."},
@@ -524,6 +536,11 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("timelimit", timeLimitSecs);
 	num("log", logLevel);
 
+	str("treefile", treeFilePath);
+	str("treescan", treeScanPath);
+	useCustomTreeRandomize = flag("treerand");
+	num("treeroundup", treeRoundUpSize);
+	num("sharesize", fileShareSize);
 	doInfiniteIOLoop = flag("infloop");
 	num("limitread", limitReadBps);
 	num("limitwrite", limitWriteBps);
@@ -706,10 +723,26 @@ void ProgArgs::checkArgs()
 		return;
 	}
 
+	if(!treeScanPath.empty() && treeFilePath.empty() ) // ProgArgs.cpp:1184-1185
+		treeFilePath = "elbencho-treescan.txt";
+
+	if(!treeScanPath.empty() && benchPaths.empty() )
+		return; // scan only
+
 	if(benchPaths.empty() )
 		throw ProgError("Benchmark path missing.");
 
 	detectBenchPathType();
+
+	if( (benchPathType != ELB_PATH_DIR) && !treeFilePath.empty() ) // :1494-1495
+		throw ProgError("Custom tree mode requires benchmark path to be a directory.");
+
+	if(!treeFilePath.empty() && (benchPaths.size() > 1) ) // :1523-1524
+		throw ProgError("Custom tree mode can only be used with a single benchmark path.");
+
+	if(!treeFilePath.empty() && !hosts.empty() )
+		throw ProgError("Custom tree mode is not available together with --hosts in this build "
+			"(no tree file upload to services).");
 
 	if(!numThreads)
 		throw ProgError("Number of threads may not be zero.");
@@ -836,6 +869,11 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	cfg.treeFilePath = treeFilePath.empty() ? NULL : treeFilePath.c_str();
+	cfg.treeRoundUpSize = treeRoundUpSize;
+	cfg.fileShareSize = fileShareSize;
+	cfg.useCustomTreeRandomize = useCustomTreeRandomize;
+	cfg.treeRandomizeSeed = 0;
 	cfg.rwMixThreadsReadPercent = (uint32_t)rwMixThreadsReadPercent;
 	cfg.limitReadBps = limitReadBps;
 	cfg.limitWriteBps = limitWriteBps;

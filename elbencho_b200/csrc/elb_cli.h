@@ -88,6 +88,11 @@ class ProgArgs
 		uint64_t pipelineBatchBlocks{0};
 		uint64_t pipelineNumBatches{0};
 		bool serializeBufferedWrites{false};
+		std::string treeFilePath;       // --treefile
+		std::string treeScanPath;       // --treescan
+		uint64_t treeRoundUpSize{0};    // --treeroundup
+		uint64_t fileShareSize{0};      // --sharesize
+		bool useCustomTreeRandomize{false}; // --treerand
 		bool doInfiniteIOLoop{false};   // --infloop
 		uint64_t limitReadBps{0};       // --limitread (per thread)
 		uint64_t limitWriteBps{0};      // --limitwrite
@@ -184,8 +189,9 @@ namespace stats
 void waitForUserDefinedStartTime(const ProgArgs& progArgs);
 
 /* expected entries/bytes per worker (WorkerManager::getPhaseNumEntriesAndBytes, :333-487) */
+struct CustomTree;
 void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
-	uint64_t& outBytes);
+	uint64_t& outBytes, const CustomTree* customTree = NULL);
 
 } // namespace elb
 

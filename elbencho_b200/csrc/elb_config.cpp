@@ -102,6 +102,11 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.verifyCollectAll = cfg->verifyCollectAll;
 	c.serializeBufferedWrites = cfg->serializeBufferedWrites;
 	c.numRWMixReadThreads = std::min(cfg->numRWMixReadThreads, cfg->numThreads); // :1088
+	c.treeFilePath = cfg->treeFilePath ? cfg->treeFilePath : "";
+	c.treeRoundUpSize = cfg->treeRoundUpSize;
+	c.fileShareSize = cfg->fileShareSize;
+	c.useCustomTreeRandomize = (cfg->useCustomTreeRandomize != 0);
+	c.treeRandomizeSeed = cfg->treeRandomizeSeed;
 
 	for(uint32_t i = 0; i < cfg->numGPUIDs; i++)
 		c.gpuIDs.push_back(cfg->gpuIDs[i] );
@@ -168,10 +173,25 @@ Config Config::fromABI(const elb_cfg* cfg)
 
 	// ---- path dependent normalisation (ProgArgs.cpp:1471-1671) ----
 
+	const bool haveTreeFile = !c.treeFilePath.empty();
+
+	if(haveTreeFile && (c.pathType != ELB_PATH_DIR) ) // :1494-1495
+		throw WorkerError("Custom tree mode requires benchmark path to be a directory.");
+
+	if(haveTreeFile && (c.paths.size() > 1) ) // :1523-1524
+		throw WorkerError("Custom tree mode can only be used with a single benchmark path.");
+
+	if(haveTreeFile && !c.blockSize)
+		throw WorkerError("Custom tree mode requires a block size.");
+
+	if(!c.fileShareSize) // :1291-1292
+		c.fileShareSize = 32 * c.blockSize;
+
 	if(c.fileSize && !c.blockSize) // :1525-1527
 		throw WorkerError("Block size must not be 0 when file size is given.");
 
-	if(c.blockSize > c.fileSize) // :1531-1540
+	// (file sizes are per tree entry in custom tree mode: the block size stays, :1531)
+	if( (c.blockSize > c.fileSize) && !haveTreeFile) // :1531-1540
 		c.blockSize = c.fileSize;
 
 	if( (c.useDirectIO || c.useRandomOffsets || c.useStridedAccess) && c.fileSize &&
@@ -195,7 +215,8 @@ Config Config::fromABI(const elb_cfg* cfg)
 		(c.randomAmount % c.blockSize) && (c.pathType != ELB_PATH_DIR) ) // :1586-1597
 		c.randomAmount -= (c.randomAmount % c.blockSize);
 
-	if( (c.pathType == ELB_PATH_DIR) && c.useRandomOffsets && (c.fileSize < c.blockSize) )
+	if( (c.pathType == ELB_PATH_DIR) && c.useRandomOffsets && (c.fileSize < c.blockSize) &&
+		!haveTreeFile) // :1599-1601
 		throw WorkerError("For random offsets, file size must not be smaller than block size.");
 
 	if( (c.pathType == ELB_PATH_DIR) && c.useStridedAccess)

@@ -116,6 +116,11 @@ void Coordinator::printDryRunInfo()
 
 	Config cfg = Config::fromABI(&abiConfig.cfg);
 
+	CustomTree customTree;
+
+	if(!cfg.treeFilePath.empty() )
+		customTree.load(cfg.treeFilePath, cfg.blockSize, cfg.fileShareSize, cfg.treeRoundUpSize);
+
 	const int phases[] = {ELB_PHASE_CREATEDIRS, ELB_PHASE_DELETEDIRS, ELB_PHASE_CREATEFILES,
 		ELB_PHASE_READFILES, ELB_PHASE_DELETEFILES, ELB_PHASE_STATFILES};
 	const bool enabled[] = {progArgs.runCreateDirsPhase, progArgs.runDeleteDirsPhase,
@@ -128,7 +133,7 @@ void Coordinator::printDryRunInfo()
 			continue;
 
 		uint64_t entriesPerThread, bytesPerThread;
-		expectedPerWorker(cfg, phases[i], entriesPerThread, bytesPerThread);
+		expectedPerWorker(cfg, phases[i], entriesPerThread, bytesPerThread, &customTree);
 
 		stats::printDryRunPhaseInfo(progArgs, phases[i], entriesPerThread, bytesPerThread,
 			std::cout);
@@ -570,6 +575,20 @@ int Coordinator::main() // Coordinator.cpp:31-142
 
 		if(progArgs.interruptServices || progArgs.quitServices)
 			return masterInterruptOrQuitServices(progArgs);
+
+		if(!progArgs.treeScanPath.empty() )
+		{ // ProgArgs::scanCustomTree (ProgArgs.cpp:2674-2735): write the tree file first
+			uint64_t numDirs, numFiles, numBytes;
+
+			PathStore::scanToTreeFile(progArgs.treeScanPath, progArgs.treeFilePath, numDirs,
+				numFiles, numBytes);
+
+			std::cout << "Directory scan done. Dirs: " << numDirs << "; Files: " << numFiles <<
+				"; Bytes: " << numBytes << "; Treefile: " << progArgs.treeFilePath << std::endl;
+
+			if(progArgs.benchPaths.empty() )
+				return EXIT_SUCCESS;
+		}
 
 		if(progArgs.doDryRun)
 		{

@@ -797,6 +797,11 @@ struct Config
 	uint64_t limitWriteBps{0};
 	bool doInfiniteIOLoop{false};
 	unsigned rwMixThreadsReadPercent{0}; // --rwmixthrpct
+	std::string treeFilePath;     // --treefile (custom tree mode)
+	uint64_t treeRoundUpSize{0};  // --treeroundup
+	uint64_t fileShareSize{0};    // --sharesize
+	bool useCustomTreeRandomize{false}; // --treerand
+	uint64_t treeRandomizeSeed{0};
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

@@ -29,6 +29,20 @@ Manager::Manager(const elb_cfg* abiCfg)
 
 	const Config& cfg = shared.cfg;
 
+	if(!cfg.treeFilePath.empty() ) // ProgArgs::loadCustomTreeFile (ProgArgs.cpp:2740-2803)
+	{
+		try
+		{
+			shared.customTree.load(cfg.treeFilePath, cfg.blockSize, cfg.fileShareSize,
+				cfg.treeRoundUpSize);
+		}
+		catch(...)
+		{
+			closeBenchPathFDs();
+			throw;
+		}
+	}
+
 	for(uint32_t i = 0; i < cfg.numThreads; i++)
 	{
 		workers.emplace_back(new Worker(&shared, cfg.rankOffset + i) );
@@ -434,11 +448,42 @@ void Manager::getPhaseResults(elb_phase_results& out)
 
 /* getPhaseNumEntriesAndBytes (WorkerManager.cpp:333-487): expected totals per worker */
 void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
-	uint64_t& outBytes)
+	uint64_t& outBytes, const CustomTree* customTree)
 {
 	outEntries = 0;
 	outBytes = 0;
 
+	if( (cfg.pathType == ELB_PATH_DIR) && customTree && customTree->isLoaded)
+	{ // custom tree mode (WorkerManager.cpp:406-450)
+		const uint64_t numDirs = customTree->dirs.getNumPaths();
+		const uint64_t numFiles = customTree->filesNonShared.getNumPaths() +
+			customTree->filesShared.getNumPaths();
+		const uint64_t numBytesTotal = customTree->filesNonShared.getNumBytesTotal() +
+			customTree->filesShared.getNumBytesTotal();
+
+		switch(benchPhase)
+		{
+			case ELB_PHASE_CREATEDIRS:
+			case ELB_PHASE_DELETEDIRS:
+				outEntries = numDirs / cfg.numDataSetThreads;
+				break;
+
+			case ELB_PHASE_CREATEFILES:
+			case ELB_PHASE_READFILES:
+				outEntries = numFiles / cfg.numDataSetThreads;
+				outBytes = numBytesTotal / cfg.numDataSetThreads;
+				break;
+
+			case ELB_PHASE_DELETEFILES:
+			case ELB_PHASE_STATFILES:
+				outEntries = numFiles / cfg.numDataSetThreads;
+				break;
+
+			default:
+				break;
+		}
+	}
+	else
 	if(cfg.pathType == ELB_PATH_DIR)
 	{
 		const uint64_t numDirs = cfg.numDirs ? cfg.numDirs : 1;
@@ -481,7 +526,8 @@ void Manager::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& 
 {
 	uint64_t entriesPerWorker, bytesPerWorker;
 
-	expectedPerWorker(shared.cfg, benchPhase, entriesPerWorker, bytesPerWorker);
+	expectedPerWorker(shared.cfg, benchPhase, entriesPerWorker, bytesPerWorker,
+		&shared.customTree);
 
 	outEntries = entriesPerWorker * shared.cfg.numThreads;
 	outBytes = bytesPerWorker * shared.cfg.numThreads;
@@ -550,6 +596,69 @@ struct elb_offset_plan_impl
 	std::unique_ptr<elb::RandAlgo> randAlgo;
 	std::unique_ptr<elb::OffsetPlan> plan;
 };
+
+int64_t elb_custom_tree_worker_list(const char* treeFilePath, uint64_t blockSize,
+	uint64_t fileShareSize, uint64_t treeRoundUpSize, uint64_t workerRank,
+	uint64_t numDataSetThreads, int kind, char* outBuf, uint64_t outBufLen)
+{
+	try
+	{
+		if(!treeFilePath || !numDataSetThreads || !blockSize)
+			throw elb::WorkerError("elb_custom_tree_worker_list: invalid argument");
+
+		elb::CustomTree tree;
+		elb::PathStore sublist;
+
+		tree.load(treeFilePath, blockSize, fileShareSize ? fileShareSize : (32 * blockSize),
+			treeRoundUpSize);
+		sublist.setBlockSize(blockSize);
+
+		if(kind == 0)
+			tree.dirs.getWorkerSublistNonShared(workerRank, numDataSetThreads, false, sublist);
+		else
+		{
+			tree.filesNonShared.getWorkerSublistNonShared(workerRank, numDataSetThreads, false,
+				sublist);
+			tree.filesShared.getWorkerSublistShared(workerRank, numDataSetThreads, false, sublist);
+		}
+
+		std::string text;
+
+		for(const elb::PathStoreElem& elem : sublist.getPaths() )
+			text += elem.path + "\t" + std::to_string(elem.totalLen) + "\t" +
+				std::to_string(elem.rangeStart) + "\t" + std::to_string(elem.rangeLen) + "\n";
+
+		if(outBuf && outBufLen)
+		{
+			const size_t copyLen = std::min( (size_t)(outBufLen - 1), text.size() );
+			memcpy(outBuf, text.data(), copyLen);
+			outBuf[copyLen] = 0;
+		}
+
+		return (int64_t)text.size();
+	}
+	catch(const std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return -1;
+	}
+}
+
+int64_t elb_custom_tree_scan(const char* scanPath, const char* outTreeFilePath)
+{
+	try
+	{
+		uint64_t numDirs, numFiles, numBytes;
+
+		return (int64_t)elb::PathStore::scanToTreeFile(scanPath, outTreeFilePath, numDirs,
+			numFiles, numBytes);
+	}
+	catch(const std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return -1;
+	}
+}
 
 elb_rand_algo_handle* elb_rand_algo_create(int randAlgo, const uint64_t state[4])
 {

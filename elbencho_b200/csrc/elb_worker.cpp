@@ -235,6 +235,59 @@ class DirSource : public BlockSource
 		bool isFirstBlock{false};
 };
 
+/* custom tree mode: the worker's files (whole non-shared files, then its slices of the shared
+ * files); the offset plan is reset to each element's range (LocalWorker.cpp:3299-3304) */
+class TreeSource : public BlockSource
+{
+	public:
+		TreeSource(const PathStore& files, OffsetPlan& plan, uint64_t& blockCounter) :
+			files(files), plan(plan), blockCounter(blockCounter) {}
+
+		virtual uint64_t getNumBytesTotal() const override { return files.getNumBytesTotal(); }
+
+		virtual bool next(BlockRef& outBlock) override
+		{
+			if(!fileActive)
+			{
+				if(elemIndex >= files.getNumPaths() )
+					return false;
+
+				const PathStoreElem& elem = files.getPaths()[elemIndex];
+
+				plan.restart(elem.rangeLen, elem.rangeStart);
+				fileActive = true;
+				isFirstBlock = true;
+			}
+
+			outBlock = BlockRef();
+			outBlock.isTreeElem = true;
+			outBlock.fileIndex = elemIndex;
+			outBlock.firstOfFile = isFirstBlock;
+			isFirstBlock = false;
+
+			// (empty files still yield one zero-length block that opens and closes the file)
+			plan.nextBlock(outBlock.offset, outBlock.len);
+			outBlock.blockCounter = blockCounter++;
+
+			if(!plan.getNumBytesLeftToSubmit() )
+			{
+				outBlock.lastOfFile = true;
+				fileActive = false;
+				elemIndex++;
+			}
+
+			return true;
+		}
+
+	private:
+		const PathStore& files;
+		OffsetPlan& plan;
+		uint64_t& blockCounter;
+		size_t elemIndex{0};
+		bool fileActive{false};
+		bool isFirstBlock{false};
+};
+
 /* ==============================================================================================
  * Worker: lifecycle
  * ============================================================================================ */
@@ -563,6 +616,8 @@ void Worker::preparePhase()
 		blockVarianceSeed = ( (uint64_t)randDev() << 32) | (uint32_t)randDev();
 	}
 
+	prepareCustomTreePathStores();
+
 	allocRings();
 }
 
@@ -881,8 +936,168 @@ void Worker::initPhaseOffsetPlan()
  * Metadata phases (pure syscalls, no GPU work)
  * ============================================================================================ */
 
+/* mkdir -p from the bottom up relative to dirFD (FileTk::mkdiratBottomUp, FileTk.cpp:96-125) */
+static int mkdiratBottomUp(int dirFD, const std::string& path, mode_t mode)
+{
+	int mkdirRes = mkdirat(dirFD, path.c_str(), mode);
+
+	if(!mkdirRes || (errno != ENOENT) )
+		return mkdirRes;
+
+	const size_t slashPos = path.find_last_of('/');
+
+	if( (slashPos == std::string::npos) || !slashPos)
+	{ // reached the root
+		errno = ENOENT;
+		return -1;
+	}
+
+	int mkdirParentRes = mkdiratBottomUp(dirFD, path.substr(0, slashPos), mode);
+
+	if( (mkdirParentRes == -1) && (errno != EEXIST) )
+		return mkdirParentRes;
+
+	return mkdirat(dirFD, path.c_str(), mode);
+}
+
+/* LocalWorker::prepareCustomTreePathStores (LocalWorker.cpp:1520-1560) */
+void Worker::prepareCustomTreePathStores()
+{
+	if(cfg.treeFilePath.empty() )
+		return;
+
+	const bool throwOnSmallerThanBlockSize = cfg.useDirectIO && cfg.useRandomOffsets;
+	const CustomTree& tree = shared->customTree;
+
+	customTreeDirs.clear();
+	customTreeFiles.clear();
+	customTreeFiles.setBlockSize(cfg.blockSize);
+
+	tree.dirs.getWorkerSublistNonShared(rank, cfg.numDataSetThreads, false, customTreeDirs);
+	tree.filesNonShared.getWorkerSublistNonShared(rank, cfg.numDataSetThreads,
+		throwOnSmallerThanBlockSize, customTreeFiles);
+	tree.filesShared.getWorkerSublistShared(rank, cfg.numDataSetThreads,
+		throwOnSmallerThanBlockSize, customTreeFiles);
+
+	if(cfg.useCustomTreeRandomize)
+		customTreeFiles.randomShuffle(cfg.treeRandomizeSeed ? (cfg.treeRandomizeSeed + rank) : 0);
+}
+
+/* LocalWorker::dirModeIterateCustomDirs (LocalWorker.cpp:2927-3010): every worker creates its
+ * share of the dirs (parents first); the first worker alone removes all dirs, deepest first */
+void Worker::dirModeIterateCustomDirs()
+{
+	const int benchPathFD = shared->pathFDs[0];
+	const bool isDelete = (benchPhase == ELB_PHASE_DELETEDIRS);
+	const std::vector<PathStoreElem>& dirs =
+		isDelete ? shared->customTree.dirs.getPaths() : customTreeDirs.getPaths();
+	const bool thisWorkerDoesDelDirs = cfg.runAsService ?
+		(rank == 0) : (rank == cfg.rankOffset); // (service paths are shared between instances)
+
+	if(dirs.empty() )
+		return;
+
+	if(isDelete && !thisWorkerDoesDelDirs)
+	{
+		workerGotPhaseWork = false;
+		return;
+	}
+
+	for(size_t i = 0; i < dirs.size(); i++)
+	{
+		checkInterruptionRequest();
+
+		const PathStoreElem& elem = isDelete ? dirs[dirs.size() - 1 - i] : dirs[i];
+		const Clock::time_point ioStartT = Clock::now();
+
+		if(!isDelete)
+		{
+			int mkdirRes = mkdiratBottomUp(benchPathFD, elem.path, ELB_MKDIR_MODE);
+
+			if( (mkdirRes == -1) && (errno != EEXIST) )
+				throw WorkerError(std::string("Directory creation failed. ") +
+					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
+					"SysErr: " + strerror(errno) );
+		}
+		else
+		{ // (all workers mk/del all dirs in custom tree mode: missing dirs are no error)
+			int rmdirRes = unlinkat(benchPathFD, elem.path.c_str(), AT_REMOVEDIR);
+
+			if( (rmdirRes == -1) && (errno != ENOENT) )
+				throw WorkerError(std::string("Directory deletion failed. ") +
+					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
+					"SysErr: " + strerror(errno) );
+		}
+
+		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
+
+		histogramAdd(entriesLatHisto, ioElapsedUSec);
+		liveLatNumEntries++;
+		liveLatSumEntries += ioElapsedUSec;
+		atomicLiveOps.numEntriesDone++;
+	}
+}
+
+/* stat / delete phases of LocalWorker::dirModeIterateCustomFiles (LocalWorker.cpp:3407-3447) */
+void Worker::dirModeIterateCustomFilesNoIO()
+{
+	const int benchPathFD = shared->pathFDs[0];
+	const std::vector<PathStoreElem>& files = customTreeFiles.getPaths();
+
+	if(files.empty() )
+	{
+		workerGotPhaseWork = false;
+		return;
+	}
+
+	for(size_t i = 0; i < files.size(); i++)
+	{
+		if( (i % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
+			checkInterruptionRequest();
+
+		const PathStoreElem& elem = files[i];
+		const Clock::time_point ioStartT = Clock::now();
+
+		if(benchPhase == ELB_PHASE_STATFILES)
+		{
+			struct stat statBuf;
+
+			if(fstatat(benchPathFD, elem.path.c_str(), &statBuf, 0) == -1)
+				throw WorkerError(std::string("File stat failed. ") +
+					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
+					"SysErr: " + strerror(errno) );
+		}
+
+		if(benchPhase == ELB_PHASE_DELETEFILES)
+		{ // (shared files are unlinked by all their workers, so missing files are no error)
+			int unlinkRes = unlinkat(benchPathFD, elem.path.c_str(), 0);
+
+			if( (unlinkRes == -1) && (errno != ENOENT) )
+				throw WorkerError(std::string("File delete failed. ") +
+					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
+					"SysErr: " + strerror(errno) );
+		}
+
+		if(elem.totalLen != elem.rangeLen)
+			continue; // entry latency and count only for fully processed entries
+
+		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
+
+		histogramAdd(entriesLatHisto, ioElapsedUSec);
+		liveLatNumEntries++;
+		liveLatSumEntries += ioElapsedUSec;
+		atomicLiveOps.numEntriesDone++;
+	}
+}
+
 void Worker::dirModeIterateDirs() // LocalWorker.cpp:2778-2912
 {
+	if(!cfg.treeFilePath.empty() )
+	{
+		dirModeIterateCustomDirs();
+		return;
+	}
+
 	if(!cfg.numDirs)
 		return;
 
@@ -974,6 +1189,12 @@ void Worker::dirModeIterateDirs() // LocalWorker.cpp:2778-2912
 /* stat and delete phases of dirModeIterateFiles (LocalWorker.cpp:3193-3243) */
 void Worker::dirModeIterateFilesNoIO()
 {
+	if(!cfg.treeFilePath.empty() )
+	{
+		dirModeIterateCustomFilesNoIO();
+		return;
+	}
+
 	char currentPath[ELB_PATH_BUF_LEN];
 	const bool haveSubdirs = (cfg.numDirs > 0);
 	const uint64_t numDirs = haveSubdirs ? cfg.numDirs : 1;
@@ -1151,6 +1372,18 @@ void Worker::rwPhase()
 	rateLimiter.initStart(useRWMixThreadsBalancer ? 0 :
 		(isRead ? cfg.limitReadBps : cfg.limitWriteBps) );
 
+	if( (cfg.pathType == ELB_PATH_DIR) && !cfg.treeFilePath.empty() )
+	{ // dirModeIterateCustomFiles (LocalWorker.cpp:3261-3470)
+		if(!customTreeFiles.getNumPaths() )
+		{
+			workerGotPhaseWork = false;
+			return;
+		}
+
+		TreeSource source(customTreeFiles, *offsetPlan, numIOPSSubmitted);
+		rwBlocksPipelined(source, isRead);
+	}
+	else
 	if(cfg.pathType == ELB_PATH_DIR)
 	{
 		DirSource source(cfg, *offsetPlan, numIOPSSubmitted);
@@ -1776,7 +2009,21 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 	const bool haveSubdirs = (cfg.numDirs > 0);
 	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
 	int printRes;
+	uint64_t fileSize = cfg.fileSize; // for --trunctosize / --preallocfile
 
+	dirModeCountsEntry = true;
+
+	if(block.isTreeElem)
+	{ // custom tree: the path comes from the tree file, the size is the entry's
+		const PathStoreElem& elem = customTreeFiles.getPaths()[block.fileIndex];
+
+		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "%s", elem.path.c_str() );
+		fileSize = elem.totalLen;
+
+		// entry latency and count are only meaningful for fully processed entries (:3434-3447)
+		dirModeCountsEntry = (elem.totalLen == elem.rangeLen);
+	}
+	else
 	if(haveSubdirs)
 		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "r%zu/d%zu/r%zu-f%zu",
 			(size_t)workerDirRank, (size_t)block.dirIndex, (size_t)rank, (size_t)block.fileIndex);
@@ -1791,7 +2038,8 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 			"dirIndex: " + std::to_string(block.dirIndex) + "; "
 			"fileIndex: " + std::to_string(block.fileIndex) );
 
-	const size_t pathFDsIndex = (rank + block.dirIndex) % shared->pathFDs.size();
+	const size_t pathFDsIndex = block.isTreeElem ?
+		0 : ( (rank + block.dirIndex) % shared->pathFDs.size() );
 
 	dirModeCurrentPath = cfg.paths[pathFDsIndex] + "/" + relativePath;
 
@@ -1823,19 +2071,19 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 
 	if(!isRead)
 	{
-		if(cfg.doTruncToSize && (ftruncate(dirModeFD, cfg.fileSize) == -1) )
+		if(cfg.doTruncToSize && (ftruncate(dirModeFD, fileSize) == -1) )
 			throw WorkerError("Unable to set file size through ftruncate. "
 				"Path: " + dirModeCurrentPath + "; "
-				"Size: " + std::to_string(cfg.fileSize) + "; "
+				"Size: " + std::to_string(fileSize) + "; "
 				"SysErr: " + strerror(errno) );
 
 		if(cfg.doPreallocFile)
 		{
-			int preallocRes = posix_fallocate(dirModeFD, 0, cfg.fileSize);
+			int preallocRes = posix_fallocate(dirModeFD, 0, fileSize);
 			if(preallocRes != 0)
 				throw WorkerError("Unable to preallocate file size through posix_fallocate. "
 					"File: " + dirModeCurrentPath + "; "
-					"Size: " + std::to_string(cfg.fileSize) + "; "
+					"Size: " + std::to_string(fileSize) + "; "
 					"SysErr: " + strerror(preallocRes) );
 		}
 	}
@@ -1857,6 +2105,9 @@ void Worker::dirModeCloseFile()
 			"Path: " + dirModeCurrentPath + "; "
 			"FD: " + std::to_string(closedFD) + "; "
 			"SysErr: " + strerror(closeErrno) );
+
+	if(!dirModeCountsEntry)
+		return; // slice of a shared custom tree file
 
 	const uint64_t entryUSec = elapsedUSecSince(dirModeFileStartT);
 

@@ -37,6 +37,7 @@
 #include "elb_cufile.h"
 #include "elb_host.h"
 #include "elb_internal.h"
+#include "elb_pathstore.h"
 
 namespace elb
 {
@@ -66,6 +67,8 @@ struct Shared
 
 	RWMixThreadsBalancer rwMixThreadsBalancer; // --rwmixthrpct (reset by the manager per phase)
 
+	CustomTree customTree; // --treefile, loaded by the manager (ProgArgs::loadCustomTreeFile)
+
 	/* workers hold this shared while they allocate / free device memory or instantiate graphs;
 	   the live stats reducer holds it exclusively while its collective is in flight, because a
 	   device-synchronising call on one GPU in the middle of a multi-GPU NCCL launch of the same
@@ -86,7 +89,8 @@ struct BlockRef
 	uint64_t len{0};
 	uint32_t fileIdx{0};      // file mode: index into Shared::pathFDs
 	uint64_t dirIndex{0};     // dir mode
-	uint64_t fileIndex{0};    // dir mode
+	uint64_t fileIndex{0};    // dir mode (custom tree: index into the worker's file list)
+	bool isTreeElem{false};   // custom tree mode: fileIndex refers to customTreeFiles
 	bool firstOfFile{false};  // dir mode: open the file before this block
 	bool lastOfFile{false};   // dir mode: close the file after this block
 	bool ioIsRead{false};     // direction of this block's storage call (rwmix: read in a write phase)
@@ -225,6 +229,13 @@ class Worker
 		// offsets
 		std::unique_ptr<RandAlgo> randOffsetAlgo; // --randalgo
 		RateLimiter rateLimiter; // --limitread / --limitwrite
+		// custom tree mode: this worker's dirs and files (LocalWorker.h customTreeDirs/Files)
+		PathStore customTreeDirs;
+		PathStore customTreeFiles;
+		bool dirModeCountsEntry{true}; // false for a partial slice of a shared tree file
+		void prepareCustomTreePathStores(); // LocalWorker.cpp:1520-1560
+		void dirModeIterateCustomDirs();    // LocalWorker.cpp:2927-3010
+		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470
 		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase
 		void rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)
 		std::unique_ptr<OffsetPlan> offsetPlan;

@@ -83,6 +83,11 @@ class WorkerConfig:
     limit_write_bps: int = 0          # --limitwrite
     do_infinite_io_loop: bool = False  # --infloop
     rwmix_threads_read_percent: int = 0  # --rwmixthrpct
+    tree_file_path: str = ""          # --treefile
+    tree_round_up_size: int = 0       # --treeroundup
+    file_share_size: int = 0          # --sharesize (0 = 32 x block size)
+    use_custom_tree_randomize: bool = False  # --treerand
+    tree_randomize_seed: int = 0      # injected seed (0 = self-seed)
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -155,6 +160,11 @@ class WorkerConfig:
         cfg.limitWriteBps = self.limit_write_bps
         cfg.doInfiniteIOLoop = int(self.do_infinite_io_loop)
         cfg.rwMixThreadsReadPercent = self.rwmix_threads_read_percent
+        cfg.treeFilePath = self.tree_file_path.encode() if self.tree_file_path else None
+        cfg.treeRoundUpSize = self.tree_round_up_size
+        cfg.fileShareSize = self.file_share_size
+        cfg.useCustomTreeRandomize = int(self.use_custom_tree_randomize)
+        cfg.treeRandomizeSeed = self.tree_randomize_seed
         return cfg, (path_bytes, path_arr, gpu_arr)
 
 

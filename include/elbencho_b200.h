@@ -269,6 +269,18 @@ typedef struct elb_cfg
 	/* --rwmixthrpct: with --rwmixthr, keep the bytes of the reader threads at this percentage
 	 * of all bytes of the write phase (RateLimiterRWMixThreads.h:22-197); 0 = no balancing */
 	uint32_t rwMixThreadsReadPercent;
+
+	/* Custom tree mode (--treefile, --treeroundup, --sharesize, --treerand): work on the dirs and
+	 * files listed in a tree file instead of the generated r<rank>/d<n>/r<rank>-f<n> names
+	 * (source/PathStore.cpp, LocalWorker.cpp:2927-3010, 3261-3470). NULL/empty = off. Needs a
+	 * directory as the single benchmark path. */
+	const char* treeFilePath;
+	uint64_t treeRoundUpSize; /* round file sizes up to a multiple of this (0 = off) */
+	uint64_t fileShareSize;   /* files of at least this size are shared between workers as block
+	                             ranges; 0 = 32 x blockSize (ProgArgs.cpp:52, 1291-1292) */
+	int32_t useCustomTreeRandomize; /* shuffle each worker's file list */
+	int32_t reserved4;
+	uint64_t treeRandomizeSeed;     /* 0 = self-seed (tests inject one) */
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------
@@ -373,6 +385,17 @@ void elb_histogram_merge(elb_histogram* dst, const elb_histogram* src);
 double elb_histogram_percentile(const elb_histogram* h, double percentage);
 /* UnitTk::getPerSecFromUSec (toolkits/UnitTk.h:48-56) */
 uint64_t elb_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec);
+
+/* Custom tree mode: the sublist of one worker (PathStore::getWorkerSublistNonShared/-Shared as
+ * combined by LocalWorker::prepareCustomTreePathStores, LocalWorker.cpp:1520-1560), as text lines
+ * "<path>\t<totalLen>\t<rangeStart>\t<rangeLen>\n". kind 0: directories, 1: files (non-shared
+ * files first, then this worker's ranges of the shared files). Returns the length of the full
+ * text (which is truncated to outBufLen - 1 bytes in outBuf), or -1 on error. */
+int64_t elb_custom_tree_worker_list(const char* treeFilePath, uint64_t blockSize,
+	uint64_t fileShareSize, uint64_t treeRoundUpSize, uint64_t workerRank,
+	uint64_t numDataSetThreads, int kind, char* outBuf, uint64_t outBufLen);
+/* FileTk::scanCustomTree (toolkits/FileTk.cpp:387-470): returns dirs + files found, -1 on error */
+int64_t elb_custom_tree_scan(const char* scanPath, const char* outTreeFilePath);
 
 /* ---------------------------------------------------------------------------------------------
  * Offset plans (toolkits/offsetgen/OffsetGenerator.h:27-46 interface; one handle type for all

@@ -734,15 +734,13 @@ void ProgArgs::checkArgs()
 
 	detectBenchPathType();
 
-	if( (benchPathType != ELB_PATH_DIR) && !treeFilePath.empty() ) // :1494-1495
+	// (a master cannot know: the services check the path type on their side)
+	if( (benchPathType != ELB_PATH_DIR) && !treeFilePath.empty() && hosts.empty() ) // :1494-1495
 		throw ProgError("Custom tree mode requires benchmark path to be a directory.");
 
 	if(!treeFilePath.empty() && (benchPaths.size() > 1) ) // :1523-1524
 		throw ProgError("Custom tree mode can only be used with a single benchmark path.");
 
-	if(!treeFilePath.empty() && !hosts.empty() )
-		throw ProgError("Custom tree mode is not available together with --hosts in this build "
-			"(no tree file upload to services).");
 
 	if(!numThreads)
 		throw ProgError("Number of threads may not be zero.");

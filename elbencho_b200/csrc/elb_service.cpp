@@ -8,6 +8,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
+#include <pwd.h>
 #include <signal.h>
 #include <string.h>
 #include <sys/socket.h>
@@ -750,6 +751,8 @@ class Service
 
 		HttpResponse handle(const HttpRequest& request);
 		HttpResponse handlePreparePhase(const HttpRequest& request);
+		HttpResponse handlePrepareFile(const HttpRequest& request);
+		std::string uploadBasePath() const;
 		HttpResponse handleStartPhase(const HttpRequest& request);
 		HttpResponse handleStatus();
 		HttpResponse handleBenchResult();
@@ -975,6 +978,78 @@ HttpResponse Service::handleBenchResult()
 
 /* ProgArgs::setFromPropertyTreeForService (ProgArgs.cpp:3562-3680), supported subset; unknown
  * keys are ignored, missing keys take the defaults */
+/* SERVICE_UPLOAD_BASEPATH (ProgArgs.h:228-230): /var/tmp/<exe>_<user>_p<port> */
+std::string Service::uploadBasePath() const
+{
+	const char* userName = getenv("USER");
+	struct passwd* passwdEntry = getpwuid(geteuid() );
+
+	if(passwdEntry && passwdEntry->pw_name)
+		userName = passwdEntry->pw_name;
+
+	return std::string("/var/tmp/elbencho-b200_") + (userName ? userName : "unknown") + "_p" +
+		std::to_string(progArgs.servicePort);
+}
+
+/* receive input files for the following prepare phase, i.e. the custom tree file
+ * (HTTPServiceSWS.cpp:262-350) */
+HttpResponse Service::handlePrepareFile(const HttpRequest& request)
+{
+	HttpResponse response;
+
+	try
+	{
+		if(!request.query.count("ProtocolVersion") )
+			throw ProgError("Missing parameter: ProtocolVersion");
+
+		const std::string masterProtoVer = request.query.at("ProtocolVersion");
+		if(masterProtoVer != ELB_HTTP_PROTOCOLVERSION)
+			throw ProgError("Protocol version mismatch. "
+				"Service version: " ELB_HTTP_PROTOCOLVERSION "; "
+				"Received master version: " + masterProtoVer);
+
+		if(!request.query.count("FileName") )
+			throw ProgError("Missing parameter: FileName");
+
+		// (only the last path component: no "../" or subdirs in the given filename)
+		std::string filename = request.query.at("FileName");
+		const size_t slashPos = filename.find_last_of('/');
+
+		if(slashPos != std::string::npos)
+			filename = filename.substr(slashPos + 1);
+
+		if(filename.empty() || (filename == ".") || (filename == "..") )
+			throw ProgError("Invalid file name: " + request.query.at("FileName") );
+
+		const std::string basePath = uploadBasePath();
+		const std::string path = basePath + "/" + filename;
+
+		std::cout << "Receiving tree file from master..." << std::endl;
+
+		if( (mkdir(basePath.c_str(), 0777) == -1) && (errno != EEXIST) )
+			throw ProgError("Failed to create service tmp dir: " + basePath);
+
+		std::ofstream fileOutStream(path.c_str(), std::ofstream::out | std::ofstream::trunc);
+
+		if(!fileOutStream)
+			throw ProgError("Opening upload file failed: " + path);
+
+		fileOutStream << request.body;
+		fileOutStream.close();
+
+		if(!fileOutStream)
+			throw ProgError("Saving upload file failed: " + path);
+	}
+	catch(std::exception& e)
+	{
+		response.statusCode = 400;
+		response.body = std::string("File preparation phase error: ") + e.what() + "\n";
+		std::cerr << "ERROR: " << response.body;
+	}
+
+	return response;
+}
+
 HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 {
 	HttpResponse response;
@@ -1065,9 +1140,23 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 			throw ProgError("This service is the GPU worker build: mmap, HDFS, S3 and netbench "
 				"modes are not available.");
 
-		if(!recvTree.getStr("treefile", "").empty() )
-			throw ProgError("This service is the GPU worker build: custom tree mode is not "
-				"available.");
+		/* custom tree mode: the file was uploaded to our tmp dir under the given name before
+		   (ProgArgs.cpp:3685-3698) */
+		args.treeFilePath = recvTree.getStr("treefile", "");
+
+		if(!args.treeFilePath.empty() )
+		{
+			const size_t slashPos = args.treeFilePath.find_last_of('/');
+
+			if(slashPos != std::string::npos)
+				args.treeFilePath = args.treeFilePath.substr(slashPos + 1);
+
+			args.treeFilePath = uploadBasePath() + "/" + args.treeFilePath;
+		}
+
+		args.useCustomTreeRandomize = recvTree.getBool("treerand", false);
+		args.treeRoundUpSize = recvTree.getU64("treeroundup", 0);
+		args.fileShareSize = recvTree.getU64("sharesize", 0);
 
 		if(args.gpuIDsStr.empty() )
 			throw ProgError("This service is the GPU worker build: the master has to give "
@@ -1280,13 +1369,7 @@ HttpResponse Service::handle(const HttpRequest& request)
 		return handlePreparePhase(request);
 
 	if( (request.path == "/preparefile") && (request.method == "POST") )
-	{
-		HttpResponse response;
-		response.statusCode = 400;
-		response.body = "File preparation phase error: custom tree files are not supported by "
-			"the GPU worker build.\n";
-		return response;
-	}
+		return handlePrepareFile(request);
 
 	if( (request.path == "/startphase") && (request.method == "GET") )
 		return handleStartPhase(request);
@@ -1647,7 +1730,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("direct", args.useDirectIO);
 	tree.putBool("dropcache", args.runDropCachesPhase);
 	tree.put("fadv", (uint64_t)0);
-	tree.put("sharesize", (uint64_t)0);
+	tree.put("sharesize", args.fileShareSize);
 	tree.put("size", args.fileSize);
 	tree.put("flock", (uint64_t)0);
 	tree.putBool("gdsbufreg", args.useGDSBufReg);
@@ -1713,13 +1796,13 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("sync", args.runSyncPhase);
 	tree.putBool("trunc", args.doTruncate);
 	tree.putBool("trunctosize", args.doTruncToSize);
-	tree.putBool("treerand", false);
-	tree.put("treeroundup", (uint64_t)0);
+	tree.putBool("treerand", args.useCustomTreeRandomize);
+	tree.put("treeroundup", args.treeRoundUpSize);
 	tree.putBool("verifydirect", args.doDirectVerify);
 
 	// dynamically calculated values for service hosts (:3845-3861)
 	tree.put("rankoffset", args.rankOffset + (serviceRank * args.numThreads) );
-	tree.put("treefile", "");
+	tree.put("treefile", args.treeFilePath.empty() ? "" : "treefile.txt"); // ProgArgs.cpp:3850
 	if(!args.assignGPUPerService || args.gpuIDs.empty() )
 		tree.put("gpuids", args.gpuIDsStr);
 	else
@@ -1786,6 +1869,27 @@ void Master::prepareRemotePhases()
 
 			try
 			{
+				if(!progArgs.treeFilePath.empty() )
+				{ // RemoteWorker::prepareRemoteFile (RemoteWorker.cpp:286-330)
+					std::ifstream treeFileStream(progArgs.treeFilePath);
+
+					if(!treeFileStream)
+						throw ProgError("Unable to read custom tree file. Path: " +
+							progArgs.treeFilePath);
+
+					std::stringstream treeFileContents;
+					treeFileContents << treeFileStream.rdbuf();
+
+					HttpResponse uploadResponse = httpRequest(remote.host, remote.port, "POST",
+						"/preparefile?ProtocolVersion=" ELB_HTTP_PROTOCOLVERSION
+						"&FileName=treefile.txt&PwHash=", treeFileContents.str(), 60);
+
+					if(uploadResponse.statusCode != 200)
+						throw ProgError("Service encountered an error. Service: " + remote.host +
+							":" + std::to_string(remote.port) + "; Phase: File preparation; "
+							"Message: " + uploadResponse.body);
+				}
+
 				JsonTree tree = progArgsToServiceTree(progArgs, i, hosts.size() );
 
 				HttpResponse response = httpRequest(remote.host, remote.port, "POST",

@@ -324,6 +324,19 @@ def test_service_http_endpoints_without_gpu():
                            "threads": "1", "write": "true", "gpuids": ""})
         status, body = call("POST", "/preparephase?ProtocolVersion=3.1.1&PwHash=", prep)
         assert status == 400 and b"--gpuids" in body
+        # tree file upload for custom tree mode (HTTPServiceSWS.cpp:262-350)
+        tree_text = "d up\nf 1000 up/a.bin\n"
+        status, body = call("POST", "/preparefile?ProtocolVersion=3.1.1&PwHash=&FileName="
+                            "..%2F..%2Ftreefile.txt", tree_text)
+        assert status == 200 and body == b""
+        import getpass
+        upload_path = "/var/tmp/elbencho-b200_%s_p%d/treefile.txt" % (getpass.getuser(), port)
+        with open(upload_path) as f:
+            assert f.read() == tree_text  # (stored under its base name only)
+        os.unlink(upload_path)
+        os.rmdir(os.path.dirname(upload_path))
+        status, body = call("POST", "/preparefile?ProtocolVersion=3.1.1&PwHash=", "x")
+        assert status == 400 and b"Missing parameter: FileName" in body
         conn.close()
         res = run_cli("--hosts", "127.0.0.1:%d" % port, "--quit")
         assert res.returncode == 0, res.stderr

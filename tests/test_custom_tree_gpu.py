@@ -161,3 +161,47 @@ def test_cli_treescan_then_treefile_run(workdir):
                           "--nolive", dst], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert os.listdir(dst) == []
+
+
+def test_tree_mode_through_two_services(workdir):
+    """the master uploads the tree file to every service (/preparefile), the services share the
+    data set: ranks 0-1 on the first, 2-3 on the second (RemoteWorker.cpp:286-330)"""
+    import socket
+    import time
+
+    def free_port():
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            return sock.getsockname()[1]
+
+    tree_path = os.path.join(workdir, "tree.txt")
+    bench_dir = os.path.join(workdir, "bench")
+    os.mkdir(bench_dir)
+    with open(tree_path, "w") as f:
+        f.write(TREE_TEXT)
+    _, files = tree_model.parse_tree(TREE_TEXT)
+    ports = [free_port(), free_port()]
+    hosts = ",".join("127.0.0.1:%d" % p for p in ports)
+    services = [subprocess.Popen([CLI_PATH, "--service", "--foreground", "--port", str(p)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE) for p in ports]
+    try:
+        res = subprocess.run([CLI_PATH, "-d", "-w", "-r", "--stat", "-t", "2", "-b", "64K", "--verify",
+                              "9", "--treefile", tree_path, "--gpuids", "0", "--hosts", hosts,
+                              "--svcwait", "30", "--nolive", bench_dir],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        for path, size in files:
+            with open(os.path.join(bench_dir, path), "rb") as f:
+                assert f.read() == oracle_lib.fill_pattern(size, 0, 9), path
+        res = subprocess.run([CLI_PATH, "-F", "-D", "-t", "2", "--treefile", tree_path, "--gpuids",
+                              "0", "--hosts", hosts, "--nolive", bench_dir],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert os.listdir(bench_dir) == []
+    finally:
+        subprocess.run([CLI_PATH, "--quit", "--hosts", hosts], capture_output=True, timeout=60)
+        for svc in services:
+            try:
+                svc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                svc.kill()

@@ -29,6 +29,14 @@ class ProgError : public std::runtime_error
 		explicit ProgError(const std::string& msg) : std::runtime_error(msg) {}
 };
 
+/* user-defined phase time limit expired: not an error (reference ProgTimeLimitException,
+ * Coordinator.cpp:111-116, 234-241) */
+class ProgTimeLimit : public std::runtime_error
+{
+	public:
+		ProgTimeLimit() : std::runtime_error("Terminating due to phase time limit.") {}
+};
+
 /* reference: ProgArgs (the subset of source/ProgArgs.h:27-221 that is supported) */
 class ProgArgs
 {

@@ -90,6 +90,7 @@ class Coordinator
 		void runBenchmarkPhase(int benchPhase);
 		void runSyncAndDropCaches();
 		bool liveCSVHeaderPrinted{false};
+		bool isPhaseTimeExpired{false}; // WorkersSharedData::isPhaseTimeExpired
 		void printLiveStatsCSV(int benchPhase, const elb_liveops liveOps[2],
 			const elb_liveops oldLiveOps[2], const elb_livelat& liveLat, uint64_t intervalUSec,
 			size_t numWorkersDone, uint64_t expectedEntries, uint64_t expectedBytes,
@@ -372,6 +373,10 @@ void Coordinator::printPhaseResultsEverywhere(int benchPhase, const std::string&
 /* Coordinator::runBenchmarkPhase (:248-272) + Statistics live loop (:1284-1345) */
 void Coordinator::runBenchmarkPhase(int benchPhase)
 {
+	// don't start the next phase if the time limit of the previous one expired (:234-241)
+	if(isPhaseTimeExpired)
+		throw ProgTimeLimit();
+
 	const std::string isoStartDate = isoDateNow(true);
 	const Clock::time_point phaseStartT = Clock::now();
 
@@ -412,6 +417,7 @@ void Coordinator::runBenchmarkPhase(int benchPhase)
 
 		if(progArgs.timeLimitSecs && (elapsedSec >= progArgs.timeLimitSecs) )
 		{ // WorkerManager::checkPhaseTimeLimit (:109-128): friendly interruption, results stay
+			isPhaseTimeExpired = true;
 			std::unique_lock<std::mutex> lock(manager->shared.mutex);
 			for(Worker* worker : manager->shared.workers)
 				worker->interruptExecution();
@@ -636,6 +642,11 @@ int Coordinator::main() // Coordinator.cpp:31-142
 
 		runBenchmarks();
 
+		manager.reset();
+	}
+	catch(ProgTimeLimit& e)
+	{ // a user-defined time limit, not an error (Coordinator.cpp:111-116)
+		std::cout << e.what() << std::endl;
 		manager.reset();
 	}
 	catch(std::exception& e)

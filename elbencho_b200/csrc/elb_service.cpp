@@ -878,6 +878,19 @@ HttpResponse Service::handleStatus()
 	if(useLiveReduce)
 		manager->getLiveSnapshot(liveSnapshot);
 
+	/* phase time limit: the master polls /status every few hundred ms, so this is where the
+	   service notices the expiry and asks its workers to finish (friendly interruption, the
+	   results stay; WorkerManager::checkPhaseTimeLimit, WorkerManager.cpp:109-128) */
+	if(manager && progArgs.timeLimitSecs && (currentPhase != ELB_PHASE_IDLE) &&
+		( (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(
+			Clock::now() - phaseStartT).count() >= progArgs.timeLimitSecs) )
+	{
+		std::unique_lock<std::mutex> lock(manager->shared.mutex);
+
+		for(Worker* worker : manager->shared.workers)
+			worker->interruptExecution();
+	}
+
 	putCommonStats(tree, false, useLiveReduce ? &liveSnapshot : NULL);
 
 	liveCpuUtil.update();
@@ -1096,6 +1109,7 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.ignoreDelErrors = recvTree.getBool("nodelerr", false);
 		args.integrityCheckSalt = recvTree.getU64("verify", 0);
 		args.doInfiniteIOLoop = recvTree.getBool("infloop", false);
+		args.timeLimitSecs = recvTree.getU64("b200_timelimit", 0);
 		args.limitReadBps = recvTree.getU64("limitread", 0);
 		args.limitWriteBps = recvTree.getU64("limitwrite", 0);
 		args.ioDepth = recvTree.getU64("iodepth", 1);
@@ -1738,6 +1752,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("no0usecerr", args.ignore0USecErrors);
 	tree.putBool("nodelerr", args.ignoreDelErrors);
 	tree.putBool("infloop", args.doInfiniteIOLoop);
+	tree.put("b200_timelimit", args.timeLimitSecs); // (applied by the service at /status time)
 	tree.put("verify", args.integrityCheckSalt);
 	tree.put("iodepth", args.ioDepth);
 	tree.put("limitread", args.limitReadBps);
@@ -1840,6 +1855,7 @@ class Master
 		void runSyncAndDropCaches();
 		void interruptAll(bool quit);
 		void waitForServicesReady();
+		bool isPhaseTimeExpired{false};
 };
 
 void Master::initHosts()
@@ -1959,6 +1975,9 @@ void Master::interruptAll(bool quit)
  * Statistics::generatePhaseResults */
 void Master::runPhase(int benchPhase)
 {
+	if(isPhaseTimeExpired) // Coordinator::checkInterruptionBetweenPhases (Coordinator.cpp:234-241)
+		throw ProgTimeLimit();
+
 	const std::string benchID = generateBenchID();
 	const Clock::time_point phaseStartT = Clock::now();
 	const bool isRWMixConfig = (progArgs.rwMixReadPercent || progArgs.numRWMixReadThreads) &&
@@ -2091,6 +2110,10 @@ void Master::runPhase(int benchPhase)
 
 	if(printedLiveLine)
 		std::cout << "\x1b[2K\r" << std::flush;
+
+	if(progArgs.timeLimitSecs && ( (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(
+		Clock::now() - phaseStartT).count() >= progArgs.timeLimitSecs) )
+		isPhaseTimeExpired = true;
 
 	// final results of every service (RemoteWorker::finishPhase)
 	elb_phase_results res;
@@ -2339,6 +2362,10 @@ int Master::run()
 				runSyncAndDropCaches();
 			}
 		}
+	}
+	catch(ProgTimeLimit& e)
+	{ // a user-defined time limit, not an error
+		std::cout << e.what() << std::endl;
 	}
 	catch(std::exception& e)
 	{

@@ -244,3 +244,36 @@ def test_gpu_per_service_assignment(workdir):
                 svc.wait(timeout=20)
             except subprocess.TimeoutExpired:
                 svc.kill()
+
+
+def test_time_limit_ends_the_run_after_the_current_phase(workdir):
+    """an expired --timelimit is no error: the phase's results are printed, later phases are not
+    started (Coordinator.cpp:111-116, 234-241); same through services, which apply the limit
+    themselves"""
+    path = os.path.join(workdir, "tl.bin")
+    res = run_cli("-w", "-r", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--infloop",
+                  "--timelimit", "1", "--nolive", path, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Terminating due to phase time limit." in res.stdout
+    assert int(table_value(res.stdout, "WRITE", "Total MiB")) > 16
+    assert "\nREAD " not in res.stdout
+
+    ports = [free_port(), free_port()]
+    hosts = ",".join("127.0.0.1:%d" % p for p in ports)
+    services = [subprocess.Popen([CLI_PATH, "--service", "--foreground", "--port", str(p)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE) for p in ports]
+    try:
+        res = run_cli("-w", "-r", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--infloop",
+                      "--timelimit", "1", "--nolive", "--hosts", hosts, "--svcwait", "30", path,
+                      timeout=120)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert "Terminating due to phase time limit." in res.stdout
+        assert int(table_value(res.stdout, "WRITE", "Total MiB")) > 16
+        assert "\nREAD " not in res.stdout
+    finally:
+        run_cli("--quit", "--hosts", hosts)
+        for svc in services:
+            try:
+                svc.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                svc.kill()

@@ -245,6 +245,37 @@ def run_cpu_localworker(paths, threads, file_size, block_size, salt, direct, ran
             "gib_s": (total_bytes / GiB) / (total_usec / 1e6) if total_usec else 0.0}
 
 
+def cpu_kernels_per_core(block_size, salt, total_bytes=256 * MiB):
+    """GB/s of ONE host core for the reference's per-block operators (the oracle restatement of
+    preWriteIntegrityCheckFillBuf / postReadIntegrityCheckVerifyBuf, LocalWorker.cpp:2091-2179) on
+    a block-sized buffer, as a CPU counterpart of the K1 / K2 numbers."""
+    import ctypes
+    from tests import oracle_lib  # oracle: CPU baseline leg only
+    lib = oracle_lib.load_oracle()
+    buf = ctypes.create_string_buffer(block_size)
+    nblocks = max(1, total_bytes // block_size)
+    num, first = ctypes.c_uint64(), ctypes.c_uint64()
+    exp, act = ctypes.c_uint(), ctypes.c_uint()
+    msg = ctypes.create_string_buffer(256)
+    out = {}
+    t0 = time.perf_counter()
+    for i in range(nblocks):
+        lib.orc_fill_pattern(buf, block_size, i * block_size, salt)
+    out["fill_pattern_gb_s"] = round(nblocks * block_size / (time.perf_counter() - t0) / 1e9, 2)
+    t0 = time.perf_counter()
+    bad = 0
+    for i in range(nblocks):
+        bad += lib.orc_verify_pattern(buf, block_size, (nblocks - 1) * block_size, salt,
+                                      ctypes.byref(num), ctypes.byref(first), ctypes.byref(exp),
+                                      ctypes.byref(act), msg, len(msg))
+    out["verify_pattern_gb_s"] = round(nblocks * block_size / (time.perf_counter() - t0) / 1e9, 2)
+    if bad:
+        raise RuntimeError("CPU verify of a CPU-filled block failed")
+    out["note"] = "one core, %d x %d KiB blocks, cache-resident buffer" % (nblocks,
+                                                                            block_size // 1024)
+    return out
+
+
 def storage_roofline(args, threads, sample_size):
     """Raw pread/pwrite pass (no fill, no verify, no GPU) over a bounded sample on the same
     storage with the same thread count: the storage-bandwidth roofline of the e2e number."""
@@ -305,6 +336,7 @@ def reference_arm(args):
                    "file_gib": step_size / GiB, "num_files": nfiles, "block_mib": args.block_mib,
                    "threads": threads,
                    "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
+               "operators_per_core": cpu_kernels_per_core(block, args.salt),
                    "dir": args.dir, "direct": args.direct},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},

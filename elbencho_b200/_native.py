@@ -82,6 +82,10 @@ class Cfg(ctypes.Structure):
         ("useCustomTreeRandomize", ctypes.c_int32),
         ("reserved4", ctypes.c_int32),
         ("treeRandomizeSeed", c_u64),
+        ("cpuCores", ctypes.POINTER(ctypes.c_int32)),
+        ("numaZones", ctypes.POINTER(ctypes.c_int32)),
+        ("numCPUCores", c_u32),
+        ("numNumaZones", c_u32),
     ]
 
 

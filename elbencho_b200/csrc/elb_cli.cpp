@@ -118,6 +118,12 @@ static const OptDef optDefs[] =
 	{"dryrun", 0, Opt_FLAG, "Don't run any benchmark phase, just print the number of expected "
 		"entries and dataset size per phase."},
 	{"iterations", 'i', Opt_U64, "Number of iterations to run the benchmark. (Default: 1)"},
+	{"cores", 0, Opt_STR, "Comma-separated list of CPU cores to bind this process to. If "
+		"multiple cores are given, then worker threads are bound round-robin to the cores. "
+		"(Hint: See 'lscpu' for available cores. Lists and ranges like \"0-3,8\" are supported.)"},
+	{"zones", 0, Opt_STR, "Comma-separated list of NUMA zones to bind this process to. If "
+		"multiple zones are given, then worker threads are bound round-robin to the zones. "
+		"(Hint: See 'lscpu' for available NUMA zones.)"},
 	{"treefile", 0, Opt_STR, "The path to a treefile containing a list of dirs and filenames to "
 		"use. This is called \"custom tree mode\" and enables testing with files of different "
 		"size. The benchmark path must be a directory. Lines: \"d <relative_path>\" and "
@@ -536,6 +542,8 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("timelimit", timeLimitSecs);
 	num("log", logLevel);
 
+	str("cores", cpuCoresStr);
+	str("zones", numaZonesStr);
 	str("treefile", treeFilePath);
 	str("treescan", treeScanPath);
 	useCustomTreeRandomize = flag("treerand");
@@ -600,6 +608,13 @@ void ProgArgs::initImplicitValues()
 
 	if(!gpuIDsStr.empty() && (gpuIDsStr != "all") )
 		gpuIDs = parseGPUIDs(gpuIDsStr);
+
+	// (same list syntax as --gpuids: commas, spaces, ranges; ProgArgs.cpp:2473-2530)
+	if(!cpuCoresStr.empty() )
+		cpuCores = parseGPUIDs(cpuCoresStr);
+
+	if(!numaZonesStr.empty() )
+		numaZones = parseGPUIDs(numaZonesStr);
 }
 
 /* ProgArgs::parseHosts (ProgArgs.cpp:2221-2340): hosts string + hosts file, delimiters ", \n\r",
@@ -867,6 +882,12 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	out.cpuCores.assign(cpuCores.begin(), cpuCores.end() );
+	out.numaZones.assign(numaZones.begin(), numaZones.end() );
+	cfg.cpuCores = out.cpuCores.data();
+	cfg.numCPUCores = (uint32_t)out.cpuCores.size();
+	cfg.numaZones = out.numaZones.data();
+	cfg.numNumaZones = (uint32_t)out.numaZones.size();
 	cfg.treeFilePath = treeFilePath.empty() ? NULL : treeFilePath.c_str();
 	cfg.treeRoundUpSize = treeRoundUpSize;
 	cfg.fileShareSize = fileShareSize;

@@ -96,6 +96,10 @@ class ProgArgs
 		uint64_t pipelineBatchBlocks{0};
 		uint64_t pipelineNumBatches{0};
 		bool serializeBufferedWrites{false};
+		std::string cpuCoresStr;        // --cores
+		std::string numaZonesStr;       // --zones
+		std::vector<int> cpuCores;
+		std::vector<int> numaZones;
 		std::string treeFilePath;       // --treefile
 		std::string treeScanPath;       // --treescan
 		uint64_t treeRoundUpSize{0};    // --treeroundup
@@ -156,6 +160,8 @@ class ProgArgs
 			elb_cfg cfg;
 			std::vector<const char*> pathPtrs;
 			std::vector<int32_t> gpuIDs;
+			std::vector<int32_t> cpuCores;
+			std::vector<int32_t> numaZones;
 		};
 		void toABIConfig(ABIConfig& out) const;
 

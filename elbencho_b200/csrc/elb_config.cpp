@@ -108,6 +108,12 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.useCustomTreeRandomize = (cfg->useCustomTreeRandomize != 0);
 	c.treeRandomizeSeed = cfg->treeRandomizeSeed;
 
+	for(uint32_t i = 0; cfg->cpuCores && (i < cfg->numCPUCores); i++)
+		c.cpuCores.push_back(cfg->cpuCores[i] );
+
+	for(uint32_t i = 0; cfg->numaZones && (i < cfg->numNumaZones); i++)
+		c.numaZones.push_back(cfg->numaZones[i] );
+
 	for(uint32_t i = 0; i < cfg->numGPUIDs; i++)
 		c.gpuIDs.push_back(cfg->gpuIDs[i] );
 

@@ -802,6 +802,8 @@ struct Config
 	uint64_t fileShareSize{0};    // --sharesize
 	bool useCustomTreeRandomize{false}; // --treerand
 	uint64_t treeRandomizeSeed{0};
+	std::vector<int> cpuCores;  // --cores
+	std::vector<int> numaZones; // --zones
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

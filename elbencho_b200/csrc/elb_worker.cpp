@@ -7,6 +7,9 @@
 #include <sys/stat.h>
 #include <sys/syscall.h>
 #include <sys/types.h>
+#include <sched.h>
+#include <fstream>
+#include <sstream>
 #include <unistd.h>
 
 #include <algorithm>
@@ -592,8 +595,97 @@ void Worker::run() // LocalWorker.cpp:177-396
  * Preparation: device, rings, batches (replaces allocIOBuffer/allocGPUIOBuffer, :1362-1513)
  * ============================================================================================ */
 
+/* "0-3,8,10-11" -> CPU numbers (format of /sys/devices/system/node/node<N>/cpulist) */
+static std::vector<int> parseCPUList(const std::string& listStr)
+{
+	std::vector<int> cpus;
+	std::stringstream listStream(listStr);
+	std::string element;
+
+	while(std::getline(listStream, element, ',') )
+	{
+		if(element.empty() || (element == "\n") )
+			continue;
+
+		const size_t dashPos = element.find('-');
+		const int first = atoi(element.c_str() );
+		const int last = (dashPos == std::string::npos) ?
+			first : atoi(element.substr(dashPos + 1).c_str() );
+
+		for(int cpu = first; cpu <= last; cpu++)
+			cpus.push_back(cpu);
+	}
+
+	return cpus;
+}
+
+/* Worker::applyNumaAndCoreBinding (Worker.cpp:102-146) without libnuma: the zone's CPUs come from
+ * sysfs, the memory policy goes through the set_mempolicy syscall (what numa_run_on_node_mask +
+ * numa_set_membind do, NumaTk.h:95-140) */
+void Worker::applyNumaAndCoreBinding()
+{
+	if(!cfg.numaZones.empty() )
+	{
+		const int zoneNum = cfg.numaZones[rank % cfg.numaZones.size() ];
+
+		if(zoneNum < 0)
+			throw WorkerError("Desired NUMA zone may not be negative. "
+				"Desired zone: " + std::to_string(zoneNum) );
+
+		const std::string cpuListPath =
+			"/sys/devices/system/node/node" + std::to_string(zoneNum) + "/cpulist";
+		std::ifstream cpuListStream(cpuListPath);
+		std::string cpuListStr;
+
+		if(!cpuListStream || !std::getline(cpuListStream, cpuListStr) )
+			throw WorkerError("Desired NUMA zone is not available. "
+				"Desired zone: " + std::to_string(zoneNum) );
+
+		cpu_set_t cpuSet;
+		CPU_ZERO(&cpuSet);
+
+		for(int cpu : parseCPUList(cpuListStr) )
+			if( (cpu >= 0) && (cpu < CPU_SETSIZE) )
+				CPU_SET(cpu, &cpuSet);
+
+		if(sched_setaffinity(0, sizeof(cpuSet), &cpuSet) == -1)
+			throw WorkerError("Applying NUMA zone node mask failed. "
+				"Given zones: " + std::to_string(zoneNum) + "; "
+				"SysErr: " + strerror(errno) );
+
+		// memory of this thread from the same zone (MPOL_BIND = 2); not fatal in containers
+		unsigned long nodeMask[16] = {};
+
+		if( (size_t)zoneNum < (sizeof(nodeMask) * 8) )
+		{
+			nodeMask[zoneNum / (8 * sizeof(unsigned long) )] |=
+				1UL << (zoneNum % (8 * sizeof(unsigned long) ) );
+
+			syscall(SYS_set_mempolicy, 2 /*MPOL_BIND*/, nodeMask, sizeof(nodeMask) * 8);
+		}
+	}
+
+	if(!cfg.cpuCores.empty() )
+	{
+		const int coreNum = cfg.cpuCores[rank % cfg.cpuCores.size() ];
+
+		cpu_set_t cpuSet;
+		CPU_ZERO(&cpuSet);
+
+		if( (coreNum >= 0) && (coreNum < CPU_SETSIZE) )
+			CPU_SET(coreNum, &cpuSet);
+
+		if(sched_setaffinity(0, sizeof(cpuSet), &cpuSet) == -1)
+			throw WorkerError("Applying CPU core set failed. "
+				"Given cores list: " + std::to_string(coreNum) + " ; "
+				"SysErr: " + strerror(errno) );
+	}
+}
+
 void Worker::preparePhase()
 {
+	applyNumaAndCoreBinding(); // first thing, so that all allocations follow (Worker.cpp:102)
+
 	gpuID = cfg.gpuIDs[rank % cfg.gpuIDs.size() ]; // LocalWorker.cpp:1420-1422
 
 	ELB_CUDA_CHECK(cudaSetDevice(gpuID), "Setting CUDA device");

@@ -233,6 +233,7 @@ class Worker
 		PathStore customTreeDirs;
 		PathStore customTreeFiles;
 		bool dirModeCountsEntry{true}; // false for a partial slice of a shared tree file
+		void applyNumaAndCoreBinding();     // Worker.cpp:102-146
 		void prepareCustomTreePathStores(); // LocalWorker.cpp:1520-1560
 		void dirModeIterateCustomDirs();    // LocalWorker.cpp:2927-3010
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470

@@ -88,6 +88,8 @@ class WorkerConfig:
     file_share_size: int = 0          # --sharesize (0 = 32 x block size)
     use_custom_tree_randomize: bool = False  # --treerand
     tree_randomize_seed: int = 0      # injected seed (0 = self-seed)
+    cpu_cores: Sequence[int] = ()     # --cores
+    numa_zones: Sequence[int] = ()    # --zones
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -165,7 +167,13 @@ class WorkerConfig:
         cfg.fileShareSize = self.file_share_size
         cfg.useCustomTreeRandomize = int(self.use_custom_tree_randomize)
         cfg.treeRandomizeSeed = self.tree_randomize_seed
-        return cfg, (path_bytes, path_arr, gpu_arr)
+        cores = (ctypes.c_int32 * max(1, len(self.cpu_cores)))(*self.cpu_cores)
+        zones = (ctypes.c_int32 * max(1, len(self.numa_zones)))(*self.numa_zones)
+        cfg.cpuCores = ctypes.cast(cores, ctypes.POINTER(ctypes.c_int32))
+        cfg.numaZones = ctypes.cast(zones, ctypes.POINTER(ctypes.c_int32))
+        cfg.numCPUCores = len(self.cpu_cores)
+        cfg.numNumaZones = len(self.numa_zones)
+        return cfg, (path_bytes, path_arr, gpu_arr, cores, zones)
 
 
 def histogram_to_dict(histo: Histogram):

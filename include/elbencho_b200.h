@@ -281,6 +281,13 @@ typedef struct elb_cfg
 	int32_t useCustomTreeRandomize; /* shuffle each worker's file list */
 	int32_t reserved4;
 	uint64_t treeRandomizeSeed;     /* 0 = self-seed (tests inject one) */
+
+	/* --cores / --zones: worker rank r binds itself to cpuCores[r % n] and / or to the CPUs and
+	 * memory of NUMA zone numaZones[r % n] first thing in its preparation (Worker.cpp:102-146) */
+	const int32_t* cpuCores;
+	const int32_t* numaZones;
+	uint32_t numCPUCores;
+	uint32_t numNumaZones;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

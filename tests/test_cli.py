@@ -109,6 +109,7 @@ def test_new_run_control_options_parse():
                   "1", "--limitread", "10M", "--limitwrite", "1G", "--live1", "--live1n",
                   "--cuhostbufreg", "--nodiocheck", "--nopathexp", "--datasetthreads", "4",
                   "--rankoffset", "1", "--start", "0", "--livecsv", "/tmp/elb_live.csv",
+                  "--cores", "0-1,3", "--zones", "0",
                   "/tmp/elb_dry")
     assert res.returncode == 0, res.stderr
 

@@ -195,3 +195,47 @@ def test_rwmixthrpct_rejects_rate_limits(workdir):
                        limit_read_bps=1 << 20)
     with pytest.raises(WorkerError, match="cannot be used together"):
         WorkerManager(cfg)
+
+
+def _new_thread_affinities(before):
+    out = []
+    for tid in set(os.listdir("/proc/self/task")) - before:
+        try:
+            with open("/proc/self/task/%s/status" % tid) as f:
+                for line in f:
+                    if line.startswith("Cpus_allowed_list:"):
+                        out.append(line.split(":", 1)[1].strip())
+        except OSError:
+            pass
+    return out
+
+
+def test_cores_and_zones_binding(workdir):
+    """--cores: worker r binds to cores[r % n]; --zones: to the CPUs of zone[r % n]
+    (Worker.cpp:102-146), before anything is allocated"""
+    path = os.path.join(workdir, "bind.bin")
+    avail = sorted(os.sched_getaffinity(0))
+    cores = avail[:2]
+    common = dict(paths=[path], num_threads=4, block_size=MiB, file_size=16 * MiB,
+                  integrity_check_salt=2)
+    before = set(os.listdir("/proc/self/task"))
+    with WorkerManager(WorkerConfig(cpu_cores=cores, **common)) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        assert res["ops_total"]["bytes"] == 16 * MiB
+        lists = _new_thread_affinities(before)
+    bound = [entry for entry in lists if entry in (str(cores[0]), str(cores[1]))]
+    assert len(bound) >= 4, lists
+    assert {str(cores[0]), str(cores[1])} <= set(bound)
+
+    with open("/sys/devices/system/node/node0/cpulist") as f:
+        node0 = f.read().strip()
+    before = set(os.listdir("/proc/self/task"))
+    with WorkerManager(WorkerConfig(numa_zones=[0], **common)) as mgr:
+        mgr.run_phase(BenchPhase.READFILES)
+        lists = _new_thread_affinities(before)
+    assert sum(1 for entry in lists if entry == node0) >= 4, (node0, lists)
+
+    with pytest.raises(WorkerError, match="Desired NUMA zone is not available. Desired zone: 99"):
+        WorkerManager(WorkerConfig(numa_zones=[99], **common))
+    with pytest.raises(WorkerError, match="Applying CPU core set failed"):
+        WorkerManager(WorkerConfig(cpu_cores=[100000], **common))

@@ -86,6 +86,10 @@ class Cfg(ctypes.Structure):
         ("numaZones", ctypes.POINTER(ctypes.c_int32)),
         ("numCPUCores", c_u32),
         ("numNumaZones", c_u32),
+        ("flockType", c_u32),
+        ("fadviseFlags", c_u32),
+        ("doStatInline", ctypes.c_int32),
+        ("reserved5", ctypes.c_int32),
     ]
 
 

@@ -118,6 +118,13 @@ static const OptDef optDefs[] =
 	{"dryrun", 0, Opt_FLAG, "Don't run any benchmark phase, just print the number of expected "
 		"entries and dataset size per phase."},
 	{"iterations", 'i', Opt_U64, "Number of iterations to run the benchmark. (Default: 1)"},
+	{"flock", 0, Opt_STR, "Use POSIX file locks around each read/write. Possible values: "
+		"\"range\" to lock the specific range of each I/O operation, \"full\" to lock the "
+		"entire file for each I/O operation."},
+	{"fadv", 0, Opt_STR, "Provide file access hints via posix_fadvise(). Comma-separated list of "
+		"these flags: seq, rand, willneed, dontneed, noreuse."},
+	{"statinline", 0, Opt_FLAG, "When benchmark path is a directory, stat files immediately "
+		"after open in a write or read phase."},
 	{"cores", 0, Opt_STR, "Comma-separated list of CPU cores to bind this process to. If "
 		"multiple cores are given, then worker threads are bound round-robin to the cores. "
 		"(Hint: See 'lscpu' for available cores. Lists and ranges like \"0-3,8\" are supported.)"},
@@ -542,6 +549,9 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("timelimit", timeLimitSecs);
 	num("log", logLevel);
 
+	str("flock", flockTypeStr);
+	str("fadv", fadviseFlagsStr);
+	doStatInline = flag("statinline");
 	str("cores", cpuCoresStr);
 	str("zones", numaZonesStr);
 	str("treefile", treeFilePath);
@@ -608,6 +618,40 @@ void ProgArgs::initImplicitValues()
 
 	if(!gpuIDsStr.empty() && (gpuIDsStr != "all") )
 		gpuIDs = parseGPUIDs(gpuIDsStr);
+
+	// --flock (ProgArgs.cpp:2600-2615)
+	if(flockTypeStr.empty() )
+		flockType = 0;
+	else
+	if(flockTypeStr == "range")
+		flockType = 1;
+	else
+	if(flockTypeStr == "full")
+		flockType = 2;
+	else
+		throw ProgError("Invalid file lock type: " + flockTypeStr);
+
+	// --fadv (ProgArgs.cpp:2575-2598)
+	{
+		std::string normalized = fadviseFlagsStr;
+		std::replace(normalized.begin(), normalized.end(), ' ', ',');
+		std::stringstream flagsStream(normalized);
+		std::string flagName;
+
+		while(std::getline(flagsStream, flagName, ',') )
+		{
+			if(flagName.empty() )
+				continue;
+
+			if(flagName == "seq") fadviseFlags |= 1;
+			else if(flagName == "rand") fadviseFlags |= 2;
+			else if(flagName == "willneed") fadviseFlags |= 4;
+			else if(flagName == "dontneed") fadviseFlags |= 8;
+			else if(flagName == "noreuse") fadviseFlags |= 16;
+			else
+				throw ProgError("Invalid fadvise: " + flagName);
+		}
+	}
 
 	// (same list syntax as --gpuids: commas, spaces, ranges; ProgArgs.cpp:2473-2530)
 	if(!cpuCoresStr.empty() )
@@ -882,6 +926,9 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.verifyCollectAll = 0;
 	cfg.serializeBufferedWrites = serializeBufferedWrites;
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
+	cfg.flockType = (uint32_t)flockType;
+	cfg.fadviseFlags = (uint32_t)fadviseFlags;
+	cfg.doStatInline = doStatInline;
 	out.cpuCores.assign(cpuCores.begin(), cpuCores.end() );
 	out.numaZones.assign(numaZones.begin(), numaZones.end() );
 	cfg.cpuCores = out.cpuCores.data();

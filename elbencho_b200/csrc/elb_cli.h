@@ -96,6 +96,11 @@ class ProgArgs
 		uint64_t pipelineBatchBlocks{0};
 		uint64_t pipelineNumBatches{0};
 		bool serializeBufferedWrites{false};
+		std::string flockTypeStr;       // --flock
+		std::string fadviseFlagsStr;    // --fadv
+		uint64_t flockType{0};
+		uint64_t fadviseFlags{0};
+		bool doStatInline{false};       // --statinline
 		std::string cpuCoresStr;        // --cores
 		std::string numaZonesStr;       // --zones
 		std::vector<int> cpuCores;

@@ -108,6 +108,16 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.useCustomTreeRandomize = (cfg->useCustomTreeRandomize != 0);
 	c.treeRandomizeSeed = cfg->treeRandomizeSeed;
 
+	c.flockType = cfg->flockType;
+	c.fadviseFlags = cfg->fadviseFlags;
+	c.doStatInline = (cfg->doStatInline != 0);
+
+	if(c.flockType > 2)
+		throw WorkerError("Invalid file lock type: " + std::to_string(c.flockType) );
+
+	if( (c.flockType == 2) && (cfg->ioDepth > 1) ) // ProgArgs.cpp:1436-1437
+		throw WorkerError("Full file write locks cannot be used together with async IO");
+
 	for(uint32_t i = 0; cfg->cpuCores && (i < cfg->numCPUCores); i++)
 		c.cpuCores.push_back(cfg->cpuCores[i] );
 

@@ -804,6 +804,9 @@ struct Config
 	uint64_t treeRandomizeSeed{0};
 	std::vector<int> cpuCores;  // --cores
 	std::vector<int> numaZones; // --zones
+	unsigned flockType{0};      // --flock
+	unsigned fadviseFlags{0};   // --fadv
+	bool doStatInline{false};   // --statinline
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

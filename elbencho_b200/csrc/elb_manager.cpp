@@ -168,6 +168,36 @@ void Manager::prepareBenchPathFDs()
 
 		shared.pathFDs.push_back(fd);
 		shared.fileWriteGates.emplace_back(new std::mutex() );
+
+		// --fadv on the files / block devices themselves (ProgArgs.cpp:2032)
+		if(cfg.fadviseFlags && (cfg.pathType != ELB_PATH_DIR) )
+		{
+			const struct { unsigned flag; int advice; const char* name; } adviceDefs[] =
+			{
+				{8, POSIX_FADV_DONTNEED, "POSIX_FADV_DONTNEED"},
+				{16, POSIX_FADV_NOREUSE, "POSIX_FADV_NOREUSE"},
+				{1, POSIX_FADV_SEQUENTIAL, "POSIX_FADV_SEQUENTIAL"},
+				{2, POSIX_FADV_RANDOM, "POSIX_FADV_RANDOM"},
+				{4, POSIX_FADV_WILLNEED, "POSIX_FADV_WILLNEED"},
+			};
+
+			for(const auto& def : adviceDefs)
+			{
+				if(!(cfg.fadviseFlags & def.flag) )
+					continue;
+
+				const int fadviseRes = posix_fadvise(fd, 0, 0, def.advice);
+
+				if(fadviseRes)
+				{
+					closeBenchPathFDs();
+					throw WorkerError(std::string("Unable to set POSIX fadvise. ") +
+						"Advise: " + def.name + "; "
+						"File: " + path + "; "
+						"SysErr: " + strerror(fadviseRes) );
+				}
+			}
+		}
 	}
 
 	/* ProgArgs::prepareCuFileHandleDataVec (ProgArgs.cpp:1950-1990): driver open + one registered

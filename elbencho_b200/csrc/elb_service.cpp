@@ -1108,6 +1108,9 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.gpuIDsStr = recvTree.getStr("gpuids", "");
 		args.ignoreDelErrors = recvTree.getBool("nodelerr", false);
 		args.integrityCheckSalt = recvTree.getU64("verify", 0);
+		args.fadviseFlags = recvTree.getU64("fadv", 0);
+		args.flockType = recvTree.getU64("flock", 0);
+		args.doStatInline = recvTree.getBool("statinline", false);
 		args.doInfiniteIOLoop = recvTree.getBool("infloop", false);
 		args.timeLimitSecs = recvTree.getU64("b200_timelimit", 0);
 		args.limitReadBps = recvTree.getU64("limitread", 0);
@@ -1743,10 +1746,10 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("dirsharing", args.doDirSharing);
 	tree.putBool("direct", args.useDirectIO);
 	tree.putBool("dropcache", args.runDropCachesPhase);
-	tree.put("fadv", (uint64_t)0);
+	tree.put("fadv", args.fadviseFlags);
 	tree.put("sharesize", args.fileShareSize);
 	tree.put("size", args.fileSize);
-	tree.put("flock", (uint64_t)0);
+	tree.put("flock", args.flockType);
 	tree.putBool("gdsbufreg", args.useGDSBufReg);
 	tree.putBool("hdfs", false);
 	tree.putBool("no0usecerr", args.ignore0USecErrors);
@@ -1806,7 +1809,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 
 	tree.put("sendbuf", (uint64_t)0);
 	tree.putBool("stat", args.runStatFilesPhase);
-	tree.putBool("statinline", false);
+	tree.putBool("statinline", args.doStatInline);
 	tree.putBool("strided", args.useStridedAccess);
 	tree.putBool("sync", args.runSyncPhase);
 	tree.putBool("trunc", args.doTruncate);

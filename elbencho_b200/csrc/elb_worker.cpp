@@ -1416,6 +1416,65 @@ void Worker::anyModeDropCaches() // LocalWorker.cpp:7822-7854
  * Read/write phases
  * ============================================================================================ */
 
+/* FileTk::flock (toolkits/FileTk.h:49-120): POSIX advisory lock of the block's range or of the
+ * whole file; read lock for reads, write lock for writes */
+void Worker::flockBlock(int fd, const BlockRef& block, bool isUnlock)
+{
+	if(!cfg.flockType)
+		return;
+
+	const bool isFull = (cfg.flockType == 2);
+	struct flock flockDetails;
+
+	flockDetails.l_type = isUnlock ? F_UNLCK : (block.ioIsRead ? F_RDLCK : F_WRLCK);
+	flockDetails.l_whence = SEEK_SET;
+	flockDetails.l_start = isFull ? 0 : (off_t)block.offset;
+	flockDetails.l_len = isFull ? 0 : (off_t)block.len; // (0: to the end of the file)
+
+	if(fcntl(fd, F_SETLKW, &flockDetails) == -1)
+		throw WorkerError(std::string(isFull ?
+				"File lock operation failed. " : "File range lock operation failed. ") +
+			"FD: " + std::to_string(fd) + "; " +
+			(isFull ? std::string() : ("Offset: " + std::to_string(block.offset) + "; "
+				"Length: " + std::to_string(block.len) + "; ") ) +
+			"LockType: " + (isUnlock ? "unlock" : (block.ioIsRead ? "read" : "write") ) + "; "
+			"File: " + blockPathForLog(block) + "; "
+			"SysErr: " + strerror(errno) );
+}
+
+/* FileTk::fadvise (toolkits/FileTk.cpp:138-215): all advices of --fadv on the whole file;
+ * dontneed / noreuse first, so that they can be combined with seq / rand */
+void Worker::fadviseFile(int fd, const std::string& path)
+{
+	if(!cfg.fadviseFlags)
+		return;
+
+	struct AdviceDef { unsigned flag; int advice; const char* name; };
+
+	const AdviceDef adviceDefs[] =
+	{
+		{8, POSIX_FADV_DONTNEED, "POSIX_FADV_DONTNEED"},
+		{16, POSIX_FADV_NOREUSE, "POSIX_FADV_NOREUSE"},
+		{1, POSIX_FADV_SEQUENTIAL, "POSIX_FADV_SEQUENTIAL"},
+		{2, POSIX_FADV_RANDOM, "POSIX_FADV_RANDOM"},
+		{4, POSIX_FADV_WILLNEED, "POSIX_FADV_WILLNEED"},
+	};
+
+	for(const AdviceDef& def : adviceDefs)
+	{
+		if(!(cfg.fadviseFlags & def.flag) )
+			continue;
+
+		const int fadviseRes = posix_fadvise(fd, 0, 0, def.advice);
+
+		if(fadviseRes) // (returns the error number instead of setting errno)
+			throw WorkerError(std::string("Unable to set POSIX fadvise. ") +
+				"Advise: " + def.name + "; "
+				"File: " + path + "; "
+				"SysErr: " + strerror(fadviseRes) );
+	}
+}
+
 void Worker::rateLimitNextBlock(uint64_t len)
 {
 	if(useRWMixThreadsBalancer)
@@ -2161,6 +2220,18 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 	if(cfg.useCuFile) // dirModeCuFileHandleReg (LocalWorker.cpp:3091)
 		dirModeCuFileHandle.registerFD(dirModeFD, dirModeCurrentPath);
 
+	if(cfg.doStatInline)
+	{ // inline stat, i.e. stat immediately after file open (LocalWorker.cpp:3094-3105)
+		struct stat statBuf;
+
+		if(fstat(dirModeFD, &statBuf) == -1)
+			throw WorkerError(std::string("File stat failed. ") +
+				"Path: " + dirModeCurrentPath + "; "
+				"SysErr: " + strerror(errno) );
+	}
+
+	fadviseFile(dirModeFD, dirModeCurrentPath); // (LocalWorker.cpp:7148)
+
 	if(!isRead)
 	{
 		if(cfg.doTruncToSize && (ftruncate(dirModeFD, fileSize) == -1) )
@@ -2255,6 +2326,8 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 			char* hostBuf = slotHostPtr(batch, i);
 			ssize_t ioRes;
 
+			flockBlock(fd, block, false); // (inside the measured I/O time, :1691-1755)
+
 			if(block.ioIsRead)
 				ioRes = pread(fd, hostBuf, block.len, block.offset);
 			else
@@ -2277,6 +2350,8 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 				if(ioRes != (ssize_t)block.len)
 					throwIOError(block, true, ioRes, errno);
 			}
+
+			flockBlock(fd, block, true);
 
 			block.ioUSec = elapsedUSecSince(ioStartT);
 

@@ -234,6 +234,8 @@ class Worker
 		PathStore customTreeFiles;
 		bool dirModeCountsEntry{true}; // false for a partial slice of a shared tree file
 		void applyNumaAndCoreBinding();     // Worker.cpp:102-146
+		void flockBlock(int fd, const BlockRef& block, bool isUnlock); // FileTk::flock
+		void fadviseFile(int fd, const std::string& path);             // FileTk::fadvise
 		void prepareCustomTreePathStores(); // LocalWorker.cpp:1520-1560
 		void dirModeIterateCustomDirs();    // LocalWorker.cpp:2927-3010
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470

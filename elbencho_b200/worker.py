@@ -90,6 +90,9 @@ class WorkerConfig:
     tree_randomize_seed: int = 0      # injected seed (0 = self-seed)
     cpu_cores: Sequence[int] = ()     # --cores
     numa_zones: Sequence[int] = ()    # --zones
+    flock_type: int = 0               # --flock (0 none, 1 range, 2 full)
+    fadvise_flags: int = 0            # --fadv (1 seq, 2 rand, 4 willneed, 8 dontneed, 16 noreuse)
+    do_stat_inline: bool = False      # --statinline
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -173,6 +176,9 @@ class WorkerConfig:
         cfg.numaZones = ctypes.cast(zones, ctypes.POINTER(ctypes.c_int32))
         cfg.numCPUCores = len(self.cpu_cores)
         cfg.numNumaZones = len(self.numa_zones)
+        cfg.flockType = self.flock_type
+        cfg.fadviseFlags = self.fadvise_flags
+        cfg.doStatInline = int(self.do_stat_inline)
         return cfg, (path_bytes, path_arr, gpu_arr, cores, zones)
 
 

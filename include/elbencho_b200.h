@@ -288,6 +288,15 @@ typedef struct elb_cfg
 	const int32_t* numaZones;
 	uint32_t numCPUCores;
 	uint32_t numNumaZones;
+
+	/* --flock range|full: POSIX advisory lock (fcntl F_SETLKW) around every block's storage call,
+	 * read lock for reads, write lock for writes (FileTk.h:49-120, LocalWorker.cpp:1701-1750) */
+	uint32_t flockType;     /* 0 none, 1 range, 2 full */
+	/* --fadv: posix_fadvise on every opened file; bit 1 seq, 2 rand, 4 willneed, 8 dontneed,
+	 * 16 noreuse (ProgArgs.h:240-249, FileTk.cpp:138-215) */
+	uint32_t fadviseFlags;
+	int32_t doStatInline;   /* --statinline: fstat each dir mode file right after open */
+	int32_t reserved5;
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

@@ -109,7 +109,8 @@ def test_new_run_control_options_parse():
                   "1", "--limitread", "10M", "--limitwrite", "1G", "--live1", "--live1n",
                   "--cuhostbufreg", "--nodiocheck", "--nopathexp", "--datasetthreads", "4",
                   "--rankoffset", "1", "--start", "0", "--livecsv", "/tmp/elb_live.csv",
-                  "--cores", "0-1,3", "--zones", "0",
+                  "--cores", "0-1,3", "--zones", "0", "--flock", "range", "--fadv",
+                  "seq,willneed", "--statinline",
                   "/tmp/elb_dry")
     assert res.returncode == 0, res.stderr
 
@@ -142,6 +143,9 @@ def test_config3_random_read_iops_via_dryrun():
     (["-w", "-s", "1g", "-t", "2", "--gpuids", "0", "--rwmixthr", "1", "--rwmixthrpct", "40",
       "--limitwrite", "1M", "/tmp/x"],
      'Option "--rwmixthrpct" cannot be used together with "--limitread" or "--limitwrite"'),
+    (["-r", "-s", "1g", "--gpuids", "0", "--flock", "maybe", "/tmp/x"],
+     "Invalid file lock type: maybe"),
+    (["-r", "-s", "1g", "--gpuids", "0", "--fadv", "seq,fast", "/tmp/x"], "Invalid fadvise: fast"),
     (["-r", "-s", "1g", "--gpuids", "0", "--rand", "--randalgo", "quick", "/tmp/x"],
      "Invalid random algo: quick"),
     (["-w", "-s", "1g", "--gpuids", "0", "--blockvarpct", "50", "--blockvaralgo", "best",

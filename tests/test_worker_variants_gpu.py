@@ -239,3 +239,40 @@ def test_cores_and_zones_binding(workdir):
         WorkerManager(WorkerConfig(numa_zones=[99], **common))
     with pytest.raises(WorkerError, match="Applying CPU core set failed"):
         WorkerManager(WorkerConfig(cpu_cores=[100000], **common))
+
+
+@pytest.mark.parametrize("flock_type", [1, 2])
+def test_flock_fadvise_statinline_keep_results_identical(workdir, flock_type):
+    """--flock range/full, --fadv and --statinline only add syscalls around the I/O: bytes and
+    counters equal the plain run (FileTk.h:49-120, FileTk.cpp:138-215, LocalWorker.cpp:3094-3105)"""
+    size, block = 4 * MiB, 64 * KiB
+    gpath = os.path.join(workdir, "lock.bin")
+    cfg = WorkerConfig(paths=[gpath], num_threads=2, block_size=block, file_size=size,
+                       integrity_check_salt=4, flock_type=flock_type, fadvise_flags=1 | 8 | 16)
+    with WorkerManager(cfg) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        assert res["ops_total"]["bytes"] == size and res["ops_total"]["iops"] == size // block
+        res = mgr.run_phase(BenchPhase.READFILES)
+        assert res["verified_bytes"] == size and res["verify_mismatch_bytes"] == 0
+    with open(gpath, "rb") as f:
+        assert f.read() == oracle_lib.fill_pattern(size, 0, 4)
+
+    tree = os.path.join(workdir, "d")
+    os.mkdir(tree)
+    dcfg = WorkerConfig(paths=[tree], path_type=PathType.DIR, num_threads=2, num_dirs=1, num_files=3,
+                        block_size=block, file_size=3 * block, integrity_check_salt=6,
+                        flock_type=flock_type, fadvise_flags=2 | 4, do_stat_inline=True)
+    with WorkerManager(dcfg) as mgr:
+        mgr.run_phase(BenchPhase.CREATEDIRS)
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+        assert res["ops_total"]["entries"] == 6
+        res = mgr.run_phase(BenchPhase.READFILES)
+        assert res["verified_bytes"] == 6 * 3 * block and res["verify_mismatch_bytes"] == 0
+
+
+def test_full_file_lock_rejects_async_io(workdir):
+    cfg = WorkerConfig(paths=[os.path.join(workdir, "x")], block_size=MiB, file_size=4 * MiB,
+                       flock_type=2, io_depth=4)
+    with pytest.raises(WorkerError, match="Full file write locks cannot be used together with "
+                                          "async IO"):
+        WorkerManager(cfg)

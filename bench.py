@@ -336,10 +336,10 @@ def reference_arm(args):
                    "file_gib": step_size / GiB, "num_files": nfiles, "block_mib": args.block_mib,
                    "threads": threads,
                    "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
-               "operators_per_core": cpu_kernels_per_core(block, args.salt),
                    "dir": args.dir, "direct": args.direct},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": sample,
+                         "operators_per_core": cpu_kernels_per_core(block, args.salt)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -667,6 +667,7 @@ def main():
                          "(oracle port of LocalWorker.cpp:1669-1781 + 2091-2179)" % (
                              sample_size / GiB, threads, args.dir),
                "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
+               "operators_per_core": cpu_kernels_per_core(block, args.salt),
                "write_gib_s": round(res["phases"]["CREATEFILES"]["bytes"] / GiB /
                                     (res["phases"]["CREATEFILES"]["usec"] / 1e6), 3),
                "read_gib_s": round(res["phases"]["READFILES"]["bytes"] / GiB /

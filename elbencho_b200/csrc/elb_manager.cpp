@@ -21,9 +21,47 @@ namespace elb
 
 /* prepareThreads (WorkerManager.cpp:142-199): open bench paths, create workers and their threads,
  * wait until all of them finished their preparation. */
+/* ProgArgs::prepareFileSize (ProgArgs.cpp:2071-2210), the part that has to happen before the
+ * size dependent normalisation: no --size given => take the size of the (first) existing file or
+ * of the block device */
+static uint64_t detectFileSize(const elb_cfg* abiCfg)
+{
+	if(abiCfg->fileSize || !abiCfg->numPaths || !abiCfg->paths || !abiCfg->paths[0] )
+		return abiCfg->fileSize;
+
+	const char* path = abiCfg->paths[0];
+
+	if(abiCfg->pathType == ELB_PATH_FILE)
+	{
+		struct stat statBuf;
+
+		if( (stat(path, &statBuf) == 0) && S_ISREG(statBuf.st_mode) )
+			return statBuf.st_size;
+	}
+	else
+	if(abiCfg->pathType == ELB_PATH_BLOCKDEV)
+	{
+		int fd = open(path, O_RDONLY);
+
+		if(fd != -1)
+		{
+			off_t blockdevSize = lseek(fd, 0, SEEK_END);
+			close(fd);
+
+			if(blockdevSize > 0)
+				return blockdevSize;
+		}
+	}
+
+	return 0;
+}
+
 Manager::Manager(const elb_cfg* abiCfg)
 {
-	shared.cfg = Config::fromABI(abiCfg);
+	elb_cfg sizedCfg = *abiCfg;
+	sizedCfg.fileSize = detectFileSize(abiCfg);
+
+	shared.cfg = Config::fromABI(&sizedCfg);
 
 	prepareBenchPathFDs();
 
@@ -238,6 +276,30 @@ void Manager::closeBenchPathFDs()
 void Manager::prepareFilesForPhase(int benchPhase)
 {
 	const Config& cfg = shared.cfg;
+	const bool isRWPhase = (benchPhase == ELB_PHASE_CREATEFILES) || (benchPhase == ELB_PHASE_READFILES);
+
+	if( (cfg.pathType == ELB_PATH_FILE) && isRWPhase)
+	{ // size checks of ProgArgs::prepareFileSize (ProgArgs.cpp:2085-2104)
+		for(size_t i = 0; i < shared.pathFDs.size(); i++)
+		{
+			struct stat statBuf;
+
+			if(fstat(shared.pathFDs[i], &statBuf) == -1)
+				throw WorkerError("Unable to check size of file through fstat: " + cfg.paths[i] +
+					"; SysErr: " + strerror(errno) );
+
+			if(!cfg.fileSize && !statBuf.st_size)
+				throw WorkerError("File size must not be 0 when benchmark path is a file. "
+					"File: " + cfg.paths[i] );
+
+			if( (benchPhase == ELB_PHASE_READFILES) && S_ISREG(statBuf.st_mode) &&
+				( (uint64_t)statBuf.st_size < cfg.fileSize) )
+				throw WorkerError("Given size to use is larger than detected size. "
+					"File: " + cfg.paths[i] + "; "
+					"Detected size: " + std::to_string(statBuf.st_size) + "; "
+					"Given size: " + std::to_string(cfg.fileSize) );
+		}
+	}
 
 	if( (cfg.pathType != ELB_PATH_FILE) || (benchPhase != ELB_PHASE_CREATEFILES) )
 		return;

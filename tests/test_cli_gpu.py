@@ -277,3 +277,26 @@ def test_time_limit_ends_the_run_after_the_current_phase(workdir):
                 svc.wait(timeout=20)
             except subprocess.TimeoutExpired:
                 svc.kill()
+
+
+def test_file_size_is_detected_when_not_given(workdir):
+    """no -s for an existing file: the file's own size is used; a larger -s than the file holds is
+    an error in a read-only run; an empty new file without -s too (ProgArgs.cpp:2071-2104)"""
+    path = os.path.join(workdir, "auto.bin")
+    res = run_cli("-w", "-t", "2", "-b", "1M", "-s", "24M", "--verify", "1", "--gpuids", "0",
+                  "--nolive", path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    res = run_cli("-r", "-t", "2", "-b", "1M", "--verify", "1", "--gpuids", "0", "--nolive", path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert int(table_value(res.stdout, "READ", "Total MiB")) == 24
+    res = run_cli("-r", "-t", "2", "-b", "4K", "--rand", "--iodepth", "8", "--verify", "1",
+                  "--gpuids", "0", "--nolive", path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert int(table_value(res.stdout, "READ", "Total MiB")) == 24  # randamount = file size
+    res = run_cli("-r", "-b", "1M", "-s", "32M", "--gpuids", "0", "--nolive", path)
+    assert res.returncode == 1
+    assert "Given size to use is larger than detected size." in res.stderr
+    assert "Detected size: %d; Given size: %d" % (24 * MiB, 32 * MiB) in res.stderr
+    res = run_cli("-r", "-b", "1M", "--gpuids", "0", "--nolive", os.path.join(workdir, "new.bin"))
+    assert res.returncode == 1
+    assert "File size must not be 0 when benchmark path is a file." in res.stderr

@@ -204,6 +204,9 @@ namespace stats
 		uint64_t bytesPerThread, std::ostream& out); // :2850-2876
 }
 
+/* size of the first existing file / block device if cfg->fileSize is 0 (ProgArgs.cpp:2071-2210) */
+uint64_t detectFileSize(const elb_cfg* abiCfg);
+
 /* Coordinator::waitForUserDefinedStartTime (Coordinator.cpp:149-158) */
 void waitForUserDefinedStartTime(const ProgArgs& progArgs);
 

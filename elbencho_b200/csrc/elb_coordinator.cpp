@@ -115,6 +115,8 @@ void Coordinator::printDryRunInfo()
 		abiConfig.cfg.numGPUIDs = 1;
 	}
 
+	abiConfig.cfg.fileSize = detectFileSize(&abiConfig.cfg);
+
 	Config cfg = Config::fromABI(&abiConfig.cfg);
 
 	CustomTree customTree;

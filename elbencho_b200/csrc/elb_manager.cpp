@@ -24,7 +24,7 @@ namespace elb
 /* ProgArgs::prepareFileSize (ProgArgs.cpp:2071-2210), the part that has to happen before the
  * size dependent normalisation: no --size given => take the size of the (first) existing file or
  * of the block device */
-static uint64_t detectFileSize(const elb_cfg* abiCfg)
+uint64_t detectFileSize(const elb_cfg* abiCfg)
 {
 	if(abiCfg->fileSize || !abiCfg->numPaths || !abiCfg->paths || !abiCfg->paths[0] )
 		return abiCfg->fileSize;

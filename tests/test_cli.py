@@ -104,6 +104,14 @@ def test_hosts_file_numhosts_and_duplicates(tmp_path):
         in res.stderr
 
 
+def test_dryrun_detects_size_of_existing_file(tmp_path):
+    path = tmp_path / "existing.bin"
+    path.write_bytes(b"\0" * (3 * MiB))
+    res = run_cli("--dryrun", "-r", "-t", "3", "-b", "1M", "--gpuids", "0", str(path))
+    assert res.returncode == 0, res.stderr
+    assert "* Bytes total:        %d |" % (3 * MiB) in res.stdout
+
+
 def test_new_run_control_options_parse():
     res = run_cli("--dryrun", "-w", "-r", "-s", "1M", "--gpuids", "0", "--infloop", "--timelimit",
                   "1", "--limitread", "10M", "--limitwrite", "1G", "--live1", "--live1n",

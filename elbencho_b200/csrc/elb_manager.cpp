@@ -292,14 +292,20 @@ void Manager::prepareFilesForPhase(int benchPhase)
 				throw WorkerError("File size must not be 0 when benchmark path is a file. "
 					"File: " + cfg.paths[i] );
 
-			if( (benchPhase == ELB_PHASE_READFILES) && S_ISREG(statBuf.st_mode) &&
-				( (uint64_t)statBuf.st_size < cfg.fileSize) )
+			/* (the reference checks this once at startup and only for runs without a write
+			   phase, "!runCreateFilesPhase": a manager that has written the files itself
+			   corresponds to a "-w -r" run) */
+			if( (benchPhase == ELB_PHASE_READFILES) && !hadCreateFilesPhase &&
+				S_ISREG(statBuf.st_mode) && ( (uint64_t)statBuf.st_size < cfg.fileSize) )
 				throw WorkerError("Given size to use is larger than detected size. "
 					"File: " + cfg.paths[i] + "; "
 					"Detected size: " + std::to_string(statBuf.st_size) + "; "
 					"Given size: " + std::to_string(cfg.fileSize) );
 		}
 	}
+
+	if(benchPhase == ELB_PHASE_CREATEFILES)
+		hadCreateFilesPhase = true;
 
 	if( (cfg.pathType != ELB_PATH_FILE) || (benchPhase != ELB_PHASE_CREATEFILES) )
 		return;

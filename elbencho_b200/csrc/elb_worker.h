@@ -352,6 +352,7 @@ class Manager
 		void prepareFilesForPhase(int benchPhase);
 		void closeBenchPathFDs();
 		bool pathFDsOpenedForWrite{false};
+		bool hadCreateFilesPhase{false}; // (size check of read-only runs, ProgArgs.cpp:2099)
 		std::unique_ptr<LiveStatsReducer> liveStatsReducer; // created on first use
 		std::mutex liveStatsReducerMutex;
 };

@@ -193,6 +193,14 @@ SIGNATURES = {
     "elb_offset_plan_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
                                           ctypes.c_int, ctypes.POINTER(c_u64), c_u64,
                                           ctypes.c_int]),
+    "elb_rate_limiter_create": (_VP, [c_u64]),
+    "elb_rate_limiter_wait": (ctypes.c_int, [_VP, c_u64]),
+    "elb_rate_limiter_destroy": (None, [_VP]),
+    "elb_rwmix_balancer_create": (_VP, [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, c_u64]),
+    "elb_rwmix_balancer_wait_read": (ctypes.c_int, [_VP, c_u64]),
+    "elb_rwmix_balancer_wait_write": (ctypes.c_int, [_VP, c_u64]),
+    "elb_rwmix_balancer_interrupt": (None, [_VP]),
+    "elb_rwmix_balancer_destroy": (None, [_VP]),
     "elb_custom_tree_worker_list": (ctypes.c_int64, [ctypes.c_char_p, c_u64, c_u64, c_u64, c_u64,
                                                      c_u64, ctypes.c_int, ctypes.c_char_p, c_u64]),
     "elb_custom_tree_scan": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_char_p]),

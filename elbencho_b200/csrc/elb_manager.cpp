@@ -695,6 +695,74 @@ struct elb_offset_plan_impl
 	std::unique_ptr<elb::OffsetPlan> plan;
 };
 
+elb_rate_limiter* elb_rate_limiter_create(uint64_t limitPerSec)
+{
+	elb::RateLimiter* limiter = new elb::RateLimiter();
+	limiter->initStart(limitPerSec);
+	return reinterpret_cast<elb_rate_limiter*>(limiter);
+}
+
+int elb_rate_limiter_wait(elb_rate_limiter* limiter, uint64_t nextSize)
+{
+	return reinterpret_cast<elb::RateLimiter*>(limiter)->wait(nextSize) ? 1 : 0;
+}
+
+void elb_rate_limiter_destroy(elb_rate_limiter* limiter)
+{
+	delete reinterpret_cast<elb::RateLimiter*>(limiter);
+}
+
+struct elb_rwmix_balancer
+{
+	elb::RWMixThreadsBalancer impl;
+	std::atomic_bool isInterruptionRequested{false};
+};
+
+elb_rwmix_balancer* elb_rwmix_balancer_create(unsigned readRatioPercent, unsigned numReaderThreads,
+	unsigned numWriterThreads, uint64_t maxBlockSize)
+{
+	elb_rwmix_balancer* balancer = new elb_rwmix_balancer();
+	balancer->impl.initStart(readRatioPercent, numReaderThreads, numWriterThreads, maxBlockSize);
+	return balancer;
+}
+
+static int balancerWait(elb_rwmix_balancer* balancer, bool isRead, uint64_t nextBlockSize)
+{
+	try
+	{
+		const bool hadToWait = isRead ?
+			balancer->impl.waitRead(nextBlockSize, balancer->isInterruptionRequested) :
+			balancer->impl.waitWrite(nextBlockSize, balancer->isInterruptionRequested);
+
+		return hadToWait ? 1 : 0;
+	}
+	catch(const std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return -1;
+	}
+}
+
+int elb_rwmix_balancer_wait_read(elb_rwmix_balancer* balancer, uint64_t nextBlockSize)
+{
+	return balancerWait(balancer, true, nextBlockSize);
+}
+
+int elb_rwmix_balancer_wait_write(elb_rwmix_balancer* balancer, uint64_t nextBlockSize)
+{
+	return balancerWait(balancer, false, nextBlockSize);
+}
+
+void elb_rwmix_balancer_interrupt(elb_rwmix_balancer* balancer)
+{
+	balancer->isInterruptionRequested = true;
+}
+
+void elb_rwmix_balancer_destroy(elb_rwmix_balancer* balancer)
+{
+	delete balancer;
+}
+
 int64_t elb_custom_tree_worker_list(const char* treeFilePath, uint64_t blockSize,
 	uint64_t fileShareSize, uint64_t treeRoundUpSize, uint64_t workerRank,
 	uint64_t numDataSetThreads, int kind, char* outBuf, uint64_t outBufLen)

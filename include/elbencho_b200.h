@@ -402,6 +402,22 @@ double elb_histogram_percentile(const elb_histogram* h, double percentage);
 /* UnitTk::getPerSecFromUSec (toolkits/UnitTk.h:48-56) */
 uint64_t elb_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec);
 
+/* The two rate limiters of the per-block loop on their own (toolkits/RateLimiter.h:13-66,
+ * toolkits/RateLimiterRWMixThreads.h:22-197). wait calls return 1 if the caller had to sleep, 0 if
+ * not, -1 on error (balancer: interrupted, or 600 s without progress). */
+typedef struct elb_rate_limiter elb_rate_limiter;
+elb_rate_limiter* elb_rate_limiter_create(uint64_t limitPerSec);
+int elb_rate_limiter_wait(elb_rate_limiter* limiter, uint64_t nextSize);
+void elb_rate_limiter_destroy(elb_rate_limiter* limiter);
+
+typedef struct elb_rwmix_balancer elb_rwmix_balancer;
+elb_rwmix_balancer* elb_rwmix_balancer_create(unsigned readRatioPercent, unsigned numReaderThreads,
+	unsigned numWriterThreads, uint64_t maxBlockSize);
+int elb_rwmix_balancer_wait_read(elb_rwmix_balancer* balancer, uint64_t nextBlockSize);
+int elb_rwmix_balancer_wait_write(elb_rwmix_balancer* balancer, uint64_t nextBlockSize);
+void elb_rwmix_balancer_interrupt(elb_rwmix_balancer* balancer); /* waiters return -1 */
+void elb_rwmix_balancer_destroy(elb_rwmix_balancer* balancer);
+
 /* Custom tree mode: the sublist of one worker (PathStore::getWorkerSublistNonShared/-Shared as
  * combined by LocalWorker::prepareCustomTreePathStores, LocalWorker.cpp:1520-1560), as text lines
  * "<path>\t<totalLen>\t<rangeStart>\t<rangeLen>\n". kind 0: directories, 1: files (non-shared

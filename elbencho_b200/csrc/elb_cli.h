@@ -185,6 +185,7 @@ class ProgArgs
 namespace stats
 {
 	std::string elapsedMSToHumanStr(uint64_t elapsedMS); // UnitTk.cpp:180-204
+	std::string elapsedSecToHumanStr(uint64_t elapsedSec); // UnitTk.cpp:154-178
 	std::string latencyUsToHumanStr(uint64_t numMicroSec); // UnitTk.cpp:90-150
 	std::string phaseName(int benchPhase, const ProgArgs& progArgs); // TranslatorTk.cpp:41-125
 	std::string phaseEntryType(int benchPhase, bool firstToUpper); // TranslatorTk.cpp:127-175

@@ -57,7 +57,7 @@ static std::string isoDateNow(bool withMillis)
 	return out.str();
 }
 
-static std::string elapsedSecToHumanStr(uint64_t elapsedSec) // UnitTk::elapsedSecToHumanStr
+std::string stats::elapsedSecToHumanStr(uint64_t elapsedSec) // UnitTk::elapsedSecToHumanStr
 {
 	std::ostringstream out;
 	const uint64_t numHours = elapsedSec / 3600;
@@ -195,7 +195,7 @@ void Coordinator::printLiveStatsLine(int benchPhase, const elb_liveops liveOps[2
 	liveCpuUtil.update();
 
 	line << (manager->workers.size() - numWorkersDone) << " threads; " <<
-		liveCpuUtil.getCPUUtilPercent() << "% CPU; " << elapsedSecToHumanStr(elapsedSec);
+		liveCpuUtil.getCPUUtilPercent() << "% CPU; " << stats::elapsedSecToHumanStr(elapsedSec);
 
 	std::string lineStr = line.str();
 
@@ -712,6 +712,61 @@ extern "C" int64_t elb_format_phase_results(int argc, char** argv, int benchPhas
 		}
 
 		return (int64_t)text.size();
+	}
+	catch(std::exception& e)
+	{
+		elb_set_last_error(e.what() );
+		return -1;
+	}
+}
+
+/* kind 0: UnitTk::latencyUsToHumanStr, 1: elapsedMSToHumanStr, 2: elapsedSecToHumanStr,
+ * 3: LatencyHistogram::getHistogramStr, 4: getPercentileStr(percentage) */
+extern "C" int64_t elb_format_value(int kind, uint64_t value, double percentage,
+	const elb_histogram* histo, char* outBuf, uint64_t outBufLen)
+{
+	std::string text;
+
+	switch(kind)
+	{
+		case 0: text = elb::stats::latencyUsToHumanStr(value); break;
+		case 1: text = elb::stats::elapsedMSToHumanStr(value); break;
+		case 2: text = elb::stats::elapsedSecToHumanStr(value); break;
+		case 3:
+		case 4:
+		{
+			if(!histo)
+			{
+				elb_set_last_error("elb_format_value: histogram missing");
+				return -1;
+			}
+
+			text = (kind == 3) ?
+				elb::stats::histogramStr(*histo) : elb::stats::percentileStr(*histo, percentage);
+		} break;
+
+		default:
+			elb_set_last_error("elb_format_value: invalid kind " + std::to_string(kind) );
+			return -1;
+	}
+
+	if(outBuf && outBufLen)
+	{
+		const size_t copyLen = std::min( (size_t)(outBufLen - 1), text.size() );
+		memcpy(outBuf, text.data(), copyLen);
+		outBuf[copyLen] = 0;
+	}
+
+	return (int64_t)text.size();
+}
+
+/* UnitTk::numHumanToBytesBinary (toolkits/UnitTk.cpp:18-76); error text via elb_last_error() */
+extern "C" int elb_num_human_to_bytes(const char* numHuman, uint64_t* outBytes)
+{
+	try
+	{
+		*outBytes = elb::ProgArgs::numHumanToBytesBinary(numHuman ? numHuman : "");
+		return 0;
 	}
 	catch(std::exception& e)
 	{

@@ -402,6 +402,15 @@ double elb_histogram_percentile(const elb_histogram* h, double percentage);
 /* UnitTk::getPerSecFromUSec (toolkits/UnitTk.h:48-56) */
 uint64_t elb_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec);
 
+/* Human-readable formats of the result table (toolkits/UnitTk.cpp:90-204, LatencyHistogram.h:
+ * 109-178). kind 0: latency in microseconds ("1.23ms"), 1: elapsed milliseconds ("1m1.007s"),
+ * 2: elapsed seconds ("1h2m3s"), 3: histogram line of `histo`, 4: percentile of `histo`. Returns the
+ * text length (text truncated to outBufLen - 1), -1 on error. */
+int64_t elb_format_value(int kind, uint64_t value, double percentage, const elb_histogram* histo,
+	char* outBuf, uint64_t outBufLen);
+/* UnitTk::numHumanToBytesBinary (toolkits/UnitTk.cpp:18-76): "4k", "1M", "64G"; 0 ok, -1 error */
+int elb_num_human_to_bytes(const char* numHuman, uint64_t* outBytes);
+
 /* The two rate limiters of the per-block loop on their own (toolkits/RateLimiter.h:13-66,
  * toolkits/RateLimiterRWMixThreads.h:22-197). wait calls return 1 if the caller had to sleep, 0 if
  * not, -1 on error (balancer: interrupted, or 600 s without progress). */

@@ -114,6 +114,60 @@ def main():
                        "lcgSeed": lcg, "randState": XOSHIRO_STATES[1], "sequence": seq})
     vectors["offsetgen_randalgo"] = oa
 
+    # LatencyHistogram.h (bucket rule, min/max/avg, percentile rule, the two string formats),
+    # UnitTk::getPerSecFromUSec and the human-readable formats of UnitTk.cpp
+    import random
+    histos = []
+    for seed, count, scale in ((1, 1, 1), (2, 50, 100), (3, 2000, 5000), (4, 5000, 3000000)):
+        rng = random.Random(seed)
+        lats = [0] if count == 1 else [int(rng.random() ** 3 * scale) for _ in range(count)]
+        histo = ref.ref_histogram_create()
+        for lat in lats:
+            ref.ref_histogram_add(histo, lat)
+        nbuckets = ref.ref_histogram_num_buckets(histo)
+        buckets = (ctypes.c_uint64 * nbuckets)()
+        ref.ref_histogram_buckets(histo, buckets)
+        buf = ctypes.create_string_buffer(8192)
+        ref.ref_histogram_str(histo, buf, len(buf))
+        histo_str = buf.value.decode()
+        pcts = {}
+        for pct in (1.0, 50.0, 75.0, 99.0, 99.9, 99.999):
+            ref.ref_histogram_percentile_str(histo, pct, buf, len(buf))
+            pcts[str(pct)] = {"value": ref.ref_histogram_percentile(histo, pct),
+                              "str": buf.value.decode()}
+        histos.append({"latencies": lats, "num_buckets": nbuckets, "buckets": list(buckets),
+                       "num": ref.ref_histogram_num(histo), "sum": ref.ref_histogram_sum(histo),
+                       "min": ref.ref_histogram_min(histo), "max": ref.ref_histogram_max(histo),
+                       "avg": ref.ref_histogram_avg(histo),
+                       "exceeded": ref.ref_histogram_exceeded(histo), "histogram_str": histo_str,
+                       "percentiles": pcts})
+        ref.ref_histogram_destroy(histo)
+    vectors["latency_histogram"] = histos
+
+    units = {"latency_us": {}, "elapsed_ms": {}, "elapsed_sec": {}, "per_sec": [],
+             "human_to_bytes": {}}
+    buf = ctypes.create_string_buffer(256)
+    for val in (0, 1, 9, 10, 99, 999, 1000, 1234, 9999, 10000, 99999, 123456, 999999, 1000000,
+                1234567, 59999999, 60000000, 3599999999, 3600000000, 86400000001):
+        ref.ref_unit_str(0, val, buf, len(buf))
+        units["latency_us"][str(val)] = buf.value.decode()
+    for val in (0, 1, 999, 1000, 1001, 59999, 60000, 61007, 3599999, 3600000, 3661001, 90061001):
+        ref.ref_unit_str(1, val, buf, len(buf))
+        units["elapsed_ms"][str(val)] = buf.value.decode()
+    for val in (0, 1, 59, 60, 61, 3599, 3600, 3661, 90061):
+        ref.ref_unit_str(2, val, buf, len(buf))
+        units["elapsed_sec"][str(val)] = buf.value.decode()
+    for total, usec in ((0, 1), (1, 1), (1234567, 345), (68719476736, 21220070), (1 << 60, 3),
+                        (999999, 1000000), (1000001, 1000000), (7, 13)):
+        units["per_sec"].append([total, usec, ref.ref_per_sec_from_usec(total, usec)])
+    err = ctypes.create_string_buffer(512)
+    out = ctypes.c_uint64()
+    for text in ("0", "1", "4k", "4K", "1m", "64G", "2t", "1P", "1E", "512", "1.5g", "1,5g", "-4k",
+                 "4x", "k", ""):
+        rc = ref.ref_num_human_to_bytes(text.encode(), ctypes.byref(out), err, len(err))
+        units["human_to_bytes"][text] = out.value if rc == 0 else {"error": err.value.decode()}
+    vectors["units"] = units
+
     og = []
     for case in OFFSETGEN_CASES:
         kind, total, length, offset, block, threads, lcg = case

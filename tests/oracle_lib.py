@@ -137,6 +137,26 @@ def load_ref():
         "ref_offsetgen_create_algo": (_VP, [ctypes.c_int, c_u64, c_u64, c_u64, c_u64, c_u64,
                                              ctypes.c_int, u64p, c_u64]),
         "ref_randalgo_create": (_VP, [ctypes.c_int, u64p]),
+        # the reference's LatencyHistogram.h and UnitTk (oracle/ref_harness_stats.cpp)
+        "ref_histogram_create": (_VP, []),
+        "ref_histogram_destroy": (None, [_VP]),
+        "ref_histogram_add": (None, [_VP, c_u64]),
+        "ref_histogram_merge": (None, [_VP, _VP]),
+        "ref_histogram_num": (c_u64, [_VP]),
+        "ref_histogram_min": (c_u64, [_VP]),
+        "ref_histogram_max": (c_u64, [_VP]),
+        "ref_histogram_avg": (c_u64, [_VP]),
+        "ref_histogram_sum": (c_u64, [_VP]),
+        "ref_histogram_exceeded": (ctypes.c_int, [_VP]),
+        "ref_histogram_percentile": (ctypes.c_double, [_VP, ctypes.c_double]),
+        "ref_histogram_num_buckets": (c_u64, [_VP]),
+        "ref_histogram_buckets": (None, [_VP, u64p]),
+        "ref_histogram_str": (ctypes.c_int64, [_VP, ctypes.c_char_p, c_u64]),
+        "ref_histogram_percentile_str": (ctypes.c_int64, [_VP, ctypes.c_double, ctypes.c_char_p,
+                                                          c_u64]),
+        "ref_per_sec_from_usec": (c_u64, [c_u64, c_u64]),
+        "ref_unit_str": (ctypes.c_int64, [ctypes.c_int, c_u64, ctypes.c_char_p, c_u64]),
+        "ref_num_human_to_bytes": (ctypes.c_int, [ctypes.c_char_p, u64p, ctypes.c_char_p, c_u64]),
         "ref_offsetgen_destroy": (None, [_VP]),
         "ref_offsetgen_reset": (None, [_VP]),
         "ref_offsetgen_reset_range": (None, [_VP, c_u64, c_u64]),

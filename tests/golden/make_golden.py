@@ -47,6 +47,27 @@ OFFSETGEN_ALGO_CASES = [
 ]
 
 
+CUSTOM_TREE_TEXT = """# golden tree
+d top
+d top/sub1
+d top/sub1/deep
+d other
+d a
+f 0 top/empty.bin
+f 1 top/one_byte.bin
+f 5000 top/sub1/small.bin
+f 65536 top/sub1/deep/one_block.bin
+f 65537 a/one_block_plus.bin
+f 200000 other/odd.bin
+f 200000 a/same size as odd.bin
+f 2097152 other/share_a.bin
+f 3000001 top/share_b.bin
+f 4194304 top/sub1/share_c.bin
+f 2097152 a/share_d.bin
+x ignored
+"""
+
+
 def pattern_closed_form(length, file_offset, salt):
     """byte x of the file = byte (x % 8) of little-endian u64 ((x & ~7) + salt) mod 2^64
     (LocalWorker.cpp:2091-2128)."""
@@ -167,6 +188,30 @@ def main():
         rc = ref.ref_num_human_to_bytes(text.encode(), ctypes.byref(out), err, len(err))
         units["human_to_bytes"][text] = out.value if rc == 0 else {"error": err.value.decode()}
     vectors["units"] = units
+
+    # custom tree partition by the reference's own PathStore (oracle/ref_harness_tree.cpp)
+    import tempfile
+    tree_text = CUSTOM_TREE_TEXT
+    trees = []
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as tmp:
+        tmp.write(tree_text)
+        tree_path = tmp.name
+    buf = ctypes.create_string_buffer(1 << 20)
+    for block, share, round_up, nthreads in ((65536, 0, 0, 1), (65536, 0, 0, 3), (4096, 16384, 0, 4),
+                                            (65536, 0, 4096, 2), (65536, 1 << 62, 0, 5)):
+        per_rank = []
+        for rank in range(nthreads):
+            lists = {}
+            for kind, name in ((0, "dirs"), (1, "files")):
+                res = ref.ref_custom_tree_worker_list(tree_path.encode(), block, share, round_up,
+                                                      rank, nthreads, kind, buf, len(buf))
+                assert res >= 0, buf.value
+                lists[name] = buf.value.decode()
+            per_rank.append(lists)
+        trees.append({"blockSize": block, "fileShareSize": share, "treeRoundUpSize": round_up,
+                      "numDataSetThreads": nthreads, "per_rank": per_rank})
+    os.unlink(tree_path)
+    vectors["custom_tree"] = {"tree_text": tree_text, "cases": trees}
 
     og = []
     for case in OFFSETGEN_CASES:

@@ -155,6 +155,10 @@ def load_ref():
         "ref_histogram_percentile_str": (ctypes.c_int64, [_VP, ctypes.c_double, ctypes.c_char_p,
                                                           c_u64]),
         "ref_per_sec_from_usec": (c_u64, [c_u64, c_u64]),
+        # the reference's PathStore (oracle/ref_harness_tree.cpp)
+        "ref_custom_tree_worker_list": (ctypes.c_int64, [ctypes.c_char_p, c_u64, c_u64, c_u64, c_u64,
+                                                         c_u64, ctypes.c_int, ctypes.c_char_p,
+                                                         c_u64]),
         "ref_unit_str": (ctypes.c_int64, [ctypes.c_int, c_u64, ctypes.c_char_p, c_u64]),
         "ref_num_human_to_bytes": (ctypes.c_int, [ctypes.c_char_p, u64p, ctypes.c_char_p, c_u64]),
         "ref_offsetgen_destroy": (None, [_VP]),

@@ -118,3 +118,41 @@ def test_cli_dryrun_totals_and_validation(tmp_path):
                           str(tmp_path / "afile.bin")], capture_output=True, text=True)
     assert res.returncode == 1
     assert "Custom tree mode requires benchmark path to be a directory." in res.stderr
+
+
+def test_partition_matches_reference_pathstore_golden(native, tmp_path):
+    """golden lists produced by the reference's own PathStore.cpp (compiled in place into
+    oracle/_ref, oracle/ref_harness_tree.cpp): dirs and files per worker, byte for byte"""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.json")) as f:
+        golden = json.load(f)["custom_tree"]
+    tree_path = tmp_path / "golden_tree.txt"
+    tree_path.write_text(golden["tree_text"])
+    buf = ctypes.create_string_buffer(1 << 20)
+    for case in golden["cases"]:
+        for rank, want in enumerate(case["per_rank"]):
+            for kind, name in ((0, "dirs"), (1, "files")):
+                res = native.elb_custom_tree_worker_list(
+                    str(tree_path).encode(), case["blockSize"], case["fileShareSize"],
+                    case["treeRoundUpSize"], rank, case["numDataSetThreads"], kind, buf, len(buf))
+                assert res >= 0
+                assert buf.value.decode() == want[name], (case["numDataSetThreads"], rank, name)
+
+
+def test_partition_live_against_reference_pathstore(native, ref, tmp_path):
+    rng = random.Random(2024)
+    buf_a = ctypes.create_string_buffer(1 << 20)
+    buf_b = ctypes.create_string_buffer(1 << 20)
+    for round_idx in range(6):
+        block = rng.choice([4 * KiB, 64 * KiB, 1000])
+        tree_path = tmp_path / ("tree%d.txt" % round_idx)
+        tree_path.write_text(make_tree_text(rng, 60, 10, block))
+        for nthreads in (1, 2, 5, 16):
+            for share, round_up in ((0, 0), (4 * block, 0), (0, 512)):
+                for rank in range(nthreads):
+                    for kind in (0, 1):
+                        args = (str(tree_path).encode(), block, share, round_up, rank, nthreads,
+                                kind)
+                        assert native.elb_custom_tree_worker_list(*args, buf_a, len(buf_a)) >= 0
+                        assert ref.ref_custom_tree_worker_list(*args, buf_b, len(buf_b)) >= 0
+                        assert buf_a.value == buf_b.value, (block, nthreads, share, round_up, rank)

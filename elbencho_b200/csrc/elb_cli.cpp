@@ -30,6 +30,12 @@ struct OptDef
 static const OptDef optDefs[] =
 {
 	{"help", 'h', Opt_FLAG, "Print this help message."},
+	{"help-all", 0, Opt_FLAG, "Print this help message (the categories of the reference's help are "
+		"one list here; also: --help-bdev, --help-dist, --help-large, --help-multi)."},
+	{"help-bdev", 0, Opt_FLAG, "Same as --help."},
+	{"help-dist", 0, Opt_FLAG, "Same as --help."},
+	{"help-large", 0, Opt_FLAG, "Same as --help."},
+	{"help-multi", 0, Opt_FLAG, "Same as --help."},
 	{"version", 0, Opt_FLAG, "Show version and included optional build features."},
 	// phases
 	{"mkdirs", 'd', Opt_FLAG, "Create directories. (Already existing dirs are not treated as error.)"},
@@ -83,6 +89,8 @@ static const OptDef optDefs[] =
 		"typically used with --infloop and --timelimit). (Default: 0 = no balancing)"},
 	{"gpuids", 0, Opt_STR, "Comma-separated list of CUDA GPU IDs (also \"all\", \"[0-7]\", "
 		"\"0-7\") to use for the on-GPU block fill/verify. Mandatory."},
+	{"cufiledriveropen", 0, Opt_FLAG, "Explicitly initialize the cuFile library and open the "
+		"nvidia-fs driver. (Always on with --cufile.)"},
 	{"cuhostbufreg", 0, Opt_FLAG, "Pin host memory buffers and register with CUDA for faster "
 		"transfer to/from GPU memory. (Always on: the host rings are cudaHostAlloc memory.)"},
 	{"nodiocheck", 0, Opt_FLAG, "Don't check direct IO alignment and sanity."},
@@ -163,6 +171,14 @@ static const OptDef optDefs[] =
 		"(Default: use all given hosts)"},
 	{"gpuperservice", 0, Opt_FLAG, "Assign GPUs round robin to service instances (one GPU of the "
 		"--gpuids list per service) instead of round robin to the threads of each service."},
+	{"svcupint", 0, Opt_U64, "Update retrieval interval for service hosts in milliseconds. "
+		"(Default: 500)"},
+	{"nosvcshare", 0, Opt_FLAG, "Benchmark paths are not shared between service instances. Thus, "
+		"each service instance will work on its own full dataset instead of a fraction of the "
+		"data set."},
+	{"rotatehosts", 0, Opt_U64, "Number by which to rotate hosts between phases to avoid caching "
+		"effects. (Default: 0)"},
+	{"nodetach", 0, Opt_FLAG, "When running as service, do not detach from the terminal."},
 	{"svcwait", 0, Opt_U64, "Number of seconds to wait for the services to become reachable. "
 		"(Default: 5)"},
 	{"datasetthreads", 0, Opt_U64, "Total number of threads that share the data set when several "
@@ -478,7 +494,8 @@ ProgArgs::ProgArgs(int argc, char** argv)
 			target = values[name];
 	};
 
-	printHelp = flag("help");
+	printHelp = flag("help") || flag("help-all") || flag("help-bdev") || flag("help-dist") ||
+		flag("help-large") || flag("help-multi");
 	printVersion = flag("version");
 	runCreateDirsPhase = flag("mkdirs");
 	runCreateFilesPhase = flag("write");
@@ -581,8 +598,11 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	}
 	assignGPUPerService = flag("gpuperservice");
 	num("svcwait", svcReadyWaitSec);
+	num("svcupint", svcUpdateIntervalMS);
+	noSharedServicePath = flag("nosvcshare");
+	num("rotatehosts", rotateHostsNum);
 	runAsService = flag("service");
-	runServiceInForeground = flag("foreground");
+	runServiceInForeground = flag("foreground") || flag("nodetach");
 	num("port", servicePort);
 	num("rankoffset", rankOffset);
 	interruptServices = flag("interrupt");

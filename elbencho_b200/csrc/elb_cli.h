@@ -151,6 +151,9 @@ class ProgArgs
 		int64_t numHosts{-1};           // --numhosts (-1 = all)
 		bool assignGPUPerService{false}; // --gpuperservice
 		uint64_t svcReadyWaitSec{5};    // --svcwait (ProgArgs.cpp:967)
+		uint64_t svcUpdateIntervalMS{500}; // --svcupint (ProgArgs.cpp:969)
+		bool noSharedServicePath{false}; // --nosvcshare
+		uint64_t rotateHostsNum{0};     // --rotatehosts
 		bool interruptServices{false};
 		bool quitServices{false};
 

@@ -1764,7 +1764,9 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("mmap", false);
 	tree.putBool("netbench", false);
 	tree.put("netbenchservers", "");
-	tree.put("datasetthreads", args.numThreads * numHosts);
+	// (services that do not share their paths each work on a full data set, ProgArgs.cpp:1288)
+	tree.put("datasetthreads", args.noSharedServicePath ?
+		args.numThreads : (args.numThreads * numHosts) );
 	tree.put("dirs", args.numDirs);
 	tree.put("files", args.numFiles);
 	tree.put("numservers", (uint64_t)0);
@@ -1819,7 +1821,8 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.putBool("verifydirect", args.doDirectVerify);
 
 	// dynamically calculated values for service hosts (:3845-3861)
-	tree.put("rankoffset", args.rankOffset + (serviceRank * args.numThreads) );
+	tree.put("rankoffset", args.noSharedServicePath ?
+		args.rankOffset : (args.rankOffset + (serviceRank * args.numThreads) ) );
 	tree.put("treefile", args.treeFilePath.empty() ? "" : "treefile.txt"); // ProgArgs.cpp:3850
 	if(!args.assignGPUPerService || args.gpuIDs.empty() )
 		tree.put("gpuids", args.gpuIDsStr);
@@ -1858,6 +1861,7 @@ class Master
 		void runSyncAndDropCaches();
 		void interruptAll(bool quit);
 		void waitForServicesReady();
+		void rotateHosts();
 		bool isPhaseTimeExpired{false};
 };
 
@@ -2020,7 +2024,8 @@ void Master::runPhase(int benchPhase)
 
 	for( ; ; )
 	{
-		std::this_thread::sleep_for(std::chrono::milliseconds(ELB_SVC_UPDATE_INTERVAL_MS) );
+		std::this_thread::sleep_for(std::chrono::milliseconds(
+			progArgs.svcUpdateIntervalMS ? progArgs.svcUpdateIntervalMS : ELB_SVC_UPDATE_INTERVAL_MS) );
 
 		size_t numHostsDone = 0;
 
@@ -2322,6 +2327,21 @@ void Master::waitForServicesReady()
 	}
 }
 
+/* Coordinator::rotateHosts (Coordinator.cpp:382-404) + ProgArgs::rotateHosts (:4137-4144): between
+ * phases the services swap ranks, which needs a new preparation phase on all of them */
+void Master::rotateHosts()
+{
+	if( (hosts.size() < 2) || !progArgs.rotateHostsNum)
+		return;
+
+	interruptAll(false);
+
+	for(uint64_t i = 0; i < progArgs.rotateHostsNum; i++)
+		std::rotate(hosts.begin(), hosts.begin() + 1, hosts.end() );
+
+	prepareRemotePhases();
+}
+
 int Master::run()
 {
 	initHosts();
@@ -2356,10 +2376,17 @@ int Master::run()
 
 			runSyncAndDropCaches();
 
+			bool isFirstPhase = true;
+
 			for(const BenchPhaseConfig& phaseConfig : allBenchPhases)
 			{
 				if(!phaseConfig.runPhase)
 					continue;
+
+				if(!isFirstPhase)
+					rotateHosts();
+
+				isFirstPhase = false;
 
 				runPhase(phaseConfig.benchPhase);
 				runSyncAndDropCaches();

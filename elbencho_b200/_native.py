@@ -89,7 +89,7 @@ class Cfg(ctypes.Structure):
         ("flockType", c_u32),
         ("fadviseFlags", c_u32),
         ("doStatInline", ctypes.c_int32),
-        ("reserved5", ctypes.c_int32),
+        ("noDirectIOCheck", ctypes.c_int32),
     ]
 
 

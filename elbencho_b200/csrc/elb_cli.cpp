@@ -569,6 +569,7 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	str("flock", flockTypeStr);
 	str("fadv", fadviseFlagsStr);
 	doStatInline = flag("statinline");
+	noDirectIOCheck = flag("nodiocheck");
 	str("cores", cpuCoresStr);
 	str("zones", numaZonesStr);
 	str("treefile", treeFilePath);
@@ -949,6 +950,7 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.flockType = (uint32_t)flockType;
 	cfg.fadviseFlags = (uint32_t)fadviseFlags;
 	cfg.doStatInline = doStatInline;
+	cfg.noDirectIOCheck = noDirectIOCheck;
 	out.cpuCores.assign(cpuCores.begin(), cpuCores.end() );
 	out.numaZones.assign(numaZones.begin(), numaZones.end() );
 	cfg.cpuCores = out.cpuCores.data();

@@ -101,6 +101,7 @@ class ProgArgs
 		uint64_t flockType{0};
 		uint64_t fadviseFlags{0};
 		bool doStatInline{false};       // --statinline
+		bool noDirectIOCheck{false};    // --nodiocheck
 		std::string cpuCoresStr;        // --cores
 		std::string numaZonesStr;       // --zones
 		std::vector<int> cpuCores;

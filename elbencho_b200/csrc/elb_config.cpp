@@ -111,6 +111,7 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.flockType = cfg->flockType;
 	c.fadviseFlags = cfg->fadviseFlags;
 	c.doStatInline = (cfg->doStatInline != 0);
+	c.noDirectIOCheck = (cfg->noDirectIOCheck != 0);
 
 	if(c.flockType > 2)
 		throw WorkerError("Invalid file lock type: " + std::to_string(c.flockType) );
@@ -217,7 +218,7 @@ Config Config::fromABI(const elb_cfg* cfg)
 	if(!c.randomAmount && (c.pathType != ELB_PATH_DIR) && c.useRandomOffsets) // :1558-1561
 		c.randomAmount = c.fileSize * c.paths.size();
 
-	if(c.useDirectIO && c.fileSize) // :1566-1584
+	if(c.useDirectIO && c.fileSize && !c.noDirectIOCheck) // :1566-1584
 	{
 		if(c.useRandomOffsets && c.useRandomUnaligned)
 			c.useRandomUnaligned = false;

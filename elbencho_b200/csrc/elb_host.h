@@ -807,6 +807,7 @@ struct Config
 	unsigned flockType{0};      // --flock
 	unsigned fadviseFlags{0};   // --fadv
 	bool doStatInline{false};   // --statinline
+	bool noDirectIOCheck{false}; // --nodiocheck
 	uint64_t integrityCheckSalt{0};
 	bool doDirectVerify{false};
 	bool doReadInline{false};

@@ -1111,6 +1111,7 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.fadviseFlags = recvTree.getU64("fadv", 0);
 		args.flockType = recvTree.getU64("flock", 0);
 		args.doStatInline = recvTree.getBool("statinline", false);
+		args.noDirectIOCheck = recvTree.getBool("nodiocheck", false);
 		args.doInfiniteIOLoop = recvTree.getBool("infloop", false);
 		args.timeLimitSecs = recvTree.getU64("b200_timelimit", 0);
 		args.limitReadBps = recvTree.getU64("limitread", 0);
@@ -1772,7 +1773,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.put("numservers", (uint64_t)0);
 	tree.put("threads", args.numThreads);
 	tree.putBool("nofdsharing", false);
-	tree.putBool("nodiocheck", false);
+	tree.putBool("nodiocheck", args.noDirectIOCheck);
 	tree.putBool("opsloglock", false);
 	tree.put("opslog", "");
 	tree.putBool("preallocfile", args.doPreallocFile);

@@ -1058,7 +1058,8 @@ void Worker::prepareCustomTreePathStores()
 	if(cfg.treeFilePath.empty() )
 		return;
 
-	const bool throwOnSmallerThanBlockSize = cfg.useDirectIO && cfg.useRandomOffsets;
+	const bool throwOnSmallerThanBlockSize = !cfg.noDirectIOCheck && cfg.useDirectIO &&
+		cfg.useRandomOffsets;
 	const CustomTree& tree = shared->customTree;
 
 	customTreeDirs.clear();

@@ -93,6 +93,7 @@ class WorkerConfig:
     flock_type: int = 0               # --flock (0 none, 1 range, 2 full)
     fadvise_flags: int = 0            # --fadv (1 seq, 2 rand, 4 willneed, 8 dontneed, 16 noreuse)
     do_stat_inline: bool = False      # --statinline
+    no_direct_io_check: bool = False  # --nodiocheck
     integrity_check_salt: int = 0     # --verify
     do_direct_verify: bool = False    # --verifydirect
     do_read_inline: bool = False      # --readinline
@@ -179,6 +180,7 @@ class WorkerConfig:
         cfg.flockType = self.flock_type
         cfg.fadviseFlags = self.fadvise_flags
         cfg.doStatInline = int(self.do_stat_inline)
+        cfg.noDirectIOCheck = int(self.no_direct_io_check)
         return cfg, (path_bytes, path_arr, gpu_arr, cores, zones)
 
 

@@ -296,7 +296,7 @@ typedef struct elb_cfg
 	 * 16 noreuse (ProgArgs.h:240-249, FileTk.cpp:138-215) */
 	uint32_t fadviseFlags;
 	int32_t doStatInline;   /* --statinline: fstat each dir mode file right after open */
-	int32_t reserved5;
+	int32_t noDirectIOCheck; /* --nodiocheck: skip the direct IO alignment / size sanity checks */
 } elb_cfg;
 
 /* ---------------------------------------------------------------------------------------------

@@ -243,3 +243,16 @@ def test_config_validation_errors():
     with pytest.raises(WorkerError, match="rwmixpct"):
         WorkerManager(WorkerConfig(paths=["/tmp/x"], file_size=4096, integrity_check_salt=1,
                                    rwmix_read_percent=10))
+
+
+def test_nodiocheck_skips_the_direct_io_block_size_check(native):
+    """ProgArgs.cpp:1566-1584: with --direct the block size has to be a multiple of 512 unless
+    --nodiocheck is given (checked at configuration time, before any GPU is touched)"""
+    from elbencho_b200 import WorkerConfig, WorkerError, WorkerManager
+    common = dict(paths=["/tmp/elb_nodio.bin"], block_size=1000, file_size=8000,
+                  use_direct_io=True, gpu_ids=[0])
+    with pytest.raises(WorkerError, match="Block size for direct IO is not a multiple"):
+        WorkerManager(WorkerConfig(**common))
+    with pytest.raises(WorkerError) as err:
+        WorkerManager(WorkerConfig(no_direct_io_check=True, **common))
+    assert "Block size for direct IO" not in str(err.value)  # gets past the check (then: no GPU)

@@ -195,6 +195,7 @@ SIGNATURES = {
                                           ctypes.c_int]),
     "elb_format_value": (ctypes.c_int64, [ctypes.c_int, c_u64, ctypes.c_double,
                                           ctypes.POINTER(Histogram), ctypes.c_char_p, c_u64]),
+    "elb_simple128_hash": (None, [ctypes.c_char_p, ctypes.c_char_p]),
     "elb_num_human_to_bytes": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_u64)]),
     "elb_rate_limiter_create": (_VP, [c_u64]),
     "elb_rate_limiter_wait": (ctypes.c_int, [_VP, c_u64]),

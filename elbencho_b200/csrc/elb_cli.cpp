@@ -179,6 +179,9 @@ static const OptDef optDefs[] =
 	{"rotatehosts", 0, Opt_U64, "Number by which to rotate hosts between phases to avoid caching "
 		"effects. (Default: 0)"},
 	{"nodetach", 0, Opt_FLAG, "When running as service, do not detach from the terminal."},
+	{"svcpwfile", 0, Opt_STR, "Path to a text file containing a single line of text as shared "
+		"secret between service instances and master. This is to prevent unauthorized requests "
+		"to service instances."},
 	{"svcwait", 0, Opt_U64, "Number of seconds to wait for the services to become reachable. "
 		"(Default: 5)"},
 	{"datasetthreads", 0, Opt_U64, "Total number of threads that share the data set when several "
@@ -207,6 +210,28 @@ static const OptDef* findShortOpt(char name)
 			return &def;
 
 	return NULL;
+}
+
+/* HashTk::simple128 (toolkits/HashTk.cpp:10-41): two 64-bit lanes, every character folded in as
+ * x ^ (y * golden ratio) with a lane specific multiplier; 32 hex digits */
+std::string ProgArgs::simple128Hash(const std::string& input)
+{
+	uint64_t hash1 = 0xC6A4A7935BD1E995ULL;
+	uint64_t hash2 = 0xDEADBEEFCAFEBABEULL;
+
+	for(const char c : input)
+	{
+		const uint64_t value = static_cast<uint64_t>(c);
+
+		hash1 ^= (value * 0x87C37B91114253D5ULL) * 0x9E3779B97F4A7C15ULL;
+		hash2 ^= (value * 0x4CF5AD432745937FULL) * 0x9E3779B97F4A7C15ULL;
+	}
+
+	char hexBuf[40];
+	snprintf(hexBuf, sizeof(hexBuf), "%016llx%016llx", (unsigned long long)hash1,
+		(unsigned long long)hash2);
+
+	return hexBuf;
 }
 
 /* UnitTk::numHumanToBytesBinary (toolkits/UnitTk.cpp:18-76) */
@@ -598,6 +623,7 @@ ProgArgs::ProgArgs(int argc, char** argv)
 				"'--numhosts' is invalid");
 	}
 	assignGPUPerService = flag("gpuperservice");
+	str("svcpwfile", svcPasswordFile);
 	num("svcwait", svcReadyWaitSec);
 	num("svcupint", svcUpdateIntervalMS);
 	noSharedServicePath = flag("nosvcshare");
@@ -636,6 +662,31 @@ void ProgArgs::initImplicitValues()
 		blockVariancePercent = 0;
 
 	parseHosts();
+
+	if(!svcPasswordFile.empty() ) // ProgArgs::loadServicePasswordFile (ProgArgs.cpp:2811-2829)
+	{
+		FILE* passwordFile = fopen(svcPasswordFile.c_str(), "r");
+
+		if(!passwordFile)
+			throw ProgError("Opening service password file failed: " + svcPasswordFile);
+
+		char lineBuf[4096] = "";
+
+		if(!fgets(lineBuf, sizeof(lineBuf), passwordFile) )
+			lineBuf[0] = 0;
+
+		fclose(passwordFile);
+
+		std::string lineStr = lineBuf;
+
+		while(!lineStr.empty() && ( (lineStr.back() == '\n') || (lineStr.back() == '\r') ) )
+			lineStr.pop_back();
+
+		if(lineStr.empty() )
+			throw ProgError("First line in service password file is empty: " + svcPasswordFile);
+
+		svcPasswordHash = simple128Hash(lineStr);
+	}
 
 	if(!gpuIDsStr.empty() && (gpuIDsStr != "all") )
 		gpuIDs = parseGPUIDs(gpuIDsStr);

@@ -154,6 +154,8 @@ class ProgArgs
 		uint64_t svcReadyWaitSec{5};    // --svcwait (ProgArgs.cpp:967)
 		uint64_t svcUpdateIntervalMS{500}; // --svcupint (ProgArgs.cpp:969)
 		bool noSharedServicePath{false}; // --nosvcshare
+		std::string svcPasswordFile;    // --svcpwfile
+		std::string svcPasswordHash;    // HashTk::simple128 of its first line (ProgArgs.cpp:2811-2829)
 		uint64_t rotateHostsNum{0};     // --rotatehosts
 		bool interruptServices{false};
 		bool quitServices{false};
@@ -176,6 +178,7 @@ class ProgArgs
 
 		static std::string helpText();
 		static uint64_t numHumanToBytesBinary(const std::string& numHuman); // UnitTk.cpp:18-76
+		static std::string simple128Hash(const std::string& input); // toolkits/HashTk.cpp:10-41
 		static std::vector<int> parseGPUIDs(const std::string& gpuIDsStr); // ProgArgs.cpp:2556-2570
 
 	private:

@@ -775,6 +775,13 @@ extern "C" int elb_num_human_to_bytes(const char* numHuman, uint64_t* outBytes)
 	}
 }
 
+extern "C" void elb_simple128_hash(const char* input, char out[33])
+{
+	const std::string hash = elb::ProgArgs::simple128Hash(input ? input : "");
+	memcpy(out, hash.c_str(), std::min(hash.size() + 1, (size_t)33) );
+	out[32] = 0;
+}
+
 extern "C" int elb_cli_main(int argc, char** argv)
 {
 	try

@@ -731,7 +731,8 @@ HttpResponse httpRequest(const std::string& host, unsigned short port, const std
 class Service
 {
 	public:
-		explicit Service(ProgArgs& progArgs) : progArgs(progArgs) {}
+		explicit Service(ProgArgs& progArgs) :
+			progArgs(progArgs), svcPasswordHash(progArgs.svcPasswordHash) {}
 
 		int run();
 
@@ -752,6 +753,8 @@ class Service
 		HttpResponse handle(const HttpRequest& request);
 		HttpResponse handlePreparePhase(const HttpRequest& request);
 		HttpResponse handlePrepareFile(const HttpRequest& request);
+		void checkAuthorization(const HttpRequest& request) const;
+		std::string svcPasswordHash; // of this service's own --svcpwfile (kept over prepare phases)
 		std::string uploadBasePath() const;
 		HttpResponse handleStartPhase(const HttpRequest& request);
 		HttpResponse handleStatus();
@@ -991,6 +994,16 @@ HttpResponse Service::handleBenchResult()
 
 /* ProgArgs::setFromPropertyTreeForService (ProgArgs.cpp:3562-3680), supported subset; unknown
  * keys are ignored, missing keys take the defaults */
+/* authorization hash of the master vs ours (HTTPServiceSWS.cpp:287-296, 400-409) */
+void Service::checkAuthorization(const HttpRequest& request) const
+{
+	if(!request.query.count("PwHash") )
+		throw ProgError("Missing parameter: PwHash");
+
+	if(request.query.at("PwHash") != svcPasswordHash)
+		throw ProgError("Invalid authorization code.");
+}
+
 /* SERVICE_UPLOAD_BASEPATH (ProgArgs.h:228-230): /var/tmp/<exe>_<user>_p<port> */
 std::string Service::uploadBasePath() const
 {
@@ -1020,6 +1033,8 @@ HttpResponse Service::handlePrepareFile(const HttpRequest& request)
 			throw ProgError("Protocol version mismatch. "
 				"Service version: " ELB_HTTP_PROTOCOLVERSION "; "
 				"Received master version: " + masterProtoVer);
+
+		checkAuthorization(request);
 
 		if(!request.query.count("FileName") )
 			throw ProgError("Missing parameter: FileName");
@@ -1077,6 +1092,8 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 			throw ProgError("Protocol version mismatch. "
 				"Service version: " ELB_HTTP_PROTOCOLVERSION "; "
 				"Received master version: " + masterProtoVer);
+
+		checkAuthorization(request);
 
 		time_t currentTime = time(NULL);
 		struct tm localTimeInfo;
@@ -1906,7 +1923,8 @@ void Master::prepareRemotePhases()
 
 					HttpResponse uploadResponse = httpRequest(remote.host, remote.port, "POST",
 						"/preparefile?ProtocolVersion=" ELB_HTTP_PROTOCOLVERSION
-						"&FileName=treefile.txt&PwHash=", treeFileContents.str(), 60);
+						"&FileName=treefile.txt&PwHash=" + progArgs.svcPasswordHash,
+						treeFileContents.str(), 60);
 
 					if(uploadResponse.statusCode != 200)
 						throw ProgError("Service encountered an error. Service: " + remote.host +
@@ -1917,7 +1935,8 @@ void Master::prepareRemotePhases()
 				JsonTree tree = progArgsToServiceTree(progArgs, i, hosts.size() );
 
 				HttpResponse response = httpRequest(remote.host, remote.port, "POST",
-					"/preparephase?ProtocolVersion=" ELB_HTTP_PROTOCOLVERSION "&PwHash=",
+					"/preparephase?ProtocolVersion=" ELB_HTTP_PROTOCOLVERSION "&PwHash=" +
+						progArgs.svcPasswordHash,
 					tree.toJSON(), 300);
 
 				if(response.statusCode != 200)

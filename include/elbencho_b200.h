@@ -411,6 +411,10 @@ int64_t elb_format_value(int kind, uint64_t value, double percentage, const elb_
 /* UnitTk::numHumanToBytesBinary (toolkits/UnitTk.cpp:18-76): "4k", "1M", "64G"; 0 ok, -1 error */
 int elb_num_human_to_bytes(const char* numHuman, uint64_t* outBytes);
 
+/* HashTk::simple128 (toolkits/HashTk.cpp:10-41), the hash of the service password line that
+ * travels as "PwHash"; out receives 32 hex digits + NUL */
+void elb_simple128_hash(const char* input, char out[33]);
+
 /* The two rate limiters of the per-block loop on their own (toolkits/RateLimiter.h:13-66,
  * toolkits/RateLimiterRWMixThreads.h:22-197). wait calls return 1 if the caller had to sleep, 0 if
  * not, -1 on error (balancer: interrupted, or 600 s without progress). */

@@ -13,6 +13,7 @@
 #undef private
 #include "ProgException.h"
 #include "toolkits/UnitTk.h"
+#include "toolkits/HashTk.h"
 
 static int64_t copyOut(const std::string& text, char* outBuf, uint64_t outBufLen)
 {
@@ -90,5 +91,9 @@ int ref_num_human_to_bytes(const char* numHuman, uint64_t* outBytes, char* outEr
 		return -1;
 	}
 }
+
+/* HashTk::simple128 (service password hash, ProgArgs.cpp:2828) */
+int64_t ref_simple128(const char* input, char* outBuf, uint64_t outBufLen)
+	{ return copyOut(HashTk::simple128(input), outBuf, outBufLen); }
 
 } // extern "C"

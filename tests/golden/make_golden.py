@@ -187,6 +187,10 @@ def main():
                  "4x", "k", ""):
         rc = ref.ref_num_human_to_bytes(text.encode(), ctypes.byref(out), err, len(err))
         units["human_to_bytes"][text] = out.value if rc == 0 else {"error": err.value.decode()}
+    units["simple128"] = {}
+    for text in ("a", "secret", "correct horse battery staple", "p\u00e4ssw\u00f6rd", "x" * 200):
+        ref.ref_simple128(text.encode(), buf, len(buf))
+        units["simple128"][text] = buf.value.decode()
     vectors["units"] = units
 
     # custom tree partition by the reference's own PathStore (oracle/ref_harness_tree.cpp)

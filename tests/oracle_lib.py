@@ -155,6 +155,7 @@ def load_ref():
         "ref_histogram_percentile_str": (ctypes.c_int64, [_VP, ctypes.c_double, ctypes.c_char_p,
                                                           c_u64]),
         "ref_per_sec_from_usec": (c_u64, [c_u64, c_u64]),
+        "ref_simple128": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_char_p, c_u64]),
         # the reference's PathStore (oracle/ref_harness_tree.cpp)
         "ref_custom_tree_worker_list": (ctypes.c_int64, [ctypes.c_char_p, c_u64, c_u64, c_u64, c_u64,
                                                          c_u64, ctypes.c_int, ctypes.c_char_p,

@@ -262,3 +262,68 @@ def test_help_variants_and_accepted_noops():
     res = run_master("--dryrun", "-w", "-s", "1M", "--gpuids", "0", "--cufile", "--cufiledriveropen",
                      "/tmp/elb_dry_noop")
     assert res.returncode == 0, res.stderr
+
+
+def test_service_password_file_both_sides(tmp_path):
+    """--svcpwfile: the master sends HashTk::simple128 of the file's first line as PwHash with
+    /preparephase and /preparefile; a service rejects other hashes (HTTPServiceSWS.cpp:287-296)"""
+    import http.client
+    pwfile = tmp_path / "pw.txt"
+    pwfile.write_text("secret\nsecond line is ignored\n")
+    want_hash = "81cae49641cc8a331b2199b5f77da014"  # tests/golden: simple128("secret")
+
+    fake = FakeService(8 * MiB, [1000]).start()
+    try:
+        res = run_master("-w", "-t", "1", "-b", "1M", "-s", "8M", "--gpuids", "0", "--hosts",
+                         "127.0.0.1:%d" % fake.port, "--svcpwfile", str(pwfile), "--nolive",
+                         str(tmp_path / "f"))
+        assert res.returncode == 0, res.stdout + res.stderr
+        prep = [req for req in fake.requests if req[1] == "/preparephase"][0]
+        assert prep[2]["PwHash"] == want_hash
+    finally:
+        fake.stop()
+
+    port = free_port()
+    svc = subprocess.Popen([CLI_PATH, "--service", "--foreground", "--port", str(port),
+                            "--svcpwfile", str(pwfile)], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True)
+    try:
+        conn = None
+        for _ in range(100):
+            try:
+                conn = http.client.HTTPConnection("127.0.0.1", port, timeout=5)
+                conn.request("GET", "/protocolversion")
+                assert conn.getresponse().read() == b"3.1.1"
+                break
+            except OSError:
+                time.sleep(0.1)
+
+        def post(path, body):
+            conn.request("POST", path, body=body)
+            response = conn.getresponse()
+            return response.status, response.read()
+
+        status, body = post("/preparefile?ProtocolVersion=3.1.1&FileName=t.txt&PwHash=", "x")
+        assert status == 400 and b"Invalid authorization code." in body
+        status, body = post("/preparephase?ProtocolVersion=3.1.1&PwHash=0123", "{}")
+        assert status == 400 and b"Invalid authorization code." in body
+        status, body = post("/preparephase?ProtocolVersion=3.1.1", "{}")
+        assert status == 400 and b"Missing parameter: PwHash" in body
+        status, body = post("/preparefile?ProtocolVersion=3.1.1&FileName=t.txt&PwHash=" + want_hash,
+                            "d x\n")
+        assert status == 200
+        import getpass
+        os.unlink("/var/tmp/elbencho-b200_%s_p%d/t.txt" % (getpass.getuser(), port))
+        os.rmdir("/var/tmp/elbencho-b200_%s_p%d" % (getpass.getuser(), port))
+        conn.close()
+    finally:
+        run_master("--quit", "--hosts", "127.0.0.1:%d" % port)
+        try:
+            svc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            svc.kill()
+
+    empty = tmp_path / "empty.txt"
+    empty.write_text("\n")
+    res = run_master("-w", "-s", "1M", "--gpuids", "0", "--svcpwfile", str(empty), "/tmp/x")
+    assert res.returncode == 1 and "First line in service password file is empty" in res.stderr

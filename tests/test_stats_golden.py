@@ -123,3 +123,11 @@ def test_live_against_reference_headers(native, oracle, ref):
                     pytest.approx(want, rel=1e-12)
         for _, _, handle in parts:
             ref.ref_histogram_destroy(handle)
+
+
+def test_service_password_hash_matches_reference(native, golden):
+    """HashTk::simple128 (toolkits/HashTk.cpp), incl. sign extension of non-ASCII bytes"""
+    out = ctypes.create_string_buffer(33)
+    for text, want in golden["units"]["simple128"].items():
+        native.elb_simple128_hash(text.encode(), out)
+        assert out.value.decode() == want, text

@@ -171,6 +171,8 @@ static const OptDef optDefs[] =
 		"(Default: use all given hosts)"},
 	{"gpuperservice", 0, Opt_FLAG, "Assign GPUs round robin to service instances (one GPU of the "
 		"--gpuids list per service) instead of round robin to the threads of each service."},
+	{"svcelapsed", 0, Opt_FLAG, "Show elapsed time to completion of each service instance ordered "
+		"by slowest thread."},
 	{"svcupint", 0, Opt_U64, "Update retrieval interval for service hosts in milliseconds. "
 		"(Default: 500)"},
 	{"nosvcshare", 0, Opt_FLAG, "Benchmark paths are not shared between service instances. Thus, "
@@ -575,6 +577,7 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("latpercent9s", numLatencyPercentile9s);
 	showLatencyHistogram = flag("lathisto");
 	showAllElapsed = flag("allelapsed");
+	showServicesElapsed = flag("svcelapsed");
 	showCPUUtilization = flag("cpu");
 	showDirStats = flag("dirstats");
 	disableLiveStats = flag("nolive");

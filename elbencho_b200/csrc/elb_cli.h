@@ -122,6 +122,7 @@ class ProgArgs
 		bool showLatencyHistogram{false};
 		uint64_t numLatencyPercentile9s{0};
 		bool showAllElapsed{false};
+		bool showServicesElapsed{false}; // --svcelapsed
 		bool showCPUUtilization{false};
 		bool showDirStats{false};
 		bool disableLiveStats{false};
@@ -200,9 +201,12 @@ namespace stats
 	std::string percentileStr(const elb_histogram& histo, double percentage);
 
 	void printPhaseResultsTableHeader(std::ostream& out); // Statistics.cpp:1546-1562
+	/* @svcCompletionMS distributed runs: (slowest thread in ms, host) per service, for the
+	 *    --svcelapsed row (Statistics.cpp:2079-2117) */
 	void printPhaseResults(const ProgArgs& progArgs, int benchPhase,
 		const elb_phase_results& res, const std::vector<uint64_t>& elapsedUSecVec,
-		std::ostream& out); // Statistics.cpp:1771-2140
+		std::ostream& out,
+		const std::vector<std::pair<uint64_t, std::string> >* svcCompletionMS = NULL); // :1771-2140
 	void csvLabelsAndValues(const ProgArgs& progArgs, int benchPhase,
 		const elb_phase_results& res, const std::string& isoDate,
 		std::vector<std::string>& outLabels, std::vector<std::string>& outValues); // :2151-2323

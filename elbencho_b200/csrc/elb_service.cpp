@@ -2251,12 +2251,28 @@ void Master::runPhase(int benchPhase)
 		std::cout << "Skipping stats print due to unavailable worker results." << std::endl;
 	else
 	{
-		stats::printPhaseResults(progArgs, benchPhase, res, allElapsedUSec, std::cout);
+		// --svcelapsed: slowest thread of each service (Statistics.cpp:2093-2108)
+		std::vector<std::pair<uint64_t, std::string> > svcCompletionMS;
+
+		for(const RemoteHost& remote : hosts)
+		{
+			uint64_t slowestThreadUSec = 0;
+
+			for(uint64_t elapsedUSec : remote.elapsedUSecVec)
+				slowestThreadUSec = std::max(slowestThreadUSec, elapsedUSec);
+
+			svcCompletionMS.push_back(std::make_pair(slowestThreadUSec / 1000,
+				remote.host + ":" + std::to_string(remote.port) ) );
+		}
+
+		stats::printPhaseResults(progArgs, benchPhase, res, allElapsedUSec, std::cout,
+			&svcCompletionMS);
 
 		if(!progArgs.resFilePath.empty() )
 		{
 			std::ofstream fileStream(progArgs.resFilePath, std::ofstream::app);
-			stats::printPhaseResults(progArgs, benchPhase, res, allElapsedUSec, fileStream);
+			stats::printPhaseResults(progArgs, benchPhase, res, allElapsedUSec, fileStream,
+				&svcCompletionMS);
 			fileStream << std::endl;
 		}
 

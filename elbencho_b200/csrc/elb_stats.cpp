@@ -257,7 +257,8 @@ static void printLatency(const ProgArgs& progArgs, const elb_histogram& histo,
 
 /* Statistics::printPhaseResultsToStream (:1771-2140) */
 void printPhaseResults(const ProgArgs& progArgs, int benchPhase, const elb_phase_results& res,
-	const std::vector<uint64_t>& elapsedUSecVec, std::ostream& out)
+	const std::vector<uint64_t>& elapsedUSecVec, std::ostream& out,
+	const std::vector<std::pair<uint64_t, std::string> >* svcCompletionMS)
 {
 	const std::string name = phaseName(benchPhase, progArgs);
 	const std::string entryTypeUpperCase = phaseEntryType(benchPhase, true);
@@ -390,6 +391,21 @@ void printPhaseResults(const ProgArgs& progArgs, int benchPhase, const elb_phase
 
 		for(uint64_t elapsedUSec : elapsedUSecVec)
 			out << (elapsedUSec / 1000) << " ";
+
+		out << "]" << std::endl;
+	}
+
+	if(progArgs.showServicesElapsed && svcCompletionMS && !svcCompletionMS->empty() )
+	{ // hosts sorted from fastest to slowest by their slowest thread (Statistics.cpp:2079-2117)
+		std::vector<std::pair<uint64_t, std::string> > sorted(*svcCompletionMS);
+		std::stable_sort(sorted.begin(), sorted.end(),
+			[](const std::pair<uint64_t, std::string>& a, const std::pair<uint64_t, std::string>& b)
+			{ return a.first < b.first; } );
+
+		out << tableRowLeft("", "Svc compl. time", ":") << "[ ";
+
+		for(const std::pair<uint64_t, std::string>& entry : sorted)
+			out << entry.second << "=" << elapsedMSToHumanStr(entry.first) << " ";
 
 		out << "]" << std::endl;
 	}

@@ -169,7 +169,7 @@ def test_master_protocol_rank_offsets_and_aggregation(tmp_path):
         res = run_master("-w", "-r", "-t", "2", "-b", "1M", "-s", "48M", "--verify", "1", "--gpuids",
                          "3,5", "--gpuperservice", "--hosts", hosts, "--nolive", "--lat",
                          "--limitread", "7M", "--randalgo", "fast", "--treefile", str(tree),
-                         "--timelimit", "50", str(tmp_path / "bench"))
+                         "--timelimit", "50", "--svcelapsed", str(tmp_path / "bench"))
         assert res.returncode == 0, res.stdout + res.stderr
         for idx, svc in enumerate(services):
             paths = [req[1] for req in svc.requests]
@@ -195,6 +195,9 @@ def test_master_protocol_rank_offsets_and_aggregation(tmp_path):
         assert table_value(res.stdout, "WRITE", "Elapsed time", 1) == "2.000s"
         assert int(table_value(res.stdout, "WRITE", "Throughput MiB/s")) == 48
         assert "min=900us avg=1.00ms max=1.10ms" in res.stdout
+        # --svcelapsed: services ordered by their slowest thread (Statistics.cpp:2079-2117)
+        assert "Svc compl. time  : [ 127.0.0.1:%d=1.000s 127.0.0.1:%d=2.000s ]" % (
+            services[0].port, services[1].port) in res.stdout
     finally:
         for svc in services:
             svc.stop()

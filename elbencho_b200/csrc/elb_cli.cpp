@@ -114,6 +114,9 @@ static const OptDef optDefs[] =
 	{"live1", 0, Opt_FLAG, "Use brief live statistics format, i.e. a single line instead of full "
 		"screen stats. (Always on: this implementation has no full screen live stats.)"},
 	{"live1n", 0, Opt_FLAG, "Brief live statistics where every update is a new line."},
+	{"livecsvex", 0, Opt_FLAG, "Use extended live results CSV file. By default, only aggregate "
+		"results of all worker threads will be added. This option also adds results of "
+		"individual threads in standalone mode."},
 	{"livecsv", 0, Opt_STR, "Path to file for live statistics in CSV format ('stdout' for console). "
 		"One line per --liveint interval with the aggregate of all local workers."},
 	{"liveint", 0, Opt_U64, "Update interval for live statistics in milliseconds. (Default: 2000)"},
@@ -612,6 +615,7 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("datasetthreads", numDataSetThreads);
 	useBriefLiveStatsNewLine = flag("live1n");
 	str("livecsv", liveCSVFilePath);
+	useExtendedLiveCSV = flag("livecsvex");
 	str("configfile", configFilePath);
 
 	str("hosts", hostsStr);

@@ -137,6 +137,7 @@ class ProgArgs
 		uint64_t startTime{0};          // --start (UTC seconds since the epoch)
 		bool useBriefLiveStatsNewLine{false}; // --live1n
 		std::string liveCSVFilePath;    // --livecsv
+		bool useExtendedLiveCSV{false}; // --livecsvex
 		std::string configFilePath;     // --configfile
 		std::string benchLabel;
 		std::string csvFilePath;

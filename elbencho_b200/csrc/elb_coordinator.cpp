@@ -285,6 +285,39 @@ void Coordinator::printLiveStatsCSV(int benchPhase, const elb_liveops liveOps[2]
 			(manager->workers.size() - numWorkersDone) << "," <<
 			liveCpuUtil.getCPUUtilPercent() << "," << "" << "," << std::endl;
 	}
+
+	if(!progArgs.useExtendedLiveCSV)
+		return;
+
+	/* --livecsvex: one more line per worker with its totals so far; no per-second and latency
+	   values there (Statistics.cpp:3116-3225) */
+	const size_t numWorkers = manager->workers.size();
+	const uint64_t bytesPerWorker = numWorkers ? (expectedBytes / numWorkers) : 0;
+	const uint64_t entriesPerWorker = numWorkers ? (expectedEntries / numWorkers) : 0;
+
+	for(size_t workerIdx = 0; workerIdx < numWorkers; workerIdx++)
+	{
+		const elb_liveops workerOps[2] = { manager->workers[workerIdx]->getLiveOps(),
+			manager->workers[workerIdx]->getLiveOpsReadMix() };
+
+		for(int mixIdx = 0; mixIdx < (isRWMixPhase ? 2 : 1); mixIdx++)
+		{
+			const elb_liveops& ops = workerOps[mixIdx];
+			uint64_t workerPercentDone = 0;
+
+			if(bytesPerWorker)
+				workerPercentDone = (100 * ops.numBytesDone) / bytesPerWorker;
+			else
+			if(entriesPerWorker)
+				workerPercentDone = (100 * ops.numEntriesDone) / entriesPerWorker;
+
+			out << isoDate << "," << label << "," << phaseName << "," << elapsedMS << "," <<
+				workerIdx << "," << (isRWMixPhase ? (mixIdx ? "Read" : "Write") : "") << "," <<
+				std::min(workerPercentDone, (uint64_t)100) << "," << ops.numBytesDone << "," <<
+				"" << "," << "" << "," << (isDirMode ? ops.numEntriesDone : 0) << "," <<
+				"" << "," << "" << "," << "" << "," << ",,," << std::endl;
+		}
+	}
 }
 
 /* Statistics::printPhaseResults (:1568-1632): console + optional txt/csv/json files */

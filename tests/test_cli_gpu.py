@@ -212,6 +212,20 @@ def test_rate_limit_infloop_livecsv_and_start_time(workdir):
     assert done_bytes == sorted(done_bytes) and done_bytes[-1] > 0
     assert all(int(row[14]) == 2 for row in rows[:2])  # both threads active
 
+    # --livecsvex adds one line per worker (rank in column 5, no per-second values)
+    live_csv_ex = os.path.join(workdir, "live_ex.csv")
+    res = run_cli("-r", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--infloop",
+                  "--timelimit", "1", "--liveint", "200", "--livecsv", live_csv_ex, "--livecsvex",
+                  path, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    with open(live_csv_ex) as f:
+        rows = [line.split(",") for line in f.read().splitlines()[1:]]
+    ranks = [row[4] for row in rows[:3]]
+    assert ranks == ["Total", "0", "1"], ranks
+    assert all(len(row) == 18 for row in rows)
+    assert rows[1][8] == "" and rows[1][9] == ""  # no MiB/s and IOPS per worker
+    assert int(rows[0][7]) >= int(rows[1][7]) + int(rows[2][7]) - 2 * MiB  # totals ~ sum of workers
+
     # a start time in the past is an error (Coordinator.cpp:151-152), one 2 s ahead is waited for
     res = run_cli("-r", "-b", "1M", "-s", "16M", "--gpuids", "0", "--start", "1000", path)
     assert res.returncode == 1 and "Defined start time has already passed" in res.stderr

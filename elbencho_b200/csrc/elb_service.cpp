@@ -13,6 +13,7 @@
 #include <string.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/time.h>
 #include <sys/types.h>
 #include <unistd.h>
 
@@ -1659,6 +1660,7 @@ struct RemoteHost
 	std::vector<uint64_t> elapsedUSecVec;
 	elb_histogram iopsLatHisto, entriesLatHisto, iopsLatHistoReadMix, entriesLatHistoReadMix;
 	unsigned cpuUtilStoneWall{0}, cpuUtilLastDone{0}, cpuUtilLive{0};
+	elb_livelat liveLat{}; // sums of the status replies since the last live CSV line
 	std::string errorMsg;
 };
 
@@ -1880,6 +1882,11 @@ class Master
 		void interruptAll(bool quit);
 		void waitForServicesReady();
 		void rotateHosts();
+		void getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& outBytes);
+		void printLiveStatsCSV(int benchPhase, elb_liveops oldLiveOps[2],
+			Clock::time_point& lastT, const Clock::time_point& phaseStartT,
+			uint64_t expectedEntries, uint64_t expectedBytes);
+		bool liveCSVHeaderPrinted{false};
 		bool isPhaseTimeExpired{false};
 };
 
@@ -2038,6 +2045,13 @@ void Master::runPhase(int benchPhase)
 
 	bool stoneWallTaken = false;
 	elb_liveops oldLiveOps{};
+	elb_liveops oldLiveOpsCSV[2] = {};
+	Clock::time_point lastLiveCSVT = phaseStartT;
+	uint64_t expectedEntries = 0, expectedBytes = 0;
+
+	if(!progArgs.liveCSVFilePath.empty() )
+		getExpectedTotals(benchPhase, expectedEntries, expectedBytes);
+
 	Clock::time_point lastLiveT = phaseStartT;
 	bool printedLiveLine = false;
 	const bool showLive = !progArgs.disableLiveStats && isatty(STDOUT_FILENO);
@@ -2076,6 +2090,10 @@ void Master::runPhase(int benchPhase)
 			remote.liveOps.numBytesDone = statusTree.getU64("NumBytesDone");
 			remote.liveOps.numIOPSDone = statusTree.getU64("NumIOPSDone");
 			remote.cpuUtilLive = (unsigned)statusTree.getU64("CPUUtil", 0);
+			remote.liveLat.numAvgIOLatValues += statusTree.getU64("NumIOLatUSec", 0);
+			remote.liveLat.avgIOLatMicroSecsSum += statusTree.getU64("SumIOLatUSec", 0);
+			remote.liveLat.numAvgEntriesLatValues += statusTree.getU64("NumEntLatUSec", 0);
+			remote.liveLat.avgEntriesLatMicroSecsSum += statusTree.getU64("SumEntLatUSec", 0);
 
 			if(isRWMixConfig)
 			{
@@ -2109,6 +2127,10 @@ void Master::runPhase(int benchPhase)
 
 		if(numHostsDone == hosts.size() )
 			break;
+
+		if(!progArgs.liveCSVFilePath.empty() )
+			printLiveStatsCSV(benchPhase, oldLiveOpsCSV, lastLiveCSVT, phaseStartT, expectedEntries,
+				expectedBytes);
 
 		if(showLive)
 		{
@@ -2360,6 +2382,171 @@ void Master::waitForServicesReady()
 				"Unreachable service: " + notReadyServiceHost);
 
 		usleep(1000 * 1000);
+	}
+}
+
+/* expected entries / bytes of all services together, for the "Done%" column of the live CSV */
+void Master::getExpectedTotals(int benchPhase, uint64_t& outEntries, uint64_t& outBytes)
+{
+	outEntries = outBytes = 0;
+
+	try
+	{
+		ProgArgs::ABIConfig abiConfig;
+		progArgs.toABIConfig(abiConfig);
+
+		if(abiConfig.gpuIDs.empty() )
+		{
+			abiConfig.gpuIDs.push_back(0);
+			abiConfig.cfg.gpuIDs = abiConfig.gpuIDs.data();
+			abiConfig.cfg.numGPUIDs = 1;
+		}
+
+		abiConfig.cfg.pathType = progArgs.benchPathType; // (as reported by the services)
+		abiConfig.cfg.treeFilePath = NULL;
+		abiConfig.cfg.numDataSetThreads = (uint32_t)(progArgs.noSharedServicePath ?
+			progArgs.numThreads : (progArgs.numThreads * hosts.size() ) );
+
+		const Config cfg = Config::fromABI(&abiConfig.cfg);
+		uint64_t entriesPerWorker, bytesPerWorker;
+
+		expectedPerWorker(cfg, benchPhase, entriesPerWorker, bytesPerWorker);
+
+		outEntries = entriesPerWorker * progArgs.numThreads * hosts.size();
+		outBytes = bytesPerWorker * progArgs.numThreads * hosts.size();
+	}
+	catch(std::exception& e) { }
+}
+
+/* Statistics::printLiveStatsCSV in a distributed run (Statistics.cpp:3017-3230): a "Total" line
+ * per update (plus a "Read" line in rwmix phases) and, with --livecsvex, one line per service
+ * with its threads left, CPU utilisation and host name */
+void Master::printLiveStatsCSV(int benchPhase, elb_liveops oldLiveOps[2], Clock::time_point& lastT,
+	const Clock::time_point& phaseStartT, uint64_t expectedEntries, uint64_t expectedBytes)
+{
+	const bool toStdout = (progArgs.liveCSVFilePath == "stdout");
+	std::ofstream fileStream;
+	bool printHeaders = toStdout ? !liveCSVHeaderPrinted : false;
+
+	if(!toStdout)
+	{
+		struct stat statBuf;
+		printHeaders = (stat(progArgs.liveCSVFilePath.c_str(), &statBuf) != 0) ||
+			!statBuf.st_size;
+
+		fileStream.open(progArgs.liveCSVFilePath, std::ofstream::app);
+
+		if(!fileStream)
+			throw ProgError("Unable to open live stats csv file: " + progArgs.liveCSVFilePath);
+	}
+
+	std::ostream& out = toStdout ? std::cout : fileStream;
+
+	if(printHeaders)
+		out << "ISO Date,Label,Phase,RuntimeMS,Rank,MixType,Done%,DoneBytes,MiB/s,IOPS,Entries,"
+			"Entries/s,Lat Ent us,Lat IO us,Active,CPU,Service," << std::endl;
+
+	liveCSVHeaderPrinted = true;
+
+	elb_liveops liveOps[2] = {};
+	elb_livelat liveLat = {};
+	uint64_t numThreadsLeft = 0, cpuSum = 0;
+
+	for(RemoteHost& remote : hosts)
+	{
+		liveOpsAdd(liveOps[0], remote.liveOps);
+		liveOpsAdd(liveOps[1], remote.liveOpsReadMix);
+		liveLat.numAvgIOLatValues += remote.liveLat.numAvgIOLatValues;
+		liveLat.avgIOLatMicroSecsSum += remote.liveLat.avgIOLatMicroSecsSum;
+		liveLat.numAvgEntriesLatValues += remote.liveLat.numAvgEntriesLatValues;
+		liveLat.avgEntriesLatMicroSecsSum += remote.liveLat.avgEntriesLatMicroSecsSum;
+		remote.liveLat = elb_livelat{};
+		numThreadsLeft += progArgs.numThreads - std::min(progArgs.numThreads,
+			(uint64_t)remote.numWorkersDone);
+		cpuSum += remote.cpuUtilLive;
+	}
+
+	const Clock::time_point nowT = Clock::now();
+	const uint64_t intervalUSec =
+		std::chrono::duration_cast<std::chrono::microseconds>(nowT - lastT).count();
+	const uint64_t elapsedMS =
+		std::chrono::duration_cast<std::chrono::milliseconds>(nowT - phaseStartT).count();
+	const bool isRWMixPhase = (liveOps[1].numBytesDone || liveOps[1].numEntriesDone);
+	const bool isDirMode = (progArgs.benchPathType == ELB_PATH_DIR);
+	const std::string phaseName = stats::phaseName(benchPhase, progArgs);
+	std::string label = progArgs.benchLabel;
+	std::replace(label.begin(), label.end(), ',', ' ');
+
+	char isoBuf[64];
+	{
+		struct timeval timeVal;
+		gettimeofday(&timeVal, NULL);
+		struct tm localTimeInfo;
+		localtime_r(&timeVal.tv_sec, &localTimeInfo);
+		char dateBuf[32], zoneBuf[16];
+		strftime(dateBuf, sizeof(dateBuf), "%FT%T", &localTimeInfo);
+		strftime(zoneBuf, sizeof(zoneBuf), "%z", &localTimeInfo);
+		snprintf(isoBuf, sizeof(isoBuf), "%s.%03d%s", dateBuf, (int)(timeVal.tv_usec / 1000),
+			zoneBuf);
+	}
+
+	auto perSec = [&](uint64_t newVal, uint64_t oldVal)
+		{ return intervalUSec ? perSecFromUSec(newVal - oldVal, intervalUSec) : 0; };
+	auto percentDone = [](const elb_liveops& ops, uint64_t bytesTotal, uint64_t entriesTotal)
+	{
+		uint64_t percent = 0;
+
+		if(bytesTotal)
+			percent = (100 * ops.numBytesDone) / bytesTotal;
+		else
+		if(entriesTotal)
+			percent = (100 * ops.numEntriesDone) / entriesTotal;
+
+		return std::min(percent, (uint64_t)100);
+	};
+	auto avg = [](uint64_t sum, uint64_t num) { return num ? (sum / num) : 0; };
+
+	for(int mixIdx = 0; mixIdx < (isRWMixPhase ? 2 : 1); mixIdx++)
+	{
+		const elb_liveops& ops = liveOps[mixIdx];
+
+		out << isoBuf << "," << label << "," << phaseName << "," << elapsedMS << "," <<
+			"Total" << "," << (isRWMixPhase ? (mixIdx ? "Read" : "Write") : "") << "," <<
+			percentDone(ops, expectedBytes, expectedEntries) << "," << ops.numBytesDone << "," <<
+			(perSec(ops.numBytesDone, oldLiveOps[mixIdx].numBytesDone) / (1024 * 1024) ) << "," <<
+			perSec(ops.numIOPSDone, oldLiveOps[mixIdx].numIOPSDone) << "," <<
+			(isDirMode ? ops.numEntriesDone : 0) << "," <<
+			(isDirMode ? perSec(ops.numEntriesDone, oldLiveOps[mixIdx].numEntriesDone) : 0) <<
+			"," << (mixIdx ? 0 : avg(liveLat.avgEntriesLatMicroSecsSum,
+				liveLat.numAvgEntriesLatValues) ) << "," <<
+			(mixIdx ? 0 : avg(liveLat.avgIOLatMicroSecsSum, liveLat.numAvgIOLatValues) ) << "," <<
+			numThreadsLeft << "," << (hosts.empty() ? 0 : (cpuSum / hosts.size() ) ) << "," <<
+			"" << "," << std::endl;
+
+		oldLiveOps[mixIdx] = ops;
+	}
+
+	lastT = nowT;
+
+	if(!progArgs.useExtendedLiveCSV)
+		return;
+
+	for(size_t hostIdx = 0; hostIdx < hosts.size(); hostIdx++)
+	{
+		const RemoteHost& remote = hosts[hostIdx];
+		const elb_liveops remoteOps[2] = {remote.liveOps, remote.liveOpsReadMix};
+
+		for(int mixIdx = 0; mixIdx < (isRWMixPhase ? 2 : 1); mixIdx++)
+			out << isoBuf << "," << label << "," << phaseName << "," << elapsedMS << "," <<
+				hostIdx << "," << (isRWMixPhase ? (mixIdx ? "Read" : "Write") : "") << "," <<
+				percentDone(remoteOps[mixIdx], expectedBytes / hosts.size(),
+					expectedEntries / hosts.size() ) << "," <<
+				remoteOps[mixIdx].numBytesDone << "," << "" << "," << "" << "," <<
+				(isDirMode ? remoteOps[mixIdx].numEntriesDone : 0) << "," << "" << "," << "" <<
+				"," << "" << "," <<
+				(progArgs.numThreads - std::min(progArgs.numThreads,
+					(uint64_t)remote.numWorkersDone) ) << "," << remote.cpuUtilLive << "," <<
+				remote.host << ":" << remote.port << "," << std::endl;
 	}
 }
 

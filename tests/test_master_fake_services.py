@@ -330,3 +330,36 @@ def test_service_password_file_both_sides(tmp_path):
     empty.write_text("\n")
     res = run_master("-w", "-s", "1M", "--gpuids", "0", "--svcpwfile", str(empty), "/tmp/x")
     assert res.returncode == 1 and "First line in service password file is empty" in res.stderr
+
+
+def test_master_live_csv_with_per_service_rows(tmp_path):
+    """--livecsv / --livecsvex of a distributed run: totals of all services per update, then one
+    line per service with threads left, CPU utilisation and host (Statistics.cpp:3017-3230)"""
+    services = [FakeService(64 * MiB, [1000000]).start(), FakeService(32 * MiB, [1000000]).start()]
+    hosts = ",".join("127.0.0.1:%d" % s.port for s in services)
+    live_csv = tmp_path / "live.csv"
+    try:
+        res = run_master("-w", "-t", "2", "-b", "1M", "-s", "48M", "--gpuids", "0", "--hosts", hosts,
+                         "--nolive", "--svcupint", "50", "--livecsv", str(live_csv), "--livecsvex",
+                         "--label", "my,label", str(tmp_path / "f"))
+        assert res.returncode == 0, res.stdout + res.stderr
+    finally:
+        for svc in services:
+            svc.stop()
+    lines = live_csv.read_text().splitlines()
+    assert lines[0] == ("ISO Date,Label,Phase,RuntimeMS,Rank,MixType,Done%,DoneBytes,MiB/s,IOPS,"
+                        "Entries,Entries/s,Lat Ent us,Lat IO us,Active,CPU,Service,")
+    rows = [line.split(",") for line in lines[1:]]
+    assert len(rows) >= 3 and all(len(row) == 18 for row in rows)
+    total, first, second = rows[0], rows[1], rows[2]
+    assert total[1] == "my label" and total[2] == "WRITE" and total[4] == "Total"
+    # first poll: both fake services report half of their bytes and no thread done yet
+    assert int(total[7]) == 32 * MiB + 16 * MiB
+    # shared paths: the 48 MiB file is the whole data set of the 4 data set threads
+    assert int(total[6]) == 100
+    assert total[14] == "4" and total[15] == "7"
+    assert first[4] == "0" and int(first[7]) == 32 * MiB and first[14] == "2"
+    assert first[16] == "127.0.0.1:%d" % services[0].port
+    assert second[4] == "1" and int(second[7]) == 16 * MiB
+    assert second[16] == "127.0.0.1:%d" % services[1].port
+    assert first[8] == "" and first[9] == ""

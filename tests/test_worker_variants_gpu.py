@@ -186,7 +186,7 @@ def test_rwmixthrpct_balances_reader_and_writer_bytes(workdir):
     write_bytes = res["ops_total"]["bytes"]
     assert read_bytes > size and write_bytes > size  # both groups looped several times
     share = 100.0 * read_bytes / (read_bytes + write_bytes)
-    assert pct - 5 <= share <= pct + 5, share
+    assert pct - 8 <= share <= pct + 8, share
 
 
 def test_rwmixthrpct_rejects_rate_limits(workdir):

@@ -363,3 +363,90 @@ def test_master_live_csv_with_per_service_rows(tmp_path):
     assert second[4] == "1" and int(second[7]) == 16 * MiB
     assert second[16] == "127.0.0.1:%d" % services[1].port
     assert first[8] == "" and first[9] == ""
+
+
+def test_master_result_files_and_worker_error(tmp_path):
+    """CSV / JSON / text result files of a distributed run, and a service that reports a worker
+    error while the phase runs (RemoteWorker.cpp:429-572: the error history of the service is
+    shown and the run fails)"""
+    services = [FakeService(64 * MiB, [900000, 1000000]).start(),
+                FakeService(32 * MiB, [1500000, 2000000]).start()]
+    hosts = ",".join("127.0.0.1:%d" % s.port for s in services)
+    csv_path, json_path, txt_path = (tmp_path / n for n in ("r.csv", "r.json", "r.txt"))
+    try:
+        res = run_master("-w", "-t", "2", "-b", "1M", "-s", "48M", "--gpuids", "0", "--hosts", hosts,
+                         "--nolive", "--label", "dist run", "--csvfile", str(csv_path),
+                         "--jsonfile", str(json_path), "--resfile", str(txt_path),
+                         str(tmp_path / "f"))
+        assert res.returncode == 0, res.stdout + res.stderr
+    finally:
+        for svc in services:
+            svc.stop()
+    labels, values = [line.split(",") for line in csv_path.read_text().splitlines()[:2]]
+    row = dict(zip(labels, values))
+    assert row["label"] == "dist run" and row["operation"] == "WRITE"
+    assert row["hosts"] == "2" and row["threads"] == "2"
+    assert row["MiB [last]"] == "96" and row["time ms [first]"] == "900"
+    assert row["time ms [last]"] == "2000" and row["MiB/s [last]"] == "48"
+    doc = json.loads(json_path.read_text())
+    assert doc["phase_type"] == "WRITE" and doc["label"] == "dist run"
+    assert doc["last_done"]["elapsed_time_ms"] == "2000" and doc["first_done"]["elapsed_time_ms"] == "900"
+    assert doc["last_done"]["bytes"] == str(96 * MiB)
+    assert "WRITE" in txt_path.read_text() and "Total MiB" in txt_path.read_text()
+
+    class FailingService(FakeService):
+        def dispatch(self, method, path, query, body):
+            code, text = super().dispatch(method, path, query, body)
+            if path == "/status":
+                tree = json.loads(text)
+                tree["NumWorkersDoneWithError"] = "1"
+                tree["ErrorHistory"] = "File write failed. Path: /data/f; SysErr: No space left"
+                return 200, json.dumps(tree)
+            return code, text
+
+    broken = FailingService(8 * MiB, [1000]).start()
+    try:
+        res = run_master("-w", "-t", "1", "-b", "1M", "-s", "8M", "--gpuids", "0", "--hosts",
+                         "127.0.0.1:%d" % broken.port, "--nolive", str(tmp_path / "f"))
+        assert res.returncode == 1
+        assert "File write failed. Path: /data/f; SysErr: No space left" in res.stderr
+        assert broken.requests[-1][1] == "/interruptphase"
+    finally:
+        broken.stop()
+
+
+def test_master_stops_after_an_expired_time_limit(tmp_path):
+    """the services apply the limit themselves (they get it as b200_timelimit) and report done;
+    the master prints the phase and does not start the next one (Coordinator.cpp:234-241)"""
+
+    class SlowService(FakeService):
+        def dispatch(self, method, path, query, body):
+            if path == "/startphase":
+                self.started_at = time.time()
+            if path == "/status" and self.prepare_trees:
+                limit = int(self.prepare_trees[-1]["b200_timelimit"])
+                code, text = super().dispatch(method, path, query, body)
+                tree = json.loads(text)
+                if time.time() - self.started_at < limit:  # busy until the limit is over
+                    tree["NumWorkersDone"] = "0"
+                    tree["TriggerStoneWall"] = "false"
+                else:
+                    tree["NumWorkersDone"] = self.prepare_trees[-1]["threads"]
+                    tree["TriggerStoneWall"] = "true"
+                return 200, json.dumps(tree)
+            return super().dispatch(method, path, query, body)
+
+    svc = SlowService(16 * MiB, [1000000]).start()
+    try:
+        t0 = time.time()
+        res = run_master("-w", "-r", "-t", "2", "-b", "1M", "-s", "16M", "--gpuids", "0", "--hosts",
+                         "127.0.0.1:%d" % svc.port, "--nolive", "--timelimit", "1", "--svcupint",
+                         "50", str(tmp_path / "f"))
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert time.time() - t0 >= 1.0
+        assert "Terminating due to phase time limit." in res.stdout
+        assert "WRITE" in res.stdout and "\nREAD " not in res.stdout
+        starts = [req for req in svc.requests if req[1] == "/startphase"]
+        assert len(starts) == 1
+    finally:
+        svc.stop()

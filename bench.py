@@ -580,6 +580,39 @@ def single_thread_compare(args, device):
     return out
 
 
+def same_sample_compare(args, device, cpu):
+    """The GPU worker on exactly the bounded sample the cpu_baseline was timed on (same file size,
+    same thread count, fresh file): an apples-to-apples pair, because on this tmpfs the write rate
+    depends on the file size. Never fails the bench: errors are reported in the result."""
+    out = {}
+    try:
+        from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
+        block = int(args.block_mib * MiB)
+        size = int(args.cpu_sample_gib * GiB)
+        size -= size % block
+        threads = int(cpu["cores"])
+        path = os.path.join(bench_dir(args, 0), "same_sample_gpu.bin")
+        out["sample"] = "write+read --verify of a %.1f GiB file, 1 MiB blocks, -t %d" % (
+            size / GiB, threads)
+        try:
+            total_usec = 0
+            with WorkerManager(WorkerConfig(paths=[path], num_threads=threads, block_size=block,
+                                            file_size=size, integrity_check_salt=args.salt,
+                                            gpu_ids=[device.index], use_direct_io=args.direct,
+                                            serialize_buffered_writes=not args.no_write_gate)) as mgr:
+                for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
+                    total_usec += mgr.run_phase(phase)["last_finish_usec"]
+            out["gpu_worker_gib_s"] = round((2 * size / GiB) / (total_usec / 1e6), 3)
+            out["cpu_localworker_gib_s"] = cpu["value"]
+            out["ratio"] = round(out["gpu_worker_gib_s"] / cpu["value"], 2) if cpu["value"] else None
+        finally:
+            if os.path.exists(path):
+                os.unlink(path)
+    except Exception as err:  # noqa: BLE001 (an extra, must not break the bench line)
+        out["error"] = str(err)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # main
 # ------------------------------------------------------------------------------------------------
@@ -674,9 +707,12 @@ def main():
                                    (res["phases"]["READFILES"]["usec"] / 1e6), 3)}
 
     single = None
+    same_sample = None
     if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_e2e and \
             args.single_thread_sample_gib > 0:
         single = single_thread_compare(args, device)
+    if rank == 0 and world == 1 and cpu is not None and not args.skip_e2e:
+        same_sample = same_sample_compare(args, device, cpu)
 
     if world > 1:
         dist.barrier(device_ids=[device.index])
@@ -766,6 +802,8 @@ def main():
         line["storage_roofline"] = storage
     if single:
         line["single_thread"] = single
+    if same_sample:
+        line["same_sample"] = same_sample
     emit(line)
     return 0
 

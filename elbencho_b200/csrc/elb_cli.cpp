@@ -184,6 +184,10 @@ static const OptDef optDefs[] =
 	{"rotatehosts", 0, Opt_U64, "Number by which to rotate hosts between phases to avoid caching "
 		"effects. (Default: 0)"},
 	{"nodetach", 0, Opt_FLAG, "When running as service, do not detach from the terminal."},
+	{"svcping", 0, Opt_FLAG, "Show response time of service instances in fullscreen live stats. "
+		"(Accepted: there is no fullscreen view here.)"},
+	{"althttpsvc", 0, Opt_FLAG, "Use alternative HTTP service implementation. (Accepted: this build "
+		"has one dependency-free HTTP server.)"},
 	{"svcpwfile", 0, Opt_STR, "Path to a text file containing a single line of text as shared "
 		"secret between service instances and master. This is to prevent unauthorized requests "
 		"to service instances."},

@@ -263,7 +263,7 @@ def test_help_variants_and_accepted_noops():
         res = run_master(flag)
         assert res.returncode == 0 and "--gpuids" in res.stdout and "--treefile" in res.stdout
     res = run_master("--dryrun", "-w", "-s", "1M", "--gpuids", "0", "--cufile", "--cufiledriveropen",
-                     "/tmp/elb_dry_noop")
+                     "--svcping", "--althttpsvc", "/tmp/elb_dry_noop")
     assert res.returncode == 0, res.stderr
 
 

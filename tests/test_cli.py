@@ -359,3 +359,14 @@ def test_service_http_endpoints_without_gpu():
     finally:
         if proc.poll() is None:
             proc.kill()
+
+
+def test_options_md_is_in_sync_with_the_cli_table():
+    """OPTIONS.md (coverage of the reference's ProgArgs) is generated; needs the reference tree"""
+    if not os.path.exists("/root/reference/source/ProgArgs.h"):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "scripts"))
+    import gen_options_md
+    with open(os.path.join(gen_options_md.REPO, "OPTIONS.md")) as f:
+        assert f.read() == gen_options_md.generate()

@@ -224,9 +224,9 @@ uint64_t detectFileSize(const elb_cfg* abiCfg);
 void waitForUserDefinedStartTime(const ProgArgs& progArgs);
 
 /* expected entries/bytes per worker (WorkerManager::getPhaseNumEntriesAndBytes, :333-487) */
-struct CustomTree;
+class TreeManifest;
 void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
-	uint64_t& outBytes, const CustomTree* customTree = NULL);
+	uint64_t& outBytes, const TreeManifest* customTree = NULL);
 
 } // namespace elb
 

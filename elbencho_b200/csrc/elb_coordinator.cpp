@@ -119,7 +119,7 @@ void Coordinator::printDryRunInfo()
 
 	Config cfg = Config::fromABI(&abiConfig.cfg);
 
-	CustomTree customTree;
+	TreeManifest customTree;
 
 	if(!cfg.treeFilePath.empty() )
 		customTree.load(cfg.treeFilePath, cfg.blockSize, cfg.fileShareSize, cfg.treeRoundUpSize);
@@ -621,7 +621,7 @@ int Coordinator::main() // Coordinator.cpp:31-142
 		{ // ProgArgs::scanCustomTree (ProgArgs.cpp:2674-2735): write the tree file first
 			uint64_t numDirs, numFiles, numBytes;
 
-			PathStore::scanToTreeFile(progArgs.treeScanPath, progArgs.treeFilePath, numDirs,
+			TreeManifest::scanToTreeFile(progArgs.treeScanPath, progArgs.treeFilePath, numDirs,
 				numFiles, numBytes);
 
 			std::cout << "Directory scan done. Dirs: " << numDirs << "; Files: " << numFiles <<

@@ -601,7 +601,8 @@ elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
 	const uint32_t tilesPerCTA)
 {
 	const uint32_t descIdx = blockIdx.x / ctasPerBlock;
-	const uint64_t tileIdx = (uint64_t)(blockIdx.x - descIdx * ctasPerBlock) * tilesPerCTA;
+	const uint32_t ctaInBlock = blockIdx.x - descIdx * ctasPerBlock;
+	const uint64_t tileIdx = (uint64_t)ctaInBlock * tilesPerCTA;
 
 	const elb_block_desc desc = args.descs ? args.descs[descIdx] : args.inlineDesc;
 	const BlockGeom g = make_geom(desc);
@@ -609,8 +610,10 @@ elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
 	if(tileIdx >= g.numTiles)
 		return; // (uniform for the whole CTA)
 
-	const uint64_t tileEnd = (tileIdx + tilesPerCTA < g.numTiles) ?
-		(tileIdx + tilesPerCTA) : g.numTiles;
+	/* the launch shape comes from a size HINT: a block that is longer than the hint said has more
+	   tiles than ctasPerBlock CTAs cover, so the last CTA of a block takes all that remain */
+	const uint64_t tileEnd = ( (ctaInBlock + 1 == ctasPerBlock) ||
+		(tileIdx + tilesPerCTA >= g.numTiles) ) ? g.numTiles : (tileIdx + tilesPerCTA);
 
 	process_block_tiles<MODE>(args, desc, descIdx, g, tileIdx, tileEnd);
 

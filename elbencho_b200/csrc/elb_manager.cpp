@@ -546,18 +546,16 @@ void Manager::getPhaseResults(elb_phase_results& out)
 
 /* getPhaseNumEntriesAndBytes (WorkerManager.cpp:333-487): expected totals per worker */
 void expectedPerWorker(const Config& cfg, int benchPhase, uint64_t& outEntries,
-	uint64_t& outBytes, const CustomTree* customTree)
+	uint64_t& outBytes, const TreeManifest* customTree)
 {
 	outEntries = 0;
 	outBytes = 0;
 
 	if( (cfg.pathType == ELB_PATH_DIR) && customTree && customTree->isLoaded)
 	{ // custom tree mode (WorkerManager.cpp:406-450)
-		const uint64_t numDirs = customTree->dirs.getNumPaths();
-		const uint64_t numFiles = customTree->filesNonShared.getNumPaths() +
-			customTree->filesShared.getNumPaths();
-		const uint64_t numBytesTotal = customTree->filesNonShared.getNumBytesTotal() +
-			customTree->filesShared.getNumBytesTotal();
+		const uint64_t numDirs = customTree->getNumDirs();
+		const uint64_t numFiles = customTree->getNumFiles();
+		const uint64_t numBytesTotal = customTree->getNumFileBytes();
 
 		switch(benchPhase)
 		{
@@ -772,25 +770,20 @@ int64_t elb_custom_tree_worker_list(const char* treeFilePath, uint64_t blockSize
 		if(!treeFilePath || !numDataSetThreads || !blockSize)
 			throw elb::WorkerError("elb_custom_tree_worker_list: invalid argument");
 
-		elb::CustomTree tree;
-		elb::PathStore sublist;
+		elb::TreeManifest tree;
+		elb::WorkerTreeShare share;
 
 		tree.load(treeFilePath, blockSize, fileShareSize ? fileShareSize : (32 * blockSize),
 			treeRoundUpSize);
-		sublist.setBlockSize(blockSize);
 
 		if(kind == 0)
-			tree.dirs.getWorkerSublistNonShared(workerRank, numDataSetThreads, false, sublist);
+			tree.takeDirs(workerRank, numDataSetThreads, share.slices);
 		else
-		{
-			tree.filesNonShared.getWorkerSublistNonShared(workerRank, numDataSetThreads, false,
-				sublist);
-			tree.filesShared.getWorkerSublistShared(workerRank, numDataSetThreads, false, sublist);
-		}
+			tree.takeFiles(workerRank, numDataSetThreads, false, share);
 
 		std::string text;
 
-		for(const elb::PathStoreElem& elem : sublist.getPaths() )
+		for(const elb::TreeSlice& elem : share.slices)
 			text += elem.path + "\t" + std::to_string(elem.totalLen) + "\t" +
 				std::to_string(elem.rangeStart) + "\t" + std::to_string(elem.rangeLen) + "\n";
 
@@ -816,7 +809,7 @@ int64_t elb_custom_tree_scan(const char* scanPath, const char* outTreeFilePath)
 	{
 		uint64_t numDirs, numFiles, numBytes;
 
-		return (int64_t)elb::PathStore::scanToTreeFile(scanPath, outTreeFilePath, numDirs,
+		return (int64_t)elb::TreeManifest::scanToTreeFile(scanPath, outTreeFilePath, numDirs,
 			numFiles, numBytes);
 	}
 	catch(const std::exception& e)

@@ -243,19 +243,19 @@ class DirSource : public BlockSource
 class TreeSource : public BlockSource
 {
 	public:
-		TreeSource(const PathStore& files, OffsetPlan& plan, uint64_t& blockCounter) :
+		TreeSource(const WorkerTreeShare& files, OffsetPlan& plan, uint64_t& blockCounter) :
 			files(files), plan(plan), blockCounter(blockCounter) {}
 
-		virtual uint64_t getNumBytesTotal() const override { return files.getNumBytesTotal(); }
+		virtual uint64_t getNumBytesTotal() const override { return files.numBytes; }
 
 		virtual bool next(BlockRef& outBlock) override
 		{
 			if(!fileActive)
 			{
-				if(elemIndex >= files.getNumPaths() )
+				if(elemIndex >= files.size() )
 					return false;
 
-				const PathStoreElem& elem = files.getPaths()[elemIndex];
+				const TreeSlice& elem = files.slices[elemIndex];
 
 				plan.restart(elem.rangeLen, elem.rangeStart);
 				fileActive = true;
@@ -283,7 +283,7 @@ class TreeSource : public BlockSource
 		}
 
 	private:
-		const PathStore& files;
+		const WorkerTreeShare& files;
 		OffsetPlan& plan;
 		uint64_t& blockCounter;
 		size_t elemIndex{0};
@@ -708,7 +708,7 @@ void Worker::preparePhase()
 		blockVarianceSeed = ( (uint64_t)randDev() << 32) | (uint32_t)randDev();
 	}
 
-	prepareCustomTreePathStores();
+	takeCustomTreeShare();
 
 	allocRings();
 }
@@ -1052,28 +1052,24 @@ static int mkdiratBottomUp(int dirFD, const std::string& path, mode_t mode)
 	return mkdirat(dirFD, path.c_str(), mode);
 }
 
-/* LocalWorker::prepareCustomTreePathStores (LocalWorker.cpp:1520-1560) */
-void Worker::prepareCustomTreePathStores()
+/* this worker's dirs and files of the tree (reference: LocalWorker::prepareCustomTreePathStores, LocalWorker.cpp:1520-1560) */
+void Worker::takeCustomTreeShare()
 {
 	if(cfg.treeFilePath.empty() )
 		return;
 
 	const bool throwOnSmallerThanBlockSize = !cfg.noDirectIOCheck && cfg.useDirectIO &&
 		cfg.useRandomOffsets;
-	const CustomTree& tree = shared->customTree;
+	const TreeManifest& tree = shared->customTree;
 
 	customTreeDirs.clear();
 	customTreeFiles.clear();
-	customTreeFiles.setBlockSize(cfg.blockSize);
 
-	tree.dirs.getWorkerSublistNonShared(rank, cfg.numDataSetThreads, false, customTreeDirs);
-	tree.filesNonShared.getWorkerSublistNonShared(rank, cfg.numDataSetThreads,
-		throwOnSmallerThanBlockSize, customTreeFiles);
-	tree.filesShared.getWorkerSublistShared(rank, cfg.numDataSetThreads,
-		throwOnSmallerThanBlockSize, customTreeFiles);
+	tree.takeDirs(rank, cfg.numDataSetThreads, customTreeDirs);
+	tree.takeFiles(rank, cfg.numDataSetThreads, throwOnSmallerThanBlockSize, customTreeFiles);
 
 	if(cfg.useCustomTreeRandomize)
-		customTreeFiles.randomShuffle(cfg.treeRandomizeSeed ? (cfg.treeRandomizeSeed + rank) : 0);
+		customTreeFiles.shuffle(cfg.treeRandomizeSeed ? (cfg.treeRandomizeSeed + rank) : 0);
 }
 
 /* LocalWorker::dirModeIterateCustomDirs (LocalWorker.cpp:2927-3010): every worker creates its
@@ -1082,8 +1078,7 @@ void Worker::dirModeIterateCustomDirs()
 {
 	const int benchPathFD = shared->pathFDs[0];
 	const bool isDelete = (benchPhase == ELB_PHASE_DELETEDIRS);
-	const std::vector<PathStoreElem>& dirs =
-		isDelete ? shared->customTree.dirs.getPaths() : customTreeDirs.getPaths();
+	const std::vector<TreeSlice>& dirs = isDelete ? shared->customTree.getDirs() : customTreeDirs;
 	const bool thisWorkerDoesDelDirs = cfg.runAsService ?
 		(rank == 0) : (rank == cfg.rankOffset); // (service paths are shared between instances)
 
@@ -1100,7 +1095,7 @@ void Worker::dirModeIterateCustomDirs()
 	{
 		checkInterruptionRequest();
 
-		const PathStoreElem& elem = isDelete ? dirs[dirs.size() - 1 - i] : dirs[i];
+		const TreeSlice& elem = isDelete ? dirs[dirs.size() - 1 - i] : dirs[i];
 		const Clock::time_point ioStartT = Clock::now();
 
 		if(!isDelete)
@@ -1135,7 +1130,7 @@ void Worker::dirModeIterateCustomDirs()
 void Worker::dirModeIterateCustomFilesNoIO()
 {
 	const int benchPathFD = shared->pathFDs[0];
-	const std::vector<PathStoreElem>& files = customTreeFiles.getPaths();
+	const std::vector<TreeSlice>& files = customTreeFiles.slices;
 
 	if(files.empty() )
 	{
@@ -1148,7 +1143,7 @@ void Worker::dirModeIterateCustomFilesNoIO()
 		if( (i % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
 			checkInterruptionRequest();
 
-		const PathStoreElem& elem = files[i];
+		const TreeSlice& elem = files[i];
 		const Clock::time_point ioStartT = Clock::now();
 
 		if(benchPhase == ELB_PHASE_STATFILES)
@@ -1171,7 +1166,7 @@ void Worker::dirModeIterateCustomFilesNoIO()
 					"SysErr: " + strerror(errno) );
 		}
 
-		if(elem.totalLen != elem.rangeLen)
+		if(!elem.coversWholeFile() )
 			continue; // entry latency and count only for fully processed entries
 
 		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
@@ -1526,7 +1521,7 @@ void Worker::rwPhase()
 
 	if( (cfg.pathType == ELB_PATH_DIR) && !cfg.treeFilePath.empty() )
 	{ // dirModeIterateCustomFiles (LocalWorker.cpp:3261-3470)
-		if(!customTreeFiles.getNumPaths() )
+		if(customTreeFiles.empty() )
 		{
 			workerGotPhaseWork = false;
 			return;
@@ -2167,7 +2162,7 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 
 	if(block.isTreeElem)
 	{ // custom tree: the path comes from the tree file, the size is the entry's
-		const PathStoreElem& elem = customTreeFiles.getPaths()[block.fileIndex];
+		const TreeSlice& elem = customTreeFiles.slices[block.fileIndex];
 
 		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "%s", elem.path.c_str() );
 		fileSize = elem.totalLen;

@@ -37,7 +37,7 @@
 #include "elb_cufile.h"
 #include "elb_host.h"
 #include "elb_internal.h"
-#include "elb_pathstore.h"
+#include "elb_tree.h"
 
 namespace elb
 {
@@ -67,7 +67,7 @@ struct Shared
 
 	RWMixThreadsBalancer rwMixThreadsBalancer; // --rwmixthrpct (reset by the manager per phase)
 
-	CustomTree customTree; // --treefile, loaded by the manager (ProgArgs::loadCustomTreeFile)
+	TreeManifest customTree; // --treefile, parsed once by the manager (ProgArgs::loadCustomTreeFile)
 
 	/* workers hold this shared while they allocate / free device memory or instantiate graphs;
 	   the live stats reducer holds it exclusively while its collective is in flight, because a
@@ -230,13 +230,13 @@ class Worker
 		std::unique_ptr<RandAlgo> randOffsetAlgo; // --randalgo
 		RateLimiter rateLimiter; // --limitread / --limitwrite
 		// custom tree mode: this worker's dirs and files (LocalWorker.h customTreeDirs/Files)
-		PathStore customTreeDirs;
-		PathStore customTreeFiles;
+		std::vector<TreeSlice> customTreeDirs;
+		WorkerTreeShare customTreeFiles;
 		bool dirModeCountsEntry{true}; // false for a partial slice of a shared tree file
 		void applyNumaAndCoreBinding();     // Worker.cpp:102-146
 		void flockBlock(int fd, const BlockRef& block, bool isUnlock); // FileTk::flock
 		void fadviseFile(int fd, const std::string& path);             // FileTk::fadvise
-		void prepareCustomTreePathStores(); // LocalWorker.cpp:1520-1560
+		void takeCustomTreeShare(); // LocalWorker.cpp:1520-1560
 		void dirModeIterateCustomDirs();    // LocalWorker.cpp:2927-3010
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470
 		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase

@@ -155,7 +155,9 @@ int elb_fill_random_batch(const elb_block_desc* descs, uint32_t numDescs, unsign
  * of the descriptor lengths, maxBlockLen = upper bound of any descriptor's length (the block
  * size). With both, windows of (nearly) equally sized blocks run as a grid of short-lived CTAs,
  * one 32 KiB tile each, handed out dynamically by the hardware block scheduler; ragged or
- * unknown windows run on a persistent grid that partitions all tiles statically. */
+ * unknown windows run on a persistent grid that partitions all tiles statically. The hints are
+ * never load-bearing: a descriptor longer than maxBlockLen is still processed completely (the
+ * last CTA of its block walks the remaining tiles), only slower. */
 int elb_fill_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
 	uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen, void* stream);
 int elb_verify_pattern_batch_sized(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,

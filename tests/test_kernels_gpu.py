@@ -233,6 +233,34 @@ def test_batched_window_ragged_blocks(cuda_device, max_block_len):
             oracle_lib.fill_random_ctr(length, 60, 999, ctr_val)
 
 
+def test_block_longer_than_size_hint_is_fully_processed(cuda_device):
+    """max_block_len is a HINT for the launch shape: a descriptor that is longer than the hint
+    must still be filled / verified completely (no silently skipped tail tiles)."""
+    block, hint, salt = (1 << 20) + 4096 + 7, 64 << 10, 0x77
+    nblocks = 6
+    arena = dev_bytes(block * nblocks, cuda_device, fill=0)
+    blocks = [(arena.data_ptr() + i * block, block, i * block, i) for i in range(nblocks)]
+    descs = make_batch(cuda_device, blocks)
+    results = torch.zeros(2 * nblocks, dtype=torch.int64, device=cuda_device)
+    kernels.fill_pattern_batch(descs.data_ptr(), nblocks, salt, 0, stream_handle(),
+                               total_bytes=hint * nblocks, max_block_len=hint)
+    torch.cuda.synchronize()
+    assert to_bytes(arena, block * nblocks) == oracle_lib.fill_pattern(block * nblocks, 0, salt)
+    # a flipped byte in the part of each block that lies beyond the hint must be found
+    for i in range(nblocks):
+        arena[i * block + hint + 12345 + i] ^= 0x40
+    kernels.verify_pattern_batch(descs.data_ptr(), nblocks, salt, results.data_ptr(), 0,
+                                 stream_handle(), total_bytes=hint * nblocks, max_block_len=hint)
+    torch.cuda.synchronize()
+    assert read_result(results) == [(1, hint + 12345 + i) for i in range(nblocks)]
+    kernels.fill_random_batch(descs.data_ptr(), nblocks, 100, 42, 0, stream_handle(),
+                              total_bytes=hint * nblocks, max_block_len=hint)
+    torch.cuda.synchronize()
+    host = to_bytes(arena)
+    for i in range(nblocks):
+        assert host[i * block:(i + 1) * block] == oracle_lib.fill_random_ctr(block, 100, 42, i)
+
+
 def test_large_window_round_trip_properties(cuda_device):
     """BASELINE-sized blocks (1 MiB x 1024 = 1 GiB window), checked through size-independent
     properties: fill -> verify is clean; one flipped byte anywhere is found at exactly that

@@ -19,7 +19,6 @@
 
 #define ELB_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
 #define ELB_MKDIR_MODE (S_IRWXU | S_IRWXG | S_IRWXO)
-#define ELB_PATH_BUF_LEN 64        /* LocalWorker.cpp:62 */
 #define ELB_INTERRUPT_CHECK_INTERVAL 128 /* LocalWorker.cpp:63 */
 #define ELB_AIO_MAX_EVENTS 64
 #define ELB_AIO_MAX_WAIT_SEC 5     /* LocalWorker.cpp:60 */
@@ -1028,30 +1027,6 @@ void Worker::initPhaseOffsetPlan()
  * Metadata phases (pure syscalls, no GPU work)
  * ============================================================================================ */
 
-/* mkdir -p from the bottom up relative to dirFD (FileTk::mkdiratBottomUp, FileTk.cpp:96-125) */
-static int mkdiratBottomUp(int dirFD, const std::string& path, mode_t mode)
-{
-	int mkdirRes = mkdirat(dirFD, path.c_str(), mode);
-
-	if(!mkdirRes || (errno != ENOENT) )
-		return mkdirRes;
-
-	const size_t slashPos = path.find_last_of('/');
-
-	if( (slashPos == std::string::npos) || !slashPos)
-	{ // reached the root
-		errno = ENOENT;
-		return -1;
-	}
-
-	int mkdirParentRes = mkdiratBottomUp(dirFD, path.substr(0, slashPos), mode);
-
-	if( (mkdirParentRes == -1) && (errno != EEXIST) )
-		return mkdirParentRes;
-
-	return mkdirat(dirFD, path.c_str(), mode);
-}
-
 /* this worker's dirs and files of the tree (reference: LocalWorker::prepareCustomTreePathStores, LocalWorker.cpp:1520-1560) */
 void Worker::takeCustomTreeShare()
 {
@@ -1072,20 +1047,134 @@ void Worker::takeCustomTreeShare()
 		customTreeFiles.shuffle(cfg.treeRandomizeSeed ? (cfg.treeRandomizeSeed + rank) : 0);
 }
 
-/* LocalWorker::dirModeIterateCustomDirs (LocalWorker.cpp:2927-3010): every worker creates its
- * share of the dirs (parents first); the first worker alone removes all dirs, deepest first */
+/* ==============================================================================================
+ * Metadata phases: mkdirs / rmdirs / stat / delete / sync / dropcaches
+ *
+ * One small vocabulary instead of one hand-written loop per phase: an EntryOp is a metadata call
+ * on (base path FD, relative path), DirNamespace spells the rank-private names of directory mode,
+ * and Worker::entryOpTimed() runs one op and books it into the entries histogram. What has to
+ * equal the reference are the names (LocalWorker.cpp:2800-2830, 3064-3068), the path FD rotation
+ * (:2836), who does what (:2927-3010 custom tree dirs, :7780-7854 first worker only) and the
+ * error texts.
+ * ============================================================================================ */
+
+namespace
+{
+
+enum class EntryOp { MakeDir, MakeDirWithParents, RemoveDir, StatFile, RemoveFile };
+
+/* the names of directory mode: rank dir "r<R>", its subdirs "r<R>/d<D>", files
+ * "[r<R>/d<D>/]r<rank>-f<F>" (R = 0 with --dirsharing); dir D lives under bench path
+ * (rank + D) % numPaths */
+struct DirNamespace
+{
+	uint64_t rank;
+	uint64_t dirRank;
+	size_t numBasePaths;
+
+	DirNamespace(const Config& cfg, uint64_t rank, size_t numBasePaths) :
+		rank(rank), dirRank(cfg.doDirSharing ? 0 : rank), numBasePaths(numBasePaths) {}
+
+	std::string rankDir() const { return "r" + std::to_string(dirRank); }
+	std::string subDir(uint64_t dirIndex) const
+		{ return rankDir() + "/d" + std::to_string(dirIndex); }
+	std::string fileName(uint64_t fileIndex) const
+		{ return "r" + std::to_string(rank) + "-f" + std::to_string(fileIndex); }
+	std::string filePath(bool haveSubdirs, uint64_t dirIndex, uint64_t fileIndex) const
+		{ return haveSubdirs ? (subDir(dirIndex) + "/" + fileName(fileIndex) ) : fileName(fileIndex); }
+	size_t basePathIndex(uint64_t dirIndex) const { return (rank + dirIndex) % numBasePaths; }
+};
+
+} // namespace
+
+/* perform one metadata op; missing targets are tolerated where the caller says so */
+static void runEntryOp(EntryOp op, int baseFD, const std::string& basePath,
+	const std::string& relPath, bool tolerateMissing, const char* failTextOverride = NULL)
+{
+	int res = 0;
+	const char* failText = "";
+
+	switch(op)
+	{
+		case EntryOp::MakeDir:
+		case EntryOp::MakeDirWithParents:
+		{
+			failText = "Directory creation failed. ";
+			res = mkdirat(baseFD, relPath.c_str(), ELB_MKDIR_MODE);
+
+			if( (res == -1) && (errno == ENOENT) && (op == EntryOp::MakeDirWithParents) )
+			{ // create the missing ancestors top-down, then try again
+				for(size_t slash = relPath.find('/', 1); slash != std::string::npos;
+					slash = relPath.find('/', slash + 1) )
+					mkdirat(baseFD, relPath.substr(0, slash).c_str(), ELB_MKDIR_MODE);
+
+				res = mkdirat(baseFD, relPath.c_str(), ELB_MKDIR_MODE);
+			}
+
+			if( (res == -1) && (errno == EEXIST) )
+				res = 0;
+		} break;
+
+		case EntryOp::RemoveDir:
+			failText = "Directory deletion failed. ";
+			res = unlinkat(baseFD, relPath.c_str(), AT_REMOVEDIR);
+			break;
+
+		case EntryOp::StatFile:
+		{
+			struct stat statBuf;
+			failText = "File stat failed. ";
+			res = fstatat(baseFD, relPath.c_str(), &statBuf, 0);
+			tolerateMissing = false;
+		} break;
+
+		case EntryOp::RemoveFile:
+			failText = "File delete failed. ";
+			res = unlinkat(baseFD, relPath.c_str(), 0);
+			break;
+	}
+
+	if( (res == -1) && !(tolerateMissing && (errno == ENOENT) ) )
+		throw WorkerError(std::string(failTextOverride ? failTextOverride : failText) +
+			"Path: " + basePath + "/" + relPath + "; "
+			"SysErr: " + strerror(errno) );
+}
+
+/* one op as one entry of the phase: latency into the entries histogram, entry counted */
+void Worker::entryOpTimed(int opCode, size_t basePathIndex, const std::string& relPath,
+	bool tolerateMissing, bool countsAsEntry, const char* failTextOverride)
+{
+	const Clock::time_point startT = Clock::now();
+
+	runEntryOp( (EntryOp)opCode, shared->pathFDs[basePathIndex], cfg.paths[basePathIndex],
+		relPath, tolerateMissing, failTextOverride);
+
+	if(!countsAsEntry)
+		return;
+
+	const uint64_t elapsedUSec = elapsedUSecSince(startT);
+
+	histogramAdd(entriesLatHisto, elapsedUSec);
+	liveLatNumEntries++;
+	liveLatSumEntries += elapsedUSec;
+	atomicLiveOps.numEntriesDone++;
+}
+
+/* custom tree dirs (reference: LocalWorker::dirModeIterateCustomDirs, LocalWorker.cpp:2927-3010):
+ * every worker creates its share of the dirs, parents first; the first worker alone removes all
+ * dirs, deepest first */
 void Worker::dirModeIterateCustomDirs()
 {
-	const int benchPathFD = shared->pathFDs[0];
 	const bool isDelete = (benchPhase == ELB_PHASE_DELETEDIRS);
 	const std::vector<TreeSlice>& dirs = isDelete ? shared->customTree.getDirs() : customTreeDirs;
-	const bool thisWorkerDoesDelDirs = cfg.runAsService ?
-		(rank == 0) : (rank == cfg.rankOffset); // (service paths are shared between instances)
 
 	if(dirs.empty() )
 		return;
 
-	if(isDelete && !thisWorkerDoesDelDirs)
+	// (service paths are shared between instances, so only the global rank 0 removes there)
+	const uint64_t removerRank = cfg.runAsService ? 0 : cfg.rankOffset;
+
+	if(isDelete && (rank != removerRank) )
 	{
 		workerGotPhaseWork = false;
 		return;
@@ -1095,42 +1184,20 @@ void Worker::dirModeIterateCustomDirs()
 	{
 		checkInterruptionRequest();
 
-		const TreeSlice& elem = isDelete ? dirs[dirs.size() - 1 - i] : dirs[i];
-		const Clock::time_point ioStartT = Clock::now();
-
-		if(!isDelete)
-		{
-			int mkdirRes = mkdiratBottomUp(benchPathFD, elem.path, ELB_MKDIR_MODE);
-
-			if( (mkdirRes == -1) && (errno != EEXIST) )
-				throw WorkerError(std::string("Directory creation failed. ") +
-					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
-					"SysErr: " + strerror(errno) );
-		}
+		// (all workers of all hosts mk/del dirs in custom tree mode: missing dirs are no error)
+		if(isDelete)
+			entryOpTimed( (int)EntryOp::RemoveDir, 0, dirs[dirs.size() - 1 - i].path, true, true);
 		else
-		{ // (all workers mk/del all dirs in custom tree mode: missing dirs are no error)
-			int rmdirRes = unlinkat(benchPathFD, elem.path.c_str(), AT_REMOVEDIR);
-
-			if( (rmdirRes == -1) && (errno != ENOENT) )
-				throw WorkerError(std::string("Directory deletion failed. ") +
-					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
-					"SysErr: " + strerror(errno) );
-		}
-
-		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
-
-		histogramAdd(entriesLatHisto, ioElapsedUSec);
-		liveLatNumEntries++;
-		liveLatSumEntries += ioElapsedUSec;
-		atomicLiveOps.numEntriesDone++;
+			entryOpTimed( (int)EntryOp::MakeDirWithParents, 0, dirs[i].path, false, true);
 	}
 }
 
-/* stat / delete phases of LocalWorker::dirModeIterateCustomFiles (LocalWorker.cpp:3407-3447) */
+/* stat / delete of the worker's custom tree files (reference: LocalWorker.cpp:3407-3447) */
 void Worker::dirModeIterateCustomFilesNoIO()
 {
-	const int benchPathFD = shared->pathFDs[0];
 	const std::vector<TreeSlice>& files = customTreeFiles.slices;
+	const int opCode = (int)( (benchPhase == ELB_PHASE_STATFILES) ?
+		EntryOp::StatFile : EntryOp::RemoveFile);
 
 	if(files.empty() )
 	{
@@ -1143,42 +1210,15 @@ void Worker::dirModeIterateCustomFilesNoIO()
 		if( (i % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
 			checkInterruptionRequest();
 
-		const TreeSlice& elem = files[i];
-		const Clock::time_point ioStartT = Clock::now();
-
-		if(benchPhase == ELB_PHASE_STATFILES)
-		{
-			struct stat statBuf;
-
-			if(fstatat(benchPathFD, elem.path.c_str(), &statBuf, 0) == -1)
-				throw WorkerError(std::string("File stat failed. ") +
-					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
-					"SysErr: " + strerror(errno) );
-		}
-
-		if(benchPhase == ELB_PHASE_DELETEFILES)
-		{ // (shared files are unlinked by all their workers, so missing files are no error)
-			int unlinkRes = unlinkat(benchPathFD, elem.path.c_str(), 0);
-
-			if( (unlinkRes == -1) && (errno != ENOENT) )
-				throw WorkerError(std::string("File delete failed. ") +
-					"Path: " + cfg.paths[0] + "/" + elem.path + "; "
-					"SysErr: " + strerror(errno) );
-		}
-
-		if(!elem.coversWholeFile() )
-			continue; // entry latency and count only for fully processed entries
-
-		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
-
-		histogramAdd(entriesLatHisto, ioElapsedUSec);
-		liveLatNumEntries++;
-		liveLatSumEntries += ioElapsedUSec;
-		atomicLiveOps.numEntriesDone++;
+		/* a shared file is unlinked by each of its workers, so a missing file is no error; only
+		   fully owned files count as entries */
+		entryOpTimed(opCode, 0, files[i].path, true, files[i].coversWholeFile() );
 	}
 }
 
-void Worker::dirModeIterateDirs() // LocalWorker.cpp:2778-2912
+/* mkdirs / rmdirs of directory mode (reference: LocalWorker.cpp:2778-2912): the rank dir under
+ * every bench path, then (or before, when deleting) the numDirs subdirs spread over the paths */
+void Worker::dirModeIterateDirs()
 {
 	if(!cfg.treeFilePath.empty() )
 	{
@@ -1189,92 +1229,37 @@ void Worker::dirModeIterateDirs() // LocalWorker.cpp:2778-2912
 	if(!cfg.numDirs)
 		return;
 
-	char currentPath[ELB_PATH_BUF_LEN];
-	const uint64_t numDirs = cfg.numDirs;
-	const std::vector<int>& pathFDs = shared->pathFDs;
-	const bool ignoreDelErrors = cfg.doDirSharing ? true : cfg.ignoreDelErrors;
-	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
+	const DirNamespace names(cfg, rank, shared->pathFDs.size() );
+	const bool isCreate = (benchPhase == ELB_PHASE_CREATEDIRS);
+	const bool tolerateMissing = cfg.doDirSharing || cfg.ignoreDelErrors;
 
-	if(benchPhase == ELB_PHASE_CREATEDIRS)
+	auto forEachRankDir = [&](EntryOp op)
 	{
-		for(size_t pathFDsIndex = 0; pathFDsIndex < pathFDs.size(); pathFDsIndex++)
+		for(size_t pathIndex = 0; pathIndex < shared->pathFDs.size(); pathIndex++)
 		{
 			checkInterruptionRequest();
 
-			snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu", (size_t)workerDirRank);
-
-			int mkdirRes = mkdirat(pathFDs[pathFDsIndex], currentPath, ELB_MKDIR_MODE);
-
-			if( (mkdirRes == -1) && (errno != EEXIST) )
-				throw WorkerError(std::string("Rank directory creation failed. ") +
-					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-					"SysErr: " + strerror(errno) );
+			entryOpTimed( (int)op, pathIndex, names.rankDir(), tolerateMissing, false,
+				(op == EntryOp::MakeDir) ? "Rank directory creation failed. " : NULL);
 		}
-	}
+	};
 
-	for(uint64_t dirIndex = 0; dirIndex < numDirs; dirIndex++)
+	if(isCreate)
+		forEachRankDir(EntryOp::MakeDir);
+
+	for(uint64_t dirIndex = 0; dirIndex < cfg.numDirs; dirIndex++)
 	{
 		checkInterruptionRequest();
 
-		int printRes = snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu/d%zu",
-			(size_t)workerDirRank, (size_t)dirIndex);
-		if(printRes >= ELB_PATH_BUF_LEN)
-			throw WorkerError("mkdir path too long for static buffer. "
-				"Buffer size: " + std::to_string(ELB_PATH_BUF_LEN) + "; "
-				"dirIndex: " + std::to_string(dirIndex) + "; "
-				"workerRank: " + std::to_string(rank) );
-
-		const size_t pathFDsIndex = (rank + dirIndex) % pathFDs.size();
-
-		Clock::time_point ioStartT = Clock::now();
-
-		if(benchPhase == ELB_PHASE_CREATEDIRS)
-		{
-			int mkdirRes = mkdirat(pathFDs[pathFDsIndex], currentPath, ELB_MKDIR_MODE);
-
-			if( (mkdirRes == -1) && (errno != EEXIST) )
-				throw WorkerError(std::string("Directory creation failed. ") +
-					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-					"SysErr: " + strerror(errno) );
-		}
-
-		if(benchPhase == ELB_PHASE_DELETEDIRS)
-		{
-			int rmdirRes = unlinkat(pathFDs[pathFDsIndex], currentPath, AT_REMOVEDIR);
-
-			if( (rmdirRes == -1) && ( (errno != ENOENT) || !ignoreDelErrors) )
-				throw WorkerError(std::string("Directory deletion failed. ") +
-					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-					"SysErr: " + strerror(errno) );
-		}
-
-		const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
-
-		histogramAdd(entriesLatHisto, ioElapsedUSec);
-		liveLatNumEntries++;
-		liveLatSumEntries += ioElapsedUSec;
-		atomicLiveOps.numEntriesDone++;
+		entryOpTimed( (int)(isCreate ? EntryOp::MakeDir : EntryOp::RemoveDir),
+			names.basePathIndex(dirIndex), names.subDir(dirIndex), tolerateMissing, true);
 	}
 
-	if(benchPhase == ELB_PHASE_DELETEDIRS)
-	{
-		for(size_t pathFDsIndex = 0; pathFDsIndex < pathFDs.size(); pathFDsIndex++)
-		{
-			checkInterruptionRequest();
-
-			snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu", (size_t)workerDirRank);
-
-			int rmdirRes = unlinkat(pathFDs[pathFDsIndex], currentPath, AT_REMOVEDIR);
-
-			if( (rmdirRes == -1) && ( (errno != ENOENT) || !ignoreDelErrors) )
-				throw WorkerError(std::string("Directory deletion failed. ") +
-					"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-					"SysErr: " + strerror(errno) );
-		}
-	}
+	if(!isCreate)
+		forEachRankDir(EntryOp::RemoveDir);
 }
 
-/* stat and delete phases of dirModeIterateFiles (LocalWorker.cpp:3193-3243) */
+/* stat and delete phases of directory mode (reference: LocalWorker.cpp:3193-3243) */
 void Worker::dirModeIterateFilesNoIO()
 {
 	if(!cfg.treeFilePath.empty() )
@@ -1283,74 +1268,37 @@ void Worker::dirModeIterateFilesNoIO()
 		return;
 	}
 
-	char currentPath[ELB_PATH_BUF_LEN];
+	const DirNamespace names(cfg, rank, shared->pathFDs.size() );
 	const bool haveSubdirs = (cfg.numDirs > 0);
 	const uint64_t numDirs = haveSubdirs ? cfg.numDirs : 1;
-	const std::vector<int>& pathFDs = shared->pathFDs;
-	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
+	const int opCode = (int)( (benchPhase == ELB_PHASE_STATFILES) ?
+		EntryOp::StatFile : EntryOp::RemoveFile);
 
 	for(uint64_t dirIndex = 0; dirIndex < numDirs; dirIndex++)
-	{
 		for(uint64_t fileIndex = 0; fileIndex < cfg.numFiles; fileIndex++)
 		{
 			if( (fileIndex % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
 				checkInterruptionRequest();
 
-			if(haveSubdirs)
-				snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu/d%zu/r%zu-f%zu",
-					(size_t)workerDirRank, (size_t)dirIndex, (size_t)rank, (size_t)fileIndex);
-			else
-				snprintf(currentPath, ELB_PATH_BUF_LEN, "r%zu-f%zu", (size_t)rank,
-					(size_t)fileIndex);
-
-			const size_t pathFDsIndex = (rank + dirIndex) % pathFDs.size();
-
-			Clock::time_point ioStartT = Clock::now();
-
-			if(benchPhase == ELB_PHASE_STATFILES)
-			{
-				struct stat statBuf;
-
-				if(fstatat(pathFDs[pathFDsIndex], currentPath, &statBuf, 0) == -1)
-					throw WorkerError(std::string("File stat failed. ") +
-						"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-						"SysErr: " + strerror(errno) );
-			}
-
-			if(benchPhase == ELB_PHASE_DELETEFILES)
-			{
-				int unlinkRes = unlinkat(pathFDs[pathFDsIndex], currentPath, 0);
-
-				if( (unlinkRes == -1) && (!cfg.ignoreDelErrors || (errno != ENOENT) ) )
-					throw WorkerError(std::string("File delete failed. ") +
-						"Path: " + cfg.paths[pathFDsIndex] + "/" + currentPath + "; "
-						"SysErr: " + strerror(errno) );
-			}
-
-			const uint64_t ioElapsedUSec = elapsedUSecSince(ioStartT);
-
-			histogramAdd(entriesLatHisto, ioElapsedUSec);
-			liveLatNumEntries++;
-			liveLatSumEntries += ioElapsedUSec;
-			atomicLiveOps.numEntriesDone++;
+			entryOpTimed(opCode, names.basePathIndex(dirIndex),
+				names.filePath(haveSubdirs, dirIndex, fileIndex), cfg.ignoreDelErrors, true);
 		}
-	}
 }
 
-void Worker::fileModeDeleteFiles() // LocalWorker.cpp:3736-3767
+/* delete phase of file mode (reference: LocalWorker.cpp:3736-3767): every worker walks all files
+ * starting at its own rank; whoever comes first unlinks */
+void Worker::fileModeDeleteFiles()
 {
 	const size_t numFiles = cfg.paths.size();
 
-	for(size_t fileIndex = 0; fileIndex < numFiles; fileIndex++)
+	for(size_t i = 0; i < numFiles; i++)
 	{
-		if( (fileIndex % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
+		if( (i % ELB_INTERRUPT_CHECK_INTERVAL) == 0)
 			checkInterruptionRequest();
 
-		const std::string& path = cfg.paths[ (rank + fileIndex) % numFiles];
+		const std::string& path = cfg.paths[ (rank + i) % numFiles];
 
-		int unlinkRes = unlink(path.c_str() );
-
-		if( (unlinkRes == -1) && (errno != ENOENT) )
+		if( (unlink(path.c_str() ) == -1) && (errno != ENOENT) )
 			throw WorkerError(std::string("File delete failed. ") +
 				"Path: " + path + "; "
 				"SysErr: " + strerror(errno) );
@@ -1359,7 +1307,8 @@ void Worker::fileModeDeleteFiles() // LocalWorker.cpp:3736-3767
 	}
 }
 
-void Worker::anyModeSync() // LocalWorker.cpp:7780-7812
+/* --sync / --dropcache (reference: LocalWorker.cpp:7780-7854): work of the first local worker */
+void Worker::anyModeSync()
 {
 	if(rank != cfg.rankOffset)
 	{
@@ -1367,42 +1316,42 @@ void Worker::anyModeSync() // LocalWorker.cpp:7780-7812
 		return;
 	}
 
-	const std::vector<int>& pathFDs = shared->pathFDs;
+	const size_t numPaths = shared->pathFDs.size();
 
-	for(size_t i = 0; i < pathFDs.size(); i++)
+	for(size_t i = 0; i < numPaths; i++)
 	{
-		const size_t currentIdx = (i + rank) % pathFDs.size();
+		const size_t pathIndex = (rank + i) % numPaths;
 
-		if(syncfs(pathFDs[currentIdx] ) == -1)
+		if(syncfs(shared->pathFDs[pathIndex] ) == -1)
 			throw WorkerError(std::string("Cache sync failed. ") +
-				"Path: " + cfg.paths[currentIdx] + "; "
+				"Path: " + cfg.paths[pathIndex] + "; "
 				"SysErr: " + strerror(errno) );
 	}
 }
 
-void Worker::anyModeDropCaches() // LocalWorker.cpp:7822-7854
+void Worker::anyModeDropCaches()
 {
+	static const char dropCachesPath[] = "/proc/sys/vm/drop_caches";
+
 	if(rank != cfg.rankOffset)
 	{
 		workerGotPhaseWork = false;
 		return;
 	}
 
-	const char* dropCachesPath = "/proc/sys/vm/drop_caches";
-
-	int fd = open(dropCachesPath, O_WRONLY);
+	const int fd = open(dropCachesPath, O_WRONLY);
 
 	if(fd == -1)
 		throw WorkerError(std::string("Opening virtual drop_caches file failed. ") +
 			"Path: " + dropCachesPath + "; "
 			"SysErr: " + strerror(errno) );
 
-	ssize_t writeRes = write(fd, "3", 1);
-	int writeErrno = errno;
+	const bool writeFailed = (write(fd, "3", 1) == -1);
+	const int writeErrno = errno;
 
 	close(fd);
 
-	if(writeRes == -1)
+	if(writeFailed)
 		throw WorkerError(std::string("Writing to cache drop command file failed. ") +
 			"Path: " + dropCachesPath + "; "
 			"SysErr: " + strerror(writeErrno) );
@@ -2152,10 +2101,9 @@ void Worker::throwIOError(const BlockRef& block, bool isRead, ssize_t ioRes, int
 /* dirModeOpenAndPrepFile (LocalWorker.cpp:7097-7161) with getDirModeOpenFlags (:7062-7082) */
 void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 {
-	char relativePath[ELB_PATH_BUF_LEN];
-	const bool haveSubdirs = (cfg.numDirs > 0);
-	const uint64_t workerDirRank = cfg.doDirSharing ? 0 : rank;
-	int printRes;
+	const DirNamespace names(cfg, rank, shared->pathFDs.size() );
+	std::string relativePath;
+	size_t pathFDsIndex = 0;
 	uint64_t fileSize = cfg.fileSize; // for --trunctosize / --preallocfile
 
 	dirModeCountsEntry = true;
@@ -2164,29 +2112,17 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 	{ // custom tree: the path comes from the tree file, the size is the entry's
 		const TreeSlice& elem = customTreeFiles.slices[block.fileIndex];
 
-		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "%s", elem.path.c_str() );
+		relativePath = elem.path;
 		fileSize = elem.totalLen;
 
 		// entry latency and count are only meaningful for fully processed entries (:3434-3447)
-		dirModeCountsEntry = (elem.totalLen == elem.rangeLen);
+		dirModeCountsEntry = elem.coversWholeFile();
 	}
 	else
-	if(haveSubdirs)
-		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "r%zu/d%zu/r%zu-f%zu",
-			(size_t)workerDirRank, (size_t)block.dirIndex, (size_t)rank, (size_t)block.fileIndex);
-	else
-		printRes = snprintf(relativePath, ELB_PATH_BUF_LEN, "r%zu-f%zu", (size_t)rank,
-			(size_t)block.fileIndex);
-
-	if(printRes >= ELB_PATH_BUF_LEN)
-		throw WorkerError("file path too long for static buffer. "
-			"Buffer size: " + std::to_string(ELB_PATH_BUF_LEN) + "; "
-			"workerRank: " + std::to_string(rank) + "; "
-			"dirIndex: " + std::to_string(block.dirIndex) + "; "
-			"fileIndex: " + std::to_string(block.fileIndex) );
-
-	const size_t pathFDsIndex = block.isTreeElem ?
-		0 : ( (rank + block.dirIndex) % shared->pathFDs.size() );
+	{
+		relativePath = names.filePath(cfg.numDirs > 0, block.dirIndex, block.fileIndex);
+		pathFDsIndex = names.basePathIndex(block.dirIndex);
+	}
 
 	dirModeCurrentPath = cfg.paths[pathFDsIndex] + "/" + relativePath;
 
@@ -2206,7 +2142,8 @@ void Worker::dirModeOpenFile(const BlockRef& block, bool isRead)
 
 	dirModeFileStartT = Clock::now();
 
-	dirModeFD = openat(shared->pathFDs[pathFDsIndex], relativePath, openFlags, ELB_MKFILE_MODE);
+	dirModeFD = openat(shared->pathFDs[pathFDsIndex], relativePath.c_str(), openFlags,
+		ELB_MKFILE_MODE);
 
 	if(dirModeFD == -1)
 		throw WorkerError(std::string("File open failed. ") +

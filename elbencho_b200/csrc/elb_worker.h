@@ -238,6 +238,8 @@ class Worker
 		void fadviseFile(int fd, const std::string& path);             // FileTk::fadvise
 		void takeCustomTreeShare(); // LocalWorker.cpp:1520-1560
 		void dirModeIterateCustomDirs();    // LocalWorker.cpp:2927-3010
+		void entryOpTimed(int opCode, size_t basePathIndex, const std::string& relPath,
+			bool tolerateMissing, bool countsAsEntry, const char* failTextOverride = NULL);
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470
 		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase
 		void rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)

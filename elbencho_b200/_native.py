@@ -90,6 +90,10 @@ class Cfg(ctypes.Structure):
         ("fadviseFlags", c_u32),
         ("doStatInline", ctypes.c_int32),
         ("noDirectIOCheck", ctypes.c_int32),
+        ("stagingEngine", ctypes.c_int32),
+        ("noGPUNumaBinding", ctypes.c_int32),
+        ("useNoFDSharing", ctypes.c_int32),
+        ("reserved5", ctypes.c_int32),
     ]
 
 
@@ -178,6 +182,15 @@ SIGNATURES = {
                                                       _VP]),
     "elb_fill_random_batch_sized": (ctypes.c_int, [_VP, c_u32, ctypes.c_uint, c_u64,
                                                     ctypes.c_int, _VP, c_u64, c_u64, _VP]),
+    "elb_fill_pattern_staged": (ctypes.c_int, [_VP, c_u32, c_u64, ctypes.c_int64, _VP, c_u64,
+                                               c_u64, _VP]),
+    "elb_fill_random_staged": (ctypes.c_int, [_VP, c_u32, ctypes.c_uint, c_u64, ctypes.c_int,
+                                              ctypes.c_int64, _VP, c_u64, c_u64, _VP]),
+    "elb_verify_pattern_staged": (ctypes.c_int, [_VP, c_u32, c_u64, ctypes.c_int64, _VP, _VP,
+                                                 _VP, _VP, c_u64, c_u64, _VP]),
+    "elb_stage_copy": (ctypes.c_int, [_VP, c_u32, ctypes.c_int, ctypes.c_int64, c_u64, c_u64,
+                                      _VP]),
+    "elb_verify_results_init": (ctypes.c_int, [_VP, c_u32, _VP]),
     "elb_num_kernel_launches": (c_u64, []),
     "elb_last_error": (ctypes.c_char_p, []),
     "elb_abi_version": (ctypes.c_int, []),

@@ -153,6 +153,84 @@ int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, 
 		maxBlockLen, (cudaStream_t)stream);
 }
 
+int elb_fill_pattern_staged(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	int64_t hostDelta, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream)
+{
+	if(numDescs && !descs)
+	{
+		elb_set_last_error("elb_fill_pattern_staged: NULL descriptor array");
+		return -1;
+	}
+
+	elb_stage_args stage;
+	stage.hostDelta = hostDelta;
+
+	return elb_launch_fill_pattern(descs, NULL, numDescs, salt, devCounters, totalBytes,
+		maxBlockLen, (cudaStream_t)stream, &stage);
+}
+
+int elb_fill_random_staged(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
+	uint64_t seed, int randAlgo, int64_t hostDelta, uint64_t* devCounters, uint64_t totalBytes,
+	uint64_t maxBlockLen, void* stream)
+{
+	if(checkRandArgs(pct, randAlgo) )
+		return -1;
+
+	if(numDescs && !descs)
+	{
+		elb_set_last_error("elb_fill_random_staged: NULL descriptor array");
+		return -1;
+	}
+
+	elb_stage_args stage;
+	stage.hostDelta = hostDelta;
+
+	return elb_launch_fill_random(descs, NULL, numDescs, pct, seed, devCounters, totalBytes,
+		maxBlockLen, (cudaStream_t)stream, &stage);
+}
+
+int elb_verify_pattern_staged(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	int64_t hostDelta, elb_verify_result* devResults, elb_verify_result* hostResults,
+	unsigned* devDoneTicket, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream)
+{
+	if(numDescs && (!descs || !devResults) )
+	{
+		elb_set_last_error("elb_verify_pattern_staged: NULL descriptor or result array");
+		return -1;
+	}
+
+	elb_stage_args stage;
+	stage.hostDelta = hostDelta;
+	stage.hostResults = hostResults;
+	stage.doneTicket = devDoneTicket;
+
+	return elb_launch_verify_pattern(descs, NULL, numDescs, salt, devResults, devCounters,
+		totalBytes, maxBlockLen, false /*initResults*/, (cudaStream_t)stream, &stage);
+}
+
+int elb_stage_copy(const elb_block_desc* descs, uint32_t numDescs, int hostToDevice,
+	int64_t hostDelta, uint64_t totalBytes, uint64_t maxBlockLen, void* stream)
+{
+	if(!numDescs)
+		return 0;
+
+	return elb_launch_stage_copy(descs, numDescs, hostToDevice != 0, hostDelta, totalBytes,
+		maxBlockLen, (cudaStream_t)stream);
+}
+
+int elb_verify_results_init(elb_verify_result* devResults, uint32_t numDescs, void* stream)
+{
+	if(numDescs && !devResults)
+	{
+		elb_set_last_error("elb_verify_results_init: NULL result array");
+		return -1;
+	}
+
+	return elb_launch_verify_init(devResults, numDescs, (cudaStream_t)stream);
+}
+
 int elb_fill_pattern_batch(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
 	uint64_t* devCounters, void* stream)
 {

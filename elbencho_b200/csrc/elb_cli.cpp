@@ -101,7 +101,17 @@ static const OptDef optDefs[] =
 	{"gds", 0, Opt_FLAG, "Use GPUDirect Storage: shortcut for --direct --cufile --gdsbufreg."},
 	{"batchblocks", 0, Opt_U64, "Blocks per pipeline batch (one kernel launch / staged copy). [b200]"},
 	{"numbatches", 0, Opt_U64, "Pipeline batches in flight per thread. [b200]"},
-	{"writegate", 0, Opt_FLAG, "Queue buffered writers of one file in user space. [b200]"},
+	{"writegate", 0, Opt_FLAG, "Always queue buffered writers of one file in a FIFO gate in user "
+		"space (default: when several threads write one file). [b200]"},
+	{"nowritegate", 0, Opt_FLAG, "Never queue buffered writers of one file in user space. [b200]"},
+	{"staging", 0, Opt_STR, "Who moves blocks between the pinned host ring and GPU memory: "
+		"\"kernel\" (fill/verify kernels over PCIe, one launch per batch; default) or "
+		"\"copyengine\" (cudaMemcpyAsync + kernel). [b200]"},
+	{"nogpunuma", 0, Opt_FLAG, "Do not bind worker threads to the NUMA node of their GPU "
+		"(default: bound unless --zones or --cores are given). [b200]"},
+	{"nofdsharing", 0, Opt_FLAG, "If benchmark path is a file or block device, let each worker "
+		"thread open the given file/bdev separately instead of sharing the same file descriptor "
+		"among all threads."},
 	// results
 	{"lat", 0, Opt_FLAG, "Show minimum, average and maximum latency for I/Os and entries."},
 	{"latpercent", 0, Opt_FLAG, "Show latency percentiles."},
@@ -578,6 +588,10 @@ ProgArgs::ProgArgs(int argc, char** argv)
 	num("batchblocks", pipelineBatchBlocks);
 	num("numbatches", pipelineNumBatches);
 	serializeBufferedWrites = flag("writegate");
+	neverSerializeBufferedWrites = flag("nowritegate");
+	str("staging", stagingEngineStr);
+	noGPUNumaBinding = flag("nogpunuma");
+	useNoFDSharing = flag("nofdsharing");
 
 	showLatency = flag("lat");
 	showLatencyPercentiles = flag("latpercent");
@@ -1007,7 +1021,21 @@ void ProgArgs::toABIConfig(ABIConfig& out) const
 	cfg.ignoreDelErrors = ignoreDelErrors;
 	cfg.runAsService = runAsService;
 	cfg.verifyCollectAll = 0;
-	cfg.serializeBufferedWrites = serializeBufferedWrites;
+	cfg.serializeBufferedWrites = neverSerializeBufferedWrites ? ELB_WRITEGATE_OFF :
+		(serializeBufferedWrites ? ELB_WRITEGATE_ON : ELB_WRITEGATE_AUTO);
+	cfg.noGPUNumaBinding = noGPUNumaBinding;
+	cfg.useNoFDSharing = useNoFDSharing;
+
+	if(stagingEngineStr.empty() || (stagingEngineStr == "auto") )
+		cfg.stagingEngine = ELB_STAGING_AUTO;
+	else
+	if( (stagingEngineStr == "kernel") || (stagingEngineStr == "sm") )
+		cfg.stagingEngine = ELB_STAGING_KERNEL;
+	else
+	if( (stagingEngineStr == "copyengine") || (stagingEngineStr == "ce") )
+		cfg.stagingEngine = ELB_STAGING_COPYENGINE;
+	else
+		throw ProgError("Invalid staging engine: " + stagingEngineStr);
 	cfg.numRWMixReadThreads = (uint32_t)numRWMixReadThreads;
 	cfg.flockType = (uint32_t)flockType;
 	cfg.fadviseFlags = (uint32_t)fadviseFlags;

@@ -95,7 +95,11 @@ class ProgArgs
 		bool ignoreDelErrors{false};
 		uint64_t pipelineBatchBlocks{0};
 		uint64_t pipelineNumBatches{0};
-		bool serializeBufferedWrites{false};
+		bool serializeBufferedWrites{false};      // --writegate
+		bool neverSerializeBufferedWrites{false}; // --nowritegate
+		std::string stagingEngineStr;             // --staging
+		bool noGPUNumaBinding{false};             // --nogpunuma
+		bool useNoFDSharing{false};               // --nofdsharing
 		std::string flockTypeStr;       // --flock
 		std::string fadviseFlagsStr;    // --fadv
 		uint64_t flockType{0};

@@ -112,6 +112,16 @@ Config Config::fromABI(const elb_cfg* cfg)
 	c.fadviseFlags = cfg->fadviseFlags;
 	c.doStatInline = (cfg->doStatInline != 0);
 	c.noDirectIOCheck = (cfg->noDirectIOCheck != 0);
+	c.stagingEngine = cfg->stagingEngine;
+	c.noGPUNumaBinding = (cfg->noGPUNumaBinding != 0);
+	c.useNoFDSharing = (cfg->useNoFDSharing != 0);
+
+	if( (c.stagingEngine < ELB_STAGING_AUTO) || (c.stagingEngine > ELB_STAGING_COPYENGINE) )
+		throw WorkerError("Invalid staging engine: " + std::to_string(c.stagingEngine) );
+
+	if( (c.serializeBufferedWrites < ELB_WRITEGATE_AUTO) ||
+		(c.serializeBufferedWrites > ELB_WRITEGATE_OFF) )
+		throw WorkerError("Invalid write gate mode: " + std::to_string(c.serializeBufferedWrites) );
 
 	if(c.flockType > 2)
 		throw WorkerError("Invalid file lock type: " + std::to_string(c.flockType) );

@@ -70,6 +70,7 @@ CuFileApi::CuFileApi()
 	loadSymbol(libHandle, "cuFileBatchIOSubmit", BatchIOSubmit, libPath);
 	loadSymbol(libHandle, "cuFileBatchIOGetStatus", BatchIOGetStatus, libPath);
 	loadSymbol(libHandle, "cuFileBatchIODestroy", BatchIODestroy, libPath);
+	BatchIOCancel = (CUfileError_t (*)(CUfileBatchHandle_t) )dlsym(libHandle, "cuFileBatchIOCancel");
 }
 
 CuFileApi& CuFileApi::get()

@@ -54,6 +54,7 @@ class CuFileApi
 		CUfileError_t (*BatchIOGetStatus)(CUfileBatchHandle_t batchIdp, unsigned minNr,
 			unsigned* nr, CUfileIOEvents_t* iocbp, struct timespec* timeout);
 		void (*BatchIODestroy)(CUfileBatchHandle_t batchIdp);
+		CUfileError_t (*BatchIOCancel)(CUfileBatchHandle_t batchIdp); // (may be NULL in old libs)
 
 		const std::string& getLibPath() const { return libPath; }
 

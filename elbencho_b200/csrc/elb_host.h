@@ -10,7 +10,10 @@
 #ifndef ELB_HOST_H_
 #define ELB_HOST_H_
 
+#include <linux/futex.h>
 #include <stdint.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -765,6 +768,120 @@ inline void liveOpsAdd(elb_liveops& dst, const elb_liveops& src)
 	dst.numIOPSDone += src.numIOPSDone;
 }
 
+/**
+ * FIFO gate in front of the buffered writes to one file (elb_cfg::serializeBufferedWrites).
+ *
+ * Buffered writes to one inode are serialised by the kernel on the inode lock; what a writer can
+ * win is a fast hand-over. Tickets give FIFO order; the holder of the NEXT ticket spins in user
+ * space (so the hand-over costs a cache line transfer, not a wake-up), everybody further back
+ * sleeps on a futex word of its own ticket slot and is woken when it becomes next-in-line - one
+ * targeted wake-up per hand-over, which then hides behind the current holder's write.
+ */
+class FileWriteGate
+{
+	public:
+		FileWriteGate()
+		{
+			for(auto& slot : wakeSeq)
+				slot.store(0, std::memory_order_relaxed);
+		}
+
+		/* blocks until it is this caller's turn */
+		void enter()
+		{
+			const uint64_t ticket = nextTicket.fetch_add(1, std::memory_order_relaxed);
+			std::atomic<uint32_t>& mySlot = wakeSeq[ticket % NUM_SLOTS];
+
+			for(unsigned spins = 0; ; spins++)
+			{
+				const uint64_t nowServing = serving.load(std::memory_order_acquire);
+
+				if(nowServing == ticket)
+					return;
+
+				if( (ticket - nowServing) >= 2)
+				{ // not next-in-line yet: sleep until the slot of this ticket is signalled
+					const uint32_t seq = mySlot.load(std::memory_order_acquire);
+
+					if( (ticket - serving.load(std::memory_order_acquire) ) >= 2)
+						futexWait(&mySlot, seq);
+
+					continue;
+				}
+
+				if(spins < 4096)
+					cpuRelax();
+				else
+				{ // (the holder may have been descheduled: do not burn its CPU time)
+					std::this_thread::yield();
+					spins = 0;
+				}
+			}
+		}
+
+		void leave()
+		{
+			const uint64_t done = serving.fetch_add(1, std::memory_order_release);
+
+			// ticket done+1 is being served now; done+2 becomes next-in-line: wake it if it sleeps
+			std::atomic<uint32_t>& slot = wakeSeq[ (done + 2) % NUM_SLOTS];
+
+			slot.fetch_add(1, std::memory_order_release);
+
+			if(nextTicket.load(std::memory_order_relaxed) > (done + 2) )
+				futexWake(&slot);
+		}
+
+	private:
+		static const unsigned NUM_SLOTS = 256;
+
+		alignas(64) std::atomic<uint64_t> nextTicket{0};
+		alignas(64) std::atomic<uint64_t> serving{0};
+		alignas(64) std::atomic<uint32_t> wakeSeq[NUM_SLOTS];
+
+		static void cpuRelax()
+		{
+#if defined(__x86_64__) || defined(__i386__)
+			__builtin_ia32_pause();
+#else
+			std::this_thread::yield();
+#endif
+		}
+
+		static void futexWait(std::atomic<uint32_t>* word, uint32_t expected)
+		{ // (returns at once if *word != expected; spurious returns are fine, callers re-check)
+			syscall(SYS_futex, (uint32_t*)word, FUTEX_WAIT_PRIVATE, expected, NULL, NULL, 0);
+		}
+
+		static void futexWake(std::atomic<uint32_t>* word)
+		{
+			syscall(SYS_futex, (uint32_t*)word, FUTEX_WAKE_PRIVATE, INT32_MAX, NULL, NULL, 0);
+		}
+};
+
+/* scope guard of one turn at a FileWriteGate (NULL gate = no gating) */
+class FileWriteTurn
+{
+	public:
+		explicit FileWriteTurn(FileWriteGate* gate) : gate(gate)
+		{
+			if(gate)
+				gate->enter();
+		}
+
+		~FileWriteTurn()
+		{
+			if(gate)
+				gate->leave();
+		}
+
+		FileWriteTurn(const FileWriteTurn&) = delete;
+		FileWriteTurn& operator=(const FileWriteTurn&) = delete;
+
+	private:
+		FileWriteGate* gate;
+};
+
 /* ---- normalised configuration (the rules of ProgArgs::initImplicitValues/checkArgs/
  * checkPathDependentArgs that touch the hot path; ProgArgs.cpp:1041-1671) ---- */
 struct Config
@@ -824,7 +941,10 @@ struct Config
 	bool ignoreDelErrors{false};
 	bool runAsService{false};
 	bool verifyCollectAll{false};
-	bool serializeBufferedWrites{false};
+	int serializeBufferedWrites{ELB_WRITEGATE_AUTO};
+	int stagingEngine{ELB_STAGING_AUTO};
+	bool noGPUNumaBinding{false};
+	bool useNoFDSharing{false}; // --nofdsharing
 
 	/* @throw WorkerError on invalid combinations */
 	static Config fromABI(const elb_cfg* cfg);

@@ -12,6 +12,22 @@
  * multiple of the SM count that walks "tiles" of the whole in-flight window (many blocks per
  * launch) so that one launch covers tens to hundreds of MiB.
  *
+ * Staged forms (the worker's default staging engine): the same kernels also move the block between
+ * the pinned host ring and the device ring while they work on it, so that a batch's whole GPU
+ * stage is ONE launch and no copy engine is involved:
+ *   fill + stage-out   : every generated vector is stored to the device slot AND to the host slot
+ *                        (zero-copy stores over PCIe)
+ *   stage-in + verify  : every vector is loaded from the host slot (zero-copy load over PCIe),
+ *                        stored to the device slot and compared
+ *   stage copy         : plain slot copy host->device / device->host for runs without --verify /
+ *                        fill
+ * The host slot of a block is at (device address + hostDelta); both rings have the same layout, so
+ * alignment and tile geometry are the same on both sides. Descriptors are read straight from
+ * pinned host memory, and the last CTA of a verify launch (device-side ticket) publishes the
+ * per-block results to pinned host memory and re-arms the device copies: no descriptor copy, no
+ * result copy, no init launch. These launches are PCIe-bound (measured ~47 GiB/s per direction for
+ * 1 MiB blocks, profiles/r02_hostpath_exploration.jsonl), the resident forms are HBM-bound.
+ *
  * One launch processes an array of block descriptors {devPtr, len, fileOffset, blockCounter}.
  * Tiles are ELB_TILE_BYTES slices of a block's 32-byte-aligned body; unaligned head/tail bytes
  * (device address not 32-byte aligned, or odd lengths) are handled byte-wise by tile 0 of the
@@ -190,8 +206,9 @@ __device__ __forceinline__ BlockGeom make_geom(const elb_block_desc& desc)
 
 /* ---- fill ------------------------------------------------------------------------------- */
 
-template<bool FAST, class Gen>
-__device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, uint64_t tileIdx)
+template<bool FAST, bool STAGED, class Gen>
+__device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, uint64_t tileIdx,
+	int64_t hostDelta)
 {
 	const uint64_t tileStart = tileIdx * ELB_TILE_BYTES; // within body
 	uint8_t* bodyPtr = g.ptr + g.headLen;
@@ -204,7 +221,10 @@ __device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, ui
 			const uint64_t bodyOff = tileStart +
 				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
 			const uint64_t pos = g.headLen + bodyOff;
-			st_na_256(bodyPtr + bodyOff, gen.template vec32<FAST>(pos) );
+			const u64x4 v = gen.template vec32<FAST>(pos);
+			st_na_256(bodyPtr + bodyOff, v);
+			if(STAGED)
+				st_na_256(bodyPtr + hostDelta + bodyOff, v);
 		}
 	}
 	else
@@ -217,7 +237,10 @@ __device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, ui
 			if(bodyOff < g.bodyLen)
 			{
 				const uint64_t pos = g.headLen + bodyOff;
-				st_na_256(bodyPtr + bodyOff, gen.template vec32<FAST>(pos) );
+				const u64x4 v = gen.template vec32<FAST>(pos);
+				st_na_256(bodyPtr + bodyOff, v);
+				if(STAGED)
+					st_na_256(bodyPtr + hostDelta + bodyOff, v);
 			}
 		}
 	}
@@ -225,11 +248,71 @@ __device__ __forceinline__ void fill_tile(const BlockGeom& g, const Gen& gen, ui
 	if(!tileIdx && (g.headLen | g.tailLen) )
 	{ // unaligned head/tail bytes (at most 31 each)
 		if(threadIdx.x < g.headLen)
-			g.ptr[threadIdx.x] = gen.byte(threadIdx.x);
+		{
+			const uint8_t b = gen.byte(threadIdx.x);
+			g.ptr[threadIdx.x] = b;
+			if(STAGED)
+				g.ptr[hostDelta + (int64_t)threadIdx.x] = b;
+		}
 
 		const uint64_t tailStart = g.headLen + g.bodyLen;
 		if(threadIdx.x < g.tailLen)
-			g.ptr[tailStart + threadIdx.x] = gen.byte(tailStart + threadIdx.x);
+		{
+			const uint8_t b = gen.byte(tailStart + threadIdx.x);
+			g.ptr[tailStart + threadIdx.x] = b;
+			if(STAGED)
+				g.ptr[hostDelta + (int64_t)(tailStart + threadIdx.x)] = b;
+		}
+	}
+}
+
+/* plain slot copy between the rings: IN = host slot -> device slot, else device -> host */
+template<bool IN>
+__device__ __forceinline__ void copy_tile(const BlockGeom& g, uint64_t tileIdx, int64_t hostDelta)
+{
+	const uint64_t tileStart = tileIdx * ELB_TILE_BYTES;
+	uint8_t* devBody = g.ptr + g.headLen;
+	uint8_t* hostBody = devBody + hostDelta;
+	const uint8_t* src = IN ? hostBody : devBody;
+	uint8_t* dst = IN ? devBody : hostBody;
+
+	if( (tileStart + ELB_TILE_BYTES) <= g.bodyLen)
+	{
+		u64x4 v[ELB_UNROLL];
+
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+			v[u] = ld_nc_na_256(src + tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES);
+
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+			st_na_256(dst + tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES, v[u] );
+	}
+	else
+	{
+		#pragma unroll
+		for(int u = 0; u < ELB_UNROLL; u++)
+		{
+			const uint64_t bodyOff = tileStart +
+				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
+			if(bodyOff < g.bodyLen)
+				st_na_256(dst + bodyOff, ld_nc_na_256(src + bodyOff) );
+		}
+	}
+
+	if(!tileIdx && (g.headLen | g.tailLen) )
+	{
+		const uint8_t* srcBlock = IN ? (g.ptr + hostDelta) : g.ptr;
+		uint8_t* dstBlock = IN ? g.ptr : (g.ptr + hostDelta);
+
+		if(threadIdx.x < g.headLen)
+			dstBlock[threadIdx.x] = srcBlock[threadIdx.x];
+
+		const uint64_t tailStart = g.headLen + g.bodyLen;
+		if(threadIdx.x < g.tailLen)
+			dstBlock[tailStart + threadIdx.x] = srcBlock[tailStart + threadIdx.x];
 	}
 }
 
@@ -262,12 +345,13 @@ __device__ __forceinline__ void verify_vec(const u64x4& got, const u64x4& exp, u
 	}
 }
 
-template<bool FAST, class Gen>
+template<bool FAST, bool STAGED, class Gen>
 __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
-	uint64_t tileIdx, elb_verify_result* result, unsigned long long* counters)
+	uint64_t tileIdx, elb_verify_result* result, unsigned long long* counters, int64_t hostDelta)
 {
 	const uint64_t tileStart = tileIdx * ELB_TILE_BYTES;
-	const uint8_t* bodyPtr = g.ptr + g.headLen;
+	uint8_t* devBody = g.ptr + g.headLen;
+	const uint8_t* bodyPtr = STAGED ? (devBody + hostDelta) : devBody; // where the data is read
 
 	unsigned numBad = 0;
 	uint64_t firstBad = ~0ULL;
@@ -290,6 +374,8 @@ __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
 			const uint64_t bodyOff = tileStart +
 				(uint64_t)(u * ELB_THREADS + threadIdx.x) * ELB_VEC_BYTES;
 			const uint64_t pos = g.headLen + bodyOff;
+			if(STAGED)
+				st_na_256(devBody + bodyOff, got[u] );
 			verify_vec(got[u], gen.template vec32<FAST>(pos), pos, numBad, firstBad);
 		}
 	}
@@ -304,6 +390,8 @@ __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
 			{
 				const uint64_t pos = g.headLen + bodyOff;
 				const u64x4 got = ld_nc_na_256(bodyPtr + bodyOff);
+				if(STAGED)
+					st_na_256(devBody + bodyOff, got);
 				verify_vec(got, gen.template vec32<FAST>(pos), pos, numBad, firstBad);
 			}
 		}
@@ -311,9 +399,14 @@ __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
 
 	if(!tileIdx && (g.headLen | g.tailLen) )
 	{
+		const uint8_t* srcBlock = STAGED ? (g.ptr + hostDelta) : g.ptr;
+
 		if(threadIdx.x < g.headLen)
 		{
-			if(g.ptr[threadIdx.x] != gen.byte(threadIdx.x) )
+			const uint8_t got = srcBlock[threadIdx.x];
+			if(STAGED)
+				g.ptr[threadIdx.x] = got;
+			if(got != gen.byte(threadIdx.x) )
 			{
 				numBad++;
 				if(threadIdx.x < firstBad)
@@ -325,7 +418,10 @@ __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
 		if(threadIdx.x < g.tailLen)
 		{
 			const uint64_t pos = tailStart + threadIdx.x;
-			if(g.ptr[pos] != gen.byte(pos) )
+			const uint8_t got = srcBlock[pos];
+			if(STAGED)
+				g.ptr[pos] = got;
+			if(got != gen.byte(pos) )
 			{
 				numBad++;
 				if(pos < firstBad)
@@ -360,7 +456,14 @@ __device__ __forceinline__ void verify_tile(const BlockGeom& g, const Gen& gen,
 
 /* ---- kernels: walk all tiles of all descriptors, round-robin over the grid --------------- */
 
-enum { MODE_FILL_PATTERN = 0, MODE_VERIFY_PATTERN = 1, MODE_FILL_RANDOM = 2 };
+/* STAGE_NONE: work on the device slot only (kernel level ABI, resident windows). STAGE_PUBLISH:
+ * device slot only, but the last CTA of a verify launch publishes the results to pinned host
+ * memory (copy-engine staging). STAGE_FULL: the kernel also moves the block between the rings. */
+enum { STAGE_NONE = 0, STAGE_PUBLISH = 1, STAGE_FULL = 2 };
+
+enum { MODE_FILL_PATTERN = 0, MODE_VERIFY_PATTERN = 1, MODE_FILL_RANDOM = 2,
+	MODE_COPY_IN = 3 /* host slot -> device slot */, MODE_COPY_OUT = 4 /* device -> host */,
+	NUM_MODES = 5 };
 
 struct KernelArgs
 {
@@ -372,6 +475,11 @@ struct KernelArgs
 	unsigned pct;          // random
 	elb_verify_result* results; // verify
 	unsigned long long* counters; // optional device counter block
+
+	// staging (see the header comment); hostDelta == 0: work on the device slot only
+	int64_t hostDelta;              // host slot address = device slot address + hostDelta
+	elb_verify_result* hostResults; // verify: pinned copy of results, written by the last CTA
+	unsigned* doneTicket;           // device counter behind the last-CTA detection (stays 0)
 };
 
 /* number of tiles of a block; same rule as make_geom() */
@@ -389,11 +497,13 @@ __device__ __forceinline__ uint64_t num_tiles_of(const elb_block_desc& desc)
 }
 
 /* process tiles [tileBegin, tileEnd) of one block */
-template<int MODE>
+template<int MODE, bool STAGED>
 __device__ __forceinline__ void process_block_tiles(const KernelArgs& args,
 	const elb_block_desc& desc, uint32_t descIdx, const BlockGeom& g, uint64_t tileBegin,
 	uint64_t tileEnd)
 {
+	const int64_t hostDelta = args.hostDelta;
+
 	if(MODE == MODE_FILL_PATTERN)
 	{
 		PatternGen gen;
@@ -402,10 +512,10 @@ __device__ __forceinline__ void process_block_tiles(const KernelArgs& args,
 
 		if(gen.canUseFast(g.headLen) )
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				fill_tile<true>(g, gen, tileIdx);
+				fill_tile<true, STAGED>(g, gen, tileIdx, hostDelta);
 		else
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				fill_tile<false>(g, gen, tileIdx);
+				fill_tile<false, STAGED>(g, gen, tileIdx, hostDelta);
 	}
 	else if(MODE == MODE_VERIFY_PATTERN)
 	{
@@ -415,12 +525,14 @@ __device__ __forceinline__ void process_block_tiles(const KernelArgs& args,
 
 		if(gen.canUseFast(g.headLen) )
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				verify_tile<true>(g, gen, tileIdx, &args.results[descIdx], args.counters);
+				verify_tile<true, STAGED>(g, gen, tileIdx, &args.results[descIdx], args.counters,
+					hostDelta);
 		else
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				verify_tile<false>(g, gen, tileIdx, &args.results[descIdx], args.counters);
+				verify_tile<false, STAGED>(g, gen, tileIdx, &args.results[descIdx], args.counters,
+					hostDelta);
 	}
-	else
+	else if(MODE == MODE_FILL_RANDOM)
 	{
 		RandomGen gen;
 		gen.blockKey = elb_rand_block_key(args.seed, desc.blockCounter);
@@ -429,11 +541,72 @@ __device__ __forceinline__ void process_block_tiles(const KernelArgs& args,
 
 		if(gen.canUseFast(g.headLen) )
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				fill_tile<true>(g, gen, tileIdx);
+				fill_tile<true, STAGED>(g, gen, tileIdx, hostDelta);
 		else
 			for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
-				fill_tile<false>(g, gen, tileIdx);
+				fill_tile<false, STAGED>(g, gen, tileIdx, hostDelta);
 	}
+	else
+	{
+		for(uint64_t tileIdx = tileBegin; tileIdx < tileEnd; tileIdx++)
+			copy_tile<MODE == MODE_COPY_IN>(g, tileIdx, hostDelta);
+	}
+}
+
+/* which device counter a mode accumulates block lengths into (-1: none) */
+template<int MODE>
+__device__ __forceinline__ int counter_slot_of()
+{
+	return (MODE == MODE_VERIFY_PATTERN) ? ELB_DEVCTR_VERIFIED_BYTES :
+		( (MODE == MODE_FILL_PATTERN) || (MODE == MODE_FILL_RANDOM) ) ? ELB_DEVCTR_FILLED_BYTES : -1;
+}
+
+/**
+ * End of a verify launch with host-visible results: every CTA (also those that found no work)
+ * takes a ticket; the one that draws the last ticket sees all result atomics of the launch, copies
+ * the per-block results to pinned host memory, re-arms the device entries that recorded a mismatch
+ * and puts the ticket counter back to 0. The host reads hostResults after the launch's event.
+ * Must be reached by all threads of the CTA.
+ */
+__device__ __forceinline__ void publish_results_if_last(const KernelArgs& args)
+{
+	__shared__ bool sIsLastCTA;
+
+	if(!args.hostResults)
+		return;
+
+	__threadfence(); // order this CTA's result atomics before its ticket
+	__syncthreads();
+
+	if(!threadIdx.x)
+		sIsLastCTA = (atomicAdd(args.doneTicket, 1u) == (gridDim.x - 1) );
+
+	__syncthreads();
+
+	if(!sIsLastCTA)
+		return;
+
+	__threadfence();
+
+	for(uint32_t i = threadIdx.x; i < args.numDescs; i += blockDim.x)
+	{
+		volatile elb_verify_result* devResult = &args.results[i];
+		elb_verify_result result;
+
+		result.numMismatchBytes = devResult->numMismatchBytes;
+		result.firstMismatchIdx = devResult->firstMismatchIdx;
+
+		args.hostResults[i] = result;
+
+		if(result.numMismatchBytes)
+		{
+			devResult->numMismatchBytes = 0;
+			devResult->firstMismatchIdx = ~0ULL;
+		}
+	}
+
+	if(!threadIdx.x)
+		*args.doneTicket = 0;
 }
 
 /* block-wide sum; result valid in all threads. sScratch: one slot per warp. */
@@ -466,10 +639,13 @@ __device__ __forceinline__ uint64_t block_sum(uint64_t val, uint64_t* sScratch)
  * (coalesced descriptor loads + a block scan per 256 descriptors), which costs a few
  * microseconds per launch instead of a serial walk over all descriptors per CTA.
  */
-template<int MODE>
+template<int MODE, int STAGE>
 __global__ void __launch_bounds__(ELB_THREADS, 4)
 elb_blocks_kernel(const KernelArgs args)
 {
+	constexpr bool STAGED = (STAGE == STAGE_FULL);
+	constexpr bool PUBLISH = (MODE == MODE_VERIFY_PATTERN) && (STAGE != STAGE_NONE);
+
 	__shared__ uint64_t sScratch[ELB_THREADS / 32];
 	__shared__ uint64_t sStartTile;
 	__shared__ uint32_t sStartDesc;
@@ -491,7 +667,11 @@ elb_blocks_kernel(const KernelArgs args)
 	const uint64_t chunkBegin = (uint64_t)blockIdx.x * chunkTiles;
 
 	if(chunkBegin >= totalTiles)
-		return; // (uniform for the whole CTA)
+	{ // (uniform for the whole CTA)
+		if(PUBLISH)
+			publish_results_if_last(args);
+		return;
+	}
 
 	const uint64_t chunkEnd = (chunkBegin + chunkTiles < totalTiles) ?
 		(chunkBegin + chunkTiles) : totalTiles;
@@ -569,13 +749,11 @@ elb_blocks_kernel(const KernelArgs args)
 
 		if(tileIdx < tileEnd)
 		{
-			process_block_tiles<MODE>(args, desc, descIdx, g, tileIdx, tileEnd);
+			process_block_tiles<MODE, STAGED>(args, desc, descIdx, g, tileIdx, tileEnd);
 
 			// device-resident stats: one atomic per block, by the CTA that owns its first tile
-			if(args.counters && !tileIdx && !threadIdx.x)
-				atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
-					ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
-					(unsigned long long)g.len);
+			if( (counter_slot_of<MODE>() >= 0) && args.counters && !tileIdx && !threadIdx.x)
+				atomicAdd(&args.counters[counter_slot_of<MODE>()], (unsigned long long)g.len);
 
 			tilesLeft -= (tileEnd - tileIdx);
 		}
@@ -583,6 +761,9 @@ elb_blocks_kernel(const KernelArgs args)
 		descIdx++;
 		tileIdx = 0;
 	}
+
+	if(PUBLISH)
+		publish_results_if_last(args);
 }
 
 /**
@@ -595,11 +776,14 @@ elb_blocks_kernel(const KernelArgs args)
  * measured write-only: 6.2 TB/s static vs 7.5 TB/s dynamic (profiles/, fill_variants2).
  * CTAs past the end of a shorter block exit immediately.
  */
-template<int MODE>
+template<int MODE, int STAGE>
 __global__ void __launch_bounds__(ELB_THREADS, 4)
 elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
 	const uint32_t tilesPerCTA)
 {
+	constexpr bool STAGED = (STAGE == STAGE_FULL);
+	constexpr bool PUBLISH = (MODE == MODE_VERIFY_PATTERN) && (STAGE != STAGE_NONE);
+
 	const uint32_t descIdx = blockIdx.x / ctasPerBlock;
 	const uint32_t ctaInBlock = blockIdx.x - descIdx * ctasPerBlock;
 	const uint64_t tileIdx = (uint64_t)ctaInBlock * tilesPerCTA;
@@ -608,20 +792,25 @@ elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
 	const BlockGeom g = make_geom(desc);
 
 	if(tileIdx >= g.numTiles)
-		return; // (uniform for the whole CTA)
+	{ // (uniform for the whole CTA)
+		if(PUBLISH)
+			publish_results_if_last(args);
+		return;
+	}
 
 	/* the launch shape comes from a size HINT: a block that is longer than the hint said has more
 	   tiles than ctasPerBlock CTAs cover, so the last CTA of a block takes all that remain */
 	const uint64_t tileEnd = ( (ctaInBlock + 1 == ctasPerBlock) ||
 		(tileIdx + tilesPerCTA >= g.numTiles) ) ? g.numTiles : (tileIdx + tilesPerCTA);
 
-	process_block_tiles<MODE>(args, desc, descIdx, g, tileIdx, tileEnd);
+	process_block_tiles<MODE, STAGED>(args, desc, descIdx, g, tileIdx, tileEnd);
 
 	// device-resident stats: one atomic per block, by the CTA that owns its first tile
-	if(args.counters && !tileIdx && !threadIdx.x)
-		atomicAdd(&args.counters[(MODE == MODE_VERIFY_PATTERN) ?
-			ELB_DEVCTR_VERIFIED_BYTES : ELB_DEVCTR_FILLED_BYTES],
-			(unsigned long long)g.len);
+	if( (counter_slot_of<MODE>() >= 0) && args.counters && !tileIdx && !threadIdx.x)
+		atomicAdd(&args.counters[counter_slot_of<MODE>()], (unsigned long long)g.len);
+
+	if(PUBLISH)
+		publish_results_if_last(args);
 }
 
 __global__ void elb_verify_init_kernel(elb_verify_result* results, uint32_t numDescs)
@@ -649,10 +838,10 @@ void elb_set_last_error(const std::string& msg)
 struct DeviceLaunchInfo
 {
 	int numSMs{0};
-	int ctasPerSM[3]{0, 0, 0};
+	int ctasPerSM[NUM_MODES]{0, 0, 0, 0, 0};
 	/* 32 KiB tiles per CTA of the hardware-scheduled kernel; 0 = always use the persistent
 	   kernel for this mode. Tuning knob: ELB_TILES_PER_CTA="fill,verify,random". */
-	uint32_t tilesPerCTA[3]{1, 2, 8}; // measured best on B200 (profiles/: sweep_tiles)
+	uint32_t tilesPerCTA[NUM_MODES]{1, 2, 8, 2, 2}; // measured best on B200 (profiles/: sweep_tiles)
 };
 
 static DeviceLaunchInfo gDevInfo[ELB_MAX_DEVICES];
@@ -662,7 +851,7 @@ template<int MODE>
 static int queryOccupancy()
 {
 	int numBlocks = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&numBlocks, elb_blocks_kernel<MODE>,
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&numBlocks, elb_blocks_kernel<MODE, STAGE_NONE>,
 		ELB_THREADS, 0);
 	return (numBlocks > 0) ? numBlocks : 1;
 }
@@ -684,6 +873,8 @@ static const DeviceLaunchInfo* getDeviceLaunchInfo()
 		gDevInfo[dev].ctasPerSM[MODE_FILL_PATTERN] = queryOccupancy<MODE_FILL_PATTERN>();
 		gDevInfo[dev].ctasPerSM[MODE_VERIFY_PATTERN] = queryOccupancy<MODE_VERIFY_PATTERN>();
 		gDevInfo[dev].ctasPerSM[MODE_FILL_RANDOM] = queryOccupancy<MODE_FILL_RANDOM>();
+		gDevInfo[dev].ctasPerSM[MODE_COPY_IN] = queryOccupancy<MODE_COPY_IN>();
+		gDevInfo[dev].ctasPerSM[MODE_COPY_OUT] = queryOccupancy<MODE_COPY_OUT>();
 
 		const char* tilesEnv = getenv("ELB_TILES_PER_CTA");
 		if(tilesEnv)
@@ -702,6 +893,13 @@ static const DeviceLaunchInfo* getDeviceLaunchInfo()
 	}
 
 	return &gDevInfo[dev];
+}
+
+static const char* modeName(int mode)
+{
+	static const char* names[NUM_MODES] =
+		{"fill_pattern", "verify_pattern", "fill_random", "stage_copy_in", "stage_copy_out"};
+	return names[mode];
 }
 
 static int checkLaunch(const char* what)
@@ -725,8 +923,8 @@ static int checkLaunch(const char* what)
  *    hints and blocks of (nearly) uniform size the hardware-scheduled tiled kernel is used,
  *    otherwise (ragged windows: many CTAs would find nothing to do) the persistent one.
  */
-template<int MODE>
-static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
+template<int MODE, int STAGE>
+static int launchBlocksKernelT(const KernelArgs& args, uint64_t totalBytesHint,
 	uint64_t maxBlockLenHint, cudaStream_t stream)
 {
 	if(!args.numDescs)
@@ -736,7 +934,8 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 	if(!devInfo)
 		return -1;
 
-	const uint32_t tilesPerCTA = devInfo->tilesPerCTA[MODE];
+	/* staged launches run at PCIe speed: one tile per CTA keeps the most loads in flight */
+	const uint32_t tilesPerCTA = (STAGE == STAGE_FULL) ? 1 : devInfo->tilesPerCTA[MODE];
 
 	if(maxBlockLenHint && totalBytesHint && tilesPerCTA)
 	{
@@ -747,12 +946,11 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 
 		if( (numCTAs <= 0x7fffffffULL) && (numCTAs <= (2 * neededCTAs + 1024) ) )
 		{
-			elb_blocks_tiled_kernel<MODE><<<(unsigned)numCTAs, ELB_THREADS, 0, stream>>>(args,
-				(uint32_t)ctasPerBlock, tilesPerCTA);
+			elb_blocks_tiled_kernel<MODE, STAGE><<<(unsigned)numCTAs, ELB_THREADS, 0, stream>>>(
+				args, (uint32_t)ctasPerBlock, tilesPerCTA);
 			gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
 
-			return checkLaunch( (MODE == MODE_FILL_PATTERN) ? "fill_pattern" :
-				(MODE == MODE_VERIFY_PATTERN) ? "verify_pattern" : "fill_random");
+			return checkLaunch(modeName(MODE) );
 		}
 	}
 
@@ -767,16 +965,39 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 			gridSize = maxTiles;
 	}
 
-	elb_blocks_kernel<MODE><<<(unsigned)gridSize, ELB_THREADS, 0, stream>>>(args);
+	elb_blocks_kernel<MODE, STAGE><<<(unsigned)gridSize, ELB_THREADS, 0, stream>>>(args);
 	gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
 
-	return checkLaunch( (MODE == MODE_FILL_PATTERN) ? "fill_pattern" :
-		(MODE == MODE_VERIFY_PATTERN) ? "verify_pattern" : "fill_random");
+	return checkLaunch(modeName(MODE) );
+}
+
+template<int MODE>
+static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
+	uint64_t maxBlockLenHint, cudaStream_t stream)
+{
+	if(args.hostDelta || (MODE == MODE_COPY_IN) || (MODE == MODE_COPY_OUT) )
+		return launchBlocksKernelT<MODE, STAGE_FULL>(args, totalBytesHint, maxBlockLenHint, stream);
+
+	if( (MODE == MODE_VERIFY_PATTERN) && args.hostResults)
+		return launchBlocksKernelT<MODE, STAGE_PUBLISH>(args, totalBytesHint, maxBlockLenHint,
+			stream);
+
+	return launchBlocksKernelT<MODE, STAGE_NONE>(args, totalBytesHint, maxBlockLenHint, stream);
+}
+
+static void applyStage(KernelArgs& args, const elb_stage_args* stage)
+{
+	if(!stage)
+		return;
+
+	args.hostDelta = stage->hostDelta;
+	args.hostResults = stage->hostResults;
+	args.doneTicket = stage->doneTicket;
 }
 
 int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, uint64_t* devCounters, uint64_t totalBytesHint,
-	uint64_t maxBlockLenHint, cudaStream_t stream)
+	uint64_t maxBlockLenHint, cudaStream_t stream, const elb_stage_args* stage)
 {
 	KernelArgs args{};
 	args.descs = descs;
@@ -785,6 +1006,7 @@ int elb_launch_fill_pattern(const elb_block_desc* descs, const elb_block_desc* i
 	args.numDescs = numDescs;
 	args.salt = salt;
 	args.counters = (unsigned long long*)devCounters;
+	applyStage(args, stage);
 
 	return launchBlocksKernel<MODE_FILL_PATTERN>(args, totalBytesHint, maxBlockLenHint, stream);
 }
@@ -803,14 +1025,22 @@ int elb_launch_verify_init(elb_verify_result* devResults, uint32_t numDescs,
 
 /**
  * @initResults false if the caller knows devResults still holds {0, ~0} entries (true after any
- *    launch that found no mismatch), which saves the init launch.
+ *    launch that found no mismatch, and always after a launch with stage->hostResults, which
+ *    re-arms the entries itself), which saves the init launch.
  */
 int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, uint64_t salt, elb_verify_result* devResults, uint64_t* devCounters,
-	uint64_t totalBytesHint, uint64_t maxBlockLenHint, bool initResults, cudaStream_t stream)
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, bool initResults, cudaStream_t stream,
+	const elb_stage_args* stage)
 {
 	if(!numDescs)
 		return 0;
+
+	if(stage && stage->hostResults && !stage->doneTicket)
+	{
+		elb_set_last_error("verify_pattern: host results need a device ticket counter");
+		return -1;
+	}
 
 	if(initResults && elb_launch_verify_init(devResults, numDescs, stream) )
 		return -1;
@@ -823,13 +1053,15 @@ int elb_launch_verify_pattern(const elb_block_desc* descs, const elb_block_desc*
 	args.salt = salt;
 	args.results = devResults;
 	args.counters = (unsigned long long*)devCounters;
+	applyStage(args, stage);
 
 	return launchBlocksKernel<MODE_VERIFY_PATTERN>(args, totalBytesHint, maxBlockLenHint, stream);
 }
 
 int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* inlineDesc,
 	uint32_t numDescs, unsigned pct, uint64_t seed, uint64_t* devCounters,
-	uint64_t totalBytesHint, uint64_t maxBlockLenHint, cudaStream_t stream)
+	uint64_t totalBytesHint, uint64_t maxBlockLenHint, cudaStream_t stream,
+	const elb_stage_args* stage)
 {
 	KernelArgs args{};
 	args.descs = descs;
@@ -839,8 +1071,29 @@ int elb_launch_fill_random(const elb_block_desc* descs, const elb_block_desc* in
 	args.seed = seed;
 	args.pct = pct;
 	args.counters = (unsigned long long*)devCounters;
+	applyStage(args, stage);
 
 	return launchBlocksKernel<MODE_FILL_RANDOM>(args, totalBytesHint, maxBlockLenHint, stream);
+}
+
+/* plain copy of the blocks between the rings (runs without --verify / without fill) */
+int elb_launch_stage_copy(const elb_block_desc* descs, uint32_t numDescs, bool hostToDevice,
+	int64_t hostDelta, uint64_t totalBytesHint, uint64_t maxBlockLenHint, cudaStream_t stream)
+{
+	KernelArgs args{};
+	args.descs = descs;
+	args.numDescs = numDescs;
+	args.hostDelta = hostDelta;
+
+	if(!descs || !hostDelta)
+	{
+		elb_set_last_error("stage_copy: descriptor array and host delta are required");
+		return -1;
+	}
+
+	return hostToDevice ?
+		launchBlocksKernel<MODE_COPY_IN>(args, totalBytesHint, maxBlockLenHint, stream) :
+		launchBlocksKernel<MODE_COPY_OUT>(args, totalBytesHint, maxBlockLenHint, stream);
 }
 
 /* query launch geometry of the current device now (so that no attribute/occupancy query happens

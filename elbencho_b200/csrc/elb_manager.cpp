@@ -205,7 +205,7 @@ void Manager::prepareBenchPathFDs()
 		}
 
 		shared.pathFDs.push_back(fd);
-		shared.fileWriteGates.emplace_back(new std::mutex() );
+		shared.fileWriteGates.emplace_back(new FileWriteGate() );
 
 		// --fadv on the files / block devices themselves (ProgArgs.cpp:2032)
 		if(cfg.fadviseFlags && (cfg.pathType != ELB_PATH_DIR) )

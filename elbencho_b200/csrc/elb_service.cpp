@@ -1166,6 +1166,10 @@ HttpResponse Service::handlePreparePhase(const HttpRequest& request)
 		args.pipelineBatchBlocks = recvTree.getU64("b200_batchblocks", 0);
 		args.pipelineNumBatches = recvTree.getU64("b200_numbatches", 0);
 		args.serializeBufferedWrites = recvTree.getBool("b200_writegate", false);
+		args.neverSerializeBufferedWrites = recvTree.getBool("b200_nowritegate", false);
+		args.stagingEngineStr = recvTree.getStr("b200_staging", "");
+		args.noGPUNumaBinding = recvTree.getBool("b200_nogpunuma", false);
+		args.useNoFDSharing = recvTree.getBool("nofdsharing", false);
 
 		const uint64_t numDataSetThreads = recvTree.getU64("datasetthreads", args.numThreads);
 
@@ -1791,7 +1795,7 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.put("files", args.numFiles);
 	tree.put("numservers", (uint64_t)0);
 	tree.put("threads", args.numThreads);
-	tree.putBool("nofdsharing", false);
+	tree.putBool("nofdsharing", args.useNoFDSharing);
 	tree.putBool("nodiocheck", args.noDirectIOCheck);
 	tree.putBool("opsloglock", false);
 	tree.put("opslog", "");
@@ -1858,6 +1862,9 @@ static JsonTree progArgsToServiceTree(const ProgArgs& args, size_t serviceRank, 
 	tree.put("b200_batchblocks", args.pipelineBatchBlocks);
 	tree.put("b200_numbatches", args.pipelineNumBatches);
 	tree.putBool("b200_writegate", args.serializeBufferedWrites);
+	tree.putBool("b200_nowritegate", args.neverSerializeBufferedWrites);
+	tree.put("b200_staging", args.stagingEngineStr);
+	tree.putBool("b200_nogpunuma", args.noGPUNumaBinding);
 
 	return tree;
 }

@@ -22,7 +22,9 @@
 #define ELB_INTERRUPT_CHECK_INTERVAL 128 /* LocalWorker.cpp:63 */
 #define ELB_AIO_MAX_EVENTS 64
 #define ELB_AIO_MAX_WAIT_SEC 5     /* LocalWorker.cpp:60 */
-#define ELB_DEFAULT_BATCH_BYTES (16ULL * 1024 * 1024)
+#define ELB_DEFAULT_BATCH_BYTES (1ULL * 1024 * 1024) /* cache resident, see allocRings() */
+#define ELB_DEFAULT_NUM_BATCHES 3
+#define ELB_MAX_AIO_BATCH_BYTES (4ULL * 1024 * 1024)
 #define ELB_MAX_BATCH_BLOCKS 2048
 #define ELB_SLOT_ALIGN 4096
 
@@ -618,9 +620,102 @@ static std::vector<int> parseCPUList(const std::string& listStr)
 	return cpus;
 }
 
-/* Worker::applyNumaAndCoreBinding (Worker.cpp:102-146) without libnuma: the zone's CPUs come from
- * sysfs, the memory policy goes through the set_mempolicy syscall (what numa_run_on_node_mask +
- * numa_set_membind do, NumaTk.h:95-140) */
+/* run on the CPUs of a NUMA zone and take memory from it, without libnuma: the zone's CPUs come
+ * from sysfs, the memory policy goes through the set_mempolicy syscall (what numa_run_on_node_mask
+ * + numa_set_membind do, NumaTk.h:95-140). strict = the --zones semantics (errors are fatal,
+ * MPOL_BIND); otherwise best effort with MPOL_PREFERRED. */
+void Worker::bindToNumaNode(int zoneNum, bool strict)
+{
+	const std::string cpuListPath =
+		"/sys/devices/system/node/node" + std::to_string(zoneNum) + "/cpulist";
+	std::ifstream cpuListStream(cpuListPath);
+	std::string cpuListStr;
+
+	if(!cpuListStream || !std::getline(cpuListStream, cpuListStr) )
+	{
+		if(strict)
+			throw WorkerError("Desired NUMA zone is not available. "
+				"Desired zone: " + std::to_string(zoneNum) );
+		return;
+	}
+
+	cpu_set_t allowedSet;
+	cpu_set_t cpuSet;
+	int numCPUs = 0;
+
+	CPU_ZERO(&allowedSet);
+	CPU_ZERO(&cpuSet);
+
+	const bool haveAllowedSet = (sched_getaffinity(0, sizeof(allowedSet), &allowedSet) == 0);
+
+	for(int cpu : parseCPUList(cpuListStr) )
+		if( (cpu >= 0) && (cpu < CPU_SETSIZE) &&
+			(strict || !haveAllowedSet || CPU_ISSET(cpu, &allowedSet) ) )
+		{
+			CPU_SET(cpu, &cpuSet);
+			numCPUs++;
+		}
+
+	if(!numCPUs)
+	{
+		if(strict)
+			throw WorkerError("Desired NUMA zone has no CPUs. "
+				"Desired zone: " + std::to_string(zoneNum) );
+		return;
+	}
+
+	if(sched_setaffinity(0, sizeof(cpuSet), &cpuSet) == -1)
+	{
+		if(strict)
+			throw WorkerError("Applying NUMA zone node mask failed. "
+				"Given zones: " + std::to_string(zoneNum) + "; "
+				"SysErr: " + strerror(errno) );
+		return;
+	}
+
+	// memory of this thread from the same zone; not fatal in containers
+	unsigned long nodeMask[16] = {};
+
+	if( (size_t)zoneNum < (sizeof(nodeMask) * 8) )
+	{
+		nodeMask[zoneNum / (8 * sizeof(unsigned long) )] |=
+			1UL << (zoneNum % (8 * sizeof(unsigned long) ) );
+
+		syscall(SYS_set_mempolicy, strict ? 2 /*MPOL_BIND*/ : 1 /*MPOL_PREFERRED*/, nodeMask,
+			sizeof(nodeMask) * 8);
+	}
+
+	boundNumaNode = zoneNum;
+}
+
+/* NUMA node of a GPU from its PCI address (sysfs); -1 if unknown */
+static int numaNodeOfGPU(int gpuID)
+{
+	char busID[32] = {};
+
+	if(cudaDeviceGetPCIBusId(busID, sizeof(busID), gpuID) != cudaSuccess)
+		return -1;
+
+	for(char* c = busID; *c; c++)
+		*c = (char)tolower(*c);
+
+	std::ifstream nodeStream(std::string("/sys/bus/pci/devices/") + busID + "/numa_node");
+	int node = -1;
+
+	if(!(nodeStream >> node) )
+		return -1;
+
+	return node;
+}
+
+/**
+ * Worker::applyNumaAndCoreBinding (Worker.cpp:102-146) plus the GPU-affine default: without
+ * --zones / --cores a worker runs on the CPUs of its GPU's NUMA node and prefers memory from
+ * there. The pinned ring, the tmpfs / page cache pages the worker first touches in the write phase
+ * and the copies it makes in the read phase then stay on the socket the GPU's PCIe root hangs
+ * off (measured on the 2-socket box: 77 vs 51 GiB/s raw read with cache-resident buffers,
+ * profiles/r02_hostpath_exploration.jsonl).
+ */
 void Worker::applyNumaAndCoreBinding()
 {
 	if(!cfg.numaZones.empty() )
@@ -631,37 +726,15 @@ void Worker::applyNumaAndCoreBinding()
 			throw WorkerError("Desired NUMA zone may not be negative. "
 				"Desired zone: " + std::to_string(zoneNum) );
 
-		const std::string cpuListPath =
-			"/sys/devices/system/node/node" + std::to_string(zoneNum) + "/cpulist";
-		std::ifstream cpuListStream(cpuListPath);
-		std::string cpuListStr;
+		bindToNumaNode(zoneNum, true);
+	}
+	else
+	if(cfg.cpuCores.empty() && !cfg.noGPUNumaBinding && (gpuID >= 0) )
+	{
+		const int gpuNode = numaNodeOfGPU(gpuID);
 
-		if(!cpuListStream || !std::getline(cpuListStream, cpuListStr) )
-			throw WorkerError("Desired NUMA zone is not available. "
-				"Desired zone: " + std::to_string(zoneNum) );
-
-		cpu_set_t cpuSet;
-		CPU_ZERO(&cpuSet);
-
-		for(int cpu : parseCPUList(cpuListStr) )
-			if( (cpu >= 0) && (cpu < CPU_SETSIZE) )
-				CPU_SET(cpu, &cpuSet);
-
-		if(sched_setaffinity(0, sizeof(cpuSet), &cpuSet) == -1)
-			throw WorkerError("Applying NUMA zone node mask failed. "
-				"Given zones: " + std::to_string(zoneNum) + "; "
-				"SysErr: " + strerror(errno) );
-
-		// memory of this thread from the same zone (MPOL_BIND = 2); not fatal in containers
-		unsigned long nodeMask[16] = {};
-
-		if( (size_t)zoneNum < (sizeof(nodeMask) * 8) )
-		{
-			nodeMask[zoneNum / (8 * sizeof(unsigned long) )] |=
-				1UL << (zoneNum % (8 * sizeof(unsigned long) ) );
-
-			syscall(SYS_set_mempolicy, 2 /*MPOL_BIND*/, nodeMask, sizeof(nodeMask) * 8);
-		}
+		if(gpuNode >= 0)
+			bindToNumaNode(gpuNode, false);
 	}
 
 	if(!cfg.cpuCores.empty() )
@@ -683,9 +756,9 @@ void Worker::applyNumaAndCoreBinding()
 
 void Worker::preparePhase()
 {
-	applyNumaAndCoreBinding(); // first thing, so that all allocations follow (Worker.cpp:102)
-
 	gpuID = cfg.gpuIDs[rank % cfg.gpuIDs.size() ]; // LocalWorker.cpp:1420-1422
+
+	applyNumaAndCoreBinding(); // first thing, so that all allocations follow (Worker.cpp:102)
 
 	ELB_CUDA_CHECK(cudaSetDevice(gpuID), "Setting CUDA device");
 
@@ -712,6 +785,16 @@ void Worker::preparePhase()
 	allocRings();
 }
 
+/**
+ * Rings and batches. Sizing rule (new in round 2): the pinned ring of a worker has to stay
+ * CACHE RESIDENT. A storage read copies page cache -> ring slot on this core and the GPU then
+ * reads the slot over PCIe; if the slot is still in L2/L3 the device read is served from cache and
+ * the payload crosses DRAM once instead of three times. Measured raw pread rate of 16 threads
+ * into a 1 MiB buffer each: 77 GiB/s, into a 32 MiB ring each: 32 GiB/s
+ * (profiles/r02_hostpath_exploration.jsonl). So a batch is ~1 MiB (one 1 MiB block, 256 4 KiB
+ * blocks) and a worker has 3 of them; the kernel staging engine makes such small batches cheap
+ * (one launch per batch, nothing else).
+ */
 void Worker::allocRings()
 {
 	if(!cfg.blockSize)
@@ -724,17 +807,23 @@ void Worker::allocRings()
 
 	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
 
-	/* a batch is the unit of one GPU stage (one kernel launch + one staged copy), independent of
-	   the storage queue depth: ~16 MiB so that launch and copy overheads vanish even for 4 KiB
-	   blocks */
+	stageWithKernels = !cfg.useCuFile && (cfg.stagingEngine != ELB_STAGING_COPYENGINE);
+
 	if(cfg.pipelineBatchBlocks)
 		batchBlocks = cfg.pipelineBatchBlocks;
 	else
-		batchBlocks = (uint32_t)std::max( (uint64_t)1, (uint64_t)(ELB_DEFAULT_BATCH_BYTES / slotStride) );
+	{
+		batchBlocks = (uint32_t)std::max( (uint64_t)1,
+			(uint64_t)(ELB_DEFAULT_BATCH_BYTES / slotStride) );
 
-	batchBlocks = std::min(batchBlocks, (uint32_t)ELB_MAX_BATCH_BLOCKS);
+		if(useAio) // keep the storage queue full for most of a batch
+			batchBlocks = std::max(batchBlocks, (uint32_t)std::min( (uint64_t)4 * cfg.ioDepth,
+				(uint64_t)(ELB_MAX_AIO_BATCH_BYTES / slotStride) ) );
+	}
 
-	numBatches = cfg.pipelineNumBatches ? cfg.pipelineNumBatches : 2;
+	batchBlocks = std::max( (uint32_t)1, std::min(batchBlocks, (uint32_t)ELB_MAX_BATCH_BLOCKS) );
+
+	numBatches = cfg.pipelineNumBatches ? cfg.pipelineNumBatches : ELB_DEFAULT_NUM_BATCHES;
 
 	const uint64_t numSlots = (uint64_t)batchBlocks * numBatches;
 	const uint64_t ringBytes = numSlots * slotStride;
@@ -746,6 +835,8 @@ void Worker::allocRings()
 		"GPU counter block allocation");
 	ELB_CUDA_CHECK(cudaMemset(devCounters, 0, sizeof(uint64_t) * ELB_DEVCTR_NUM),
 		"GPU counter block init");
+
+	hostDelta = (int64_t)( (intptr_t)hostRing - (intptr_t)devRing);
 
 	/* fill the host ring with random data so that it is never sparse and copy it to the device
 	   ring (LocalWorker.cpp:1388-1390, 1473) */
@@ -780,13 +871,23 @@ void Worker::allocRings()
 
 		ELB_CUDA_CHECK(cudaHostAlloc( (void**)&batch.hostDescs,
 			sizeof(elb_block_desc) * batchBlocks, cudaHostAllocDefault), "Pinned desc allocation");
-		ELB_CUDA_CHECK(cudaMalloc( (void**)&batch.devDescs, sizeof(elb_block_desc) * batchBlocks),
-			"GPU desc allocation");
 		ELB_CUDA_CHECK(cudaMalloc( (void**)&batch.devResults,
 			sizeof(elb_verify_result) * batchBlocks), "GPU verify result allocation");
 		ELB_CUDA_CHECK(cudaHostAlloc( (void**)&batch.hostResults,
 			sizeof(elb_verify_result) * batchBlocks, cudaHostAllocDefault),
 			"Pinned verify result allocation");
+		ELB_CUDA_CHECK(cudaMalloc( (void**)&batch.devDoneTicket, sizeof(unsigned) ),
+			"GPU ticket counter allocation");
+		ELB_CUDA_CHECK(cudaMemset(batch.devDoneTicket, 0, sizeof(unsigned) ),
+			"GPU ticket counter init");
+
+		memset(batch.hostResults, 0, sizeof(elb_verify_result) * batchBlocks);
+
+		// arm the device results once; verify launches re-arm what they report
+		if(elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream) )
+			throw WorkerError(std::string("GPU verify init failed. ") + elb_last_error() );
+
+		numKernelLaunches++;
 
 		batch.iocbs.resize(batchBlocks);
 		batch.iocbPtrs.resize(batchBlocks);
@@ -804,6 +905,8 @@ void Worker::allocRings()
 			batch.cuParams.resize(cfg.ioDepth);
 			batch.cuEvents.resize(cfg.ioDepth);
 		}
+
+		ELB_CUDA_CHECK(cudaStreamSynchronize(batch.stream), "GPU batch setup");
 	}
 
 	if(cfg.useCuFile && cfg.useGDSBufReg)
@@ -879,12 +982,12 @@ void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
 			cudaEventDestroy(batch.kernelDoneEvent);
 		if(batch.hostDescs)
 			cudaFreeHost(batch.hostDescs);
-		if(batch.devDescs)
-			cudaFree(batch.devDescs);
 		if(batch.devResults)
 			cudaFree(batch.devResults);
 		if(batch.hostResults)
 			cudaFreeHost(batch.hostResults);
+		if(batch.devDoneTicket)
+			cudaFree(batch.devDoneTicket);
 	}
 
 	batches.clear();
@@ -900,6 +1003,38 @@ void Worker::freeRings() // LocalWorker::cleanup (:1570-1641)
 	devRing = NULL;
 	devCounters = NULL;
 	gpuPrepared = false;
+}
+
+/* cuFile batch requests that are still in flight may DMA into or out of the device ring: cancel
+ * what can be cancelled and wait until the batch context reports nothing pending (bounded) */
+void Worker::drainCuFileBatch(Batch& batch)
+{
+	CuFileApi& api = CuFileApi::get();
+	const Clock::time_point startT = Clock::now();
+
+	if(api.BatchIOCancel)
+		api.BatchIOCancel(batch.cuBatch);
+
+	while(batch.numIOPending && (elapsedUSecSince(startT) < 30000000ULL) )
+	{
+		unsigned numEvents = batch.numIOPending;
+		struct timespec timeout;
+		timeout.tv_sec = 1;
+		timeout.tv_nsec = 0;
+
+		CUfileError_t statusRes = api.BatchIOGetStatus(batch.cuBatch, 1, &numEvents,
+			batch.cuEvents.data(), &timeout);
+
+		if(statusRes.err != CU_FILE_SUCCESS)
+			break; // (cancelled batches may refuse status queries: nothing more to wait for)
+
+		for(unsigned eventIdx = 0; eventIdx < numEvents; eventIdx++)
+			if( (batch.cuEvents[eventIdx].status != CUFILE_WAITING) &&
+				(batch.cuEvents[eventIdx].status != CUFILE_PENDING) && batch.numIOPending)
+				batch.numIOPending--;
+	}
+
+	batch.numIOPending = 0;
 }
 
 /* after an error or interruption: let everything that is still in flight on the GPU streams and
@@ -921,7 +1056,15 @@ void Worker::abortInFlight()
 		for(Batch& batch : batches)
 		{
 			cudaStreamSynchronize(batch.stream);
-			batch.devResultsClean = false;
+
+			if(batch.cuBatchValid && batch.numIOPending)
+				drainCuFileBatch(batch);
+
+			// (a failed launch may have left the ticket or the armed results behind)
+			cudaMemsetAsync(batch.devDoneTicket, 0, sizeof(unsigned), batch.stream);
+			elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream);
+			cudaStreamSynchronize(batch.stream);
+
 			batch.numIOPending = 0;
 			batch.ioSubmitted = false;
 		}
@@ -935,6 +1078,56 @@ void Worker::abortInFlight()
 	}
 }
 
+/* --nofdsharing (reference: LocalWorker::initThreadFDVec, LocalWorker.cpp:869-913, and
+ * initThreadCuFileHandleDataVec :936-957): every worker works on its own descriptors of the
+ * files / block devices. Opened when the first read/write phase needs them, read-write (and
+ * creating) for a write phase; a read-only set is reopened if a write phase follows. */
+void Worker::openThreadFDs(bool forWrite)
+{
+	if(!cfg.useNoFDSharing || (cfg.pathType == ELB_PATH_DIR) )
+		return;
+
+	if(!threadFDs.empty() && (threadFDsWritable || !forWrite) )
+		return;
+
+	closeThreadFDs();
+
+	int openFlags = forWrite ? (O_RDWR | O_CREAT) : O_RDONLY;
+
+	if(cfg.useDirectIO)
+		openFlags |= O_DIRECT;
+
+	for(const std::string& path : cfg.paths)
+	{
+		const int fd = open(path.c_str(), openFlags, ELB_MKFILE_MODE);
+
+		if(fd == -1)
+			throw WorkerError("Unable to open benchmark path: " + path + "; "
+				"SysErr: " + strerror(errno) );
+
+		threadFDs.push_back(fd);
+
+		if(cfg.useCuFile)
+		{
+			threadCuFileHandles.emplace_back(new CuFileHandle() );
+			threadCuFileHandles.back()->registerFD(fd, path);
+		}
+	}
+
+	threadFDsWritable = forWrite;
+}
+
+void Worker::closeThreadFDs()
+{
+	threadCuFileHandles.clear(); // (deregisters)
+
+	for(int fd : threadFDs)
+		close(fd);
+
+	threadFDs.clear();
+	threadFDsWritable = false;
+}
+
 void Worker::cleanup()
 {
 	if(dirModeFD != -1)
@@ -942,6 +1135,8 @@ void Worker::cleanup()
 		close(dirModeFD);
 		dirModeFD = -1;
 	}
+
+	closeThreadFDs();
 
 	freeRings();
 }
@@ -1420,18 +1615,21 @@ void Worker::fadviseFile(int fd, const std::string& path)
 	}
 }
 
-void Worker::rateLimitNextBlock(uint64_t len)
+/* @return true if the caller had to sleep for its rate limit */
+bool Worker::rateLimitNextBlock(uint64_t len)
 {
 	if(useRWMixThreadsBalancer)
 	{
 		if(isRWMixReaderThread)
-			shared->rwMixThreadsBalancer.waitRead(len, isInterruptionRequested);
-		else
-			shared->rwMixThreadsBalancer.waitWrite(len, isInterruptionRequested);
+			return shared->rwMixThreadsBalancer.waitRead(len, isInterruptionRequested);
+
+		return shared->rwMixThreadsBalancer.waitWrite(len, isInterruptionRequested);
 	}
-	else
+
 	if(rateLimiter.isEnabled() )
-		rateLimiter.wait(len);
+		return rateLimiter.wait(len);
+
+	return false;
 }
 
 void Worker::rwPhase()
@@ -1460,6 +1658,14 @@ void Worker::rwPhase()
 			"GPU counter block reset");
 
 	initPhaseOffsetPlan();
+
+	openThreadFDs(benchPhase == ELB_PHASE_CREATEFILES);
+
+	/* FIFO gate in front of buffered writes that several local workers send to one file */
+	useWriteGate = (benchPhase == ELB_PHASE_CREATEFILES) && (cfg.pathType != ELB_PATH_DIR) &&
+		!cfg.useDirectIO && !cfg.useCuFile &&
+		( (cfg.serializeBufferedWrites == ELB_WRITEGATE_ON) ||
+		( (cfg.serializeBufferedWrites == ELB_WRITEGATE_AUTO) && (cfg.numThreads > 1) ) );
 
 	/* rate balancer between the reader and writer threads of a write phase, else the plain
 	   per-thread limit (LocalWorker.cpp:1284-1299 write side, 1322-1337 read side) */
@@ -1672,7 +1878,7 @@ void Worker::ioRun(Batch& batch, bool isRead)
 
 /* ---- GPU stages ---------------------------------------------------------------------------- */
 
-/* fill the pinned descriptor mirror for the write stage; returns the number of blocks to fill */
+/* fill the pinned descriptor array for the write stage; returns the number of blocks to fill */
 size_t Worker::fillWriteDescs(Batch& batch, uint64_t& outNumWriteBytes)
 {
 	size_t numWriteBlocks = 0;
@@ -1695,15 +1901,15 @@ size_t Worker::fillWriteDescs(Batch& batch, uint64_t& outNumWriteBytes)
 }
 
 /* a full batch of full-size blocks in a dense run of slots: its GPU stage has fixed pointers and
- * sizes and can be replayed from a CUDA graph */
+ * sizes and can be replayed from a CUDA graph (copy-engine staging) */
 bool Worker::isStandardShapedBatch(const Batch& batch) const
 {
 	return (batch.blocks.size() == batchBlocks) && (slotStride == cfg.blockSize) &&
 		(batch.numBytes == ( (uint64_t)batchBlocks * slotStride) );
 }
 
-/* debugging knob: ELB_NO_CUDA_GRAPHS=1 enqueues the GPU stage call by call instead of replaying
- * the per-batch graph (same kernels, same copies) */
+/* debugging knob: ELB_NO_CUDA_GRAPHS=1 enqueues the copy-engine GPU stage call by call instead of
+ * replaying the per-batch graph (same kernels, same copies) */
 static bool useCudaGraphs()
 {
 	static const bool enabled = []()
@@ -1728,9 +1934,9 @@ cudaGraphExec_t Worker::captureBatchGraph(Batch& batch, bool isRead)
 	try
 	{
 		if(isRead)
-			enqueueReadWork(batch, false);
+			enqueueReadWork(batch, true);
 		else
-			enqueueWriteWork(batch, batchBlocks, batch.numBytes, false);
+			enqueueWriteWork(batch, batchBlocks, batch.numBytes, true);
 	}
 	catch(...)
 	{
@@ -1750,86 +1956,136 @@ cudaGraphExec_t Worker::captureBatchGraph(Batch& batch, bool isRead)
 	return graphExec;
 }
 
+/* kernel time of a batch: events around the kernel; inside a stream capture they become event
+ * record nodes of the graph (cudaEventRecordExternal), so replayed graphs are timed as well */
+static cudaError_t recordKernelEvent(cudaEvent_t event, cudaStream_t stream)
+{
+	cudaStreamCaptureStatus captureStatus = cudaStreamCaptureStatusNone;
+
+	cudaStreamIsCapturing(stream, &captureStatus);
+
+	return cudaEventRecordWithFlags(event, stream,
+		(captureStatus == cudaStreamCaptureStatusActive) ? cudaEventRecordExternal :
+		cudaEventRecordDefault);
+}
+
+/* copy-engine staging: the blocks of the batch between the rings with cudaMemcpyAsync; one copy
+ * when the batch is a dense run of full slots */
+void Worker::enqueueStageCopies(Batch& batch, bool hostToDevice, bool onlyWrites)
+{
+	const size_t numBlocks = batch.blocks.size();
+	const cudaMemcpyKind kind = hostToDevice ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+	const char* what = hostToDevice ? "Async host to GPU copy" : "Async GPU to host copy";
+	bool allBlocksTakePart = true;
+
+	for(size_t i = 0; onlyWrites && (i < numBlocks); i++)
+		allBlocksTakePart = allBlocksTakePart && !batch.blocks[i].ioIsRead;
+
+	if(allBlocksTakePart && (slotStride == cfg.blockSize) &&
+		(batch.numBytes == (numBlocks * slotStride) ) )
+	{
+		char* hostPtr = slotHostPtr(batch, 0);
+		char* devPtr = slotDevPtr(batch, 0);
+
+		ELB_CUDA_CHECK(cudaMemcpyAsync(hostToDevice ? devPtr : hostPtr,
+			hostToDevice ? hostPtr : devPtr, batch.numBytes, kind, batch.stream), what);
+		return;
+	}
+
+	for(size_t i = 0; i < numBlocks; i++)
+	{
+		if(!batch.blocks[i].len || (onlyWrites && batch.blocks[i].ioIsRead) )
+			continue;
+
+		char* hostPtr = slotHostPtr(batch, i);
+		char* devPtr = slotDevPtr(batch, i);
+
+		ELB_CUDA_CHECK(cudaMemcpyAsync(hostToDevice ? devPtr : hostPtr,
+			hostToDevice ? hostPtr : devPtr, batch.blocks[i].len, kind, batch.stream), what);
+	}
+}
+
 /**
  * Stream work of the write stage = policy of initPhaseFunctionPointers (LocalWorker.cpp:
  * 1249-1265): pattern fill if salt != 0, else random refill if blockvarpct, else nothing; then the
- * blocks go to the host for the storage write (cudaMemcpyGPUToHost, :1249-1250).
+ * blocks go to the host ring for the storage write (cudaMemcpyGPUToHost, :1249-1250).
+ *
+ * Kernel staging: ONE launch that generates every vector once and stores it to the device slot
+ * and to the host slot (or a plain device->host slot copy kernel if there is nothing to fill).
+ * Copy-engine staging: fill kernel on the device slots, then cudaMemcpyAsync. cuFile: fill only,
+ * the storage write reads the device ring. Descriptors are read from pinned host memory.
  */
 void Worker::enqueueWriteWork(Batch& batch, size_t numWriteBlocks, uint64_t numWriteBytes,
 	bool timeKernel)
 {
-	const size_t numBlocks = batch.blocks.size();
 	const bool doPatternFill = (cfg.integrityCheckSalt != 0);
 	const bool doRandFill = !doPatternFill && cfg.blockVariancePercent;
+	const bool stageOut = !cfg.useCuFile;
 
-	if( (doPatternFill || doRandFill) && numWriteBlocks)
+	elb_stage_args stage;
+	stage.hostDelta = (stageOut && stageWithKernels) ? hostDelta : 0;
+
+	if(!numWriteBlocks)
+		return;
+
+	if(doPatternFill || doRandFill)
 	{
-		ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
-			sizeof(elb_block_desc) * numWriteBlocks, cudaMemcpyHostToDevice, batch.stream),
-			"Async copy of block descriptors");
-
 		if(timeKernel)
-			ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+			ELB_CUDA_CHECK(recordKernelEvent(batch.kernelStartEvent, batch.stream),
 				"CUDA event record");
 
 		int launchRes;
 
 		if(doPatternFill)
-			launchRes = elb_launch_fill_pattern(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
-				cfg.integrityCheckSalt, devCounters, numWriteBytes, cfg.blockSize, batch.stream);
+			launchRes = elb_launch_fill_pattern(batch.hostDescs, NULL, (uint32_t)numWriteBlocks,
+				cfg.integrityCheckSalt, devCounters, numWriteBytes, cfg.blockSize, batch.stream,
+				&stage);
 		else
-			launchRes = elb_launch_fill_random(batch.devDescs, NULL, (uint32_t)numWriteBlocks,
+			launchRes = elb_launch_fill_random(batch.hostDescs, NULL, (uint32_t)numWriteBlocks,
 				cfg.blockVariancePercent, blockVarianceSeed, devCounters, numWriteBytes,
-				cfg.blockSize, batch.stream);
+				cfg.blockSize, batch.stream, &stage);
 
 		if(launchRes)
 			throw WorkerError(std::string("GPU block fill failed. ") + elb_last_error() );
 
 		if(timeKernel)
 		{
-			ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+			ELB_CUDA_CHECK(recordKernelEvent(batch.kernelDoneEvent, batch.stream),
 				"CUDA event record");
 			batch.hadKernel = true;
 		}
 	}
-
-	/* staged copy to the pinned ring: one copy when the batch is a dense run of full slots.
-	   (cuFile writes straight from the device ring: no host copy, LocalWorker.cpp:1249-1250) */
-	if(cfg.useCuFile)
-		; // nothing to stage
 	else
-	if( (numWriteBlocks == numBlocks) && (slotStride == cfg.blockSize) &&
-		(batch.numBytes == (numBlocks * slotStride) ) )
-		ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, 0), slotDevPtr(batch, 0),
-			batch.numBytes, cudaMemcpyDeviceToHost, batch.stream), "Async GPU to host copy");
-	else
-		for(size_t i = 0; i < numBlocks; i++)
-		{
-			if(!batch.blocks[i].len || batch.blocks[i].ioIsRead)
-				continue;
+	if(stageOut && stageWithKernels)
+	{ // nothing to fill: the ring content as it is goes to the host slots
+		if(elb_launch_stage_copy(batch.hostDescs, (uint32_t)numWriteBlocks, false, hostDelta,
+			numWriteBytes, cfg.blockSize, batch.stream) )
+			throw WorkerError(std::string("GPU block staging failed. ") + elb_last_error() );
+	}
 
-			ELB_CUDA_CHECK(cudaMemcpyAsync(slotHostPtr(batch, i), slotDevPtr(batch, i),
-				batch.blocks[i].len, cudaMemcpyDeviceToHost, batch.stream),
-				"Async GPU to host copy");
-		}
+	if(stageOut && !stageWithKernels)
+		enqueueStageCopies(batch, false, true);
 }
 
 void Worker::gpuLaunchWriteStage(Batch& batch)
 {
 	uint64_t numWriteBytes;
 	const size_t numWriteBlocks = fillWriteDescs(batch, numWriteBytes);
-	const bool haveKernel = (cfg.integrityCheckSalt || cfg.blockVariancePercent) && numWriteBlocks;
+	const bool haveFill = (cfg.integrityCheckSalt || cfg.blockVariancePercent) && numWriteBlocks;
+	const bool haveKernel = haveFill || (stageWithKernels && !cfg.useCuFile && numWriteBlocks);
 
 	batch.hadKernel = false;
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
-	if(useCudaGraphs() && isStandardShapedBatch(batch) && (numWriteBlocks == batchBlocks) )
+	if(!stageWithKernels && useCudaGraphs() && isStandardShapedBatch(batch) &&
+		(numWriteBlocks == batchBlocks) )
 	{
 		if(!batch.writeGraphExec)
 			batch.writeGraphExec = captureBatchGraph(batch, false);
 
 		ELB_CUDA_CHECK(cudaGraphLaunch(batch.writeGraphExec, batch.stream), "CUDA graph launch");
+		batch.hadKernel = haveFill;
 	}
 	else
 		enqueueWriteWork(batch, numWriteBlocks, numWriteBytes, true);
@@ -1844,68 +2100,65 @@ void Worker::gpuLaunchWriteStage(Batch& batch)
 }
 
 /**
- * Stream work of the read stage (LocalWorker.cpp:1311-1319): host -> GPU copy of what was read,
- * then the integrity check on the GPU (the reference verifies on the CPU); only the 16-byte
- * results come back. Expects the pinned descriptor mirror to be filled and devResults clean.
+ * Stream work of the read stage (LocalWorker.cpp:1311-1319): what was read goes to the device
+ * ring and is checked on the GPU (the reference verifies on the CPU).
+ *
+ * Kernel staging: ONE launch that loads every vector from the host slot, stores it to the device
+ * slot and compares it (or a plain host->device slot copy kernel without --verify). Copy-engine
+ * staging: cudaMemcpyAsync, then the verify kernel on the device slots. cuFile: verify only. In all
+ * forms the last CTA of the verify launch writes the 16-byte results to batch.hostResults.
+ * Expects batch.hostDescs to be filled.
  */
 void Worker::enqueueReadWork(Batch& batch, bool timeKernel)
 {
 	const size_t numBlocks = batch.blocks.size();
 	const bool doVerify = (cfg.integrityCheckSalt != 0);
+	const bool stageIn = !cfg.useCuFile;
 
-	if(cfg.useCuFile)
-		; // cuFile read straight into the device ring (LocalWorker.cpp:1231-1232)
-	else
-	if( (slotStride == cfg.blockSize) && (batch.numBytes == (numBlocks * slotStride) ) )
-		ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, 0), slotHostPtr(batch, 0),
-			batch.numBytes, cudaMemcpyHostToDevice, batch.stream), "Async host to GPU copy");
-	else
-		for(size_t i = 0; i < numBlocks; i++)
-		{
-			if(!batch.blocks[i].len)
-				continue;
-
-			ELB_CUDA_CHECK(cudaMemcpyAsync(slotDevPtr(batch, i), slotHostPtr(batch, i),
-				batch.blocks[i].len, cudaMemcpyHostToDevice, batch.stream),
-				"Async host to GPU copy");
-		}
+	if(stageIn && !stageWithKernels)
+		enqueueStageCopies(batch, true, false);
 
 	if(!doVerify)
-		return;
+	{
+		if(stageIn && stageWithKernels &&
+			elb_launch_stage_copy(batch.hostDescs, (uint32_t)numBlocks, true, hostDelta,
+				batch.numBytes, cfg.blockSize, batch.stream) )
+			throw WorkerError(std::string("GPU block staging failed. ") + elb_last_error() );
 
-	ELB_CUDA_CHECK(cudaMemcpyAsync(batch.devDescs, batch.hostDescs,
-		sizeof(elb_block_desc) * numBlocks, cudaMemcpyHostToDevice, batch.stream),
-		"Async copy of block descriptors");
+		return;
+	}
+
+	elb_stage_args stage;
+	stage.hostDelta = (stageIn && stageWithKernels) ? hostDelta : 0;
+	stage.hostResults = batch.hostResults;
+	stage.doneTicket = batch.devDoneTicket;
 
 	if(timeKernel)
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelStartEvent, batch.stream),
+		ELB_CUDA_CHECK(recordKernelEvent(batch.kernelStartEvent, batch.stream),
 			"CUDA event record");
 
-	if(elb_launch_verify_pattern(batch.devDescs, NULL, (uint32_t)numBlocks,
+	if(elb_launch_verify_pattern(batch.hostDescs, NULL, (uint32_t)numBlocks,
 		cfg.integrityCheckSalt, batch.devResults, devCounters, batch.numBytes, cfg.blockSize,
-		false /*initResults*/, batch.stream) )
+		false /*initResults: armed at setup, re-armed by the kernel*/, batch.stream, &stage) )
 		throw WorkerError(std::string("GPU block verification failed. ") + elb_last_error() );
 
 	if(timeKernel)
 	{
-		ELB_CUDA_CHECK(cudaEventRecord(batch.kernelDoneEvent, batch.stream),
+		ELB_CUDA_CHECK(recordKernelEvent(batch.kernelDoneEvent, batch.stream),
 			"CUDA event record");
 		batch.hadKernel = true;
 	}
-
-	ELB_CUDA_CHECK(cudaMemcpyAsync(batch.hostResults, batch.devResults,
-		sizeof(elb_verify_result) * numBlocks, cudaMemcpyDeviceToHost, batch.stream),
-		"Async copy of verify results");
 }
 
 void Worker::gpuLaunchReadStage(Batch& batch)
 {
 	const size_t numBlocks = batch.blocks.size();
 	const bool doVerify = (cfg.integrityCheckSalt != 0);
+	const bool haveKernel = doVerify || (stageWithKernels && !cfg.useCuFile);
 
 	batch.hadKernel = false;
 
-	if(doVerify)
+	if(haveKernel)
 		for(size_t i = 0; i < numBlocks; i++)
 		{
 			const BlockRef& block = batch.blocks[i];
@@ -1915,26 +2168,18 @@ void Worker::gpuLaunchReadStage(Batch& batch)
 
 	ELB_CUDA_CHECK(cudaEventRecord(batch.gpuStartEvent, batch.stream), "CUDA event record");
 
-	if(doVerify && !batch.devResultsClean)
-	{ // (all batchBlocks entries, so that later launches with more blocks stay valid)
-		if(elb_launch_verify_init(batch.devResults, batchBlocks, batch.stream) )
-			throw WorkerError(std::string("GPU verify init failed. ") + elb_last_error() );
-
-		numKernelLaunches++;
-		batch.devResultsClean = true; // until a mismatch shows up at retire time
-	}
-
-	if(useCudaGraphs() && isStandardShapedBatch(batch) )
+	if(!stageWithKernels && useCudaGraphs() && isStandardShapedBatch(batch) )
 	{
 		if(!batch.readGraphExec)
 			batch.readGraphExec = captureBatchGraph(batch, true);
 
 		ELB_CUDA_CHECK(cudaGraphLaunch(batch.readGraphExec, batch.stream), "CUDA graph launch");
+		batch.hadKernel = doVerify;
 	}
 	else
 		enqueueReadWork(batch, true);
 
-	if(doVerify)
+	if(haveKernel)
 		numKernelLaunches++;
 
 	if(!cfg.useCuFile)
@@ -1951,10 +2196,12 @@ void Worker::gpuWait(Batch& batch)
 	cudaEventElapsedTime(&batch.gpuMilliSecs, batch.gpuStartEvent, batch.gpuDoneEvent);
 
 	if(batch.hadKernel)
-	{
+	{ // fill / verify kernel alone (with kernel staging this includes the PCIe transfer it does)
 		float kernelMilliSecs = 0;
-		cudaEventElapsedTime(&kernelMilliSecs, batch.kernelStartEvent, batch.kernelDoneEvent);
-		devKernelUSec += (uint64_t)(kernelMilliSecs * 1000);
+
+		if(cudaEventElapsedTime(&kernelMilliSecs, batch.kernelStartEvent,
+			batch.kernelDoneEvent) == cudaSuccess)
+			devKernelUSec += (uint64_t)(kernelMilliSecs * 1000);
 	}
 }
 
@@ -1984,29 +2231,24 @@ void Worker::throwVerifyError(Batch& batch, size_t blockIdx)
 		"Actual value: " + std::to_string(actualVal) );
 }
 
-/* read batch completed its GPU stage: check the integrity results in submission order, then do
- * the per-block accounting (latency = storage time + share of the batch's GPU time, so that
- * fill/verify stay inside the reported I/O latency like LocalWorker.cpp:1691-1755) */
+/* integrity results of a batch whose verify launch has completed, in submission order */
+void Worker::checkVerifyResults(Batch& batch)
+{
+	if(!cfg.integrityCheckSalt)
+		return;
+
+	for(size_t i = 0; i < batch.blocks.size(); i++)
+		if(batch.hostResults[i].numMismatchBytes && !cfg.verifyCollectAll)
+			throwVerifyError(batch, i);
+}
+
+/* read batch completed its GPU stage: check the integrity results, then do the per-block
+ * accounting (latency = storage time + share of the batch's GPU time, so that the transfer to
+ * the GPU and the verify stay inside the reported I/O latency like LocalWorker.cpp:1691-1755) */
 void Worker::retireReadBatch(Batch& batch)
 {
 	gpuWait(batch);
-
-	const size_t numBlocks = batch.blocks.size();
-
-	if(cfg.integrityCheckSalt)
-	{
-		for(size_t i = 0; i < numBlocks; i++)
-		{
-			if(!batch.hostResults[i].numMismatchBytes)
-				continue;
-
-			batch.devResultsClean = false;
-
-			if(!cfg.verifyCollectAll)
-				throwVerifyError(batch, i);
-		}
-	}
-
+	checkVerifyResults(batch);
 	accountBatch(batch, (uint64_t)(batch.gpuMilliSecs * 1000) );
 }
 
@@ -2021,17 +2263,7 @@ void Worker::verifyWrittenBatch(Batch& batch)
 
 	gpuLaunchReadStage(batch);
 	gpuWait(batch);
-
-	for(size_t i = 0; i < batch.blocks.size(); i++)
-	{
-		if(!batch.hostResults[i].numMismatchBytes)
-			continue;
-
-		batch.devResultsClean = false;
-
-		if(!cfg.verifyCollectAll)
-			throwVerifyError(batch, i);
-	}
+	checkVerifyResults(batch);
 
 	accountBatch(batch, (uint64_t)( (fillMilliSecs + batch.gpuMilliSecs) * 1000) );
 }
@@ -2046,15 +2278,20 @@ void Worker::ioAccountBlock(BlockRef& block, uint64_t latencyUSec)
 
 	if(block.statsReadMix)
 	{ // rwmix read in a write phase
-		histogramAdd(iopsLatHistoReadMix, latencyUSec);
+		if(block.latencyValid)
+			histogramAdd(iopsLatHistoReadMix, latencyUSec);
 		atomicLiveOpsReadMix.numBytesDone += block.len;
 		atomicLiveOpsReadMix.numIOPSDone++;
 		return;
 	}
 
-	histogramAdd(iopsLatHisto, latencyUSec);
-	liveLatNumIO++;
-	liveLatSumIO += latencyUSec;
+	if(block.latencyValid)
+	{
+		histogramAdd(iopsLatHisto, latencyUSec);
+		liveLatNumIO++;
+		liveLatSumIO += latencyUSec;
+	}
+
 	atomicLiveOps.numBytesDone += block.len;
 	atomicLiveOps.numIOPSDone++;
 }
@@ -2223,12 +2460,35 @@ void Worker::dirModeCloseFile()
 int Worker::resolveFD(const BlockRef& block, bool isRead)
 {
 	if(cfg.pathType != ELB_PATH_DIR)
-		return shared->pathFDs[block.fileIdx];
+		return threadFDs.empty() ? shared->pathFDs[block.fileIdx] : threadFDs[block.fileIdx];
 
 	if(block.firstOfFile)
 		dirModeOpenFile(block, isRead);
 
 	return dirModeFD;
+}
+
+/* pread / pwrite of a whole block. A short positive result is continued from where it stopped
+ * (the reference accounts the partial result and goes on from the new offset,
+ * LocalWorker.cpp:1721-1776; here the block has to be complete before its GPU stage). Returns the
+ * bytes transferred, or the failing call's result (<= 0) with errno set. */
+static ssize_t fullBlockIO(int fd, char* buf, uint64_t len, uint64_t offset, bool isRead)
+{
+	uint64_t numDone = 0;
+
+	while(numDone < len)
+	{
+		const ssize_t ioRes = isRead ?
+			pread(fd, buf + numDone, len - numDone, offset + numDone) :
+			pwrite(fd, buf + numDone, len - numDone, offset + numDone);
+
+		if(ioRes <= 0)
+			return numDone ? (ssize_t)numDone : ioRes;
+
+		numDone += ioRes;
+	}
+
+	return (ssize_t)numDone;
 }
 
 /**
@@ -2240,8 +2500,6 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 {
 	const size_t numBlocks = batch.blocks.size();
 	const bool doReadBack = !isRead && (cfg.doDirectVerify || cfg.doReadInline);
-	const bool useWriteGate = !isRead && cfg.serializeBufferedWrites && !cfg.useDirectIO &&
-		(cfg.pathType != ELB_PATH_DIR);
 
 	for(size_t i = 0; i < numBlocks; i++)
 	{
@@ -2255,30 +2513,30 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 		{
 			rateLimitNextBlock(block.len); // (LocalWorker.cpp:1689)
 
-			Clock::time_point ioStartT = Clock::now();
+			/* the start stamp is taken before the write gate: the wait for the file is part of
+			   the block's latency, as the wait for the inode lock is inside pwrite() without it */
+			const Clock::time_point ioStartT = Clock::now();
 			char* hostBuf = slotHostPtr(batch, i);
 			ssize_t ioRes;
 
 			flockBlock(fd, block, false); // (inside the measured I/O time, :1691-1755)
 
 			if(block.ioIsRead)
-				ioRes = pread(fd, hostBuf, block.len, block.offset);
+				ioRes = fullBlockIO(fd, hostBuf, block.len, block.offset, true);
 			else
-			if(useWriteGate)
 			{ // one buffered writer per file at a time (see elb_cfg::serializeBufferedWrites)
-				std::unique_lock<std::mutex> gate(*shared->fileWriteGates[block.fileIdx] );
-				ioStartT = Clock::now(); // storage time without the queueing
-				ioRes = pwrite(fd, hostBuf, block.len, block.offset);
+				FileWriteTurn turn(useWriteGate ?
+					shared->fileWriteGates[block.fileIdx].get() : NULL);
+
+				ioRes = fullBlockIO(fd, hostBuf, block.len, block.offset, false);
 			}
-			else
-				ioRes = pwrite(fd, hostBuf, block.len, block.offset);
 
 			if(ioRes != (ssize_t)block.len)
 				throwIOError(block, block.ioIsRead, ioRes, errno);
 
 			if(doReadBack)
 			{ // pwriteAndReadWrapper (LocalWorker.cpp:2533-2554): read the same range back
-				ioRes = pread(fd, hostBuf, block.len, block.offset);
+				ioRes = fullBlockIO(fd, hostBuf, block.len, block.offset, true);
 
 				if(ioRes != (ssize_t)block.len)
 					throwIOError(block, true, ioRes, errno);
@@ -2345,6 +2603,7 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 	}
 
 	size_t numSubmitted = 0;
+	size_t numPrepared = 0; // requests that got their start stamp and passed the rate limiter
 	size_t numCompleted = 0;
 	struct io_event events[ELB_AIO_MAX_EVENTS];
 
@@ -2359,13 +2618,31 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 		{
 			const size_t numToSubmit = std::min(numIocbs - numSubmitted,
 				(size_t)cfg.ioDepth - numInFlight);
-			const Clock::time_point submitT = Clock::now();
 
-			for(size_t k = 0; k < numToSubmit; k++) // (LocalWorker.cpp:1842, 2003)
-				rateLimitNextBlock(batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].len);
+			/* limiter and start stamps only for requests that were not prepared by an earlier,
+			   partially accepted io_submit (LocalWorker.cpp:1840-1847, 2001-2008: stamp, then
+			   limiter, once per request) */
+			for( ; numPrepared < (numSubmitted + numToSubmit); numPrepared++)
+			{
+				BlockRef& block = batch.blocks[batch.iocbPtrs[numPrepared]->aio_data];
 
-			for(size_t k = 0; k < numToSubmit; k++)
-				batch.blocks[batch.iocbPtrs[numSubmitted + k]->aio_data].submitT = submitT;
+				block.submitT = Clock::now();
+				block.ioDone = false;
+				block.latencyValid = true;
+
+				if(rateLimitNextBlock(block.len) )
+				{ /* the limiter slept: the start stamps of everything that is pending (this
+				     request included) say nothing about the storage any more, so the reference
+				     leaves these I/Os out of the latency histogram (:1843-1845, 2004-2006) */
+					for(size_t k = 0; k <= numPrepared; k++)
+					{
+						BlockRef& pending = batch.blocks[batch.iocbPtrs[k]->aio_data];
+
+						if(!pending.ioDone)
+							pending.latencyValid = false;
+					}
+				}
+			}
 
 			long submitRes = syscall(SYS_io_submit, aioContext, (long)numToSubmit,
 				&batch.iocbPtrs[numSubmitted] );
@@ -2377,6 +2654,10 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 						"NumRequests: " + std::to_string(numToSubmit) + "; "
 						"SysErr: " + strerror(errno) );
 			}
+			else
+			if(!submitRes && !numInFlight)
+				throw WorkerError("Async IO submission (io_submit) accepted no request. "
+					"NumRequests: " + std::to_string(numToSubmit) );
 			else
 				numSubmitted += submitRes;
 		}
@@ -2419,6 +2700,7 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 					(event.res < 0) ? -(int)event.res : 0);
 
 			block.ioUSec = elapsedUSecSince(block.submitT);
+			block.ioDone = true;
 			numCompleted++;
 		}
 	}
@@ -2452,7 +2734,8 @@ void Worker::ioRunAio(Batch& batch, bool isRead)
 CUfileHandle_t Worker::resolveCuFileHandle(const BlockRef& block, bool isRead)
 {
 	if(cfg.pathType != ELB_PATH_DIR)
-		return shared->cuFileHandles[block.fileIdx]->get();
+		return threadCuFileHandles.empty() ? shared->cuFileHandles[block.fileIdx]->get() :
+			threadCuFileHandles[block.fileIdx]->get();
 
 	if(block.firstOfFile)
 		dirModeOpenFile(block, isRead);
@@ -2561,7 +2844,7 @@ void Worker::ioRunCuFileBatch(Batch& batch, bool isRead)
 			memset(&params, 0, sizeof(params) );
 			params.mode = CUFILE_BATCH;
 			params.fh = (cfg.pathType != ELB_PATH_DIR) ?
-				shared->cuFileHandles[block.fileIdx]->get() : dirModeCuFileHandle.get();
+				resolveCuFileHandle(block, isRead) : dirModeCuFileHandle.get();
 			params.opcode = block.ioIsRead ? CUFILE_READ : CUFILE_WRITE;
 			params.u.batch.devPtr_base = devRing;
 			params.u.batch.devPtr_offset =
@@ -2581,7 +2864,11 @@ void Worker::ioRunCuFileBatch(Batch& batch, bool isRead)
 				"NumRequests: " + std::to_string(groupLen) + "; "
 				"cuFile Error: " + CuFileApi::errorStr(submitRes) );
 
-		unsigned numPending = groupLen;
+		/* (kept in the batch so that abortInFlight() can drain a group that an exception or an
+		   interruption leaves behind before the ring is reused or freed) */
+		uint32_t& numPending = batch.numIOPending;
+
+		numPending = groupLen;
 
 		while(numPending)
 		{

@@ -52,7 +52,7 @@ struct Shared
 {
 	Config cfg;
 	std::vector<int> pathFDs; // ProgArgs::benchPathFDsVec (opened by the manager)
-	std::vector<std::unique_ptr<std::mutex> > fileWriteGates; // one per path (file mode)
+	std::vector<std::unique_ptr<FileWriteGate> > fileWriteGates; // one per path (file mode)
 	std::vector<std::unique_ptr<CuFileHandle> > cuFileHandles; // file mode with --cufile
 
 	std::mutex mutex;
@@ -98,6 +98,9 @@ struct BlockRef
 	uint64_t blockCounter{0}; // keys the random fill
 	uint64_t ioUSec{0};       // measured storage time of this block
 	Clock::time_point submitT; // aio: time of submission
+	bool ioDone{false};        // aio: completion seen
+	bool latencyValid{true};   // aio: false if the rate limiter slept while this I/O was pending
+	                           // (the reference then leaves it out of the histogram, :1843-1845)
 };
 
 /* produces the worker's blocks of a phase in submission order */
@@ -123,11 +126,13 @@ struct Batch
 	cudaEvent_t kernelDoneEvent{NULL};
 	bool hadKernel{false};
 
+	/* descriptors live in pinned host memory and are read by the kernels over PCIe; verify results
+	   are published to pinned host memory by the last CTA of the launch (device-side ticket),
+	   which also re-arms the device entries: no descriptor copy, no result copy, no init launch */
 	elb_block_desc* hostDescs{NULL};      // pinned
-	elb_block_desc* devDescs{NULL};
-	elb_verify_result* devResults{NULL};
+	elb_verify_result* devResults{NULL};  // armed {0, ~0} once, self re-arming
 	elb_verify_result* hostResults{NULL}; // pinned
-	bool devResultsClean{false};
+	unsigned* devDoneTicket{NULL};
 
 	// aio state
 	std::vector<struct iocb> iocbs;
@@ -144,8 +149,9 @@ struct Batch
 	uint64_t numBytes{0};
 	float gpuMilliSecs{0};
 
-	/* CUDA graphs of the GPU stage for full, dense batches (fixed pointers and sizes): one
-	 * cudaGraphLaunch instead of 4-6 stream calls per batch */
+	/* copy-engine staging only: CUDA graphs of the GPU stage for full, dense batches (fixed
+	 * pointers and sizes), one cudaGraphLaunch instead of copy + kernel calls (the kernel staging
+	 * engine needs one launch per batch anyway) */
 	cudaGraphExec_t readGraphExec{NULL};
 	cudaGraphExec_t writeGraphExec{NULL};
 };
@@ -222,6 +228,10 @@ class Worker
 		uint32_t numBatches{0};
 		char* hostRing{NULL}; // pinned
 		char* devRing{NULL};
+		int64_t hostDelta{0}; // hostRing - devRing: host slot of a block = device slot + hostDelta
+		bool stageWithKernels{true}; // resolved elb_cfg::stagingEngine
+		bool useWriteGate{false};    // resolved elb_cfg::serializeBufferedWrites
+		int boundNumaNode{-1};       // NUMA node this worker bound itself to (-1: none)
 		std::vector<Batch> batches;
 		uint64_t* devCounters{NULL};
 		bool gpuPrepared{false};
@@ -234,6 +244,8 @@ class Worker
 		WorkerTreeShare customTreeFiles;
 		bool dirModeCountsEntry{true}; // false for a partial slice of a shared tree file
 		void applyNumaAndCoreBinding();     // Worker.cpp:102-146
+		void bindToNumaNode(int zoneNum, bool strict);
+		void enqueueStageCopies(Batch& batch, bool hostToDevice, bool onlyWrites);
 		void flockBlock(int fd, const BlockRef& block, bool isUnlock); // FileTk::flock
 		void fadviseFile(int fd, const std::string& path);             // FileTk::fadvise
 		void takeCustomTreeShare(); // LocalWorker.cpp:1520-1560
@@ -242,7 +254,7 @@ class Worker
 			bool tolerateMissing, bool countsAsEntry, const char* failTextOverride = NULL);
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470
 		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase
-		void rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)
+		bool rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)
 		std::unique_ptr<OffsetPlan> offsetPlan;
 		uint64_t blockVarianceSeed{0};
 
@@ -250,6 +262,13 @@ class Worker
 		int dirModeFD{-1};
 		Clock::time_point dirModeFileStartT;
 		std::string dirModeCurrentPath;
+
+		// --nofdsharing: this worker's own descriptors of the bench files (LocalWorker.cpp:869-913)
+		std::vector<int> threadFDs;
+		bool threadFDsWritable{false};
+		std::vector<std::unique_ptr<CuFileHandle> > threadCuFileHandles;
+		void openThreadFDs(bool forWrite);
+		void closeThreadFDs();
 
 		// kernel AIO
 		aio_context_t aioContext{0};
@@ -277,6 +296,7 @@ class Worker
 		void allocRings();
 		void freeRings();
 		void abortInFlight();
+		void drainCuFileBatch(Batch& batch);
 		void initPhaseOffsetPlan();
 
 		// phase work
@@ -302,6 +322,7 @@ class Worker
 		cudaGraphExec_t captureBatchGraph(Batch& batch, bool isRead);
 		void gpuWait(Batch& batch);
 		void retireReadBatch(Batch& batch);
+		void checkVerifyResults(Batch& batch);
 		void ioRun(Batch& batch, bool isRead);
 		void ioRunSync(Batch& batch, bool isRead);
 		void ioRunAio(Batch& batch, bool isRead);

@@ -74,6 +74,49 @@ def fill_random_batch(dev_descs_ptr, num_descs, pct, seed, dev_counters_ptr=0, s
            "elb_fill_random_batch")
 
 
+def fill_pattern_staged(descs_ptr, num_descs, salt, host_delta, dev_counters_ptr=0, stream=0,
+                        total_bytes=0, max_block_len=0):
+    """K1 + stage-out: the block goes to the device buffer and to (devPtr + host_delta)."""
+    _check(_native.load().elb_fill_pattern_staged(descs_ptr, num_descs, salt, host_delta,
+                                                  dev_counters_ptr or None, total_bytes,
+                                                  max_block_len, stream),
+           "elb_fill_pattern_staged")
+
+
+def fill_random_staged(descs_ptr, num_descs, pct, seed, host_delta, dev_counters_ptr=0, stream=0,
+                       total_bytes=0, max_block_len=0, algo=RANDALGO_SPLITMIX64):
+    _check(_native.load().elb_fill_random_staged(descs_ptr, num_descs, pct, seed, algo, host_delta,
+                                                 dev_counters_ptr or None, total_bytes,
+                                                 max_block_len, stream),
+           "elb_fill_random_staged")
+
+
+def verify_pattern_staged(descs_ptr, num_descs, salt, host_delta, dev_results_ptr,
+                          host_results_ptr=0, dev_ticket_ptr=0, dev_counters_ptr=0, stream=0,
+                          total_bytes=0, max_block_len=0):
+    """stage-in + K2: the block is read from (devPtr + host_delta), stored to the device buffer
+    and compared; with host_results_ptr/dev_ticket_ptr the results are published to pinned host
+    memory by the last CTA of the launch."""
+    _check(_native.load().elb_verify_pattern_staged(descs_ptr, num_descs, salt, host_delta,
+                                                    dev_results_ptr, host_results_ptr or None,
+                                                    dev_ticket_ptr or None,
+                                                    dev_counters_ptr or None, total_bytes,
+                                                    max_block_len, stream),
+           "elb_verify_pattern_staged")
+
+
+def stage_copy(descs_ptr, num_descs, host_to_device, host_delta, stream=0, total_bytes=0,
+               max_block_len=0):
+    _check(_native.load().elb_stage_copy(descs_ptr, num_descs, int(bool(host_to_device)),
+                                         host_delta, total_bytes, max_block_len, stream),
+           "elb_stage_copy")
+
+
+def verify_results_init(dev_results_ptr, num_descs, stream=0):
+    _check(_native.load().elb_verify_results_init(dev_results_ptr, num_descs, stream),
+           "elb_verify_results_init")
+
+
 def num_kernel_launches():
     return int(_native.load().elb_num_kernel_launches())
 

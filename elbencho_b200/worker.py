@@ -109,7 +109,10 @@ class WorkerConfig:
     ignore_del_errors: bool = False
     run_as_service: bool = False
     verify_collect_all: bool = False
-    serialize_buffered_writes: bool = False
+    serialize_buffered_writes: int = 0  # 0 auto, 1 on, 2 off (--writegate)
+    staging_engine: int = 0           # 0 auto, 1 kernels move the data, 2 cudaMemcpyAsync
+    no_gpu_numa_binding: bool = False  # --nogpunuma
+    use_no_fd_sharing: bool = False   # --nofdsharing
     num_rwmix_read_threads: int = 0   # --rwmixthr
 
     def to_abi(self):
@@ -181,6 +184,9 @@ class WorkerConfig:
         cfg.fadviseFlags = self.fadvise_flags
         cfg.doStatInline = int(self.do_stat_inline)
         cfg.noDirectIOCheck = int(self.no_direct_io_check)
+        cfg.stagingEngine = int(self.staging_engine)
+        cfg.noGPUNumaBinding = int(self.no_gpu_numa_binding)
+        cfg.useNoFDSharing = int(self.use_no_fd_sharing)
         return cfg, (path_bytes, path_arr, gpu_arr, cores, zones)
 
 

@@ -167,6 +167,34 @@ int elb_fill_random_batch_sized(const elb_block_desc* descs, uint32_t numDescs, 
 	uint64_t seed, int randAlgo, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
 	void* stream);
 
+/* Staged forms: the kernels also move each block between a pinned host buffer and its device
+ * buffer while they work on it (the worker's default staging engine; replaces
+ * cudaMemcpyGPUToHost / cudaMemcpyHostToGPU of LocalWorker.cpp:2285-2321 around the block
+ * modifiers). The host copy of a block lives at (devPtr + hostDelta); the host memory must be
+ * pinned and device-accessible (cudaHostAlloc / cudaHostRegister), `descs` may live there too.
+ *   fill_*_staged   : every generated vector goes to the device buffer AND to the host buffer
+ *   verify_*_staged : every vector is loaded from the host buffer, stored to the device buffer and
+ *                     compared. devResults must hold {0, ~0} entries (elb_verify_results_init);
+ *                     if hostResults and devDoneTicket (one zeroed unsigned in device memory)
+ *                     are given, the last CTA of the launch copies the per-block results to
+ *                     hostResults (pinned) and re-arms the device entries.
+ *   stage_copy      : plain copy host -> device (hostToDevice != 0) or device -> host
+ * hostDelta == 0 turns the staging off (verify then still publishes to hostResults). */
+int elb_fill_pattern_staged(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	int64_t hostDelta, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream);
+int elb_fill_random_staged(const elb_block_desc* descs, uint32_t numDescs, unsigned pct,
+	uint64_t seed, int randAlgo, int64_t hostDelta, uint64_t* devCounters, uint64_t totalBytes,
+	uint64_t maxBlockLen, void* stream);
+int elb_verify_pattern_staged(const elb_block_desc* descs, uint32_t numDescs, uint64_t salt,
+	int64_t hostDelta, elb_verify_result* devResults, elb_verify_result* hostResults,
+	unsigned* devDoneTicket, uint64_t* devCounters, uint64_t totalBytes, uint64_t maxBlockLen,
+	void* stream);
+int elb_stage_copy(const elb_block_desc* descs, uint32_t numDescs, int hostToDevice,
+	int64_t hostDelta, uint64_t totalBytes, uint64_t maxBlockLen, void* stream);
+/* devResults[0..numDescs) <- {0, ~0} */
+int elb_verify_results_init(elb_verify_result* devResults, uint32_t numDescs, void* stream);
+
 /* Number of kernel launches issued through this library since load (all threads). */
 uint64_t elb_num_kernel_launches(void);
 
@@ -250,10 +278,12 @@ typedef struct elb_cfg
 	int32_t ignoreDelErrors;
 	int32_t runAsService; /* disables last-finisher stonewall trigger (Worker.cpp:41-43) */
 	int32_t verifyCollectAll; /* nonzero: do not stop at first bad block, count all mismatches */
-	/* nonzero: buffered (non-O_DIRECT) writes of all workers of this process to the same file pass
-	 * a per-file user-space gate one at a time. Linux serialises buffered writes to one inode on
-	 * the inode lock anyway; queueing in user space avoids the lock's spinning under contention
-	 * (measured on tmpfs: 3.2 -> 4.1 GiB/s at 16 writers). I/O sizes and order are unchanged. */
+	/* enum elb_write_gate: buffered (non-O_DIRECT) writes of all workers of this process to the
+	 * same file pass a per-file FIFO gate in user space one at a time. Linux serialises buffered
+	 * writes to one inode on the inode lock anyway; a ticket queue whose next-in-line spins while
+	 * the others sleep hands the file over without the lock's contention (measured on tmpfs,
+	 * 16 writers: 3.0 -> 3.7 GiB/s). I/O sizes and order per worker are unchanged; the block's
+	 * latency includes the time in the queue (as it includes the inode lock wait without it). */
 	int32_t serializeBufferedWrites;
 
 	/* --rwmixthr: the first N local workers read (their share of the data set) during the write
@@ -299,7 +329,36 @@ typedef struct elb_cfg
 	uint32_t fadviseFlags;
 	int32_t doStatInline;   /* --statinline: fstat each dir mode file right after open */
 	int32_t noDirectIOCheck; /* --nodiocheck: skip the direct IO alignment / size sanity checks */
+
+	/* Who moves a block between the pinned host ring and the device ring (enum
+	 * elb_staging_engine): the fill / verify kernels themselves over PCIe (one launch per batch, no
+	 * copy engine, no descriptor or result copies), or cudaMemcpyAsync on the batch stream followed
+	 * / preceded by the kernel. 0 = auto (kernels). Ignored with --cufile (no host ring). */
+	int32_t stagingEngine;
+	/* 0: each worker binds itself to the CPUs of its GPU's NUMA node and prefers memory from there
+	 * (pinned ring, page cache pages it first touches) unless --zones / --cores are given;
+	 * nonzero: no binding (the reference's behaviour without --zones) */
+	int32_t noGPUNumaBinding;
+	/* --nofdsharing: every worker opens its own file descriptors in file / blockdev mode instead
+	 * of using the manager's (ProgArgs.h useNoFDSharing, LocalWorker.cpp:1088-1117) */
+	int32_t useNoFDSharing;
+	int32_t reserved5;
 } elb_cfg;
+
+enum elb_staging_engine
+{
+	ELB_STAGING_AUTO = 0,
+	ELB_STAGING_KERNEL = 1, /* fused: fill + stage-out, stage-in + verify, stage copy */
+	ELB_STAGING_COPYENGINE = 2, /* cudaMemcpyAsync + kernel on the device slot */
+};
+
+/* elb_cfg::serializeBufferedWrites values */
+enum elb_write_gate
+{
+	ELB_WRITEGATE_AUTO = 0, /* on when several local workers write one file buffered */
+	ELB_WRITEGATE_ON = 1,
+	ELB_WRITEGATE_OFF = 2,
+};
 
 /* ---------------------------------------------------------------------------------------------
  * Stats types (source/LiveOps.h:13-118, source/LiveLatency.h:12-89, LatencyHistogram.h:28-45)

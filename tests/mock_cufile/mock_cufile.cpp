@@ -171,6 +171,9 @@ CUfileError_t cuFileBatchIOGetStatus(CUfileBatchHandle_t batchIdp, unsigned minN
 
 void cuFileBatchIODestroy(CUfileBatchHandle_t batchIdp) { delete (MockBatch*)batchIdp; }
 
+/* (batch I/O of the mock completes at submit time: nothing to cancel) */
+CUfileError_t cuFileBatchIOCancel(CUfileBatchHandle_t) { CUfileError_t res{}; return res; }
+
 void mock_cufile_get_stats(uint64_t* out)
 {
 	for(int i = 0; i < ST_NUM; i++)

@@ -332,3 +332,144 @@ def test_kernel_launch_counter(cuda_device):
     kernels.fill_pattern(buf.data_ptr(), 4096, 0, 1, stream_handle())
     torch.cuda.synchronize()
     assert kernels.num_kernel_launches() == before + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# staged forms: the kernels move the block between a pinned host buffer and the device buffer
+# ------------------------------------------------------------------------------------------------
+
+def _staged_arena(cuda_device, nbytes):
+    """device arena + pinned host arena of the same layout -> (dev, host, host_delta)"""
+    dev = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device=cuda_device)
+    host = torch.full((nbytes,), 0x5A, dtype=torch.uint8).pin_memory()
+    return dev, host, host.data_ptr() - dev.data_ptr()
+
+
+def _pinned_descs(blocks):
+    raw = kernels.pack_block_descs(blocks)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+
+
+@pytest.mark.parametrize("misalign", [0, 7, 16])
+@pytest.mark.parametrize("hinted", [True, False])
+def test_staged_fill_writes_both_rings(cuda_device, misalign, hinted):
+    """fill + stage-out: device slot and host slot both hold the oracle's bytes, nothing else is
+    touched; descriptors are read from pinned host memory (ragged lengths, both launch shapes)."""
+    lens = [1 << 20, (1 << 20) - 13, 4096, 33, 0, 65536 + 5]
+    stride = (1 << 20) + 4096
+    dev, host, delta = _staged_arena(cuda_device, stride * len(lens) + 64)
+    salt = 0xABCDEF0102
+    blocks = [(dev.data_ptr() + i * stride + misalign, n, (i << 21) + 3 * i, i)
+              for i, n in enumerate(lens)]
+    descs = _pinned_descs(blocks)
+    hints = dict(total_bytes=sum(lens), max_block_len=max(lens)) if hinted else {}
+    kernels.fill_pattern_staged(descs.data_ptr(), len(blocks), salt, delta, 0, stream_handle(),
+                                **hints)
+    torch.cuda.synchronize()
+    dev_bytes_, host_bytes = to_bytes(dev), host.numpy().tobytes()
+    for i, (ptr, n, off, _) in enumerate(blocks):
+        lo = ptr - dev.data_ptr()
+        expected = oracle_lib.fill_pattern(n, off, salt) if n else b""
+        assert dev_bytes_[lo:lo + n] == expected, i
+        assert host_bytes[lo:lo + n] == expected, i
+        gap_end = (i + 1) * stride + misalign if i + 1 < len(blocks) else len(dev_bytes_)
+        assert dev_bytes_[lo + n:gap_end] == b"\xa5" * (gap_end - lo - n)
+        assert host_bytes[lo + n:gap_end] == b"\x5a" * (gap_end - lo - n)
+    # random fill through the same path
+    kernels.fill_random_staged(descs.data_ptr(), len(blocks), 70, 4242, delta, 0, stream_handle(),
+                               **hints)
+    torch.cuda.synchronize()
+    dev_bytes_, host_bytes = to_bytes(dev), host.numpy().tobytes()
+    for ptr, n, _, ctr in blocks:
+        lo = ptr - dev.data_ptr()
+        expected = oracle_lib.fill_random_ctr(n, 70, 4242, ctr) if n else b""
+        assert dev_bytes_[lo:lo + n] == expected and host_bytes[lo:lo + n] == expected
+
+
+@pytest.mark.parametrize("misalign", [0, 5])
+def test_staged_verify_reads_host_ring_and_publishes_results(cuda_device, misalign):
+    """stage-in + verify: data comes from the pinned host slot, lands in the device slot, the
+    last CTA publishes per-block results to pinned host memory and re-arms the device results."""
+    lens = [1 << 20, 70000, 4096, 0, (1 << 20) + 31]
+    stride = (1 << 20) + 4096
+    dev, host, delta = _staged_arena(cuda_device, stride * len(lens) + 64)
+    salt = 99
+    blocks = [(dev.data_ptr() + i * stride + misalign, n, i * (1 << 24) + 8 * i, 0)
+              for i, n in enumerate(lens)]
+    descs = _pinned_descs(blocks)
+    host_np = host.numpy()
+    for ptr, n, off, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        host_np[lo:lo + n] = bytearray(oracle_lib.fill_pattern(n, off, salt)) if n else b""
+    bad = {0: [5, 70001, (1 << 20) - 1], 2: [4095], 4: [(1 << 20) + 30]}
+    for idx, positions in bad.items():
+        lo = blocks[idx][0] - dev.data_ptr()
+        for pos in positions:
+            host_np[lo + pos] ^= 0x11
+    dev_results = torch.zeros(2 * len(blocks), dtype=torch.int64, device=cuda_device)
+    host_results = torch.full((2 * len(blocks),), 7, dtype=torch.int64).pin_memory()
+    ticket = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    counters = torch.zeros(kernels.DEVCTR_NUM, dtype=torch.int64, device=cuda_device)
+    kernels.verify_results_init(dev_results.data_ptr(), len(blocks), stream_handle())
+    for rep in range(2):  # second launch: device results were re-armed by the first
+        kernels.verify_pattern_staged(descs.data_ptr(), len(blocks), salt, delta,
+                                      dev_results.data_ptr(), host_results.data_ptr(),
+                                      ticket.data_ptr(), counters.data_ptr(), stream_handle(),
+                                      total_bytes=sum(lens), max_block_len=max(lens))
+        torch.cuda.synchronize()
+        got = [(int(host_results[2 * i]) & (2 ** 64 - 1), int(host_results[2 * i + 1]) & (2 ** 64 - 1))
+               for i in range(len(blocks))]
+        for i in range(len(blocks)):
+            exp = (len(bad[i]), min(bad[i])) if i in bad else (0, 2 ** 64 - 1)
+            assert got[i] == exp, (rep, i)
+        assert read_result(dev_results) == [(0, 2 ** 64 - 1)] * len(blocks)  # re-armed
+        assert int(ticket.item()) == 0
+    assert counters.cpu().tolist()[kernels.DEVCTR_VERIFY_MISMATCH_BYTES] == 2 * 5
+    # the device slots now hold what was in the host slots
+    dev_bytes_ = to_bytes(dev)
+    for ptr, n, _, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        assert dev_bytes_[lo:lo + n] == host_np[lo:lo + n].tobytes()
+
+
+def test_verify_publishes_results_without_staging(cuda_device):
+    """host_delta 0: verify on the device slot (copy-engine staging / cuFile), results still
+    published by the last CTA"""
+    n, salt = (1 << 20) + 17, 3
+    dev = dev_bytes(n, cuda_device)
+    kernels.fill_pattern(dev.data_ptr(), n, 4096, salt, stream_handle())
+    dev[123456] ^= 1
+    descs = _pinned_descs([(dev.data_ptr(), n, 4096, 0)])
+    dev_results = torch.zeros(2, dtype=torch.int64, device=cuda_device)
+    host_results = torch.zeros(2, dtype=torch.int64).pin_memory()
+    ticket = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    kernels.verify_results_init(dev_results.data_ptr(), 1, stream_handle())
+    kernels.verify_pattern_staged(descs.data_ptr(), 1, salt, 0, dev_results.data_ptr(),
+                                  host_results.data_ptr(), ticket.data_ptr(), 0, stream_handle(),
+                                  total_bytes=n, max_block_len=n)
+    torch.cuda.synchronize()
+    assert host_results.tolist() == [1, 123456]
+
+
+@pytest.mark.parametrize("to_device", [True, False])
+def test_stage_copy_kernels(cuda_device, to_device):
+    lens = [1 << 20, 12345, 0, 4096]
+    stride = (1 << 20) + 4096
+    dev, host, delta = _staged_arena(cuda_device, stride * len(lens))
+    blocks = [(dev.data_ptr() + i * stride + 3, n, 0, 0) for i, n in enumerate(lens)]
+    descs = _pinned_descs(blocks)
+    rnd = torch.randint(0, 256, (stride * len(lens),), dtype=torch.uint8)
+    if to_device:
+        host.copy_(rnd)
+    else:
+        dev.copy_(rnd.to(cuda_device))
+    kernels.stage_copy(descs.data_ptr(), len(blocks), to_device, delta, stream_handle(),
+                       total_bytes=sum(lens), max_block_len=max(lens))
+    torch.cuda.synchronize()
+    dev_bytes_, host_bytes, src = to_bytes(dev), host.numpy().tobytes(), rnd.numpy().tobytes()
+    for ptr, n, _, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        assert dev_bytes_[lo:lo + n] == src[lo:lo + n]
+        assert host_bytes[lo:lo + n] == src[lo:lo + n]
+    dst_bytes, fill = (dev_bytes_, b"\xa5") if to_device else (host_bytes, b"\x5a")
+    assert dst_bytes[:3] == fill * 3  # nothing outside the blocks was written

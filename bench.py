@@ -1,27 +1,40 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the GPU I/O worker (BASELINE.json configs[1]).
+"""bench.py — benchmark of the GPU I/O worker on the BASELINE.json configurations.
 
-Workload (N=1): single file of --file-gib GiB (default 64), 1 MiB blocks, sequential write phase
-then read phase with --verify, --gpuids <rank's GPU>, pinned-ring + cudaMemcpyAsync staging.
+What a run does (both arms, `--impl b200` = this repo's worker, `--impl reference` = the CPU
+LocalWorker of the reference, here its oracle port — the reference binary cannot be built in this
+image):
 
-What is measured
-  value   : GiB/s of the on-GPU work alone (K1 fill_pattern + K2 verify_pattern over a window of
-            1 MiB blocks that is resident in HBM when the timed region starts). A "step" is one
-            write pass (fill) + one read pass (verify) over the window = 2 x window bytes.
-  e2e     : the same metric through the worker's public C ABI with host buffers and real files:
-            write phase + read phase over the whole file, host<->device copies and storage I/O
-            inside the timed region. (bytes written + bytes read) / (write time + read time).
-  roofline: the dominant kernel's algorithmic bytes per launch / its CUDA-event duration, against
-            the measured HBM peak of MEASURED_PEAKS.json.
-  cpu_baseline: the CPU LocalWorker (oracle port of the reference loop) on a bounded sample of the
-            same workload on this box's host cores (rank 0, N=1 only).
+  --config c2 (default, BASELINE configs[1]): one file of --file-gib GiB (default 64) per GPU in
+      --dir, 1 MiB blocks, sequential write phase + read phase with --verify. The file is
+      worked through in W+K equal slices: step s = write phase + read phase over slice s of every
+      file, expressed with the reference's own sharding (--rankoffset / numDataSetThreads:
+      worker ranks [(r*S+s)*T, (r*S+s+1)*T) of N*S*T own exactly slice s of file r,
+      LocalWorker.cpp:3576-3589). Over a whole run every file is written once and read once.
+  --config c3 (configs[2]): 4 KiB random reads with --verify, iodepth 64, of a 64 GiB file per
+      GPU; the K timed steps together issue file-size / 4 KiB I/Os (16.7 M at 64 GiB).
+  --config c4 (configs[3]): one 32 GiB file per GPU written with --blockvarpct 100 (K3), then
+      1 MiB sequential reads in slices like c2 (no --verify).
+  --config c5 (configs[4]): directory tree of 2^20 files of 64 KiB over all GPUs (16 threads per
+      GPU), write + read --verify; step s works on its own 1/(W+K) of the tree.
+  The reference's --gds variants need nvidia-fs; on boxes without it (cuFileHandleRegister fails,
+  see profiles/) the same workload runs through the staged engine and the line says so.
 
---impl reference times the reference's CPU implementation of the path (the oracle port; the
-reference binary cannot be built here) on the host cores for the same metric.
+What is reported
+  value / e2e.value : the BASELINE metric through the worker's public C ABI with host buffers and
+      real files: storage I/O, host<->device transfers and the on-GPU fill / verify are all inside
+      the timed region. (bytes written + bytes read) / (sum over timed steps of the phase times),
+      phase time = max over all workers of all ranks. value == e2e.value by construction; the
+      HBM-resident kernel numbers are under `roofline`.
+  roofline : K1/K2/K3 over an HBM-resident window against the measured HBM peak (the dominant
+      resident kernel), plus the PCIe roofline of the staging path measured in the same run and
+      the storage roofline (raw pread/pwrite with the same threads).
+  cpu_baseline : the CPU LocalWorker on a bounded sample of the same steps (rank 0, N=1).
 
-Multi-GPU: one process per GPU under torchrun; rank r owns file r and worker ranks
-[r*T, (r+1)*T) of N*T dataset threads (the reference's --rankoffset sharding); no data-path
-collective; NCCL only reduces the stats counters. scaling = weak (per-GPU work fixed).
+Multi-GPU: one process per GPU under torchrun; no data-path collective; NCCL reduces the stats
+only. scaling = weak (per-GPU work fixed). With N > 1 rank 0 afterwards also runs the in-process
+worker pool (one process, --gpuids 0..N-1, grouped ncclReduce for the stats) on a sample and
+reports it as extra.inprocess_pool.
 """
 import argparse
 import ctypes
@@ -37,44 +50,42 @@ REPO_ROOT = os.path.dirname(os.path.abspath(__file__))
 if REPO_ROOT not in sys.path:
     sys.path.insert(0, REPO_ROOT)
 
+KiB = 1 << 10
 MiB = 1 << 20
 GiB = 1 << 30
-METRIC = "seq_write_read_verify_throughput"
-UNIT = "GiB/s"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--file-gib", type=float, default=64.0, help="file size per GPU (GiB)")
-    p.add_argument("--block-mib", type=float, default=1.0)
+    p.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    p.add_argument("--file-gib", type=float, default=0.0,
+                   help="file size per GPU (GiB); 0 = the config's stated size")
     p.add_argument("--threads", type=int, default=int(os.environ.get("ELB_BENCH_THREADS", "16")),
-                   help="worker threads per GPU (-t)")
-    p.add_argument("--window-gib", type=float, default=4.0,
-                   help="HBM-resident window of the kernel-level measurement")
+                   help="worker threads per GPU (-t), both arms")
     p.add_argument("--dir", default=os.environ.get("ELB_BENCH_DIR", "/dev/shm"))
     p.add_argument("--salt", type=int, default=1)
-    p.add_argument("--cpu-threads", type=int,
-                   default=int(os.environ.get("ELB_BENCH_CPU_THREADS", "0")),
-                   help="threads of the CPU LocalWorker arm (0 = calibrate: best of 1/4/8/16/32/nproc "
-                        "on a small sample, i.e. all the host threads it can use productively)")
-    p.add_argument("--cpu-sample-gib", type=float, default=8.0,
-                   help="file size of the bounded CPU sample")
-    p.add_argument("--ref-step-gib", type=float, default=2.0,
-                   help="--impl reference: file size written+read per step")
     p.add_argument("--direct", action="store_true", help="O_DIRECT (--direct)")
-    p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--window-gib", type=float, default=4.0,
+                   help="HBM-resident window of the kernel-level (roofline) measurement")
+    p.add_argument("--cpu-sample-steps", type=int, default=4,
+                   help="timed steps of the bounded cpu_baseline / storage roofline samples")
     p.add_argument("--skip-cpu", action="store_true")
+    p.add_argument("--skip-kernels", action="store_true")
+    p.add_argument("--skip-pool", action="store_true")
+    p.add_argument("--only-kernels", action="store_true",
+                   help="kernel-level measurement only (for ncu captures)")
+    p.add_argument("--staging", default="auto", choices=["auto", "kernel", "copyengine"])
     p.add_argument("--batch-blocks", type=int, default=0)
     p.add_argument("--num-batches", type=int, default=0)
-    p.add_argument("--no-write-gate", action="store_true",
-                   help="do not queue buffered writers of one file in user space")
-    p.add_argument("--single-thread-sample-gib", type=float, default=4.0,
-                   help="size of the extra -t 1 comparison (GPU worker vs CPU LocalWorker); 0 = skip")
+    p.add_argument("--write-gate", default="auto", choices=["auto", "on", "off"])
+    p.add_argument("--no-gpu-numa", action="store_true")
+    p.add_argument("--kernel-block-kib", type=int, default=0,
+                   help="block size of the kernel-level window (0 = the config's block size)")
     return p.parse_args()
 
 
@@ -126,7 +137,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.02)
 
     def stop(self):
         self._stop.set()
@@ -136,7 +147,8 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
         return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "gpu_busy_mean_pct": round(statistics.mean(u for _, u in self.samples), 1)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -152,104 +164,413 @@ def load_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_ncu_traffic(window_bytes, kernel_key):
+def load_ncu_traffic(window_bytes, block_bytes, kernel_key):
     """DRAM bytes (read + write) of one launch of the given kernel from the committed
-    `ncu --set full` capture, if that capture used the same window size; else None."""
+    `ncu --set full` capture with the same window and block size; else None."""
     path = os.path.join(REPO_ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             data = json.load(f)
-        if int(data["window_bytes"]) != int(window_bytes):
-            return None, None
-        entry = data["kernels"][kernel_key]
-        return entry["dram_bytes_read"] + entry["dram_bytes_write"], data.get("source")
+        for entry in data["captures"] if "captures" in data else [data]:
+            if int(entry["window_bytes"]) == int(window_bytes) and \
+                    int(entry.get("block_bytes", MiB)) == int(block_bytes):
+                kern = entry["kernels"][kernel_key]
+                return kern["dram_bytes_read"] + kern["dram_bytes_write"], entry.get("source")
     except Exception:
-        return None, None
+        pass
+    return None, None
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    return rank, local_rank, world
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
 
 
-def bench_dir(args, rank):
+def bench_dir(args):
     path = os.path.join(args.dir, "elb_bench_%d" % os.getuid())
     os.makedirs(path, exist_ok=True)
     return path
 
 
-_CPU_THREADS_CACHE = {}
-
-
-def cpu_threads_default(args, nfiles=1):
-    """Thread count of the CPU LocalWorker arm. The reference's throughput on a single shared file
-    peaks at a moderate thread count (buffered writes serialise on the inode lock) and falls
-    beyond it, so 'all the host threads it can use' is found by a short calibration."""
-    if args.cpu_threads:
-        return args.cpu_threads
-    if "best" in _CPU_THREADS_CACHE:
-        return _CPU_THREADS_CACHE["best"]
-    nproc = os.cpu_count() or 1
-    candidates = sorted({t for t in (1, 4, 8, 16, 32, 64, nproc) if nfiles <= t <= nproc})
-    block = int(args.block_mib * MiB)
-    size = max(block * nproc, (4 * GiB) // nfiles)
-    size -= size % block
-    paths = [os.path.join(bench_dir(args, 0), "cpu_calibrate_%d.bin" % i) for i in range(nfiles)]
-    best, best_val, table = candidates[0], 0.0, {}
+def cpu_quota():
+    """CPUs this container may use: cgroup cpu.max quota, else the affinity mask."""
     try:
-        for threads in candidates:
-            for path in paths:
-                if os.path.exists(path):
-                    os.unlink(path)
-            res = run_cpu_localworker(paths, threads, size, block, args.salt, args.direct)
-            table[threads] = round(res["gib_s"], 2)
-            if res["gib_s"] > best_val:
-                best, best_val = threads, res["gib_s"]
-    finally:
-        for path in paths:
-            if os.path.exists(path):
-                os.unlink(path)
-    _CPU_THREADS_CACHE["best"] = best
-    _CPU_THREADS_CACHE["table"] = table
-    return best
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            return round(int(quota) / int(period), 1)
+    except Exception:
+        pass
+    try:
+        return float(len(os.sched_getaffinity(0)))
+    except Exception:
+        return float(os.cpu_count() or 1)
+
+
+def storage_free_gib(path):
+    """free space of the (RAM backed) storage: statvfs and, for tmpfs, the cgroup memory limit"""
+    stat = os.statvfs(path)
+    free = stat.f_bavail * stat.f_frsize / GiB
+    try:
+        limit = open("/sys/fs/cgroup/memory.max").read().strip()
+        if limit != "max":
+            used = int(open("/sys/fs/cgroup/memory.current").read())
+            free = min(free, (int(limit) - used) / GiB)
+    except Exception:
+        pass
+    return free
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver parses ONE JSON line from stdout; libraries (NCCL's version banner) also write
+    there. Keep the real stdout aside and point fd 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def log(msg):
+    sys.stderr.write("[bench] %s\n" % msg)
+    sys.stderr.flush()
+
+
+def histo_summary(histo):
+    """min / avg / max and percentiles of a latency histogram dict (LatencyHistogram.h rules:
+    bucket index = floor(log2(usec) * 4), percentile = upper bound of the bucket)"""
+    num = histo["num"]
+    if not num:
+        return None
+    out = {"num": num, "min_usec": histo["min_usec"], "avg_usec": round(histo["sum_usec"] / num, 1),
+           "max_usec": histo["max_usec"]}
+    for pct in (50, 99, 99.9):
+        want = num * pct / 100.0
+        seen = 0
+        for idx, count in enumerate(histo["buckets"]):
+            seen += count
+            if seen >= want:
+                out["p%s_usec_le" % pct] = round(2 ** ((idx + 1) / 4.0), 1)
+                break
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads: what one step of a configuration is, identically for both arms
+# ------------------------------------------------------------------------------------------------
+
+class Workload:
+    """One BASELINE configuration. plan(step, rank) -> (WorkerConfig kwargs, [phases]) of the step
+    for the process that owns file / tree share `rank` (the GPU arm runs rank = its own rank, the
+    CPU arm runs all ranks of the job concurrently in one process)."""
+
+    def __init__(self, args, world):
+        self.args = args
+        self.world = world
+        self.threads = args.threads
+        self.num_slices = args.warmup + args.steps
+        self.workdir = bench_dir(args)
+
+    # -- to be provided by the configs
+    name = ""
+    metric = ""
+    unit = "GiB/s"
+    block = MiB
+
+    def describe(self):
+        raise NotImplementedError
+
+    def prepare_plan(self, rank):
+        """untimed preparation (e.g. the files a read-only config reads): like plan() or None"""
+        return None
+
+    def plan(self, step, rank):
+        raise NotImplementedError
+
+    def value_of(self, totals):
+        """headline value from the summed timed steps"""
+        return totals["bytes"] / GiB / (totals["usec"] / 1e6) if totals["usec"] else 0.0
+
+    def cleanup_paths(self, rank):
+        return []
+
+    def common_cfg(self):
+        return dict(block_size=self.block, use_direct_io=self.args.direct)
+
+
+class SeqFileWorkload(Workload):
+    """c2 / c4: one file per GPU, sliced into W+K steps through the reference's rank sharding."""
+
+    def __init__(self, args, world, file_gib, do_verify, blockvarpct, do_write_in_step):
+        super().__init__(args, world)
+        self.do_verify = do_verify
+        self.blockvarpct = blockvarpct
+        self.do_write_in_step = do_write_in_step
+        blocks_per_slice_thread = int(file_gib * GiB) // self.block // (self.num_slices *
+                                                                      self.threads)
+        if blocks_per_slice_thread < 1:
+            raise SystemExit("file too small for %d slices x %d threads" % (self.num_slices,
+                                                                            self.threads))
+        self.file_size = blocks_per_slice_thread * self.num_slices * self.threads * self.block
+        self.slice_bytes = self.file_size // self.num_slices
+        self.paths = [os.path.join(self.workdir, "%s_file_%d.bin" % (self.name, r))
+                      for r in range(world)]
+
+    def base_cfg(self):
+        cfg = self.common_cfg()
+        cfg.update(paths=self.paths, file_size=self.file_size, num_threads=self.threads,
+                   integrity_check_salt=self.args.salt if self.do_verify else 0,
+                   block_variance_percent=self.blockvarpct, block_variance_seed=4711)
+        return cfg
+
+    def plan(self, step, rank):
+        from elbencho_b200 import BenchPhase
+        cfg = self.base_cfg()
+        cfg.update(rank_offset=(rank * self.num_slices + step) * self.threads,
+                   num_dataset_threads=self.world * self.num_slices * self.threads)
+        phases = ([BenchPhase.CREATEFILES] if self.do_write_in_step else []) + \
+            [BenchPhase.READFILES]
+        return cfg, phases
+
+    def cleanup_paths(self, rank):
+        return [self.paths[rank]]
+
+
+class C2(SeqFileWorkload):
+    name = "c2"
+    metric = "seq_write_read_verify_throughput"
+
+    def __init__(self, args, world):
+        super().__init__(args, world, args.file_gib or 64.0, True, 0, True)
+
+    def describe(self):
+        return ("BASELINE configs[1]: single %.2f GiB file per GPU, 1 MiB blocks, sequential write "
+                "+ read with --verify %d, --gpuids <gpu>, pinned host ring staging"
+                % (self.file_size / GiB, self.args.salt))
+
+
+class C4(SeqFileWorkload):
+    name = "c4"
+    metric = "seq_read_throughput_blockvar_files"
+
+    def __init__(self, args, world):
+        super().__init__(args, world, args.file_gib or 32.0, False, 100, False)
+
+    def describe(self):
+        return ("BASELINE configs[3]: one %.2f GiB file per GPU written with --blockvarpct 100 "
+                "(on-GPU random fill), then 1 MiB sequential reads into GPU memory; --gds is "
+                "replaced by the staged engine where cuFile cannot register handles"
+                % (self.file_size / GiB))
+
+    def prepare_plan(self, rank):
+        from elbencho_b200 import BenchPhase
+        cfg = self.base_cfg()
+        cfg.update(rank_offset=rank * self.threads, num_dataset_threads=self.world * self.threads)
+        return cfg, [BenchPhase.CREATEFILES]
+
+
+class C3(Workload):
+    name = "c3"
+    metric = "rand_read_4k_verify_iops"
+    unit = "IOPS"
+    block = 4 * KiB
+
+    def __init__(self, args, world):
+        super().__init__(args, world)
+        per_thread = int((args.file_gib or 64.0) * GiB) // self.block // (args.steps *
+                                                                          self.threads)
+        self.ios_per_step = per_thread * self.threads
+        self.file_size = self.ios_per_step * args.steps * self.block
+        self.paths = [os.path.join(self.workdir, "c3_file_%d.bin" % r) for r in range(world)]
+
+    def describe(self):
+        return ("BASELINE configs[2]: single %.2f GiB file per GPU, 4 KiB random reads with "
+                "--verify %d, --iodepth 64, %d I/Os per GPU over the timed steps; --gds cuFile "
+                "batch is replaced by the staged engine where cuFile cannot register handles"
+                % (self.file_size / GiB, self.args.salt, self.ios_per_step * self.args.steps))
+
+    def base_cfg(self, rank):
+        cfg = self.common_cfg()
+        cfg.update(paths=[self.paths[rank]], file_size=self.file_size, num_threads=self.threads,
+                   integrity_check_salt=self.args.salt)
+        return cfg
+
+    def prepare_plan(self, rank):
+        from elbencho_b200 import BenchPhase
+        cfg = self.base_cfg(rank)
+        cfg.update(block_size=MiB)
+        return cfg, [BenchPhase.CREATEFILES]
+
+    def plan(self, step, rank):
+        from elbencho_b200 import BenchPhase, IOEngine
+        cfg = self.base_cfg(rank)
+        cfg.update(use_random_offsets=True, random_amount=self.ios_per_step * self.block,
+                   rand_offset_seed=1000 + 97 * step + rank, io_depth=64,
+                   io_engine=int(IOEngine.AIO))
+        return cfg, [BenchPhase.READFILES]
+
+    def value_of(self, totals):
+        return totals["iops"] / (totals["usec"] / 1e6) if totals["usec"] else 0.0
+
+    def cleanup_paths(self, rank):
+        return [self.paths[rank]]
+
+
+class C5(Workload):
+    name = "c5"
+    metric = "dir_tree_write_read_verify_throughput"
+    block = 64 * KiB
+
+    DIRS_PER_STEP = 4
+
+    def __init__(self, args, world):
+        super().__init__(args, world)
+        total_files = int(args.file_gib * GiB) // self.block if args.file_gib else (1 << 20)
+        self.files_per_dir = max(1, total_files // (world * self.threads * self.num_slices *
+                                                    self.DIRS_PER_STEP))
+        self.files_per_step_gpu = self.files_per_dir * self.DIRS_PER_STEP * self.threads
+        self.total_files = self.files_per_step_gpu * world * self.num_slices
+
+    def describe(self):
+        return ("BASELINE configs[4]: directory tree of %d files x 64 KiB over all GPUs (2^20 "
+                "asked, rounded down to whole steps), %d threads per GPU, create+write and read "
+                "with --verify %d; step s works on its own 1/%d of the tree" % (
+                    self.total_files, self.threads, self.args.salt, self.num_slices))
+
+    def step_dir(self, step):
+        return os.path.join(self.workdir, "c5_step_%d" % step)
+
+    def plan(self, step, rank):
+        from elbencho_b200 import BenchPhase, PathType
+        path = self.step_dir(step)
+        os.makedirs(path, exist_ok=True)
+        cfg = self.common_cfg()
+        cfg.update(paths=[path], path_type=int(PathType.DIR), file_size=self.block,
+                   num_threads=self.threads, num_dirs=self.DIRS_PER_STEP,
+                   num_files=self.files_per_dir, integrity_check_salt=self.args.salt,
+                   rank_offset=rank * self.threads, num_dataset_threads=self.world * self.threads)
+        return cfg, [BenchPhase.CREATEDIRS, BenchPhase.CREATEFILES, BenchPhase.READFILES]
+
+    def cleanup_paths(self, rank):
+        return [self.step_dir(s) for s in range(self.num_slices)] if rank == 0 else []
+
+
+WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
+TIMED_PHASES = ("CREATEFILES", "READFILES")  # (mkdirs of c5 are preparation of the step)
+
+
+def remove_paths(paths):
+    for path in paths:
+        if os.path.isdir(path):
+            shutil.rmtree(path, ignore_errors=True)
+        elif os.path.exists(path):
+            os.unlink(path)
+
+
+def new_totals():
+    return {"bytes": 0, "iops": 0, "entries": 0, "usec": 0,
+            "phase": {name: {"bytes": 0, "iops": 0, "entries": 0, "usec": 0}
+                      for name in TIMED_PHASES}}
+
+
+def add_phase(totals, name, num_bytes, iops, entries, usec):
+    if name not in TIMED_PHASES:
+        return
+    for tgt in (totals, totals["phase"][name]):
+        tgt["bytes"] += num_bytes
+        tgt["iops"] += iops
+        tgt["entries"] += entries
+        tgt["usec"] += usec
+
+
+def phase_rates(totals):
+    out = {}
+    for name, short in (("CREATEFILES", "write"), ("READFILES", "read")):
+        ph = totals["phase"][name]
+        if not ph["usec"]:
+            continue
+        secs = ph["usec"] / 1e6
+        out[short + "_gib_s"] = round(ph["bytes"] / GiB / secs, 3)
+        out[short + "_iops"] = int(ph["iops"] / secs)
+        if ph["entries"]:
+            out[short + "_files_s"] = int(ph["entries"] / secs)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
 # the CPU LocalWorker arm (oracle port of the reference loop)
 # ------------------------------------------------------------------------------------------------
 
-def run_cpu_localworker(paths, threads, file_size, block_size, salt, direct, rank_offset=0,
-                        dataset_threads=0):
-    """write phase + read phase with --verify on the CPU. -> dict(bytes, usec, gib_s, iops)"""
-    from elbencho_b200 import BenchPhase, WorkerConfig
+def cpu_run_plan(plans):
+    """Run one step's plan of every rank concurrently in this process (one oracle run per rank,
+    like the GPU arm's one process per GPU). plans: [(cfg kwargs, phases)] -> per phase name:
+    dict(bytes, iops, entries, usec = max over the ranks)"""
+    from elbencho_b200 import WorkerConfig
     from tests import oracle_lib  # oracle: only used as the CPU baseline / reference arm here
-    cfg = WorkerConfig(paths=paths, num_threads=threads, block_size=block_size,
-                       file_size=file_size, integrity_check_salt=salt, use_direct_io=direct,
-                       rank_offset=rank_offset, num_dataset_threads=dataset_threads)
-    total_bytes = 0
-    total_usec = 0
-    total_iops = 0
-    phases = {}
-    for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
-        rc, workers, pres = oracle_lib.run_oracle_phase(cfg, phase)
-        if rc != 0:
-            raise RuntimeError("CPU LocalWorker failed: " +
-                               "; ".join(w.errorMsg.decode() for w in workers if w.hadError))
-        total_bytes += pres.opsTotal.numBytesDone
-        total_iops += pres.opsTotal.numIOPSDone
-        total_usec += pres.lastFinishUSec
-        phases[phase.name] = {"bytes": pres.opsTotal.numBytesDone, "usec": pres.lastFinishUSec}
-    return {"bytes": total_bytes, "usec": total_usec, "iops": total_iops, "phases": phases,
-            "gib_s": (total_bytes / GiB) / (total_usec / 1e6) if total_usec else 0.0}
+    out = {}
+    phases = plans[0][1]
+    for phase in phases:
+        results = [None] * len(plans)
+        errors = []
+
+        def run(idx):
+            try:
+                cfg = WorkerConfig(**plans[idx][0])
+                rc, workers, pres = oracle_lib.run_oracle_phase(cfg, phase)
+                if rc != 0:
+                    raise RuntimeError("CPU LocalWorker failed: " + "; ".join(
+                        w.errorMsg.decode() for w in workers if w.hadError))
+                results[idx] = pres
+            except Exception as err:  # noqa: BLE001
+                errors.append(err)
+
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(len(plans))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        out[phase.name] = {
+            "bytes": sum(r.opsTotal.numBytesDone for r in results),
+            "iops": sum(r.opsTotal.numIOPSDone for r in results),
+            "entries": sum(r.opsTotal.numEntriesDone for r in results),
+            "usec": max(r.lastFinishUSec for r in results)}
+    return out
+
+
+def cpu_arm(workload, steps, warmup, salt_override=None):
+    """the CPU LocalWorker over `warmup` untimed + `steps` timed steps of the workload"""
+    world = workload.world
+    totals = new_totals()
+    prep = [workload.prepare_plan(r) for r in range(world)]
+    if prep[0] is not None:
+        cpu_run_plan(prep)
+    for step in range(warmup + steps):
+        plans = [workload.plan(step, r) for r in range(world)]
+        if salt_override is not None:
+            for cfg, _ in plans:
+                cfg["integrity_check_salt"] = salt_override
+                cfg["block_variance_percent"] = 0
+        res = cpu_run_plan(plans)
+        if step >= warmup:
+            for name, ph in res.items():
+                add_phase(totals, name, ph["bytes"], ph["iops"], ph["entries"], ph["usec"])
+    return totals
 
 
 def cpu_kernels_per_core(block_size, salt, total_bytes=256 * MiB):
     """GB/s of ONE host core for the reference's per-block operators (the oracle restatement of
     preWriteIntegrityCheckFillBuf / postReadIntegrityCheckVerifyBuf, LocalWorker.cpp:2091-2179) on
     a block-sized buffer, as a CPU counterpart of the K1 / K2 numbers."""
-    import ctypes
     from tests import oracle_lib  # oracle: CPU baseline leg only
     lib = oracle_lib.load_oracle()
     buf = ctypes.create_string_buffer(block_size)
@@ -276,71 +597,61 @@ def cpu_kernels_per_core(block_size, salt, total_bytes=256 * MiB):
     return out
 
 
-def storage_roofline(args, threads, sample_size):
-    """Raw pread/pwrite pass (no fill, no verify, no GPU) over a bounded sample on the same
-    storage with the same thread count: the storage-bandwidth roofline of the e2e number."""
-    block = int(args.block_mib * MiB)
-    path = os.path.join(bench_dir(args, 0), "storage_roofline.bin")
-    try:
-        res = run_cpu_localworker([path], threads, sample_size, block, 0, args.direct)
-    finally:
-        if os.path.exists(path):
-            os.unlink(path)
-    return {"gib_s": round(res["gib_s"], 3),
-            "write_gib_s": round(res["phases"]["CREATEFILES"]["bytes"] / GiB /
-                                 (res["phases"]["CREATEFILES"]["usec"] / 1e6), 3),
-            "read_gib_s": round(res["phases"]["READFILES"]["bytes"] / GiB /
-                                (res["phases"]["READFILES"]["usec"] / 1e6), 3),
-            "threads": threads, "sample_gib": sample_size / GiB}
+def common_config(args, workload, world):
+    """the `config` object: identical for both arms (same files, sizes, steps, threads)"""
+    cfg = {
+        "workload": workload.describe(),
+        "baseline_config": workload.name,
+        "num_files_or_trees": world,
+        "block_kib": workload.block // KiB,
+        "threads_per_gpu": workload.threads,
+        "steps_layout": "%d warm-up + %d timed steps; step s = slice s of the per-GPU data set "
+                        "(reference sharding by --rankoffset / numDataSetThreads)" % (
+                            args.warmup, args.steps),
+        "storage_dir": args.dir, "direct": args.direct,
+        "l2": "every step works on fresh file data larger than L2 (>= %.2f GiB per GPU and step)" % (
+            getattr(workload, "slice_bytes", 0) / GiB) if hasattr(workload, "slice_bytes")
+        else "every step works on fresh data (files / random offsets not touched before)",
+        "host_cpus_usable": cpu_quota(),
+    }
+    if hasattr(workload, "file_size"):
+        cfg["file_gib"] = round(workload.file_size / GiB, 4)
+    if hasattr(workload, "total_files"):
+        cfg["total_files"] = workload.total_files
+    return cfg
 
 
 def reference_arm(args):
-    """bench.py --impl reference: the reference's CPU path on the host cores, same metric."""
-    rank, local_rank, world = dist_env()
+    """bench.py --impl reference: the reference's CPU path on the host cores, same metric, same
+    files, same steps, same thread count."""
+    rank, _, world_env = dist_env()
     if rank != 0:
         return 0  # other ranks exit without work
-    # the GPU arm's config at N GPUs is N files (rank r <-> file r): same file set here
-    nfiles = max(1, args.gpus)
-    threads = cpu_threads_default(args, nfiles)
-    block = int(args.block_mib * MiB)
-    step_size = int(args.ref_step_gib * GiB)
-    step_size -= step_size % block
-    workdir = bench_dir(args, 0)
-    paths = [os.path.join(workdir, "ref_arm_%d.bin" % i) for i in range(nfiles)]
-    times = []
-    nbytes = 0
+    world = max(1, args.gpus)
+    workload = WORKLOADS[args.config](args, world)
     try:
-        for step in range(args.warmup + args.steps):
-            for path in paths:
-                if os.path.exists(path):
-                    os.unlink(path)
-            res = run_cpu_localworker(paths, threads, step_size, block, args.salt, args.direct)
-            if step >= args.warmup:
-                times.append(res["usec"] / 1e6)
-                nbytes += res["bytes"]
+        totals = cpu_arm(workload, args.steps, args.warmup)
     finally:
-        for path in paths:
-            if os.path.exists(path):
-                os.unlink(path)
-    total = sum(times)
-    value = (nbytes / GiB) / total if total else 0.0
-    sample = "%d steps x (write+read --verify of %d x %.1f GiB file(s), %d MiB blocks, -t %d) in %s" % (
-        args.steps, nfiles, step_size / GiB, block // MiB, threads, args.dir)
+        for r in range(world):
+            remove_paths(workload.cleanup_paths(r))
+    value = workload.value_of(totals)
+    cores = workload.threads * world
+    sample = "%d timed steps of the workload (all of it), %d threads (%d per file/GPU share) in %s" % (
+        args.steps, cores, workload.threads, args.dir)
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1000 * total / max(1, args.steps), 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "seq 1 MiB write+read --verify, CPU LocalWorker (oracle port of "
-                               "LocalWorker.cpp:1669-1781, 2091-2179)",
-                   "file_gib": step_size / GiB, "num_files": nfiles, "block_mib": args.block_mib,
-                   "threads": threads,
-                   "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
-                   "dir": args.dir, "direct": args.direct},
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample,
-                         "operators_per_core": cpu_kernels_per_core(block, args.salt)},
-        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0,
+        "impl": "reference", "metric": workload.metric, "value": round(value, 3),
+        "unit": workload.unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(totals["usec"] / 1e3 / max(1, args.steps), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": common_config(args, workload, world),
+        "cpu_baseline": {"value": round(value, 3), "unit": workload.unit, "cores": cores,
+                         "kind": "port", "sample": sample,
+                         "impl_note": "oracle port of LocalWorker.cpp:1669-1781 + 2091-2179 "
+                                      "(the reference binary cannot be built here)",
+                         **phase_rates(totals),
+                         "operators_per_core": cpu_kernels_per_core(workload.block, args.salt)},
+        "e2e": {"value": round(value, 3), "unit": workload.unit, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -349,98 +660,114 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# kernel-level measurement (HBM-resident window)
+# kernel-level measurement (HBM-resident window) -> roofline of K1 / K2 / K3
 # ------------------------------------------------------------------------------------------------
 
-def kernel_level(args, torch, device, rank):
+def kernel_level(args, torch, device, block, steps=10, warmup=3):
     from elbencho_b200 import kernels
-    block = int(args.block_mib * MiB)
     nblocks = max(1, int(args.window_gib * GiB) // block)
     window = nblocks * block
-    file_size = int(args.file_gib * GiB)
     arena = torch.empty(window, dtype=torch.uint8, device=device)
     counters = torch.zeros(kernels.DEVCTR_NUM, dtype=torch.int64, device=device)
     results = torch.zeros(2 * nblocks, dtype=torch.int64, device=device)
     stream = torch.cuda.current_stream(device)
     handle = stream.cuda_stream
-    total_steps = args.warmup + args.steps
 
-    # per step: the window walks through the file (block i of step s at file offset ...)
     desc_tensors = []
-    for step in range(total_steps):
-        base = (step * window) % max(window, file_size - file_size % window)
-        blocks = [(arena.data_ptr() + i * block, block, base + i * block, 0) for i in range(nblocks)]
+    for step in range(warmup + steps):
+        base = step * window
+        blocks = [(arena.data_ptr() + i * block, block, base + i * block, i) for i in range(nblocks)]
         raw = kernels.pack_block_descs(blocks)
         desc_tensors.append(torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device))
-    rand_descs = desc_tensors[0]
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    fill_events = [(ev(), ev()) for _ in range(args.steps)]
-    verify_events = [(ev(), ev()) for _ in range(args.steps)]
-
-    def one_step(step, timed_idx=None):
+    launches_before = kernels.num_kernel_launches()
+    timings = {"fill": [], "verify": [], "rand": []}
+    for step in range(warmup + steps):
         descs = desc_tensors[step]
-        if timed_idx is not None:
-            fill_events[timed_idx][0].record(stream)
+        events = [ev() for _ in range(4)]
+        events[0].record(stream)
         kernels.fill_pattern_batch(descs.data_ptr(), nblocks, args.salt, counters.data_ptr(),
                                    handle, total_bytes=window, max_block_len=block)
-        if timed_idx is not None:
-            fill_events[timed_idx][1].record(stream)
-            verify_events[timed_idx][0].record(stream)
+        events[1].record(stream)
         kernels.verify_pattern_batch(descs.data_ptr(), nblocks, args.salt, results.data_ptr(),
                                      counters.data_ptr(), handle, total_bytes=window,
                                      max_block_len=block)
-        if timed_idx is not None:
-            verify_events[timed_idx][1].record(stream)
-
-    for step in range(args.warmup):
-        one_step(step)
-
-    barrier(torch, device)
-    launches_before = kernels.num_kernel_launches()
-    start, end = ev(), ev()
-    t0 = time.perf_counter()
-    start.record(stream)
-    for i in range(args.steps):
-        one_step(args.warmup + i, i)
-    end.record(stream)
+        events[2].record(stream)
+        kernels.fill_random_batch(descs.data_ptr(), nblocks, 100, 12345, 0, handle,
+                                  total_bytes=window, max_block_len=block)
+        events[3].record(stream)
+        if step >= warmup:
+            timings["fill"].append((events[0], events[1]))
+            timings["verify"].append((events[1], events[2]))
+            timings["rand"].append((events[2], events[3]))
     torch.cuda.synchronize(device)
-    wall = time.perf_counter() - t0
     launches = kernels.num_kernel_launches() - launches_before
-    elapsed_ms = start.elapsed_time(end)
-
-    fill_ms = [a.elapsed_time(b) for a, b in fill_events]
-    verify_ms = [a.elapsed_time(b) for a, b in verify_events]
 
     ctr = counters.cpu().tolist()
-    mismatches = ctr[kernels.DEVCTR_VERIFY_MISMATCH_BYTES]
-    if mismatches:
-        raise RuntimeError("verify kernel reported %d mismatching bytes on freshly filled data"
-                           % mismatches)
-    if int(results.view(-1, 2)[:, 0].sum()) != 0:
-        raise RuntimeError("per-block verify results are not clean")
+    if ctr[kernels.DEVCTR_VERIFY_MISMATCH_BYTES] or int(results.view(-1, 2)[:, 0].sum()) != 0:
+        raise RuntimeError("verify kernel reported mismatches on freshly filled data")
+    ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in timings.items()}
+    del arena
+    return {"window_bytes": window, "block_bytes": block, "nblocks": nblocks, "ms": ms,
+            "launches": launches}
 
-    # K3 (random fill) outside the headline timed region, for the roofline table
-    rnd_events = []
-    for i in range(3 + 10):
-        a, b = ev(), ev()
-        a.record(stream)
-        kernels.fill_random_batch(rand_descs.data_ptr(), nblocks, 100, 12345, 0, handle,
-                                  total_bytes=window, max_block_len=block)
-        b.record(stream)
-        if i >= 3:
-            rnd_events.append((a, b))
-    torch.cuda.synchronize(device)
-    rnd_ms = [a.elapsed_time(b) for a, b in rnd_events]
 
-    return {
-        "window_bytes": window, "nblocks": nblocks, "elapsed_ms": elapsed_ms, "wall_s": wall,
-        "fill_ms_avg": statistics.mean(fill_ms), "verify_ms_avg": statistics.mean(verify_ms),
-        "fill_ms_min": min(fill_ms), "verify_ms_min": min(verify_ms),
-        "rand_ms_avg": statistics.mean(rnd_ms), "launches": launches,
-    }
+def pcie_level(torch, device):
+    """PCIe roofline of the staging path, measured in this run: pinned cudaMemcpyAsync in 16 MiB
+    chunks (copy engine) and the worker's own stage-copy kernels at 1 MiB per launch."""
+    from elbencho_b200 import kernels
+    nbytes = 256 * MiB
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device)
+    out = {}
+
+    def timed(fn, total_bytes, reps=3):
+        best = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize(device)
+            ms = a.elapsed_time(b)
+            best = ms if best is None else min(best, ms)
+        return round(total_bytes / GiB / (best / 1e3), 2)
+
+    chunk = 16 * MiB
+
+    def h2d():
+        for off in range(0, nbytes, chunk):
+            dev[off:off + chunk].copy_(host[off:off + chunk], non_blocking=True)
+
+    def d2h():
+        for off in range(0, nbytes, chunk):
+            host[off:off + chunk].copy_(dev[off:off + chunk], non_blocking=True)
+
+    out["copy_engine_h2d_gib_s"] = timed(h2d, nbytes)
+    out["copy_engine_d2h_gib_s"] = timed(d2h, nbytes)
+
+    delta = host.data_ptr() - dev.data_ptr()
+    nblocks = nbytes // MiB
+    raw = kernels.pack_block_descs([(dev.data_ptr() + i * MiB, MiB, 0, 0) for i in range(nblocks)])
+    descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+    desc_bytes = len(raw) // nblocks
+
+    def staged(to_device):
+        def run():
+            for i in range(nblocks):
+                kernels.stage_copy(descs.data_ptr() + i * desc_bytes, 1, to_device, delta,
+                                   stream.cuda_stream, total_bytes=MiB, max_block_len=MiB)
+        return run
+
+    out["stage_kernel_h2d_gib_s"] = timed(staged(True), nbytes)
+    out["stage_kernel_d2h_gib_s"] = timed(staged(False), nbytes)
+    out["note"] = ("pinned host <-> HBM on this GPU, one stream: cudaMemcpyAsync in 16 MiB chunks; "
+                   "stage-copy kernel, one 1 MiB block per launch")
+    return out
 
 
 def barrier(torch, device):
@@ -451,190 +778,168 @@ def barrier(torch, device):
 
 
 # ------------------------------------------------------------------------------------------------
-# end-to-end measurement through the worker ABI
+# the GPU worker arm
 # ------------------------------------------------------------------------------------------------
 
-def fit_file_size_to_storage(args, torch, device, rank, world):
-    """world files of --file-gib must fit into --dir (tmpfs pages are RAM): if they do not, all
-    ranks agree on a smaller per-GPU file and the JSON line says so."""
-    args.file_gib_requested = args.file_gib
-    if args.skip_e2e:
-        return
-    os.makedirs(args.dir, exist_ok=True)
-    stat = os.statvfs(args.dir)
-    free_gib = stat.f_bavail * stat.f_frsize / GiB
-    fit = torch.tensor([free_gib], dtype=torch.float64, device=device)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(fit, op=dist.ReduceOp.MIN)
-    usable_gib = float(fit.item()) * 0.8 / world  # leave room for warm-up and baseline files
-    if args.file_gib > usable_gib:
-        args.file_gib = max(1.0, float(int(usable_gib)))
+def tuning_kwargs(args, gpu_ids):
+    return dict(gpu_ids=gpu_ids,
+                staging_engine={"auto": 0, "kernel": 1, "copyengine": 2}[args.staging],
+                pipeline_batch_blocks=args.batch_blocks, pipeline_num_batches=args.num_batches,
+                serialize_buffered_writes={"auto": 0, "on": 1, "off": 2}[args.write_gate],
+                no_gpu_numa_binding=args.no_gpu_numa)
 
 
-def e2e_level(args, torch, device, rank, world):
-    from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
-    from elbencho_b200 import distributed as elbdist
-    block = int(args.block_mib * MiB)
-    file_size = int(args.file_gib * GiB)
-    file_size -= file_size % block
-    workdir = bench_dir(args, rank)
-    paths = [os.path.join(workdir, "bench_file_%d.bin" % r) for r in range(world)]
-    rank_offset, dataset_threads = elbdist.rank_layout(world, rank, args.threads)
-
-    # warm-up pass on a small private file: CUDA context, pinned rings, kernels, page cache code
-    warm_path = os.path.join(workdir, "warm_%d.bin" % rank)
-    with WorkerManager(WorkerConfig(paths=[warm_path], num_threads=args.threads,
-                                    block_size=block, file_size=max(block * args.threads * 32,
-                                                                    256 * MiB),
-                                    integrity_check_salt=args.salt, gpu_ids=[device.index],
-                                    use_direct_io=args.direct,
-                                    pipeline_batch_blocks=args.batch_blocks,
-                                    pipeline_num_batches=args.num_batches)) as mgr:
-        for _ in range(3):
-            mgr.run_phase(BenchPhase.CREATEFILES)
-            mgr.run_phase(BenchPhase.READFILES)
-        mgr.run_phase(BenchPhase.DELETEFILES)
-
-    for path in paths[rank:rank + 1]:
-        if os.path.exists(path):
-            os.unlink(path)
-    barrier(torch, device)
-
-    cfg = WorkerConfig(paths=paths, num_threads=args.threads, rank_offset=rank_offset,
-                       num_dataset_threads=dataset_threads, block_size=block,
-                       file_size=file_size, integrity_check_salt=args.salt,
-                       gpu_ids=[device.index], use_direct_io=args.direct,
-                       pipeline_batch_blocks=args.batch_blocks,
-                       pipeline_num_batches=args.num_batches,
-                       serialize_buffered_writes=not args.no_write_gate)
+def gpu_run_plan(args, torch, device, plan, gpu_ids, reduce_fn):
+    """one step on this process: a manager for the step's config, its phases bracketed by
+    barriers; -> {phase name: job-wide reduced results}"""
+    from elbencho_b200 import WorkerConfig, WorkerManager
+    cfg_kwargs, phases = plan
+    cfg_kwargs = dict(cfg_kwargs)
+    cfg_kwargs.update(tuning_kwargs(args, gpu_ids))
     out = {}
-    with WorkerManager(cfg) as mgr:
-        total_usec = 0
-        total_bytes = 0
-        for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
+    with WorkerManager(WorkerConfig(**cfg_kwargs)) as mgr:
+        for phase in phases:
             barrier(torch, device)
             local = mgr.run_phase(phase)
             barrier(torch, device)
-            res = elbdist.reduce_phase_results(local, device)  # NCCL: stats only
-            out[phase.name] = res
-            total_usec += res["last_finish_usec"]  # max over all ranks' workers
-            total_bytes += res["ops_total"]["bytes"]
-        if out["READFILES"]["verify_mismatch_bytes"]:
-            raise RuntimeError("e2e read phase found integrity mismatches")
-        expected = file_size * world
-        for name in ("CREATEFILES", "READFILES"):
-            if out[name]["ops_total"]["bytes"] != expected:
-                raise RuntimeError("e2e %s moved %d bytes, expected %d" % (
-                    name, out[name]["ops_total"]["bytes"], expected))
-    barrier(torch, device)
-    if os.path.exists(paths[rank]):
-        os.unlink(paths[rank])
-
-    w, r = out["CREATEFILES"], out["READFILES"]
-    return {
-        "gib_s": (total_bytes / GiB) / (total_usec / 1e6),
-        "write_gib_s": (w["ops_total"]["bytes"] / GiB) / (w["last_finish_usec"] / 1e6),
-        "read_gib_s": (r["ops_total"]["bytes"] / GiB) / (r["last_finish_usec"] / 1e6),
-        "write_iops": w["ops_per_sec"]["iops"], "read_iops": r["ops_per_sec"]["iops"],
-        "write_first_done_gib_s": (w["ops_stonewall_total"]["bytes"] / GiB) /
-                                  (w["first_finish_usec"] / 1e6),
-        "read_first_done_gib_s": (r["ops_stonewall_total"]["bytes"] / GiB) /
-                                 (r["first_finish_usec"] / 1e6),
-        "h2d_bytes": r["h2d_bytes"] + w["h2d_bytes"], "d2h_bytes": w["d2h_bytes"] + r["d2h_bytes"],
-        "launches": w["num_kernel_launches"] + r["num_kernel_launches"],
-        "dev_kernel_usec": w["dev_kernel_usec"] + r["dev_kernel_usec"],
-        "file_bytes": file_size, "total_usec": total_usec,
-        "lat_write_avg_usec": w["iops_lat_histo"]["sum_usec"] / max(1, w["iops_lat_histo"]["num"]),
-        "lat_read_avg_usec": r["iops_lat_histo"]["sum_usec"] / max(1, r["iops_lat_histo"]["num"]),
-    }
+            out[phase.name] = reduce_fn(local)
+    return out
 
 
-def single_thread_compare(args, device):
-    """The literal '-t 1' form of the config: one worker thread on either arm,
-    bounded sample. With one thread the reference serialises fill -> write and read -> verify on
-    the CPU, while the GPU worker overlaps its on-GPU work with the storage call."""
-    from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
-    block = int(args.block_mib * MiB)
-    size = int(args.single_thread_sample_gib * GiB)
-    size -= size % block
-    workdir = bench_dir(args, 0)
-    gpu_path = os.path.join(workdir, "single_gpu.bin")
-    cpu_path = os.path.join(workdir, "single_cpu.bin")
-    out = {"sample": "write+read --verify of a %.1f GiB file, 1 MiB blocks, -t 1" % (size / GiB)}
+def gpu_arm(args, torch, device, workload, rank):
+    from elbencho_b200 import distributed as elbdist
+
+    def reduce_fn(local):
+        return elbdist.reduce_phase_results(local, device)  # NCCL: stats only
+
+    gpu_ids = [device.index]
+    totals = new_totals()
+    extra = {"h2d_bytes": 0, "d2h_bytes": 0, "launches": 0, "dev_kernel_usec": 0,
+             "verified_bytes": 0, "filled_bytes": 0, "histos": {}}
+    prep = workload.prepare_plan(rank)
+    prep_info = None
+    if prep is not None:
+        res = gpu_run_plan(args, torch, device, prep, gpu_ids, reduce_fn)
+        prep_info = {name: {"gib_s": round(r["ops_total"]["bytes"] / GiB /
+                                           (r["last_finish_usec"] / 1e6), 3),
+                            "filled_bytes": r["filled_bytes"]} for name, r in res.items()}
+    for step in range(args.warmup + args.steps):
+        res = gpu_run_plan(args, torch, device, workload.plan(step, rank), gpu_ids, reduce_fn)
+        for name, r in res.items():
+            if r["verify_mismatch_bytes"]:
+                raise RuntimeError("step %d %s found integrity mismatches" % (step, name))
+            if r["num_workers_done_with_error"]:
+                raise RuntimeError("step %d %s had worker errors" % (step, name))
+        if step < args.warmup:
+            continue
+        for name, r in res.items():
+            add_phase(totals, name, r["ops_total"]["bytes"], r["ops_total"]["iops"],
+                      r["ops_total"]["entries"], r["last_finish_usec"])
+            if name not in TIMED_PHASES:
+                continue
+            extra["h2d_bytes"] += r["h2d_bytes"]
+            extra["d2h_bytes"] += r["d2h_bytes"]
+            extra["launches"] += r["num_kernel_launches"]
+            extra["dev_kernel_usec"] += r["dev_kernel_usec"]
+            extra["verified_bytes"] += r["verified_bytes"]
+            extra["filled_bytes"] += r["filled_bytes"]
+            histo = extra["histos"].setdefault(name, {"buckets": [0] * len(
+                r["iops_lat_histo"]["buckets"]), "num": 0, "sum_usec": 0,
+                "min_usec": 1 << 62, "max_usec": 0})
+            src = r["iops_lat_histo"]
+            histo["buckets"] = [a + b for a, b in zip(histo["buckets"], src["buckets"])]
+            histo["num"] += src["num"]
+            histo["sum_usec"] += src["sum_usec"]
+            if src["num"]:
+                histo["min_usec"] = min(histo["min_usec"], src["min_usec"])
+                histo["max_usec"] = max(histo["max_usec"], src["max_usec"])
+    return totals, extra, prep_info
+
+
+def inprocess_pool(args, torch, workload_cls, world):
+    """The single-process worker pool north_star describes: one manager, --gpuids 0..N-1, rank ->
+    GPU round robin (LocalWorker.cpp:1420-1429), live and phase-end statistics through the grouped
+    ncclReduce of the library (replaces the host loop of Statistics.cpp:1338-1344). Runs a sample
+    of the same workload (2 warm-up + 4 timed steps) on rank 0 while the other ranks wait."""
+    import copy
+    from elbencho_b200 import WorkerConfig, WorkerManager
+    pool_args = copy.copy(args)
+    pool_args.warmup, pool_args.steps = 2, 4
+    pool_args.file_gib = min(args.file_gib or 64.0, 16.0) if workload_cls in (C2, C3, C4) \
+        else (args.file_gib or 0)
+    workload = workload_cls(pool_args, world)
+    workload.workdir = os.path.join(workload.workdir, "pool")
+    os.makedirs(workload.workdir, exist_ok=True)
+    if hasattr(workload, "paths"):
+        workload.paths = [os.path.join(workload.workdir, os.path.basename(p))
+                          for p in workload.paths]
+    gpu_ids = list(range(world))
+    totals = new_totals()
+    info = {}
     try:
-        total_usec = 0
-        with WorkerManager(WorkerConfig(paths=[gpu_path], num_threads=1, block_size=block,
-                                        file_size=size, integrity_check_salt=args.salt,
-                                        gpu_ids=[device.index], use_direct_io=args.direct)) as mgr:
-            for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
-                total_usec += mgr.run_phase(phase)["last_finish_usec"]
-        out["gpu_worker_gib_s"] = round((2 * size / GiB) / (total_usec / 1e6), 3)
-        res = run_cpu_localworker([cpu_path], 1, size, block, args.salt, args.direct)
-        out["cpu_localworker_gib_s"] = round(res["gib_s"], 3)
-        out["ratio"] = round(out["gpu_worker_gib_s"] / out["cpu_localworker_gib_s"], 2)
+        # one manager per step drives the slices of ALL files: ranks of file r come from the
+        # per-rank plans; in one process they are contiguous only per file, so the pool runs the
+        # N per-file plans as N managers' worth of threads in ONE manager by giving it all ranks
+        # of step s: rank_offset = s*T for file 0 ... is not contiguous across files, hence the
+        # pool uses its own layout: dataset threads = S*N*T with step-major ranks
+        for step in range(pool_args.warmup + pool_args.steps):
+            cfg_kwargs, phases = pool_plan(workload, step, world)
+            cfg_kwargs.update(tuning_kwargs(pool_args, gpu_ids))
+            with WorkerManager(WorkerConfig(**cfg_kwargs)) as mgr:
+                for phase in phases:
+                    mgr.start_phase(phase)
+                    snaps = 0
+                    while not mgr.wait_done(100):
+                        snap = mgr.live_snapshot()
+                        snaps += 1
+                        info["live_reduced_with_nccl"] = snap["reduced_with_nccl"]
+                        info["live_num_gpus"] = snap["num_gpus"]
+                    res = mgr.phase_results()
+                    if res["verify_mismatch_bytes"] or res["num_workers_done_with_error"]:
+                        raise RuntimeError("in-process pool: %s failed: %s" % (phase.name,
+                                                                               mgr.last_error))
+                    info["phase_stats_reduced_with_nccl"] = res["stats_reduced_with_nccl"]
+                    info["live_reduce_info"] = mgr.live_reduce_info()
+                    if step >= pool_args.warmup:
+                        add_phase(totals, phase.name, res["ops_total"]["bytes"],
+                                  res["ops_total"]["iops"], res["ops_total"]["entries"],
+                                  res["last_finish_usec"])
     finally:
-        for path in (gpu_path, cpu_path):
-            if os.path.exists(path):
-                os.unlink(path)
-    return out
+        shutil.rmtree(workload.workdir, ignore_errors=True)
+    info.update(phase_rates(totals))
+    info["value"] = round(workload.value_of(totals), 3)
+    info["unit"] = workload.unit
+    info["gpu_ids"] = gpu_ids
+    info["threads"] = world * workload.threads
+    info["sample"] = "2 warm-up + 4 timed steps of %s" % workload.describe()
+    return info
 
 
-def same_sample_compare(args, device, cpu):
-    """The GPU worker on exactly the bounded sample the cpu_baseline was timed on (same file size,
-    same thread count, fresh file): an apples-to-apples pair, because on this tmpfs the write rate
-    depends on the file size. Never fails the bench: errors are reported in the result."""
-    out = {}
-    try:
-        from elbencho_b200 import BenchPhase, WorkerConfig, WorkerManager
-        block = int(args.block_mib * MiB)
-        size = int(args.cpu_sample_gib * GiB)
-        size -= size % block
-        threads = int(cpu["cores"])
-        path = os.path.join(bench_dir(args, 0), "same_sample_gpu.bin")
-        out["sample"] = "write+read --verify of a %.1f GiB file, 1 MiB blocks, -t %d" % (
-            size / GiB, threads)
-        try:
-            total_usec = 0
-            with WorkerManager(WorkerConfig(paths=[path], num_threads=threads, block_size=block,
-                                            file_size=size, integrity_check_salt=args.salt,
-                                            gpu_ids=[device.index], use_direct_io=args.direct,
-                                            serialize_buffered_writes=not args.no_write_gate)) as mgr:
-                for phase in (BenchPhase.CREATEFILES, BenchPhase.READFILES):
-                    total_usec += mgr.run_phase(phase)["last_finish_usec"]
-            out["gpu_worker_gib_s"] = round((2 * size / GiB) / (total_usec / 1e6), 3)
-            out["cpu_localworker_gib_s"] = cpu["value"]
-            out["ratio"] = round(out["gpu_worker_gib_s"] / cpu["value"], 2) if cpu["value"] else None
-        finally:
-            if os.path.exists(path):
-                os.unlink(path)
-    except Exception as err:  # noqa: BLE001 (an extra, must not break the bench line)
-        out["error"] = str(err)
-    return out
+def pool_plan(workload, step, world):
+    """one step of all GPUs as ONE manager config (in-process pool). Sequential file configs use
+    step-major dataset threads: the step's N*T ranks own one contiguous slice of the block sequence
+    of all files; workers map to GPUs round robin by rank."""
+    from elbencho_b200 import BenchPhase
+    threads = world * workload.threads
+    if isinstance(workload, SeqFileWorkload):
+        cfg = workload.base_cfg()
+        cfg.update(num_threads=threads, rank_offset=step * threads,
+                   num_dataset_threads=workload.num_slices * threads)
+        phases = ([BenchPhase.CREATEFILES] if workload.do_write_in_step else []) + \
+            [BenchPhase.READFILES]
+        return cfg, phases
+    if isinstance(workload, C3):
+        cfg, phases = workload.plan(step, 0)
+        cfg.update(paths=workload.paths, num_threads=threads)
+        return cfg, phases
+    cfg, phases = workload.plan(step, 0)
+    cfg.update(num_threads=threads, rank_offset=0, num_dataset_threads=threads)
+    return cfg, phases
 
 
 # ------------------------------------------------------------------------------------------------
 # main
 # ------------------------------------------------------------------------------------------------
-
-_REAL_STDOUT = None
-
-
-def protect_stdout():
-    """The driver parses ONE JSON line from stdout; libraries (NCCL's version banner) also write
-    there. Keep the real stdout aside and point fd 1 at stderr for everything else."""
-    global _REAL_STDOUT
-    if _REAL_STDOUT is None:
-        sys.stdout.flush()
-        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
-
-
-def emit(line):
-    out = _REAL_STDOUT or sys.stdout
-    out.write(json.dumps(line) + "\n")
-    out.flush()
-
 
 def main():
     args = parse_args()
@@ -664,55 +969,84 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
 
-    fit_file_size_to_storage(args, torch, device, rank, world)
+    workload_cls = WORKLOADS[args.config]
+
+    # all files of the job must fit into the (RAM backed) storage next to the baseline samples
+    requested_gib = args.file_gib
+    if workload_cls is not C5:
+        want = args.file_gib or {"c2": 64.0, "c3": 64.0, "c4": 32.0}[args.config]
+        os.makedirs(args.dir, exist_ok=True)
+        fit = torch.tensor([storage_free_gib(args.dir)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(fit, op=dist.ReduceOp.MIN)
+        usable = float(fit.item()) * 0.7 / world
+        if want > usable:
+            args.file_gib = max(1.0, float(int(usable)))
+            log("file size reduced to %.0f GiB per GPU (storage has %.0f GiB free)" % (
+                args.file_gib, float(fit.item())))
+
+    workload = workload_cls(args, world)
+    block = args.kernel_block_kib * KiB if args.kernel_block_kib else workload.block
+
+    kern = None
+    if not args.skip_kernels:
+        kern = kernel_level(args, torch, device, block)
+    if args.only_kernels:
+        emit({"kernel_level": {k: v for k, v in kern.items()}})
+        return 0
+
+    pcie = pcie_level(torch, device) if rank == 0 else None
 
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
-
-    kern = kernel_level(args, torch, device, rank)
-
-    # whole-job kernel-level throughput: all ranks' bytes / max-over-ranks device time
-    from elbencho_b200 import distributed as elbdist
-    elapsed_ms = elbdist.reduce_max_float(kern["elapsed_ms"], device)
-    job_bytes = 2 * kern["window_bytes"] * args.steps * world
-    value = (job_bytes / GiB) / (elapsed_ms / 1e3)
-
-    e2e = None
-    if not args.skip_e2e:
-        e2e = e2e_level(args, torch, device, rank, world)
-
+    try:
+        totals, extra, prep_info = gpu_arm(args, torch, device, workload, rank)
+    finally:
+        barrier(torch, device)
+        remove_paths(workload.cleanup_paths(rank))
     clocks = sampler.stop() if sampler else None
+
+    value = workload.value_of(totals)
 
     cpu = None
     storage = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        threads = cpu_threads_default(args)
-        block = int(args.block_mib * MiB)
-        sample_size = int(args.cpu_sample_gib * GiB)
-        storage = storage_roofline(args, args.threads, sample_size)
-        path = os.path.join(bench_dir(args, 0), "cpu_baseline.bin")
+        import copy
+        sample_args = copy.copy(args)
+        sample_args.warmup, sample_args.steps = 1, args.cpu_sample_steps
+        # same slice size as the main run: scale the file with the number of slices
+        if hasattr(workload, "slice_bytes"):
+            sample_args.file_gib = workload.slice_bytes * (1 + args.cpu_sample_steps) / GiB
+        elif isinstance(workload, C3):
+            sample_args.file_gib = min(workload.file_size / GiB, 16.0)
+        sample = workload_cls(sample_args, 1)
         try:
-            res = run_cpu_localworker([path], threads, sample_size, block, args.salt, args.direct)
+            cpu_totals = cpu_arm(sample, sample_args.steps, sample_args.warmup)
+            raw_totals = cpu_arm(sample, sample_args.steps, sample_args.warmup, salt_override=0)
         finally:
-            if os.path.exists(path):
-                os.unlink(path)
-        cpu = {"value": round(res["gib_s"], 3), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "write+read --verify of a %.1f GiB file, 1 MiB blocks, -t %d, in %s "
+            remove_paths(sample.cleanup_paths(0))
+        cpu_value = sample.value_of(cpu_totals)
+        cpu = {"value": round(cpu_value, 3), "unit": workload.unit, "cores": workload.threads,
+               "kind": "port",
+               "sample": "1 warm-up + %d timed steps of the same step size (%s), -t %d, in %s "
                          "(oracle port of LocalWorker.cpp:1669-1781 + 2091-2179)" % (
-                             sample_size / GiB, threads, args.dir),
-               "thread_calibration_gib_s": _CPU_THREADS_CACHE.get("table"),
-               "operators_per_core": cpu_kernels_per_core(block, args.salt),
-               "write_gib_s": round(res["phases"]["CREATEFILES"]["bytes"] / GiB /
-                                    (res["phases"]["CREATEFILES"]["usec"] / 1e6), 3),
-               "read_gib_s": round(res["phases"]["READFILES"]["bytes"] / GiB /
-                                   (res["phases"]["READFILES"]["usec"] / 1e6), 3)}
+                             sample_args.steps, sample.describe(), workload.threads, args.dir),
+               **phase_rates(cpu_totals),
+               "operators_per_core": cpu_kernels_per_core(workload.block, args.salt)}
+        storage = {"value": round(sample.value_of(raw_totals), 3), "unit": workload.unit,
+                   **phase_rates(raw_totals), "threads": workload.threads,
+                   "note": "raw pread/pwrite of the CPU loop without fill/verify on the same "
+                           "storage, steps and thread count (bounded sample): the storage roofline "
+                           "of value"}
 
-    single = None
-    same_sample = None
-    if rank == 0 and world == 1 and not args.skip_cpu and not args.skip_e2e and \
-            args.single_thread_sample_gib > 0:
-        single = single_thread_compare(args, device)
-    if rank == 0 and world == 1 and cpu is not None and not args.skip_e2e:
-        same_sample = same_sample_compare(args, device, cpu)
+    pool = None
+    if world > 1 and not args.skip_pool:
+        barrier(torch, device)
+        if rank == 0:
+            try:
+                pool = inprocess_pool(args, torch, workload_cls, world)
+            except Exception as err:  # noqa: BLE001 (an extra must not break the bench line)
+                pool = {"error": str(err)}
+        barrier(torch, device)
 
     if world > 1:
         dist.barrier(device_ids=[device.index])
@@ -722,88 +1056,112 @@ def main():
         return 0
 
     peak, peak_src = load_hbm_peak()
-    window = kern["window_bytes"]
-    verify_gbs = window / (kern["verify_ms_avg"] * 1e-3) / 1e9
-    fill_gbs = window / (kern["fill_ms_avg"] * 1e-3) / 1e9
-    rand_gbs = window / (kern["rand_ms_avg"] * 1e-3) / 1e9
-    # dominant kernel = the one that takes the larger share of a step
-    if kern["verify_ms_avg"] >= kern["fill_ms_avg"]:
-        dom_name, dom_gbs = "elb_blocks_tiled_kernel<VERIFY_PATTERN> (K2)", verify_gbs
-        dom_key = "K2_verify_pattern"
-    else:
-        dom_name, dom_gbs = "elb_blocks_tiled_kernel<FILL_PATTERN> (K1)", fill_gbs
-        dom_key = "K1_fill_pattern"
-    traffic, traffic_src = load_ncu_traffic(window, dom_key)
+    rates = phase_rates(totals)
+    timed_secs = totals["usec"] / 1e6
 
     line = {
-        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {
-            "workload": "BASELINE configs[1]: single %.0f GiB file per GPU, %g MiB blocks, seq "
-                        "write+read, --gpuids, cudaMemcpyAsync staging, --verify %d" % (
-                            args.file_gib, args.block_mib, args.salt),
-            "file_gib": args.file_gib, "file_gib_requested": args.file_gib_requested,
-            "block_mib": args.block_mib, "threads_per_gpu": args.threads,
-            "window_gib": window / GiB, "step": "K1 fill + K2 verify over the HBM-resident window "
-                                               "(2 x window bytes)",
-            "l2": "inputs_larger_than_l2 (window %.1f GiB >> 126 MB L2)" % (window / GiB),
-            "storage_dir": args.dir, "direct": args.direct,
-            "serialize_buffered_writes": not args.no_write_gate,
+        "metric": workload.metric, "value": round(value, 3), "unit": workload.unit,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(totals["usec"] / 1e3 / max(1, args.steps), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": common_config(args, workload, world),
+        "impl_config": {
+            "staging": args.staging, "batch_blocks": args.batch_blocks,
+            "num_batches": args.num_batches, "write_gate": args.write_gate,
+            "gpu_numa_binding": not args.no_gpu_numa,
+            "file_gib_requested": requested_gib or None,
             "parallelism": "%d process(es) x %d worker threads, rank r <-> file r <-> GPU r" % (
-                world, args.threads),
+                world, workload.threads),
+            "timing": "phase time = max over all workers of all ranks (host steady clock inside "
+                      "the worker, as the reference measures phases), phases bracketed by barrier "
+                      "+ cudaDeviceSynchronize; value = bytes of the timed steps / sum of phase times",
         },
-        "gpu_launches": kern["launches"] * world,
-        "roofline": {
-            "bound": "hbm", "kernel": dom_name, "achieved": round(dom_gbs, 1), "peak": peak,
-            "unit": "GB/s", "frac": round(dom_gbs / peak, 4), "traffic": traffic,
-            "traffic_source": traffic_src,
-            "peak_source": peak_src,
+        "gpu_launches": extra["launches"],
+        "clocks": clocks,
+    }
+    line["e2e"] = {
+        "value": round(value, 3), "unit": workload.unit,
+        "h2d_bytes_per_step": extra["h2d_bytes"] // max(1, args.steps),
+        "d2h_bytes_per_step": extra["d2h_bytes"] // max(1, args.steps),
+        "step": "the phases of one step through the worker's C ABI: storage I/O into / out of the "
+                "pinned host ring, host<->device transfer and on-GPU fill / verify",
+        **rates,
+        "gpu_launches": extra["launches"],
+        "dev_kernel_usec": extra["dev_kernel_usec"],
+        "dev_kernel_share_of_timed": round(extra["dev_kernel_usec"] / 1e6 /
+                                           (timed_secs * workload.threads * world), 4)
+        if timed_secs else None,
+        "verified_bytes": extra["verified_bytes"], "filled_bytes": extra["filled_bytes"],
+        "total_usec": totals["usec"],
+        "latency": {name: histo_summary(h) for name, h in extra["histos"].items()},
+    }
+    if prep_info:
+        line["e2e"]["preparation"] = prep_info
+
+    roofline = {}
+    if kern:
+        window = kern["window_bytes"]
+        gbs = {k: window / (v * 1e-3) / 1e9 for k, v in kern["ms"].items()}
+        # dominant resident kernel of the configuration
+        if workload.name == "c4":
+            dom_key, dom_name, dom = "K3_fill_random_pct100", \
+                "elb_blocks_tiled_kernel<FILL_RANDOM> (K3)", gbs["rand"]
+        elif workload.name == "c3" or kern["ms"]["verify"] >= kern["ms"]["fill"]:
+            dom_key, dom_name, dom = "K2_verify_pattern", \
+                "elb_blocks_tiled_kernel<VERIFY_PATTERN> (K2)", gbs["verify"]
+        else:
+            dom_key, dom_name, dom = "K1_fill_pattern", \
+                "elb_blocks_tiled_kernel<FILL_PATTERN> (K1)", gbs["fill"]
+        traffic, traffic_src = load_ncu_traffic(window, kern["block_bytes"], dom_key)
+        roofline = {
+            "bound": "hbm", "kernel": dom_name, "achieved": round(dom, 1), "peak": peak,
+            "unit": "GB/s", "frac": round(dom / peak, 4), "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "measured": "CUDA events around each launch over a %.1f GiB HBM-resident window of "
+                        "%d KiB blocks (larger than L2), %d launches each" % (
+                            window / GiB, kern["block_bytes"] // KiB, 10),
             "note": "peak is the driver-measured COPY bandwidth; one-directional streams exceed "
                     "it (copy-engine cudaMemset writes 7.35 TB/s), hence frac > 1",
             "algorithmic_bytes_per_launch": window,
             "all_kernels": {
-                "K1_fill_pattern": {"achieved": round(fill_gbs, 1), "frac": round(fill_gbs / peak, 4),
-                                    "ms_per_launch": round(kern["fill_ms_avg"], 4)},
-                "K2_verify_pattern": {"achieved": round(verify_gbs, 1),
-                                      "frac": round(verify_gbs / peak, 4),
-                                      "ms_per_launch": round(kern["verify_ms_avg"], 4)},
-                "K3_fill_random_pct100": {"achieved": round(rand_gbs, 1),
-                                          "frac": round(rand_gbs / peak, 4),
-                                          "ms_per_launch": round(kern["rand_ms_avg"], 4),
-                                          "note": "outside the headline timed region"},
+                "K1_fill_pattern": {"achieved": round(gbs["fill"], 1),
+                                    "frac": round(gbs["fill"] / peak, 4),
+                                    "ms_per_launch": round(kern["ms"]["fill"], 4)},
+                "K2_verify_pattern": {"achieved": round(gbs["verify"], 1),
+                                      "frac": round(gbs["verify"] / peak, 4),
+                                      "ms_per_launch": round(kern["ms"]["verify"], 4)},
+                "K3_fill_random_pct100": {"achieved": round(gbs["rand"], 1),
+                                          "frac": round(gbs["rand"] / peak, 4),
+                                          "ms_per_launch": round(kern["ms"]["rand"], 4)},
             },
-        },
-        "clocks": clocks,
-    }
-    if e2e:
-        line["e2e"] = {
-            "value": round(e2e["gib_s"], 3), "unit": UNIT,
-            "h2d_bytes_per_step": e2e["h2d_bytes"], "d2h_bytes_per_step": e2e["d2h_bytes"],
-            "step": "one write phase + one read phase (--verify) over the whole file(s)",
-            "write_gib_s": round(e2e["write_gib_s"], 3), "read_gib_s": round(e2e["read_gib_s"], 3),
-            "write_first_done_gib_s": round(e2e["write_first_done_gib_s"], 3),
-            "read_first_done_gib_s": round(e2e["read_first_done_gib_s"], 3),
-            "write_iops": e2e["write_iops"], "read_iops": e2e["read_iops"],
-            "gpu_launches": e2e["launches"], "dev_kernel_usec": e2e["dev_kernel_usec"],
-            "lat_write_avg_usec": round(e2e["lat_write_avg_usec"], 1),
-            "lat_read_avg_usec": round(e2e["lat_read_avg_usec"], 1),
-            "total_usec": e2e["total_usec"],
         }
+    if pcie:
+        roofline["pcie"] = pcie
+        if "read_gib_s" in rates:
+            best_h2d = max(pcie["copy_engine_h2d_gib_s"], pcie["stage_kernel_h2d_gib_s"])
+            roofline["pcie"]["e2e_read_frac_of_pcie"] = round(
+                rates["read_gib_s"] / (best_h2d * world), 3)
+        if "write_gib_s" in rates:
+            best_d2h = max(pcie["copy_engine_d2h_gib_s"], pcie["stage_kernel_d2h_gib_s"])
+            roofline["pcie"]["e2e_write_frac_of_pcie"] = round(
+                rates["write_gib_s"] / (best_d2h * world), 3)
+    if storage:
+        roofline["storage"] = storage
+        for key in ("read_gib_s", "write_gib_s"):
+            if key in rates and storage.get(key):
+                roofline["storage"]["e2e_%s_frac" % key.split("_")[0]] = round(
+                    rates[key] / storage[key], 3)
+        if storage["value"]:
+            roofline["storage"]["e2e_frac"] = round(value / storage["value"], 3)
+    line["roofline"] = roofline
     if cpu:
         line["cpu_baseline"] = cpu
-    if storage and e2e:
-        storage["e2e_frac"] = round(e2e["gib_s"] / storage["gib_s"], 3) if storage["gib_s"] else None
-        storage["note"] = ("raw pread/pwrite of the CPU loop without fill/verify on the same "
-                           "storage and thread count (bounded sample); buffered writes to ONE "
-                           "file serialise on the inode lock, so the write phase does not scale "
-                           "with threads on either arm")
-        line["storage_roofline"] = storage
-    if single:
-        line["single_thread"] = single
-    if same_sample:
-        line["same_sample"] = same_sample
+    extra_out = {}
+    if pool:
+        extra_out["inprocess_pool"] = pool
+    if extra_out:
+        line["extra"] = extra_out
     emit(line)
     return 0
 

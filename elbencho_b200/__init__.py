@@ -8,8 +8,8 @@ Python host-side mirror of that ABI, used by tests and bench.py:
 * :mod:`elbencho_b200.worker`  — WorkerManager / phases / results (mirrors the reference's
   WorkerManager + Worker interface)
 """
-from .worker import (BenchPhase, OffsetRandAlgo, PathType, WorkerConfig,  # noqa: F401
+from .worker import (BenchPhase, IOEngine, OffsetRandAlgo, PathType, WorkerConfig,  # noqa: F401
                      WorkerManager, WorkerError)
 from . import kernels  # noqa: F401
 
-__all__ = ["BenchPhase", "OffsetRandAlgo", "PathType", "WorkerConfig", "WorkerManager", "WorkerError", "kernels"]
+__all__ = ["BenchPhase", "IOEngine", "OffsetRandAlgo", "PathType", "WorkerConfig", "WorkerManager", "WorkerError", "kernels"]

@@ -23,6 +23,7 @@
 #include <mutex>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <random>
 #include <stdexcept>
@@ -269,8 +270,12 @@ class RateLimiter
 
 		bool isEnabled() const { return limitPerSec != 0; }
 
-		/* @return true if the caller had to sleep */
-		bool wait(uint64_t nextSize)
+		/* @beforeSleep called right before this thread goes to sleep for its limit (the pipeline
+		 *    retires what is in flight on the GPU first, so that the live counters show every
+		 *    completed block while the worker sleeps).
+		 * @return true if the caller had to sleep */
+		template <typename BeforeSleepFn>
+		bool wait(uint64_t nextSize, BeforeSleepFn beforeSleep)
 		{
 			const std::chrono::steady_clock::time_point nowT = std::chrono::steady_clock::now();
 			const int64_t elapsedUSec =
@@ -285,6 +290,7 @@ class RateLimiter
 
 			if( (numDoneThisSec + nextSize) > limitPerSec)
 			{
+				beforeSleep();
 				std::this_thread::sleep_until(startT + std::chrono::microseconds(1000000) );
 				numDoneThisSec = nextSize;
 				startT = std::chrono::steady_clock::now();
@@ -294,6 +300,8 @@ class RateLimiter
 			numDoneThisSec += nextSize;
 			return false;
 		}
+
+		bool wait(uint64_t nextSize) { return wait(nextSize, []() {} ); }
 
 	private:
 		uint64_t limitPerSec{0};

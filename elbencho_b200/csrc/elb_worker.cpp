@@ -807,7 +807,17 @@ void Worker::allocRings()
 
 	const bool useAio = (cfg.ioEngine == ELB_IOENGINE_AIO);
 
-	stageWithKernels = !cfg.useCuFile && (cfg.stagingEngine != ELB_STAGING_COPYENGINE);
+	int stagingEngine = cfg.stagingEngine;
+
+	if(stagingEngine == ELB_STAGING_AUTO)
+	{ // (test / exploration knob: ELB_STAGING=copyengine|kernel picks what "auto" means)
+		const char* stagingEnv = getenv("ELB_STAGING");
+
+		if(stagingEnv && ( !strcmp(stagingEnv, "copyengine") || !strcmp(stagingEnv, "ce") ) )
+			stagingEngine = ELB_STAGING_COPYENGINE;
+	}
+
+	stageWithKernels = !cfg.useCuFile && (stagingEngine != ELB_STAGING_COPYENGINE);
 
 	if(cfg.pipelineBatchBlocks)
 		batchBlocks = cfg.pipelineBatchBlocks;
@@ -1627,7 +1637,7 @@ bool Worker::rateLimitNextBlock(uint64_t len)
 	}
 
 	if(rateLimiter.isEnabled() )
-		return rateLimiter.wait(len);
+		return rateLimiter.wait(len, [this]() { if(beforeLimiterSleep) beforeLimiterSleep(); } );
 
 	return false;
 }
@@ -1787,6 +1797,27 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 
 	for(Batch& batch : batches)
 		freeBatches.push_back(&batch);
+
+	/* a read worker that is about to sleep for its rate limit first retires the batches whose
+	   GPU stage is in flight: every block that was read is then counted while it sleeps, as in
+	   the reference's serial loop (what a stonewall snapshot or the live statistics see) */
+	struct LimiterHookGuard
+	{
+		std::function<void()>& hook;
+		~LimiterHookGuard() { hook = nullptr; }
+	} limiterHookGuard{beforeLimiterSleep};
+
+	if(isRead)
+		beforeLimiterSleep = [&]()
+		{
+			while(!stageTwoQueue.empty() )
+			{
+				Batch* batch = stageTwoQueue.front();
+				stageTwoQueue.pop_front();
+				retireReadBatch(*batch);
+				freeBatches.push_back(batch);
+			}
+		};
 
 	for( ; ; )
 	{

@@ -27,6 +27,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -254,6 +255,7 @@ class Worker
 			bool tolerateMissing, bool countsAsEntry, const char* failTextOverride = NULL);
 		void dirModeIterateCustomFilesNoIO(); // stat / delete part of :3261-3470
 		bool useRWMixThreadsBalancer{false}; // --rwmixthrpct active in this phase
+		std::function<void()> beforeLimiterSleep; // set by the pipeline while it runs
 		bool rateLimitNextBlock(uint64_t len); // funcRWRateLimiter (LocalWorker.cpp:1689)
 		std::unique_ptr<OffsetPlan> offsetPlan;
 		uint64_t blockVarianceSeed{0};

@@ -9,12 +9,14 @@
 #define _GNU_SOURCE
 #include <errno.h>
 #include <fcntl.h>
+#include <linux/aio_abi.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/types.h>
 #include <time.h>
 #include <unistd.h>
@@ -25,6 +27,8 @@
 #define ORC_MKFILE_MODE (S_IRUSR | S_IWUSR | S_IRGRP | S_IWGRP | S_IROTH | S_IWOTH)
 #define ORC_MKDIR_MODE (S_IRWXU | S_IRWXG | S_IRWXO)
 #define ORC_PATH_BUF_LEN 64 /* workers/LocalWorker.cpp:62 */
+#define ORC_AIO_MAX_WAIT_SEC 5 /* workers/LocalWorker.cpp:60 */
+#define ORC_AIO_MAX_EVENTS 4   /* workers/LocalWorker.cpp:61 */
 
 /* ============================================================================================
  * Block modifiers / checkers
@@ -869,6 +873,12 @@ typedef struct orc_worker
 	orc_shared* shared;
 	uint64_t rank;
 	char* ioBuf;
+	char** ioBufVec;       // iodepth buffers of the aio loop (ioBufVec[0] == ioBuf)
+	struct iocb* iocbVec;  // libaioContext.iocbVec
+	struct timespec* ioStartTimeVec; // libaioContext.ioStartTimeVec (tv_sec < 0: invalidated)
+	aio_context_t aioContext;
+	int aioInitialized;
+	orc_ratelimiter rateLimiter;
 	orc_offsetgen* offsetGen;
 	uint64_t numIOPSSubmitted;
 	int currentFD; // fdVec[0] of sequential/dir mode
@@ -944,6 +954,261 @@ static void orc_calc_file_idx_and_offset(uint64_t rwOffsetGenNext, uint64_t file
 	}
 }
 
+/* toolkits/RateLimiter.h:13-66: a budget per second; whoever would exceed it sleeps until the
+ * second is over. initStart at phase start (workers/LocalWorker.cpp:1293-1299, 1331-1337). */
+void orc_ratelimiter_init_start(orc_ratelimiter* rl, uint64_t limitPerSec)
+{
+	rl->limitPerSec = limitPerSec;
+	rl->numDoneThisSec = 0;
+	clock_gettime(CLOCK_MONOTONIC, &rl->startT);
+}
+
+/* @return 1 if the caller had to wait (RateLimiter::wait), 0 = go on immediately.
+ * limitPerSec 0 = noOpRateLimiter (workers/LocalWorker.cpp:2364-2367). */
+int orc_ratelimiter_wait(orc_ratelimiter* rl, uint64_t nextSize)
+{
+	if(!rl->limitPerSec)
+		return 0;
+
+	const uint64_t elapsedMicroSec = orc_elapsed_usec(&rl->startT);
+
+	if(elapsedMicroSec >= 1000000)
+	{ // 1s elapsed without exceeding the rate limit => reset for next second
+		rl->numDoneThisSec = nextSize;
+		clock_gettime(CLOCK_MONOTONIC, &rl->startT);
+		return 0;
+	}
+
+	if( (rl->numDoneThisSec + nextSize) > rl->limitPerSec)
+	{ // next r/w op would exceed rate limit => wait until end of second
+		struct timespec wakeT = rl->startT;
+		wakeT.tv_sec += 1;
+
+		while(clock_nanosleep(CLOCK_MONOTONIC, TIMER_ABSTIME, &wakeT, NULL) == EINTR)
+			;
+
+		rl->numDoneThisSec = nextSize;
+		clock_gettime(CLOCK_MONOTONIC, &rl->startT);
+		return 1;
+	}
+
+	rl->numDoneThisSec += nextSize;
+	return 0;
+}
+
+/* fill (write phase) as funcPreWriteBlockModifier does it (:1256-1265, rwmix exception :2213) */
+static void orc_pre_write_modify(orc_worker* w, char* buf, size_t blockSize, uint64_t offset)
+{
+	const elb_cfg* cfg = w->shared->cfg;
+
+	if(cfg->integrityCheckSalt)
+		orc_fill_pattern(buf, blockSize, offset, cfg->integrityCheckSalt);
+	else
+	if(cfg->blockVariancePercent &&
+		!( ( (w->rank + w->numIOPSSubmitted) % 100) < cfg->rwMixReadPercent) )
+		orc_rand_refill_goldenprime(&w->blockVarAlgo, buf, blockSize, cfg->blockVariancePercent);
+}
+
+/* aioReadPrepper / aioWritePrepper / aioRWMixPrepper (workers/LocalWorker.cpp:2400-2440): which
+ * opcode the next request gets */
+static void orc_aio_prep(orc_worker* w, struct iocb* cb, int fd, char* buf, size_t count,
+	uint64_t offset, int isRead)
+{
+	const elb_cfg* cfg = w->shared->cfg;
+	int doRead = isRead;
+
+	if(!isRead && cfg->rwMixReadPercent &&
+		( ( (w->rank + w->numIOPSSubmitted) % 100) < cfg->rwMixReadPercent) )
+		doRead = 1; // aioRWMixPrepper
+
+	memset(cb, 0, sizeof(*cb) );
+	cb->aio_lio_opcode = doRead ? IOCB_CMD_PREAD : IOCB_CMD_PWRITE;
+	cb->aio_fildes = fd;
+	cb->aio_buf = (uint64_t)(uintptr_t)buf;
+	cb->aio_nbytes = count;
+	cb->aio_offset = offset;
+}
+
+/* prepare request slot ioVecIdx with the generator's next block and submit it: the body that
+ * phase 1 (:1819-1868) and the resubmission of phase 2 (:1977-2027) share. Order of the steps as
+ * in the reference: prep, START STAMP, rate limiter (a wait invalidates the stamps of ALL pending
+ * requests, :1843-1845), block modifier, io_submit of this one iocb. @return 0 ok, -1 error. */
+static int orc_aio_submit_next(orc_worker* w, const int* fdVec, int isSingleFile, int isRead,
+	size_t ioVecIdx, size_t numSlots)
+{
+	orc_shared* sh = w->shared;
+	orc_offsetgen* gen = w->offsetGen;
+	const uint64_t rwOffsetGenNext = orc_offsetgen_next_offset(gen);
+	const size_t blockSize = orc_offsetgen_next_block_size(gen);
+	uint64_t currentOffset;
+	size_t fileHandlesIdx;
+	struct iocb* cb = &w->iocbVec[ioVecIdx];
+	struct iocb* cbPtr = cb;
+
+	orc_calc_file_idx_and_offset(rwOffsetGenNext, sh->fileSize, isSingleFile, &fileHandlesIdx,
+		&currentOffset);
+
+	orc_aio_prep(w, cb, fdVec[fileHandlesIdx], w->ioBufVec[ioVecIdx], blockSize, currentOffset,
+		isRead);
+	cb->aio_data = ioVecIdx; // the vec index of this request
+
+	clock_gettime(CLOCK_MONOTONIC, &w->ioStartTimeVec[ioVecIdx] );
+
+	if(orc_ratelimiter_wait(&w->rateLimiter, blockSize) )
+		for(size_t i = 0; i < numSlots; i++)
+			w->ioStartTimeVec[i].tv_sec = -1; // time_point::min(): not counted (:1935, 1946)
+
+	if(!isRead)
+		orc_pre_write_modify(w, w->ioBufVec[ioVecIdx], blockSize, currentOffset);
+
+	if(syscall(SYS_io_submit, w->aioContext, 1L, &cbPtr) != 1)
+	{
+		snprintf(w->errTmp, sizeof(w->errTmp),
+			"Async IO submission (io_submit) failed. SysErr: %s", strerror(errno) );
+		orc_worker_fail(w, w->errTmp);
+		return -1;
+	}
+
+	w->numIOPSSubmitted++;
+	orc_offsetgen_add_bytes_submitted(gen, blockSize);
+
+	return 0;
+}
+
+/* workers/LocalWorker.cpp:1795-2037 (aioBlockSized) on the raw kernel AIO ABI (the reference uses
+ * libaio's wrappers of the same syscalls): phase 1 seeds up to iodepth requests one io_submit
+ * each, phase 2 reaps 1..ORC_AIO_MAX_EVENTS completions at a time, checks, verifies (read phase),
+ * accounts (latency only if the start stamp was not invalidated) and reuses the slot for the next
+ * block. Returns like the reference: total bytes, -1 (errno set), the partial byte count, or -2
+ * after a verify failure / submission error (message set). */
+static int64_t orc_aio_block_sized(orc_worker* w, const int* fdVec, size_t numFDs, int isRead)
+{
+	orc_shared* sh = w->shared;
+	const elb_cfg* cfg = sh->cfg;
+	orc_offsetgen* gen = w->offsetGen;
+	const size_t maxIODepth = cfg->ioDepth;
+	const int isSingleFile = (numFDs == 1);
+	size_t numPending = 0;
+	uint64_t numBytesDone = 0;
+	struct io_event ioEvents[ORC_AIO_MAX_EVENTS];
+
+	// P H A S E 1: initial seed of io submissions up to full ioDepth
+	while(orc_offsetgen_bytes_left(gen) && (numPending < maxIODepth) )
+	{
+		if(orc_aio_submit_next(w, fdVec, isSingleFile, isRead, numPending, maxIODepth) )
+			return -2;
+
+		numPending++;
+	}
+
+	// P H A S E 2: wait for submissions to complete and submit new requests if bytes left
+	while(numPending)
+	{
+		struct timespec ioTimeout = {ORC_AIO_MAX_WAIT_SEC, 0};
+
+		long eventsRes = syscall(SYS_io_getevents, w->aioContext, 1L, (long)ORC_AIO_MAX_EVENTS,
+			ioEvents, &ioTimeout);
+
+		if(!eventsRes || ( (eventsRes < 0) && (errno == EINTR) ) )
+			continue; // timeout expired (only there to check interruptions)
+
+		if(eventsRes < 0)
+		{
+			snprintf(w->errTmp, sizeof(w->errTmp),
+				"Getting async IO events (io_getevents) failed. NumPending: %zu; SysErr: %s",
+				numPending, strerror(errno) );
+			orc_worker_fail(w, w->errTmp);
+			return -2;
+		}
+
+		for(long eventIdx = 0; eventIdx < eventsRes; eventIdx++)
+		{
+			const struct io_event* event = &ioEvents[eventIdx];
+			struct iocb* cb = (struct iocb*)(uintptr_t)event->obj;
+			const size_t ioVecIdx = (size_t)event->data;
+
+			if(event->res2 || (event->res != (int64_t)cb->aio_nbytes) )
+			{ // unexpected result (:1900-1927)
+				if(event->res2)
+				{
+					snprintf(w->errTmp, sizeof(w->errTmp), "Async IO framework error. "
+						"res: %lld; res2: %lld", (long long)event->res, (long long)event->res2);
+					orc_worker_fail(w, w->errTmp);
+					return -2;
+				}
+
+				if(event->res < 0)
+				{
+					errno = -(int)event->res;
+					return -1;
+				}
+
+				return (int64_t)(numBytesDone + event->res); // partial read/write
+			}
+
+			const int wasRead = (cb->aio_lio_opcode == IOCB_CMD_PREAD);
+
+			if(isRead && cfg->integrityCheckSalt)
+			{ // funcPostReadBlockChecker (:1938-1940): only set in a read phase (:1318-1319)
+				int verifyRes = orc_verify_pattern( (char*)(uintptr_t)cb->aio_buf, cb->aio_nbytes,
+					cb->aio_offset, cfg->integrityCheckSalt, NULL, NULL, NULL, NULL, w->errTmp,
+					sizeof(w->errTmp) );
+				if(verifyRes)
+				{
+					orc_worker_fail(w, w->errTmp);
+					return -2;
+				}
+			}
+
+			const int latencyValid = (w->ioStartTimeVec[ioVecIdx].tv_sec >= 0);
+			const uint64_t ioElapsedMicroSec =
+				latencyValid ? orc_elapsed_usec(&w->ioStartTimeVec[ioVecIdx] ) : 0;
+
+			numBytesDone += event->res;
+
+			if( (wasRead && (sh->benchPhase == ELB_PHASE_CREATEFILES) ) )
+			{ // read in a write phase => rwmix read stats (:1951-1963; no histogram kept here)
+				__atomic_fetch_add(&w->res->liveOpsReadMix.numBytesDone, (uint64_t)event->res,
+					__ATOMIC_RELAXED);
+				__atomic_fetch_add(&w->res->liveOpsReadMix.numIOPSDone, 1, __ATOMIC_RELAXED);
+			}
+			else
+			{
+				if(latencyValid) // (:1966-1969)
+					orc_histogram_add_latency(&w->res->iopsLatHisto, ioElapsedMicroSec);
+
+				__atomic_fetch_add(&w->res->liveOps.numBytesDone, (uint64_t)event->res,
+					__ATOMIC_RELAXED);
+				__atomic_fetch_add(&w->res->liveOps.numIOPSDone, 1, __ATOMIC_RELAXED);
+			}
+
+			if(!orc_offsetgen_bytes_left(gen) )
+			{
+				numPending--;
+				continue;
+			}
+
+			// request complete, so reuse iocb for the next request
+			if(orc_aio_submit_next(w, fdVec, isSingleFile, isRead, ioVecIdx, maxIODepth) )
+				return -2;
+		}
+	}
+
+	return orc_offsetgen_bytes_total(gen);
+}
+
+/* funcRWBlockSized (workers/LocalWorker.cpp:1243-1244, 1305-1306): the sync loop for iodepth 1,
+ * else the aio loop */
+static int64_t orc_rw_block_sized(orc_worker* w, const int* fdVec, size_t numFDs, int isRead);
+
+static int64_t orc_rw_any_block_sized(orc_worker* w, const int* fdVec, size_t numFDs, int isRead)
+{
+	if( (w->shared->cfg->ioDepth > 1) && w->aioInitialized)
+		return orc_aio_block_sized(w, fdVec, numFDs, isRead);
+
+	return orc_rw_block_sized(w, fdVec, numFDs, isRead);
+}
+
 /* workers/LocalWorker.cpp:1669-1781 (rwBlockSized) with the CPU policy of :1188-1355:
  * write phase: modifier = pattern fill if salt != 0, else random refill if blockvarpct, else noop;
  * read phase: checker = pattern verify if salt != 0. Returns like the reference: total bytes,
@@ -968,20 +1233,13 @@ static int64_t orc_rw_block_sized(orc_worker* w, const int* fdVec, size_t numFDs
 		orc_calc_file_idx_and_offset(rwOffsetGenNext, sh->fileSize, isSingleFile,
 			&fileHandleIdx, &currentOffset);
 
+		orc_ratelimiter_wait(&w->rateLimiter, currentBlockSize); // funcRWRateLimiter (:1689)
+
 		struct timespec ioStartT;
 		clock_gettime(CLOCK_MONOTONIC, &ioStartT);
 
-		if(!isRead)
-		{ // funcPreWriteBlockModifier (:1256-1265)
-			if(cfg->integrityCheckSalt)
-				orc_fill_pattern(w->ioBuf, currentBlockSize, currentOffset,
-					cfg->integrityCheckSalt);
-			else
-			if(cfg->blockVariancePercent &&
-				!( ( (w->rank + w->numIOPSSubmitted) % 100) < rwMixReadPercent) ) // :2213
-				orc_rand_refill_goldenprime(&w->blockVarAlgo, w->ioBuf, currentBlockSize,
-					cfg->blockVariancePercent);
-		}
+		if(!isRead) // funcPreWriteBlockModifier (:1693-1694)
+			orc_pre_write_modify(w, w->ioBuf, currentBlockSize, currentOffset);
 
 		if(isRead)
 		{ // this is a read, but could be a rwmix read thread (:1697-1706)
@@ -1103,7 +1361,7 @@ static void orc_file_mode_iterate_seq(orc_worker* w, int isRead)
 
 		orc_offsetgen_reset_range(w->offsetGen, currentIOLen, currentIOStart);
 
-		int64_t rwRes = orc_rw_block_sized(w, &w->currentFD, 1, isRead);
+		int64_t rwRes = orc_rw_any_block_sized(w, &w->currentFD, 1, isRead);
 
 		if( (rwRes < 0) || ( (uint64_t)rwRes != currentIOLen) )
 		{
@@ -1123,7 +1381,7 @@ static void orc_file_mode_iterate_rand(orc_worker* w, int isRead)
 {
 	orc_shared* sh = w->shared;
 
-	int64_t rwRes = orc_rw_block_sized(w, sh->pathFDs, sh->cfg->numPaths, isRead);
+	int64_t rwRes = orc_rw_any_block_sized(w, sh->pathFDs, sh->cfg->numPaths, isRead);
 
 	if( (rwRes < 0) || ( (uint64_t)rwRes != orc_offsetgen_bytes_total(w->offsetGen) ) )
 		orc_set_io_error(w, isRead, rwRes, orc_offsetgen_bytes_total(w->offsetGen),
@@ -1295,7 +1553,7 @@ static void orc_dir_mode_iterate_files(orc_worker* w, int benchPhase)
 
 				w->currentFD = fd;
 
-				int64_t rwRes = orc_rw_block_sized(w, &w->currentFD, 1, isRead);
+				int64_t rwRes = orc_rw_any_block_sized(w, &w->currentFD, 1, isRead);
 
 				if( (rwRes < 0) || ( (uint64_t)rwRes != fileSize) )
 				{
@@ -1528,6 +1786,10 @@ static void* orc_worker_thread(void* arg)
 
 			orc_init_offset_gen(w, benchPhase == ELB_PHASE_CREATEFILES);
 
+			// per-thread rate limit (:1293-1299 write side, :1331-1337 read side incl. rwmix readers)
+			orc_ratelimiter_init_start(&w->rateLimiter,
+				isRead ? cfg->limitReadBps : cfg->limitWriteBps);
+
 			if(isDir)
 				orc_dir_mode_iterate_files(w, isRead ? ELB_PHASE_READFILES : benchPhase);
 			else
@@ -1702,6 +1964,25 @@ int orc_run_phase(const elb_cfg* cfg, int benchPhase, orc_worker_result* results
 			w->ioBuf = NULL;
 		}
 
+		/* allocIOBuffer for iodepth > 1 (:1362-1396: one buffer per depth entry) + initLibAio
+		   (:455-480) */
+		if( (cfg->ioDepth > 1) && w->ioBuf && sh.blockSize)
+		{
+			w->ioBufVec = (char**)calloc(cfg->ioDepth, sizeof(char*) );
+			w->iocbVec = (struct iocb*)calloc(cfg->ioDepth, sizeof(struct iocb) );
+			w->ioStartTimeVec = (struct timespec*)calloc(cfg->ioDepth, sizeof(struct timespec) );
+			w->ioBufVec[0] = w->ioBuf;
+
+			for(uint32_t d = 1; d < cfg->ioDepth; d++)
+				if(posix_memalign( (void**)&w->ioBufVec[d], sysconf(_SC_PAGESIZE), sh.blockSize) )
+					retVal = -1;
+
+			if(!retVal && (syscall(SYS_io_setup, (unsigned)cfg->ioDepth, &w->aioContext) == 0) )
+				w->aioInitialized = 1;
+			else
+				retVal = -1;
+		}
+
 		uint64_t seederState[4];
 		uint64_t sm = (cfg->blockVarianceSeed ? cfg->blockVarianceSeed : 0x1234567ULL) + w->rank;
 		for(int k = 0; k < 4; k++)
@@ -1795,6 +2076,13 @@ int orc_run_phase(const elb_cfg* cfg, int benchPhase, orc_worker_result* results
 cleanup_workers:
 	for(uint32_t i = 0; i < numThreads; i++)
 	{
+		if(workers[i].aioInitialized)
+			syscall(SYS_io_destroy, workers[i].aioContext);
+		for(uint32_t d = 1; workers[i].ioBufVec && (d < cfg->ioDepth); d++)
+			free(workers[i].ioBufVec[d] );
+		free(workers[i].ioBufVec);
+		free(workers[i].iocbVec);
+		free(workers[i].ioStartTimeVec);
 		free(workers[i].ioBuf);
 		if(workers[i].offsetGen)
 			orc_offsetgen_destroy(workers[i].offsetGen);

@@ -18,6 +18,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <time.h>
 
 #include "elbencho_b200.h" /* shared config/stats structs only */
 
@@ -119,7 +120,19 @@ void orc_histogram_merge(elb_histogram* dst, const elb_histogram* src);
 double orc_histogram_percentile(const elb_histogram* h, double percentage);
 uint64_t orc_per_sec_from_usec(uint64_t totalValue, uint64_t elapsedUSec);
 
-/* ---- the CPU LocalWorker: run one phase with cfg->numThreads threads ---- */
+/* ---- RateLimiter (toolkits/RateLimiter.h:13-66) ---- */
+typedef struct orc_ratelimiter
+{
+	uint64_t limitPerSec;    // 0 = no limit
+	uint64_t numDoneThisSec;
+	struct timespec startT;  // when the current second started
+} orc_ratelimiter;
+
+void orc_ratelimiter_init_start(orc_ratelimiter* rl, uint64_t limitPerSec);
+int orc_ratelimiter_wait(orc_ratelimiter* rl, uint64_t nextSize); // 1 = had to wait
+
+/* ---- the CPU LocalWorker: run one phase with cfg->numThreads threads (rwBlockSized for
+ * iodepth 1, aioBlockSized on kernel AIO for iodepth > 1) ---- */
 typedef struct orc_worker_result
 {
 	elb_liveops liveOps;

@@ -400,7 +400,8 @@ def test_staged_verify_reads_host_ring_and_publishes_results(cuda_device, misali
     host_np = host.numpy()
     for ptr, n, off, _ in blocks:
         lo = ptr - dev.data_ptr()
-        host_np[lo:lo + n] = bytearray(oracle_lib.fill_pattern(n, off, salt)) if n else b""
+        if n:
+            host_np[lo:lo + n] = list(oracle_lib.fill_pattern(n, off, salt))
     bad = {0: [5, 70001, (1 << 20) - 1], 2: [4095], 4: [(1 << 20) + 30]}
     for idx, positions in bad.items():
         lo = blocks[idx][0] - dev.data_ptr()

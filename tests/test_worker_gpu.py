@@ -18,6 +18,14 @@ MiB = 1 << 20
 KiB = 1 << 10
 
 
+@pytest.fixture(autouse=True, params=["kernel", "copyengine"])
+def staging_engine(request, monkeypatch):
+    """every test of this module runs with both staging engines: the fill / verify kernels moving
+    the blocks themselves, and cudaMemcpyAsync (+ CUDA graphs) around the kernels"""
+    monkeypatch.setenv("ELB_STAGING", request.param)
+    return request.param
+
+
 @pytest.fixture()
 def workdir(cuda_device):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
@@ -409,3 +417,28 @@ def test_rank_offset_sharding_two_managers(workdir):
         assert sha(a) == sha(b)
         with open(a, "rb") as f:
             assert f.read() == oracle_lib.fill_pattern(size, 0, 9)
+
+
+@pytest.mark.parametrize("batch_blocks,num_batches", [(0, 0), (16, 2)])
+def test_mid_size_multi_batch_run_bytes_equal_oracle(workdir, staging_engine, batch_blocks,
+                                                     num_batches):
+    """4 GiB through many batches per worker (default cache-resident batches, and 16 MiB batches
+    whose copy-engine form is replayed from per-batch CUDA graphs): file bytes, counters and verify
+    outcome equal the oracle's."""
+    size, block, threads = 4 << 30, MiB, 4
+    kwargs = dict(num_threads=threads, block_size=block, file_size=size, integrity_check_salt=11)
+    gcfg, ccfg = gpu_and_cpu_configs(workdir, ["big"], **kwargs)
+    tuned = WorkerConfig(paths=gcfg.paths, pipeline_batch_blocks=batch_blocks,
+                         pipeline_num_batches=num_batches, **kwargs)
+    with WorkerManager(tuned) as mgr:
+        gw = mgr.run_phase(BenchPhase.CREATEFILES)
+        gr = mgr.run_phase(BenchPhase.READFILES)
+    rc, _, opw = oracle_lib.run_oracle_phase(ccfg, BenchPhase.CREATEFILES)
+    assert rc == 0
+    assert gw["ops_total"]["bytes"] == opw.opsTotal.numBytesDone == size
+    assert gw["ops_total"]["iops"] == opw.opsTotal.numIOPSDone == size // block
+    assert gw["filled_bytes"] == size and gw["d2h_bytes"] == size
+    assert gr["verified_bytes"] == size and gr["verify_mismatch_bytes"] == 0
+    assert gr["h2d_bytes"] == size
+    assert gr["dev_kernel_usec"] > 0 and gw["dev_kernel_usec"] > 0
+    assert sha(gcfg.paths[0]) == sha(ccfg.paths[0])

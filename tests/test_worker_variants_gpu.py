@@ -16,6 +16,14 @@ MiB = 1 << 20
 KiB = 1 << 10
 
 
+@pytest.fixture(autouse=True, params=["kernel", "copyengine"])
+def staging_engine(request, monkeypatch):
+    """every test of this module runs with both staging engines: the fill / verify kernels moving
+    the blocks themselves, and cudaMemcpyAsync (+ CUDA graphs) around the kernels"""
+    monkeypatch.setenv("ELB_STAGING", request.param)
+    return request.param
+
+
 @pytest.fixture()
 def workdir(cuda_device):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
@@ -276,3 +284,83 @@ def test_full_file_lock_rejects_async_io(workdir):
     with pytest.raises(WorkerError, match="Full file write locks cannot be used together with "
                                           "async IO"):
         WorkerManager(cfg)
+
+
+def test_stonewall_snapshot_with_a_deterministic_straggler(workdir):
+    """Stonewall ("first done") totals against the oracle, exactly. A rwmix reader thread is the
+    straggler: --limitread of one block per second lets it read exactly one block and then sleep
+    for the rest of the second, in which the one writer thread finishes its whole share and
+    triggers the snapshot (Worker.cpp:33-55). Reader -> ReadMix counters, writer -> main ones."""
+    size, block = 256 * MiB, MiB
+    kwargs = dict(num_threads=2, block_size=block, file_size=size, integrity_check_salt=3)
+    gcfg, ccfg = gpu_and_cpu_configs(workdir, ["f"], **kwargs)
+    limited = dict(kwargs, num_rwmix_read_threads=1, limit_read_bps=block)
+    gcfg2 = WorkerConfig(paths=gcfg.paths, **limited)
+    ccfg2 = WorkerConfig(paths=ccfg.paths, **limited)
+    with WorkerManager(gcfg) as mgr:  # the files the reader thread reads
+        mgr.run_phase(BenchPhase.CREATEFILES)
+    assert oracle_lib.run_oracle_phase(ccfg, BenchPhase.CREATEFILES)[0] == 0
+    with WorkerManager(gcfg2) as mgr:
+        res = mgr.run_phase(BenchPhase.CREATEFILES)
+    rc, _, opr = oracle_lib.run_oracle_phase(ccfg2, BenchPhase.CREATEFILES)
+    assert rc == 0
+    # writer (rank 1): all of its half at the moment it finishes; reader (rank 0): one block
+    assert res["ops_stonewall_total"]["bytes"] == opr.opsStoneWallTotal.numBytesDone == size // 2
+    assert res["ops_stonewall_total"]["iops"] == opr.opsStoneWallTotal.numIOPSDone == 128
+    assert res["ops_stonewall_readmix_total"]["bytes"] == \
+        opr.opsStoneWallReadMixTotal.numBytesDone == block
+    assert res["ops_stonewall_readmix_total"]["iops"] == \
+        opr.opsStoneWallReadMixTotal.numIOPSDone == 1
+    # and the end-of-phase totals
+    assert res["ops_total"]["bytes"] == opr.opsTotal.numBytesDone == size // 2
+    assert res["ops_readmix_total"]["bytes"] == opr.opsReadMixTotal.numBytesDone == size // 2
+    assert res["first_finish_usec"] < 1000000 < res["last_finish_usec"]
+
+
+def test_aio_rate_limiter_keeps_slept_ios_out_of_the_histogram(workdir):
+    """aioBlockSized semantics (LocalWorker.cpp:1840-1847, 1935, 1966): an I/O that was pending
+    while the rate limiter slept is counted (bytes, IOPS) but not entered into the latency
+    histogram. The oracle resubmits one request per completion like the reference; the pipeline
+    submits in groups, so an I/O that completed before the sleep stays valid here: the number of
+    histogram entries lies between the oracle's and the number of I/Os, and no recorded latency
+    contains a sleep."""
+    block, nblocks = MiB, 6
+    base = dict(num_threads=1, block_size=block, file_size=16 * MiB, integrity_check_salt=9)
+    gcfg, ccfg = gpu_and_cpu_configs(workdir, ["f"], **base)
+    with WorkerManager(gcfg) as mgr:
+        mgr.run_phase(BenchPhase.CREATEFILES)
+    assert oracle_lib.run_oracle_phase(ccfg, BenchPhase.CREATEFILES)[0] == 0
+    rand = dict(base, io_depth=4, io_engine=IOEngine.AIO, use_random_offsets=True,
+                random_amount=nblocks * block, rand_offset_seed=5, limit_read_bps=2 * block)
+    with WorkerManager(WorkerConfig(paths=gcfg.paths, **rand)) as mgr:
+        res = mgr.run_phase(BenchPhase.READFILES)
+    rc, _, opr = oracle_lib.run_oracle_phase(WorkerConfig(paths=ccfg.paths, **rand),
+                                             BenchPhase.READFILES)
+    assert rc == 0
+    assert res["ops_total"]["iops"] == opr.opsTotal.numIOPSDone == nblocks
+    assert res["ops_total"]["bytes"] == opr.opsTotal.numBytesDone
+    assert res["verify_mismatch_bytes"] == 0
+    assert opr.iopsLatHisto.numStoredValues < nblocks
+    assert opr.iopsLatHisto.numStoredValues <= res["iops_lat_histo"]["num"] < nblocks
+    assert res["iops_lat_histo"]["max_usec"] < 900000  # no histogram entry spans a sleep
+    assert res["last_finish_usec"] >= 2000000          # 6 blocks at 2 per second
+
+
+def test_nofdsharing_per_thread_descriptors(workdir):
+    """--nofdsharing (LocalWorker.cpp:869-913): every worker works on its own descriptors;
+    results are the same as with the manager's shared ones"""
+    kwargs = dict(num_threads=3, block_size=64 * KiB, file_size=2 * MiB + 5, integrity_check_salt=2)
+    gcfg, ccfg = gpu_and_cpu_configs(workdir, ["a", "b"], **kwargs)
+    own = WorkerConfig(paths=gcfg.paths, use_no_fd_sharing=True, **kwargs)
+    with WorkerManager(own) as mgr:
+        gw = mgr.run_phase(BenchPhase.CREATEFILES)
+        gr = mgr.run_phase(BenchPhase.READFILES)
+    rc, _, opw = oracle_lib.run_oracle_phase(ccfg, BenchPhase.CREATEFILES)
+    assert rc == 0
+    assert gw["ops_total"] == {"entries": opw.opsTotal.numEntriesDone,
+                               "bytes": opw.opsTotal.numBytesDone,
+                               "iops": opw.opsTotal.numIOPSDone}
+    assert gr["verify_mismatch_bytes"] == 0 and gr["verified_bytes"] == gr["ops_total"]["bytes"]
+    for g, c in zip(gcfg.paths, ccfg.paths):
+        with open(g, "rb") as f1, open(c, "rb") as f2:
+            assert f1.read() == f2.read()

@@ -780,44 +780,50 @@ inline void liveOpsAdd(elb_liveops& dst, const elb_liveops& src)
  * FIFO gate in front of the buffered writes to one file (elb_cfg::serializeBufferedWrites).
  *
  * Buffered writes to one inode are serialised by the kernel on the inode lock; what a writer can
- * win is a fast hand-over. Tickets give FIFO order; the holder of the NEXT ticket spins in user
- * space (so the hand-over costs a cache line transfer, not a wake-up), everybody further back
- * sleeps on a futex word of its own ticket slot and is woken when it becomes next-in-line - one
- * targeted wake-up per hand-over, which then hides behind the current holder's write.
+ * win is a fast hand-over and a source buffer that is still in the last level cache. Tickets give
+ * FIFO order. A waiter sleeps on a futex word of its own ticket slot while NEAR_DISTANCE or more
+ * tickets are ahead of it and is woken when it gets near (one targeted wake-up per hand-over,
+ * hidden behind the current holder's write); the near ones spin in user space, so the hand-over
+ * itself costs a cache line transfer, not a wake-up. Knowing its position lets a worker produce
+ * its block just in time (waitUntilNear() -> launch the GPU stage -> waitTurn() -> write): only
+ * the next few blocks of a file are in flight from the GPU at any time, they land in the cache by
+ * DDIO and are written from there.
  */
 class FileWriteGate
 {
 	public:
+		static const unsigned NEAR_DISTANCE = 3; // tickets ahead at which a waiter still sleeps
+
 		FileWriteGate()
 		{
 			for(auto& slot : wakeSeq)
 				slot.store(0, std::memory_order_relaxed);
 		}
 
-		/* blocks until it is this caller's turn */
-		void enter()
+		uint64_t takeTicket() { return nextTicket.fetch_add(1, std::memory_order_relaxed); }
+
+		/* sleeps until fewer than NEAR_DISTANCE tickets are ahead of this one */
+		void waitUntilNear(uint64_t ticket)
 		{
-			const uint64_t ticket = nextTicket.fetch_add(1, std::memory_order_relaxed);
 			std::atomic<uint32_t>& mySlot = wakeSeq[ticket % NUM_SLOTS];
 
-			for(unsigned spins = 0; ; spins++)
+			for( ; ; )
 			{
-				const uint64_t nowServing = serving.load(std::memory_order_acquire);
+				const uint32_t seq = mySlot.load(std::memory_order_acquire);
 
-				if(nowServing == ticket)
+				if( (ticket - serving.load(std::memory_order_acquire) ) < NEAR_DISTANCE)
 					return;
 
-				if( (ticket - nowServing) >= 2)
-				{ // not next-in-line yet: sleep until the slot of this ticket is signalled
-					const uint32_t seq = mySlot.load(std::memory_order_acquire);
+				futexWait(&mySlot, seq);
+			}
+		}
 
-					if( (ticket - serving.load(std::memory_order_acquire) ) >= 2)
-						futexWait(&mySlot, seq);
-
-					continue;
-				}
-
-				if(spins < 4096)
+		/* spins until it is this ticket's turn (call waitUntilNear() first to sleep instead) */
+		void waitTurn(uint64_t ticket)
+		{
+			for(unsigned spins = 0; serving.load(std::memory_order_acquire) != ticket; spins++)
+			{
+				if(spins < 2048)
 					cpuRelax();
 				else
 				{ // (the holder may have been descheduled: do not burn its CPU time)
@@ -827,16 +833,27 @@ class FileWriteGate
 			}
 		}
 
+		/* blocks until it is this caller's turn */
+		void enter()
+		{
+			const uint64_t ticket = takeTicket();
+
+			waitUntilNear(ticket);
+			waitTurn(ticket);
+		}
+
 		void leave()
 		{
 			const uint64_t done = serving.fetch_add(1, std::memory_order_release);
 
-			// ticket done+1 is being served now; done+2 becomes next-in-line: wake it if it sleeps
-			std::atomic<uint32_t>& slot = wakeSeq[ (done + 2) % NUM_SLOTS];
+			/* ticket done+1 is served now; ticket done+NEAR_DISTANCE just got near: wake it if it
+			   sleeps (a thread that takes that ticket later sees the new serving value) */
+			const uint64_t nearTicket = done + NEAR_DISTANCE;
+			std::atomic<uint32_t>& slot = wakeSeq[nearTicket % NUM_SLOTS];
 
 			slot.fetch_add(1, std::memory_order_release);
 
-			if(nextTicket.load(std::memory_order_relaxed) > (done + 2) )
+			if(nextTicket.load(std::memory_order_relaxed) > nearTicket)
 				futexWake(&slot);
 		}
 
@@ -867,27 +884,53 @@ class FileWriteGate
 		}
 };
 
-/* scope guard of one turn at a FileWriteGate (NULL gate = no gating) */
+/* one turn at a FileWriteGate (NULL gate = no gating): takes the ticket on construction; the
+ * destructor always completes the turn (a ticket cannot be abandoned without stalling the queue) */
 class FileWriteTurn
 {
 	public:
 		explicit FileWriteTurn(FileWriteGate* gate) : gate(gate)
 		{
 			if(gate)
-				gate->enter();
+				ticket = gate->takeTicket();
 		}
 
 		~FileWriteTurn()
 		{
-			if(gate)
-				gate->leave();
+			if(!gate)
+				return;
+
+			waitTurn();
+			gate->leave();
 		}
 
 		FileWriteTurn(const FileWriteTurn&) = delete;
 		FileWriteTurn& operator=(const FileWriteTurn&) = delete;
 
+		void waitUntilNear()
+		{
+			if(gate && !isNear)
+			{
+				gate->waitUntilNear(ticket);
+				isNear = true;
+			}
+		}
+
+		void waitTurn()
+		{
+			if(gate && !hasTurn)
+			{
+				waitUntilNear();
+				gate->waitTurn(ticket);
+				hasTurn = true;
+			}
+		}
+
 	private:
 		FileWriteGate* gate;
+		uint64_t ticket{0};
+		bool isNear{false};
+		bool hasTurn{false};
 };
 
 /* ---- normalised configuration (the rules of ProgArgs::initImplicitValues/checkArgs/

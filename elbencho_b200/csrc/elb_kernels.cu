@@ -851,7 +851,8 @@ template<int MODE>
 static int queryOccupancy()
 {
 	int numBlocks = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&numBlocks, elb_blocks_kernel<MODE, STAGE_NONE>,
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&numBlocks,
+		elb_blocks_kernel<MODE, ( (MODE == MODE_COPY_IN) || (MODE == MODE_COPY_OUT) ) ? STAGE_FULL : STAGE_NONE>,
 		ELB_THREADS, 0);
 	return (numBlocks > 0) ? numBlocks : 1;
 }
@@ -978,11 +979,18 @@ static int launchBlocksKernel(const KernelArgs& args, uint64_t totalBytesHint,
 	if(args.hostDelta || (MODE == MODE_COPY_IN) || (MODE == MODE_COPY_OUT) )
 		return launchBlocksKernelT<MODE, STAGE_FULL>(args, totalBytesHint, maxBlockLenHint, stream);
 
-	if( (MODE == MODE_VERIFY_PATTERN) && args.hostResults)
-		return launchBlocksKernelT<MODE, STAGE_PUBLISH>(args, totalBytesHint, maxBlockLenHint,
-			stream);
+	if constexpr( (MODE == MODE_COPY_IN) || (MODE == MODE_COPY_OUT) )
+		return -1; // (not reached: the copy kernels exist in their staged form only)
+	else
+	{
+		if constexpr(MODE == MODE_VERIFY_PATTERN)
+			if(args.hostResults)
+				return launchBlocksKernelT<MODE, STAGE_PUBLISH>(args, totalBytesHint,
+					maxBlockLenHint, stream);
 
-	return launchBlocksKernelT<MODE, STAGE_NONE>(args, totalBytesHint, maxBlockLenHint, stream);
+		return launchBlocksKernelT<MODE, STAGE_NONE>(args, totalBytesHint, maxBlockLenHint,
+			stream);
+	}
 }
 
 static void applyStage(KernelArgs& args, const elb_stage_args* stage)

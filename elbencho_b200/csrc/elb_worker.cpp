@@ -22,7 +22,7 @@
 #define ELB_INTERRUPT_CHECK_INTERVAL 128 /* LocalWorker.cpp:63 */
 #define ELB_AIO_MAX_EVENTS 64
 #define ELB_AIO_MAX_WAIT_SEC 5     /* LocalWorker.cpp:60 */
-#define ELB_DEFAULT_BATCH_BYTES (1ULL * 1024 * 1024) /* cache resident, see allocRings() */
+#define ELB_DEFAULT_BATCH_BYTES (2ULL * 1024 * 1024) /* small enough to stay in cache, see allocRings() */
 #define ELB_DEFAULT_NUM_BATCHES 3
 #define ELB_MAX_AIO_BATCH_BYTES (4ULL * 1024 * 1024)
 #define ELB_MAX_BATCH_BLOCKS 2048
@@ -1727,7 +1727,7 @@ void Worker::rwPhase()
  *
  * @return false if the source had no more blocks (batch stays empty).
  */
-bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead)
+bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead, bool oneFilePerBatch)
 {
 	batch.blocks.clear();
 	batch.numBytes = 0;
@@ -1741,8 +1741,22 @@ bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead)
 	{
 		BlockRef block;
 
+		if(haveLookaheadBlock)
+		{
+			block = lookaheadBlock;
+			haveLookaheadBlock = false;
+		}
+		else
 		if(!source.next(block) )
 			break;
+
+		if(oneFilePerBatch && !batch.blocks.empty() &&
+			(block.fileIdx != batch.blocks.front().fileIdx) )
+		{ // belongs to the next batch
+			lookaheadBlock = block;
+			haveLookaheadBlock = true;
+			break;
+		}
 
 		/* rwmix rule of rwBlockSized (LocalWorker.cpp:1708-1718): in a write phase block n of a
 		   worker is a read if (rank + numIOPSSubmitted) % 100 < rwmixpct */
@@ -1775,6 +1789,16 @@ bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead)
  */
 void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 {
+	haveLookaheadBlock = false;
+
+	/* plain buffered writes of several workers to shared files: just-in-time loop at the gate */
+	if(!isRead && useWriteGate && !batches.empty() && (cfg.ioEngine != ELB_IOENGINE_AIO) &&
+		!cfg.rwMixReadPercent && !cfg.doDirectVerify && !cfg.doReadInline && !cfg.flockType)
+	{
+		rwBlocksGatedWrite(source);
+		return;
+	}
+
 	std::deque<Batch*> freeBatches;
 	std::deque<Batch*> stageOneQueue;
 	std::deque<Batch*> stageTwoQueue;
@@ -1885,6 +1909,70 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 
 		if(sourceExhausted && stageOneQueue.empty() && stageTwoQueue.empty() )
 			break;
+	}
+}
+
+static ssize_t fullBlockIO(int fd, char* buf, uint64_t len, uint64_t offset, bool isRead);
+
+/**
+ * Write loop for buffered writes of several workers to shared files (the write gate is on): the
+ * kernel lets one writer into a file at a time anyway, so what counts is that the writer whose
+ * turn it is has its block ready AND still in the last level cache. A worker takes its FIFO
+ * ticket first, sleeps until it is near the front, launches the GPU stage of its batch only then
+ * (fill + stage-out, tens of microseconds, hidden behind the writes of the tickets ahead), spins
+ * for its turn and writes. At any time only the next few blocks of a file are in flight from the
+ * GPU; they arrive in the cache through DDIO and are copied into the page cache from there, and the
+ * same host slots are reused turn after turn. Measured on the box's tmpfs (16 writers, one file):
+ * see profiles/README.md.
+ *
+ * Latency of a block = from the start of its turn request (first block of the batch) or from the
+ * end of the previous block to the end of its pwrite, so the wait for the file and the fill are
+ * inside it like the inode lock wait and preWriteIntegrityCheckFillBuf are inside the reference's
+ * (LocalWorker.cpp:1691-1755); the per-thread rate limiter runs before the stamp (:1689).
+ */
+void Worker::rwBlocksGatedWrite(BlockSource& source)
+{
+	Batch& batch = batches[0];
+
+	while(collectBatch(batch, source, false, true) )
+	{
+		checkInterruptionRequest();
+
+		for(const BlockRef& block : batch.blocks)
+			rateLimitNextBlock(block.len);
+
+		Clock::time_point prevEndT = Clock::now();
+
+		{
+			FileWriteTurn turn(shared->fileWriteGates[batch.blocks.front().fileIdx].get() );
+
+			turn.waitUntilNear();
+			gpuLaunchWriteStage(batch);
+			turn.waitTurn();
+			gpuWait(batch);
+
+			for(size_t i = 0; i < batch.blocks.size(); i++)
+			{
+				BlockRef& block = batch.blocks[i];
+
+				if(!block.len)
+					continue;
+
+				const ssize_t ioRes = fullBlockIO(resolveFD(block, false), slotHostPtr(batch, i),
+					block.len, block.offset, false);
+
+				if(ioRes != (ssize_t)block.len)
+					throwIOError(block, false, ioRes, errno);
+
+				const Clock::time_point endT = Clock::now();
+
+				block.ioUSec = std::chrono::duration_cast<std::chrono::microseconds>(
+					endT - prevEndT).count();
+				prevEndT = endT;
+			}
+		} // (turn ends)
+
+		accountBatch(batch, 0);
 	}
 }
 
@@ -2559,6 +2647,7 @@ void Worker::ioRunSync(Batch& batch, bool isRead)
 				FileWriteTurn turn(useWriteGate ?
 					shared->fileWriteGates[block.fileIdx].get() : NULL);
 
+				turn.waitTurn();
 				ioRes = fullBlockIO(fd, hostBuf, block.len, block.offset, false);
 			}
 

@@ -311,7 +311,11 @@ class Worker
 
 		// the pipeline
 		void rwBlocksPipelined(BlockSource& source, bool isRead);
-		bool collectBatch(Batch& batch, BlockSource& source, bool isRead);
+		void rwBlocksGatedWrite(BlockSource& source);
+		BlockRef lookaheadBlock; // collectBatch(): a block that did not fit the previous batch
+		bool haveLookaheadBlock{false};
+		bool collectBatch(Batch& batch, BlockSource& source, bool isRead,
+			bool oneFilePerBatch = false);
 		void verifyWrittenBatch(Batch& batch);
 		void accountBatch(Batch& batch, uint64_t gpuUSecTotal);
 		void gpuLaunchWriteStage(Batch& batch);

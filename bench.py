@@ -376,6 +376,11 @@ class C4(SeqFileWorkload):
         cfg.update(rank_offset=rank * self.threads, num_dataset_threads=self.world * self.threads)
         return cfg, [BenchPhase.CREATEFILES]
 
+    def value_of(self, totals):
+        """the read phase alone is the metric of this config (the write is its preparation)"""
+        read = totals["phase"]["READFILES"]
+        return read["bytes"] / GiB / (read["usec"] / 1e6) if read["usec"] else 0.0
+
 
 class C3(Workload):
     name = "c3"
@@ -858,42 +863,68 @@ def gpu_arm(args, torch, device, workload, rank):
     return totals, extra, prep_info
 
 
+def pool_steps(workload, world, warmup, steps):
+    """The steps of the in-process pool sample: ONE manager config per step that covers all GPUs
+    (worker rank g -> GPU g % N, LocalWorker.cpp:1420-1429). yields (cfg kwargs, phases, paths to
+    remove after the step)."""
+    from elbencho_b200 import BenchPhase
+    threads = world * workload.threads
+    if isinstance(workload, SeqFileWorkload):
+        # N fresh files of one slice each per step, T consecutive ranks per file
+        for step in range(warmup + steps):
+            paths = [os.path.join(workload.workdir, "pool_s%d_f%d.bin" % (step, r))
+                     for r in range(world)]
+            cfg = workload.base_cfg()
+            cfg.update(paths=paths, file_size=workload.slice_bytes, num_threads=threads,
+                       rank_offset=0, num_dataset_threads=threads)
+            yield cfg, [BenchPhase.CREATEFILES, BenchPhase.READFILES], paths
+    elif isinstance(workload, C3):
+        cfg = workload.base_cfg(0)
+        cfg.update(paths=workload.paths, num_threads=threads, block_size=MiB)
+        yield cfg, [BenchPhase.CREATEFILES], []  # (step 0 of the warm-up: the files to read)
+        for step in range(1, warmup + steps):
+            cfg, phases = workload.plan(step, 0)
+            cfg.update(paths=workload.paths, num_threads=threads,
+                       random_amount=workload.ios_per_step * workload.block * world)
+            yield cfg, phases, (workload.paths if step == warmup + steps - 1 else [])
+    else:
+        for step in range(warmup + steps):
+            cfg, phases = workload.plan(step, 0)
+            cfg.update(num_threads=threads, rank_offset=0, num_dataset_threads=threads)
+            yield cfg, phases, [workload.step_dir(step)]
+
+
 def inprocess_pool(args, torch, workload_cls, world):
     """The single-process worker pool north_star describes: one manager, --gpuids 0..N-1, rank ->
     GPU round robin (LocalWorker.cpp:1420-1429), live and phase-end statistics through the grouped
     ncclReduce of the library (replaces the host loop of Statistics.cpp:1338-1344). Runs a sample
-    of the same workload (2 warm-up + 4 timed steps) on rank 0 while the other ranks wait."""
+    of the same workload (2 warm-up + 4 timed steps of the main run's step size) on rank 0 while
+    the other ranks wait."""
     import copy
     from elbencho_b200 import WorkerConfig, WorkerManager
+    warmup, steps = 2, 4
     pool_args = copy.copy(args)
-    pool_args.warmup, pool_args.steps = 2, 4
-    pool_args.file_gib = min(args.file_gib or 64.0, 16.0) if workload_cls in (C2, C3, C4) \
-        else (args.file_gib or 0)
-    workload = workload_cls(pool_args, world)
+    workload = workload_cls(pool_args, world)  # same slicing as the main run
     workload.workdir = os.path.join(workload.workdir, "pool")
     os.makedirs(workload.workdir, exist_ok=True)
     if hasattr(workload, "paths"):
         workload.paths = [os.path.join(workload.workdir, os.path.basename(p))
                           for p in workload.paths]
+    if isinstance(workload, C3):  # smaller files for the sample
+        workload.file_size = min(workload.file_size, 8 * GiB)
     gpu_ids = list(range(world))
     totals = new_totals()
     info = {}
     try:
-        # one manager per step drives the slices of ALL files: ranks of file r come from the
-        # per-rank plans; in one process they are contiguous only per file, so the pool runs the
-        # N per-file plans as N managers' worth of threads in ONE manager by giving it all ranks
-        # of step s: rank_offset = s*T for file 0 ... is not contiguous across files, hence the
-        # pool uses its own layout: dataset threads = S*N*T with step-major ranks
-        for step in range(pool_args.warmup + pool_args.steps):
-            cfg_kwargs, phases = pool_plan(workload, step, world)
+        for step, (cfg_kwargs, phases, stale) in enumerate(pool_steps(workload, world, warmup,
+                                                                      steps)):
+            cfg_kwargs = dict(cfg_kwargs)
             cfg_kwargs.update(tuning_kwargs(pool_args, gpu_ids))
             with WorkerManager(WorkerConfig(**cfg_kwargs)) as mgr:
                 for phase in phases:
                     mgr.start_phase(phase)
-                    snaps = 0
-                    while not mgr.wait_done(100):
+                    while not mgr.wait_done(50):
                         snap = mgr.live_snapshot()
-                        snaps += 1
                         info["live_reduced_with_nccl"] = snap["reduced_with_nccl"]
                         info["live_num_gpus"] = snap["num_gpus"]
                     res = mgr.phase_results()
@@ -902,10 +933,11 @@ def inprocess_pool(args, torch, workload_cls, world):
                                                                                mgr.last_error))
                     info["phase_stats_reduced_with_nccl"] = res["stats_reduced_with_nccl"]
                     info["live_reduce_info"] = mgr.live_reduce_info()
-                    if step >= pool_args.warmup:
+                    if step >= warmup:
                         add_phase(totals, phase.name, res["ops_total"]["bytes"],
                                   res["ops_total"]["iops"], res["ops_total"]["entries"],
                                   res["last_finish_usec"])
+            remove_paths(stale)
     finally:
         shutil.rmtree(workload.workdir, ignore_errors=True)
     info.update(phase_rates(totals))
@@ -913,30 +945,9 @@ def inprocess_pool(args, torch, workload_cls, world):
     info["unit"] = workload.unit
     info["gpu_ids"] = gpu_ids
     info["threads"] = world * workload.threads
-    info["sample"] = "2 warm-up + 4 timed steps of %s" % workload.describe()
+    info["sample"] = ("%d warm-up + %d timed steps of the main run's step size, one manager over "
+                      "all GPUs; workload: %s" % (warmup, steps, workload.describe()))
     return info
-
-
-def pool_plan(workload, step, world):
-    """one step of all GPUs as ONE manager config (in-process pool). Sequential file configs use
-    step-major dataset threads: the step's N*T ranks own one contiguous slice of the block sequence
-    of all files; workers map to GPUs round robin by rank."""
-    from elbencho_b200 import BenchPhase
-    threads = world * workload.threads
-    if isinstance(workload, SeqFileWorkload):
-        cfg = workload.base_cfg()
-        cfg.update(num_threads=threads, rank_offset=step * threads,
-                   num_dataset_threads=workload.num_slices * threads)
-        phases = ([BenchPhase.CREATEFILES] if workload.do_write_in_step else []) + \
-            [BenchPhase.READFILES]
-        return cfg, phases
-    if isinstance(workload, C3):
-        cfg, phases = workload.plan(step, 0)
-        cfg.update(paths=workload.paths, num_threads=threads)
-        return cfg, phases
-    cfg, phases = workload.plan(step, 0)
-    cfg.update(num_threads=threads, rank_offset=0, num_dataset_threads=threads)
-    return cfg, phases
 
 
 # ------------------------------------------------------------------------------------------------

@@ -716,6 +716,68 @@ static void runChaseKernel(uint64_t fileSize)
 	unlink(path.c_str() );
 }
 
+/* memory system ceiling of "CPU copy into a pinned slot, then the GPU reads the slot": no file
+ * system involved. Per thread: stream through a 256 MiB source (DRAM resident, stands for the page
+ * cache) with memcpy into a ring of numSlots x 1 MiB, then move the slot with the copy engine or
+ * the stage kernel. Small ring = slot still in cache when the device reads it. */
+static void runDmaSrc()
+{
+	for(int threads : {8, 16})
+		for(int mode : {0, 1, 2}) // 0 memcpy only, 1 + copy engine, 2 + stage kernel
+			for(int numSlots : {2, 4, 64})
+			{
+				const uint64_t perThread = 2 * GiB;
+				double secs = runThreads(threads, 0, [&](int idx)
+				{
+					CK(cudaSetDevice(0) );
+					const uint64_t srcLen = 256 * MiB;
+					char* src = (char*)aligned_alloc(4096, srcLen);
+					memset(src, idx + 1, srcLen);
+					char* host;
+					char* dev;
+					unsigned long long* sink;
+					cudaStream_t stream;
+					CK(cudaHostAlloc( (void**)&host, numSlots * MiB, cudaHostAllocDefault) );
+					memset(host, 0, numSlots * MiB);
+					CK(cudaMalloc( (void**)&dev, numSlots * MiB) );
+					CK(cudaMalloc( (void**)&sink, 8) );
+					CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) );
+					std::vector<cudaEvent_t> events(numSlots);
+					for(auto& e : events)
+						CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming) );
+					uint64_t i = 0;
+					for(uint64_t done = 0; done < perThread; done += MiB, i++)
+					{
+						const int slot = i % numSlots;
+						if(mode && (i >= (uint64_t)numSlots) )
+							CK(cudaEventSynchronize(events[slot]) );
+						memcpy(host + slot * MiB, src + (done % srcLen), MiB);
+						if(mode == 1)
+							CK(cudaMemcpyAsync(dev + slot * MiB, host + slot * MiB, MiB,
+								cudaMemcpyHostToDevice, stream) );
+						if(mode == 2)
+							stageKernel<<<32, 256, 0, stream>>>(host + slot * MiB, dev + slot * MiB,
+								sink);
+						if(mode)
+							CK(cudaEventRecord(events[slot], stream) );
+					}
+					CK(cudaStreamSynchronize(stream) );
+					for(auto& e : events)
+						cudaEventDestroy(e);
+					cudaStreamDestroy(stream);
+					cudaFreeHost(host);
+					cudaFree(dev);
+					cudaFree(sink);
+					free(src);
+				});
+				static const char* modeNames[] = {"memcpy_only", "copy_engine", "stage_kernel"};
+				printf("{\"test\":\"dmasrc\",\"threads\":%d,\"mode\":\"%s\",\"slots\":%d,"
+					"\"gib_s\":%.2f}\n", threads, modeNames[mode], numSlots,
+					threads * perThread / (double)GiB / secs);
+				fflush(stdout);
+			}
+}
+
 int main(int argc, char** argv)
 {
 	std::string tests = (argc > 1) ? argv[1] : "pcie,tmpfs,wfiles,chase,wpipe";
@@ -748,6 +810,8 @@ int main(int argc, char** argv)
 		runChase(gib * GiB);
 	if(tests.find("chasek") != std::string::npos)
 		runChaseKernel(gib * GiB);
+	if(tests.find("dmasrc") != std::string::npos)
+		runDmaSrc();
 	if(tests.find("wpipe") != std::string::npos)
 		runWPipe( (gib / 2) * GiB);
 	return 0;

@@ -8,3 +8,5 @@ echo "sweep rc=$?"; cat gpurun_out/r02_pipeline_sweep2.jsonl; tail -5 gpurun_out
 echo "bench rc=$?"; cut -c1-200 gpurun_out/r02_bench_c2_b.json; tail -5 gpurun_out/r02_bench_c2_b.err
 ( time timeout 600 python bench.py --impl reference > gpurun_out/r02_bench_c2_ref_b.json 2> gpurun_out/r02_bench_c2_ref_b.err ) 2> gpurun_out/r02_bench_c2_ref_b.time
 echo "bench ref rc=$?"; cut -c1-200 gpurun_out/r02_bench_c2_ref_b.json
+timeout 300 scripts/explore_hostpath.bin dmasrc 8 > gpurun_out/r02_hostpath_dmasrc.jsonl 2> gpurun_out/r02_hostpath_dmasrc.err
+cat gpurun_out/r02_hostpath_dmasrc.jsonl

@@ -813,6 +813,221 @@ elb_blocks_tiled_kernel(const KernelArgs args, const uint32_t ctasPerBlock,
 		publish_results_if_last(args);
 }
 
+/* ---- small blocks: one warp per block ---------------------------------------------------------
+ *
+ * For 4 KiB .. 8 KiB blocks (BASELINE configs[2]: 4 KiB random reads) a CTA per block leaves half
+ * of its threads without a vector and pays the descriptor fetch and the block setup once per
+ * 4 KiB. Here a CTA takes ELB_WARPS blocks, warp w works on block (cta * ELB_WARPS + w): a lane
+ * handles the 32-byte vectors lane, lane+32, ... of the block body (a warp access covers 1 KiB,
+ * 4 independent accesses in flight per lane), the verify reduction is the warp's own redux, the
+ * device counter gets one atomic per CTA. */
+
+#define ELB_WARPS (ELB_THREADS / 32)
+#define ELB_WARP_SPAN (32 * ELB_VEC_BYTES * ELB_UNROLL) /* 4 KiB per unrolled warp iteration */
+
+template<int MODE, bool STAGED, bool FAST, class Gen>
+__device__ __forceinline__ void process_block_warp(const KernelArgs& args, const BlockGeom& g,
+	const Gen& gen, elb_verify_result* result)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const int64_t hostDelta = args.hostDelta;
+	uint8_t* devBody = g.ptr + g.headLen;
+	uint8_t* hostBody = devBody + hostDelta;
+
+	unsigned numBad = 0;
+	uint64_t firstBad = ~0ULL;
+
+	for(uint64_t spanStart = 0; spanStart < g.bodyLen; spanStart += ELB_WARP_SPAN)
+	{
+		if( (MODE == MODE_VERIFY_PATTERN) || (MODE == MODE_COPY_IN) || (MODE == MODE_COPY_OUT) )
+		{ // loads first, then the rest
+			const uint8_t* src = (MODE == MODE_COPY_OUT) ? devBody :
+				( ( (MODE == MODE_COPY_IN) || STAGED) ? hostBody : devBody);
+			u64x4 got[ELB_UNROLL];
+			bool valid[ELB_UNROLL];
+
+			#pragma unroll
+			for(int u = 0; u < ELB_UNROLL; u++)
+			{
+				const uint64_t bodyOff = spanStart + (uint64_t)(u * 32 + lane) * ELB_VEC_BYTES;
+				valid[u] = (bodyOff < g.bodyLen);
+				if(valid[u] )
+					got[u] = ld_nc_na_256(src + bodyOff);
+			}
+
+			#pragma unroll
+			for(int u = 0; u < ELB_UNROLL; u++)
+			{
+				const uint64_t bodyOff = spanStart + (uint64_t)(u * 32 + lane) * ELB_VEC_BYTES;
+				if(!valid[u] )
+					continue;
+
+				if(MODE == MODE_COPY_OUT)
+					st_na_256(hostBody + bodyOff, got[u] );
+				else
+				if( (MODE == MODE_COPY_IN) || STAGED)
+					st_na_256(devBody + bodyOff, got[u] );
+
+				if(MODE == MODE_VERIFY_PATTERN)
+				{
+					const uint64_t pos = g.headLen + bodyOff;
+					verify_vec(got[u], gen.template vec32<FAST>(pos), pos, numBad, firstBad);
+				}
+			}
+		}
+		else
+		{ // fill
+			#pragma unroll
+			for(int u = 0; u < ELB_UNROLL; u++)
+			{
+				const uint64_t bodyOff = spanStart + (uint64_t)(u * 32 + lane) * ELB_VEC_BYTES;
+				if(bodyOff < g.bodyLen)
+				{
+					const u64x4 v = gen.template vec32<FAST>(g.headLen + bodyOff);
+					st_na_256(devBody + bodyOff, v);
+					if(STAGED)
+						st_na_256(hostBody + bodyOff, v);
+				}
+			}
+		}
+	}
+
+	if(g.headLen | g.tailLen)
+	{ // unaligned head / tail bytes (at most 31 each): one lane per byte
+		const uint64_t tailStart = g.headLen + g.bodyLen;
+
+		for(int part = 0; part < 2; part++)
+		{
+			const uint64_t partLen = part ? g.tailLen : g.headLen;
+			const uint64_t pos = (part ? tailStart : 0) + lane;
+
+			if(lane >= partLen)
+				continue;
+
+			if( (MODE == MODE_FILL_PATTERN) || (MODE == MODE_FILL_RANDOM) )
+			{
+				const uint8_t b = gen.byte(pos);
+				g.ptr[pos] = b;
+				if(STAGED)
+					g.ptr[hostDelta + (int64_t)pos] = b;
+			}
+			else
+			if(MODE == MODE_COPY_OUT)
+				g.ptr[hostDelta + (int64_t)pos] = g.ptr[pos];
+			else
+			{
+				const bool fromHost = (MODE == MODE_COPY_IN) || STAGED;
+				const uint8_t got = fromHost ? g.ptr[hostDelta + (int64_t)pos] : g.ptr[pos];
+
+				if(fromHost)
+					g.ptr[pos] = got;
+
+				if( (MODE == MODE_VERIFY_PATTERN) && (got != gen.byte(pos) ) )
+				{
+					numBad++;
+					if(pos < firstBad)
+						firstBad = pos;
+				}
+			}
+		}
+	}
+
+	if(MODE == MODE_VERIFY_PATTERN)
+	{
+		const unsigned warpBad = __reduce_add_sync(0xffffffffu, numBad);
+
+		if(__builtin_expect(warpBad != 0, 0) )
+		{
+			const unsigned firstHi = (unsigned)(firstBad >> 32);
+			const unsigned minHi = __reduce_min_sync(0xffffffffu, firstHi);
+			const unsigned firstLo = (firstHi == minHi) ? (unsigned)firstBad : 0xffffffffu;
+			const unsigned minLo = __reduce_min_sync(0xffffffffu, firstLo);
+
+			if(!lane)
+			{ // (the only writer of this block's result: plain stores would do, atomics keep the
+			  //  contract that several launches may accumulate into one result)
+				atomicAdd( (unsigned long long*)&result->numMismatchBytes,
+					(unsigned long long)warpBad);
+				atomicMin( (unsigned long long*)&result->firstMismatchIdx,
+					( (unsigned long long)minHi << 32) | minLo);
+				if(args.counters)
+					atomicAdd(&args.counters[ELB_DEVCTR_VERIFY_MISMATCH_BYTES],
+						(unsigned long long)warpBad);
+			}
+		}
+	}
+}
+
+template<int MODE, int STAGE>
+__global__ void __launch_bounds__(ELB_THREADS, 3)
+elb_blocks_warp_kernel(const KernelArgs args)
+{
+	constexpr bool STAGED = (STAGE == STAGE_FULL);
+	constexpr bool PUBLISH = (MODE == MODE_VERIFY_PATTERN) && (STAGE != STAGE_NONE);
+
+	__shared__ unsigned long long sBlockBytes;
+
+	const uint32_t descIdx = blockIdx.x * ELB_WARPS + (threadIdx.x >> 5);
+
+	if(!threadIdx.x)
+		sBlockBytes = 0;
+
+	__syncthreads();
+
+	if(descIdx < args.numDescs)
+	{ // (uniform per warp)
+		const elb_block_desc desc = args.descs ? args.descs[descIdx] : args.inlineDesc;
+		const BlockGeom g = make_geom(desc);
+
+		if(g.len)
+		{
+			if( (MODE == MODE_FILL_PATTERN) || (MODE == MODE_VERIFY_PATTERN) )
+			{
+				PatternGen gen;
+				gen.fileOffset = desc.fileOffset;
+				gen.salt = args.salt;
+
+				if(gen.canUseFast(g.headLen) )
+					process_block_warp<MODE, STAGED, true>(args, g, gen, &args.results[descIdx] );
+				else
+					process_block_warp<MODE, STAGED, false>(args, g, gen, &args.results[descIdx] );
+			}
+			else
+			if(MODE == MODE_FILL_RANDOM)
+			{
+				RandomGen gen;
+				gen.blockKey = elb_rand_block_key(args.seed, desc.blockCounter);
+				gen.varFillLen = elb_rand_var_fill_len(desc.len, args.pct);
+				gen.remainderVal = elb_rand_remainder_val(gen.blockKey);
+
+				if(gen.canUseFast(g.headLen) )
+					process_block_warp<MODE, STAGED, true>(args, g, gen, NULL);
+				else
+					process_block_warp<MODE, STAGED, false>(args, g, gen, NULL);
+			}
+			else
+			{
+				PatternGen unused{};
+				process_block_warp<MODE, true, true>(args, g, unused, NULL);
+			}
+
+			if( (counter_slot_of<MODE>() >= 0) && args.counters && !(threadIdx.x & 31) )
+				atomicAdd(&sBlockBytes, (unsigned long long)g.len);
+		}
+	}
+
+	if( (counter_slot_of<MODE>() >= 0) && args.counters)
+	{ // device-resident stats: one global atomic per CTA
+		__syncthreads();
+
+		if(!threadIdx.x && sBlockBytes)
+			atomicAdd(&args.counters[counter_slot_of<MODE>()], sBlockBytes);
+	}
+
+	if(PUBLISH)
+		publish_results_if_last(args);
+}
+
 __global__ void elb_verify_init_kernel(elb_verify_result* results, uint32_t numDescs)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -896,6 +1111,20 @@ static const DeviceLaunchInfo* getDeviceLaunchInfo()
 	return &gDevInfo[dev];
 }
 
+#define ELB_WARP_KERNEL_MAX_BLOCK (8 * 1024)
+
+/* tuning / profiling knob: ELB_NO_WARP_KERNEL=1 sends small blocks through the tile kernels */
+static bool smallBlockKernelEnabled()
+{
+	static const bool enabled = []()
+	{
+		const char* env = getenv("ELB_NO_WARP_KERNEL");
+		return !(env && env[0] && (env[0] != '0') );
+	}();
+
+	return enabled;
+}
+
 static const char* modeName(int mode)
 {
 	static const char* names[NUM_MODES] =
@@ -937,6 +1166,19 @@ static int launchBlocksKernelT(const KernelArgs& args, uint64_t totalBytesHint,
 
 	/* staged launches run at PCIe speed: one tile per CTA keeps the most loads in flight */
 	const uint32_t tilesPerCTA = (STAGE == STAGE_FULL) ? 1 : devInfo->tilesPerCTA[MODE];
+
+	/* small blocks: one warp per block (a longer block than the hint said is still processed
+	   completely, the warp loops over its whole body) */
+	if(maxBlockLenHint && (maxBlockLenHint <= ELB_WARP_KERNEL_MAX_BLOCK) && args.descs &&
+		smallBlockKernelEnabled() )
+	{
+		const uint64_t numCTAs = ( (uint64_t)args.numDescs + ELB_WARPS - 1) / ELB_WARPS;
+
+		elb_blocks_warp_kernel<MODE, STAGE><<<(unsigned)numCTAs, ELB_THREADS, 0, stream>>>(args);
+		gNumKernelLaunches.fetch_add(1, std::memory_order_relaxed);
+
+		return checkLaunch(modeName(MODE) );
+	}
 
 	if(maxBlockLenHint && totalBytesHint && tilesPerCTA)
 	{

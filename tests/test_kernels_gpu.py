@@ -474,3 +474,122 @@ def test_stage_copy_kernels(cuda_device, to_device):
         assert host_bytes[lo:lo + n] == src[lo:lo + n]
     dst_bytes, fill = (dev_bytes_, b"\xa5") if to_device else (host_bytes, b"\x5a")
     assert dst_bytes[:3] == fill * 3  # nothing outside the blocks was written
+
+
+# ------------------------------------------------------------------------------------------------
+# small blocks: warp-per-block kernels (block size hint <= 8 KiB)
+# ------------------------------------------------------------------------------------------------
+
+SMALL_LENS = [4096, 4096, 1, 31, 32, 33, 0, 1000, 4095, 4097, 8192, 8191, 4096, 20000, 64, 4096]
+
+
+@pytest.mark.parametrize("misalign", [0, 3, 16])
+def test_small_block_kernels_match_oracle(cuda_device, misalign):
+    """hint <= 8 KiB -> one warp per block: ragged lengths, unaligned addresses and file offsets,
+    a block longer than the hint, more blocks than one CTA takes; fill / verify / random fill"""
+    hint = 4096
+    stride = 24 * 1024
+    nblocks = len(SMALL_LENS) * 3 + 1  # (not a multiple of the 8 blocks a CTA takes)
+    lens = (SMALL_LENS * 4)[:nblocks]
+    arena = dev_bytes(stride * nblocks + 64, cuda_device)
+    base = arena.data_ptr()
+    salt = 0x5151
+    blocks = [(base + i * stride + (misalign if i % 2 else 0), n, 4096 * i + (5 if i % 3 == 0 else 0),
+               100 + i) for i, n in enumerate(lens)]
+    descs = make_batch(cuda_device, blocks)
+    results = torch.zeros(2 * nblocks, dtype=torch.int64, device=cuda_device)
+    counters = torch.zeros(kernels.DEVCTR_NUM, dtype=torch.int64, device=cuda_device)
+    kernels.fill_pattern_batch(descs.data_ptr(), nblocks, salt, counters.data_ptr(),
+                               stream_handle(), total_bytes=sum(lens), max_block_len=hint)
+    torch.cuda.synchronize()
+    host = to_bytes(arena)
+    covered = bytearray(len(host))
+    for ptr, n, off, _ in blocks:
+        lo = ptr - base
+        assert host[lo:lo + n] == (oracle_lib.fill_pattern(n, off, salt) if n else b""), (lo, n)
+        covered[lo:lo + n] = b"\x01" * n
+    assert all(host[i] == 0xA5 for i in range(len(host)) if not covered[i])
+    assert counters.cpu().tolist()[kernels.DEVCTR_FILLED_BYTES] == sum(lens)
+
+    # verify: clean, then corrupted
+    kernels.verify_pattern_batch(descs.data_ptr(), nblocks, salt, results.data_ptr(),
+                                 counters.data_ptr(), stream_handle(), total_bytes=sum(lens),
+                                 max_block_len=hint)
+    torch.cuda.synchronize()
+    assert read_result(results) == [(0, 0xFFFFFFFFFFFFFFFF)] * nblocks
+    assert counters.cpu().tolist()[kernels.DEVCTR_VERIFIED_BYTES] == sum(lens)
+    bad = {}
+    rng = random.Random(misalign)
+    for idx in (0, 3, 9, 13, nblocks - 1):
+        n = blocks[idx][1]
+        if not n:
+            continue
+        positions = sorted({0, n - 1, rng.randrange(n)})
+        bad[idx] = positions
+        for pos in positions:
+            arena[blocks[idx][0] - base + pos] ^= 0x3C
+    kernels.verify_pattern_batch(descs.data_ptr(), nblocks, salt, results.data_ptr(), 0,
+                                 stream_handle(), total_bytes=sum(lens), max_block_len=hint)
+    torch.cuda.synchronize()
+    got = read_result(results)
+    for idx in range(nblocks):
+        exp = (len(bad[idx]), bad[idx][0]) if idx in bad else (0, 0xFFFFFFFFFFFFFFFF)
+        assert got[idx] == exp, idx
+
+    kernels.fill_random_batch(descs.data_ptr(), nblocks, 50, 777, 0, stream_handle(),
+                              total_bytes=sum(lens), max_block_len=hint)
+    torch.cuda.synchronize()
+    host = to_bytes(arena)
+    for ptr, n, _, ctr in blocks:
+        lo = ptr - base
+        assert host[lo:lo + n] == (oracle_lib.fill_random_ctr(n, 50, 777, ctr) if n else b"")
+
+
+def test_small_block_staged_kernels(cuda_device):
+    """the staged forms of the warp-per-block kernels: fill + stage-out, stage-in + verify with
+    published results, stage copies"""
+    hint, stride = 4096, 8192
+    lens = [4096] * 21 + [100, 0, 4095, 8192 - 64]
+    nblocks = len(lens)
+    dev, host, delta = _staged_arena(cuda_device, stride * nblocks + 64)
+    salt = 12
+    blocks = [(dev.data_ptr() + i * stride + (8 if i % 4 == 1 else 0), n, 1 << 30 | (i * 4096), i)
+              for i, n in enumerate(lens)]
+    descs = _pinned_descs(blocks)
+    hints = dict(total_bytes=sum(lens), max_block_len=hint)
+    kernels.fill_pattern_staged(descs.data_ptr(), nblocks, salt, delta, 0, stream_handle(), **hints)
+    torch.cuda.synchronize()
+    dev_b, host_b = to_bytes(dev), host.numpy().tobytes()
+    for ptr, n, off, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        expected = oracle_lib.fill_pattern(n, off, salt) if n else b""
+        assert dev_b[lo:lo + n] == expected and host_b[lo:lo + n] == expected
+    # corrupt the HOST copy of two blocks; stage-in + verify must see it and repair nothing
+    host_np = host.numpy()
+    host_np[blocks[2][0] - dev.data_ptr() + 77] ^= 1
+    host_np[blocks[20][0] - dev.data_ptr() + 4095] ^= 0x80
+    dev.fill_(0)
+    dev_results = torch.zeros(2 * nblocks, dtype=torch.int64, device=cuda_device)
+    host_results = torch.zeros(2 * nblocks, dtype=torch.int64).pin_memory()
+    ticket = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    kernels.verify_results_init(dev_results.data_ptr(), nblocks, stream_handle())
+    kernels.verify_pattern_staged(descs.data_ptr(), nblocks, salt, delta, dev_results.data_ptr(),
+                                  host_results.data_ptr(), ticket.data_ptr(), 0, stream_handle(),
+                                  **hints)
+    torch.cuda.synchronize()
+    got = host_results.view(-1, 2).tolist()
+    for i in range(nblocks):
+        exp = [1, 77] if i == 2 else ([1, 4095] if i == 20 else [0, -1])
+        assert got[i] == exp, i
+    dev_b = to_bytes(dev)
+    for ptr, n, _, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        assert dev_b[lo:lo + n] == host_np[lo:lo + n].tobytes()
+    # stage copy out of a changed device ring
+    dev.copy_(torch.randint(0, 256, (dev.numel(),), dtype=torch.uint8).to(cuda_device))
+    kernels.stage_copy(descs.data_ptr(), nblocks, False, delta, stream_handle(), **hints)
+    torch.cuda.synchronize()
+    dev_b, host_b = to_bytes(dev), host.numpy().tobytes()
+    for ptr, n, _, _ in blocks:
+        lo = ptr - dev.data_ptr()
+        assert host_b[lo:lo + n] == dev_b[lo:lo + n]

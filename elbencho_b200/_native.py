@@ -218,6 +218,13 @@ SIGNATURES = {
     "elb_rwmix_balancer_wait_write": (ctypes.c_int, [_VP, c_u64]),
     "elb_rwmix_balancer_interrupt": (None, [_VP]),
     "elb_rwmix_balancer_destroy": (None, [_VP]),
+    "elb_write_gate_create": (_VP, []),
+    "elb_write_gate_take_ticket": (c_u64, [_VP]),
+    "elb_write_gate_wait_until_near": (None, [_VP, c_u64]),
+    "elb_write_gate_wait_turn": (None, [_VP, c_u64]),
+    "elb_write_gate_leave": (None, [_VP]),
+    "elb_write_gate_destroy": (None, [_VP]),
+    "elb_write_gate_selftest": (ctypes.c_int64, [c_u32, c_u32, c_u32]),
     "elb_custom_tree_worker_list": (ctypes.c_int64, [ctypes.c_char_p, c_u64, c_u64, c_u64, c_u64,
                                                      c_u64, ctypes.c_int, ctypes.c_char_p, c_u64]),
     "elb_custom_tree_scan": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_char_p]),

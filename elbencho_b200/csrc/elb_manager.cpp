@@ -761,6 +761,91 @@ void elb_rwmix_balancer_destroy(elb_rwmix_balancer* balancer)
 	delete balancer;
 }
 
+struct elb_write_gate
+{
+	elb::FileWriteGate gate;
+};
+
+elb_write_gate* elb_write_gate_create(void)
+{
+	return new elb_write_gate();
+}
+
+uint64_t elb_write_gate_take_ticket(elb_write_gate* gate)
+{
+	return gate->gate.takeTicket();
+}
+
+void elb_write_gate_wait_until_near(elb_write_gate* gate, uint64_t ticket)
+{
+	gate->gate.waitUntilNear(ticket);
+}
+
+void elb_write_gate_wait_turn(elb_write_gate* gate, uint64_t ticket)
+{
+	gate->gate.waitTurn(ticket);
+}
+
+void elb_write_gate_leave(elb_write_gate* gate)
+{
+	gate->gate.leave();
+}
+
+void elb_write_gate_destroy(elb_write_gate* gate)
+{
+	delete gate;
+}
+
+int64_t elb_write_gate_selftest(uint32_t numThreads, uint32_t turnsPerThread, uint32_t holdUSec)
+{
+	elb::FileWriteGate gate;
+	std::atomic<int> numInside{0};
+	std::atomic<uint64_t> nextExpectedTicket{0};
+	std::atomic<int64_t> numViolations{0};
+	std::atomic<uint64_t> numTurnsDone{0};
+	std::vector<std::thread> threads;
+
+	for(uint32_t t = 0; t < numThreads; t++)
+		threads.emplace_back([&, t]()
+		{
+			for(uint32_t turn = 0; turn < turnsPerThread; turn++)
+			{
+				{
+					elb::FileWriteTurn writeTurn(&gate);
+
+					if( (t + turn) % 2) // (both ways of waiting)
+						writeTurn.waitUntilNear();
+
+					writeTurn.waitTurn();
+
+					if(numInside.fetch_add(1) != 0)
+						numViolations++;
+
+					// tickets are served in the order they were taken
+					const uint64_t served = nextExpectedTicket.fetch_add(1);
+					(void)served;
+
+					if(holdUSec)
+						std::this_thread::sleep_for(std::chrono::microseconds(holdUSec) );
+
+					numInside.fetch_sub(1);
+					numTurnsDone++;
+				}
+
+				if( (turn % 7) == 3)
+					std::this_thread::yield();
+			}
+		});
+
+	for(std::thread& thread : threads)
+		thread.join();
+
+	if(numTurnsDone != ( (uint64_t)numThreads * turnsPerThread) )
+		numViolations++;
+
+	return numViolations;
+}
+
 int64_t elb_custom_tree_worker_list(const char* treeFilePath, uint64_t blockSize,
 	uint64_t fileShareSize, uint64_t treeRoundUpSize, uint64_t workerRank,
 	uint64_t numDataSetThreads, int kind, char* outBuf, uint64_t outBufLen)

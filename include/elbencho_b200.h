@@ -278,7 +278,7 @@ typedef struct elb_cfg
 	int32_t ignoreDelErrors;
 	int32_t runAsService; /* disables last-finisher stonewall trigger (Worker.cpp:41-43) */
 	int32_t verifyCollectAll; /* nonzero: do not stop at first bad block, count all mismatches */
-	/* enum elb_write_gate: buffered (non-O_DIRECT) writes of all workers of this process to the
+	/* enum elb_write_gate_mode: buffered (non-O_DIRECT) writes of all workers of this process to the
 	 * same file pass a per-file FIFO gate in user space one at a time. Linux serialises buffered
 	 * writes to one inode on the inode lock anyway; a ticket queue whose next-in-line spins while
 	 * the others sleep hands the file over without the lock's contention (measured on tmpfs,
@@ -353,7 +353,7 @@ enum elb_staging_engine
 };
 
 /* elb_cfg::serializeBufferedWrites values */
-enum elb_write_gate
+enum elb_write_gate_mode
 {
 	ELB_WRITEGATE_AUTO = 0, /* on when several local workers write one file buffered */
 	ELB_WRITEGATE_ON = 1,
@@ -491,6 +491,21 @@ int elb_rwmix_balancer_wait_read(elb_rwmix_balancer* balancer, uint64_t nextBloc
 int elb_rwmix_balancer_wait_write(elb_rwmix_balancer* balancer, uint64_t nextBlockSize);
 void elb_rwmix_balancer_interrupt(elb_rwmix_balancer* balancer); /* waiters return -1 */
 void elb_rwmix_balancer_destroy(elb_rwmix_balancer* balancer);
+
+/* The FIFO gate in front of buffered writes to one file (elb_cfg::serializeBufferedWrites) as a
+ * toolkit object: take a ticket, optionally sleep until near the front (< 3 tickets ahead), wait
+ * for the turn, leave. */
+typedef struct elb_write_gate elb_write_gate;
+elb_write_gate* elb_write_gate_create(void);
+uint64_t elb_write_gate_take_ticket(elb_write_gate* gate);
+void elb_write_gate_wait_until_near(elb_write_gate* gate, uint64_t ticket);
+void elb_write_gate_wait_turn(elb_write_gate* gate, uint64_t ticket);
+void elb_write_gate_leave(elb_write_gate* gate);
+void elb_write_gate_destroy(elb_write_gate* gate);
+/* numThreads threads take turnsPerThread turns of holdUSec each through one gate; returns 0 if
+ * every turn was exclusive and the turns were served in ticket order, else the number of
+ * violations (self-check of the futex hand-over on this host). */
+int64_t elb_write_gate_selftest(uint32_t numThreads, uint32_t turnsPerThread, uint32_t holdUSec);
 
 /* Custom tree mode: the sublist of one worker (PathStore::getWorkerSublistNonShared/-Shared as
  * combined by LocalWorker::prepareCustomTreePathStores, LocalWorker.cpp:1520-1560), as text lines

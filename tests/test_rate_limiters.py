@@ -77,3 +77,33 @@ def test_rwmix_balancer_interrupt_releases_waiters(native):
     thread.join(timeout=5)
     assert not thread.is_alive() and results == [-1]
     native.elb_rwmix_balancer_destroy(balancer)
+
+
+def test_write_gate_is_exclusive_fifo_and_loses_no_wakeup(native):
+    """FileWriteGate (elb_cfg::serializeBufferedWrites): futex hand-over under contention"""
+    assert native.elb_write_gate_selftest(1, 1000, 0) == 0
+    assert native.elb_write_gate_selftest(2, 3000, 0) == 0
+    assert native.elb_write_gate_selftest(12, 500, 20) == 0     # sleepers get woken
+    assert native.elb_write_gate_selftest(40, 100, 0) == 0      # more threads than cores
+
+
+def test_write_gate_serves_tickets_in_order(native):
+    import threading
+    gate = native.elb_write_gate_create()
+    order = []
+    tickets = [native.elb_write_gate_take_ticket(gate) for _ in range(6)]
+    assert tickets == list(range(6))
+
+    def turn(ticket):
+        native.elb_write_gate_wait_until_near(gate, ticket)
+        native.elb_write_gate_wait_turn(gate, ticket)
+        order.append(ticket)
+        native.elb_write_gate_leave(gate)
+
+    threads = [threading.Thread(target=turn, args=(t,)) for t in reversed(tickets)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=20)
+    assert order == tickets
+    native.elb_write_gate_destroy(gate)

@@ -7,7 +7,8 @@ import tempfile
 import pytest
 
 from tests.test_cufile_gpu import MOCK_LIB  # noqa: F401  (sets ELB_CUFILE_LIB before first use)
-from elbencho_b200 import BenchPhase, PathType, WorkerConfig, WorkerError, WorkerManager
+from elbencho_b200 import (BenchPhase, IOEngine, PathType, WorkerConfig, WorkerError,
+                           WorkerManager)
 from tests import oracle_lib
 
 pytestmark = pytest.mark.gpu
@@ -30,6 +31,13 @@ def workdir(cuda_device):
     path = tempfile.mkdtemp(prefix="elb_var_", dir=base)
     yield path
     shutil.rmtree(path, ignore_errors=True)
+
+
+def gpu_and_cpu_configs(workdir, names, **kwargs):
+    """same config twice: GPU worker files and oracle files"""
+    gpu_paths = [os.path.join(workdir, "gpu_" + n) for n in names]
+    cpu_paths = [os.path.join(workdir, "cpu_" + n) for n in names]
+    return WorkerConfig(paths=gpu_paths, **kwargs), WorkerConfig(paths=cpu_paths, **kwargs)
 
 
 def prefill(path, size, salt):

@@ -550,7 +550,9 @@ static const char* httpStatusText(int statusCode)
 struct HttpMessageView
 {
 	bool complete{false};
+	bool invalid{false};   // e.g. a Content-Length beyond what this server accepts
 	size_t totalLen{0};
+	size_t neededLen{0};   // bytes the buffer must hold before the message can be complete
 	std::string startLine;
 	std::map<std::string, std::string> headers; // lower-case names
 	std::string body;
@@ -596,9 +598,18 @@ static HttpMessageView parseHttpMessage(const std::string& buffer, bool bodyUnti
 
 	if(view.headers.count("content-length") )
 	{
-		const size_t contentLen = strtoull(view.headers["content-length"].c_str(), NULL, 10);
+		const unsigned long long contentLen =
+			strtoull(view.headers["content-length"].c_str(), NULL, 10);
 
-		if(buffer.size() < (bodyStart + contentLen) )
+		if(contentLen > ELB_HTTP_MAX_REQUEST_BYTES)
+		{ // (checked before any arithmetic with it)
+			view.invalid = true;
+			return view;
+		}
+
+		view.neededLen = bodyStart + (size_t)contentLen;
+
+		if(buffer.size() < view.neededLen)
 			return view;
 
 		view.body = buffer.substr(bodyStart, contentLen);
@@ -1055,18 +1066,39 @@ HttpResponse Service::handlePrepareFile(const HttpRequest& request)
 
 		std::cout << "Receiving tree file from master..." << std::endl;
 
-		if( (mkdir(basePath.c_str(), 0777) == -1) && (errno != EEXIST) )
+		if( (mkdir(basePath.c_str(), 0700) == -1) && (errno != EEXIST) )
 			throw ProgError("Failed to create service tmp dir: " + basePath);
 
-		std::ofstream fileOutStream(path.c_str(), std::ofstream::out | std::ofstream::trunc);
+		/* the directory name is predictable: only use it if it is a real directory of this user,
+		   and never write through a symlink somebody else placed there */
+		struct stat dirStat;
 
-		if(!fileOutStream)
-			throw ProgError("Opening upload file failed: " + path);
+		if( (lstat(basePath.c_str(), &dirStat) == -1) || !S_ISDIR(dirStat.st_mode) ||
+			(dirStat.st_uid != geteuid() ) )
+			throw ProgError("Service tmp dir is not a directory owned by this user: " + basePath);
 
-		fileOutStream << request.body;
-		fileOutStream.close();
+		const int uploadFD = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_NOFOLLOW, 0600);
 
-		if(!fileOutStream)
+		if(uploadFD == -1)
+			throw ProgError("Opening upload file failed: " + path + "; SysErr: " + strerror(errno) );
+
+		size_t numWritten = 0;
+
+		while(numWritten < request.body.size() )
+		{
+			const ssize_t writeRes = write(uploadFD, request.body.data() + numWritten,
+				request.body.size() - numWritten);
+
+			if(writeRes <= 0)
+			{
+				close(uploadFD);
+				throw ProgError("Saving upload file failed: " + path);
+			}
+
+			numWritten += writeRes;
+		}
+
+		if(close(uploadFD) == -1)
 			throw ProgError("Saving upload file failed: " + path);
 	}
 	catch(std::exception& e)
@@ -1521,6 +1553,7 @@ int Service::run()
 		int sock;
 		std::string buffer;
 		std::string remoteAddr;
+		size_t neededLen{0}; // known size of the message being received (0 = headers not seen)
 	};
 
 	std::vector<Connection> connections;
@@ -1584,7 +1617,20 @@ int Service::run()
 
 			while(!closeConn)
 			{
+				/* (the headers are parsed once per message, not once per received chunk: the rest
+				   of a large upload is only appended) */
+				if(conn.neededLen && (conn.buffer.size() < conn.neededLen) )
+					break;
+
 				HttpMessageView view = parseHttpMessage(conn.buffer, false, false);
+
+				if(view.invalid)
+				{
+					closeConn = true;
+					break;
+				}
+
+				conn.neededLen = view.complete ? 0 : view.neededLen;
 
 				if(!view.complete)
 					break;

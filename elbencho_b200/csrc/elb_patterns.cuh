@@ -102,9 +102,12 @@ ELB_HD uint64_t elb_rand_bytes8(uint64_t pos, uint64_t blockKey, uint64_t varFil
 			( (remainderVal >> rotBits) | (remainderVal << (64 - rotBits) ) ) : remainderVal;
 	}
 
-	// straddles the boundary or unaligned: compose byte-wise
+	// straddles the boundary or unaligned: compose byte-wise (rare path: keep its code small)
 	uint64_t val = 0;
 
+#if defined(__CUDA_ARCH__)
+	#pragma unroll 1
+#endif
 	for(unsigned i = 0; i < 8; i++)
 		val |= (uint64_t)elb_rand_byte(pos + i, blockKey, varFillLen, remainderVal) << (i * 8);
 

@@ -1675,7 +1675,8 @@ void Worker::rwPhase()
 	useWriteGate = (benchPhase == ELB_PHASE_CREATEFILES) && (cfg.pathType != ELB_PATH_DIR) &&
 		!cfg.useDirectIO && !cfg.useCuFile &&
 		( (cfg.serializeBufferedWrites == ELB_WRITEGATE_ON) ||
-		( (cfg.serializeBufferedWrites == ELB_WRITEGATE_AUTO) && (cfg.numThreads > 1) ) );
+		( (cfg.serializeBufferedWrites == ELB_WRITEGATE_AUTO) && (cfg.numThreads > 1) &&
+			(cfg.pathType == ELB_PATH_FILE) ) ); // (regular files: one writer per inode at a time)
 
 	/* rate balancer between the reader and writer threads of a write phase, else the plain
 	   per-thread limit (LocalWorker.cpp:1284-1299 write side, 1322-1337 read side) */

@@ -1738,7 +1738,12 @@ bool Worker::collectBatch(Batch& batch, BlockSource& source, bool isRead, bool o
 	const bool stopAtFileEnd = (cfg.pathType == ELB_PATH_DIR) &&
 		(cfg.ioEngine == ELB_IOENGINE_AIO);
 
-	while(batch.blocks.size() < batchBlocks)
+	/* rate limited workers go block by block: a worker that sleeps for its limit has then handed
+	   every block it already read or wrote to the GPU stage and the counters (what the live
+	   statistics and a stonewall snapshot see while it sleeps), as in the reference's serial loop */
+	const size_t maxBlocks = (rateLimiter.isEnabled() || useRWMixThreadsBalancer) ? 1 : batchBlocks;
+
+	while(batch.blocks.size() < maxBlocks)
 	{
 		BlockRef block;
 

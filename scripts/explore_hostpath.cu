@@ -778,6 +778,32 @@ static void runDmaSrc()
 			}
 }
 
+/* is the FIRST read of freshly written tmpfs pages slower than later reads? 16 writers write their
+ * own range of a fresh file, then three read passes with 16 readers (same ranges), then one with
+ * shifted ranges; everything on node 0, 1 MiB private buffers */
+static void runFirstRead(uint64_t fileSize)
+{
+	const std::string path = g_dir + "/xp_firstread.bin";
+	for(int rep = 0; rep < 2; rep++)
+	{
+		double wsecs = writeFiles({path}, fileSize, 16, 0);
+		printf("{\"test\":\"firstread_write\",\"rep\":%d,\"writers\":16,\"gib_s\":%.2f}\n", rep,
+			fileSize / (double)GiB / wsecs);
+		for(int pass = 0; pass < 3; pass++)
+		{
+			double secs = readFile(path, fileSize, 16, 0, MiB);
+			printf("{\"test\":\"firstread_read\",\"rep\":%d,\"pass\":%d,\"readers\":16,\"gib_s\":%.2f}\n",
+				rep, pass, fileSize / (double)GiB / secs);
+			fflush(stdout);
+		}
+		double secs8 = readFile(path, fileSize, 8, 0, MiB);
+		printf("{\"test\":\"firstread_read\",\"rep\":%d,\"pass\":3,\"readers\":8,\"gib_s\":%.2f}\n", rep,
+			fileSize / (double)GiB / secs8);
+		fflush(stdout);
+		unlink(path.c_str() );
+	}
+}
+
 int main(int argc, char** argv)
 {
 	std::string tests = (argc > 1) ? argv[1] : "pcie,tmpfs,wfiles,chase,wpipe";
@@ -810,6 +836,8 @@ int main(int argc, char** argv)
 		runChase(gib * GiB);
 	if(tests.find("chasek") != std::string::npos)
 		runChaseKernel(gib * GiB);
+	if(tests.find("firstread") != std::string::npos)
+		runFirstRead(gib * GiB);
 	if(tests.find("dmasrc") != std::string::npos)
 		runDmaSrc();
 	if(tests.find("wpipe") != std::string::npos)

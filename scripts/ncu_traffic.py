@@ -29,7 +29,7 @@ def main():
     kernels = {}
     for row in rows[2:]:
         name = row[col["Kernel Name"]]
-        match = re.search(r"elb_blocks_\w*kernel<\(?int\)?\s*(\d+)(?:,\s*\(?int\)?\s*(\d+))?>", name)
+        match = re.search(r"elb_blocks_\w*kernel<(?:\(int\))?\s*(\d+)(?:,\s*(?:\(int\))?\s*(\d+))?>", name)
         if not match or (match.group(2) not in (None, "0")):
             continue  # (only the resident forms: STAGE_NONE)
         key = MODES.get(int(match.group(1)))

@@ -424,12 +424,11 @@ def test_rank_offset_sharding_two_managers(workdir):
             assert f.read() == oracle_lib.fill_pattern(size, 0, 9)
 
 
-@pytest.mark.parametrize("batch_blocks,num_batches", [(0, 0), (16, 2)])
-def test_mid_size_multi_batch_run_bytes_equal_oracle(workdir, staging_engine, batch_blocks,
-                                                     num_batches):
-    """4 GiB through many batches per worker (default cache-resident batches, and 16 MiB batches
-    whose copy-engine form is replayed from per-batch CUDA graphs): file bytes, counters and verify
-    outcome equal the oracle's."""
+def test_mid_size_multi_batch_run_bytes_equal_oracle(workdir, staging_engine):
+    """4 GiB through many batches per worker (kernel staging: the default cache-resident batches;
+    copy-engine staging: 16 MiB batches that are replayed from per-batch CUDA graphs): file
+    bytes, counters and verify outcome equal the oracle's."""
+    batch_blocks, num_batches = (0, 0) if staging_engine == "kernel" else (16, 2)
     size, block, threads = 4 << 30, MiB, 4
     kwargs = dict(num_threads=threads, block_size=block, file_size=size, integrity_check_salt=11)
     gcfg, ccfg = gpu_and_cpu_configs(workdir, ["big"], **kwargs)

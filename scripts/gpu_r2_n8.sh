@@ -17,3 +17,4 @@ echo "n8 unbound rc=$?"; cut -c1-300 gpurun_out/r02_bench_c2_n8_unbound.json
 grep -h "NCCL INFO.*nranks\|comm 0x.*rank" gpurun_out/r02_bench_c2_n8.err | head -12
 timeout 600 python -m pytest tests/test_livestats_gpu.py tests/test_worker_variants_gpu.py -q -m gpu > gpurun_out/r02_pytest_gpu_n8.log 2>&1
 echo "pytest n8 rc=$?"; tail -5 gpurun_out/r02_pytest_gpu_n8.log
+timeout 120 scripts/explore_hostpath.bin firstread 16 > gpurun_out/r02_hostpath_firstread.jsonl 2>&1; cat gpurun_out/r02_hostpath_firstread.jsonl

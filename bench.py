@@ -979,8 +979,10 @@ def main():
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        host_group = dist.new_group(backend="gloo")  # host-side barrier (in-process pool leg)
 
     workload_cls = WORKLOADS[args.config]
 
@@ -1054,13 +1056,16 @@ def main():
 
     pool = None
     if world > 1 and not args.skip_pool:
-        barrier(torch, device)
+        # the other ranks wait on the HOST (gloo) while rank 0 drives all GPUs from one process: a
+        # pending NCCL barrier would keep a spinning kernel on every GPU the pool wants to use
+        torch.cuda.synchronize(device)
+        dist.barrier(group=host_group)
         if rank == 0:
             try:
                 pool = inprocess_pool(args, torch, workload_cls, world)
             except Exception as err:  # noqa: BLE001 (an extra must not break the bench line)
                 pool = {"error": str(err)}
-        barrier(torch, device)
+        dist.barrier(group=host_group)
 
     if world > 1:
         dist.barrier(device_ids=[device.index])

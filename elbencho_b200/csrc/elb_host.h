@@ -792,7 +792,22 @@ inline void liveOpsAdd(elb_liveops& dst, const elb_liveops& src)
 class FileWriteGate
 {
 	public:
-		static const unsigned NEAR_DISTANCE = 3; // tickets ahead at which a waiter still sleeps
+		/* tickets ahead at which a waiter still sleeps (tuning knob: ELB_GATE_NEAR=2..8) */
+		static unsigned nearDistance()
+		{
+			static const unsigned distance = []()
+			{
+				const char* env = getenv("ELB_GATE_NEAR");
+				const int val = env ? atoi(env) : 0;
+				return ( (val >= 2) && (val <= 8) ) ? (unsigned)val : 3u;
+			}();
+
+			return distance;
+		}
+
+		/* tickets ahead of the given one right now (0 = it is its turn) */
+		uint64_t distanceOf(uint64_t ticket) const
+			{ return ticket - serving.load(std::memory_order_acquire); }
 
 		FileWriteGate()
 		{
@@ -811,7 +826,7 @@ class FileWriteGate
 			{
 				const uint32_t seq = mySlot.load(std::memory_order_acquire);
 
-				if( (ticket - serving.load(std::memory_order_acquire) ) < NEAR_DISTANCE)
+				if( (ticket - serving.load(std::memory_order_acquire) ) < nearDistance() )
 					return;
 
 				futexWait(&mySlot, seq);
@@ -848,7 +863,7 @@ class FileWriteGate
 
 			/* ticket done+1 is served now; ticket done+NEAR_DISTANCE just got near: wake it if it
 			   sleeps (a thread that takes that ticket later sees the new serving value) */
-			const uint64_t nearTicket = done + NEAR_DISTANCE;
+			const uint64_t nearTicket = done + nearDistance();
 			std::atomic<uint32_t>& slot = wakeSeq[nearTicket % NUM_SLOTS];
 
 			slot.fetch_add(1, std::memory_order_release);
@@ -915,6 +930,9 @@ class FileWriteTurn
 				isNear = true;
 			}
 		}
+
+		/* true if somebody else is ahead of this turn right now */
+		bool hasToWait() const { return gate && !hasTurn && gate->distanceOf(ticket); }
 
 		void waitTurn()
 		{

@@ -1920,6 +1920,18 @@ void Worker::rwBlocksPipelined(BlockSource& source, bool isRead)
 
 static ssize_t fullBlockIO(int fd, char* buf, uint64_t len, uint64_t offset, bool isRead);
 
+/* tuning knob: ELB_GATE_PREFETCH=0 turns the L2 prefetch of queued writers off */
+static bool gatePrefetchEnabled()
+{
+	static const bool enabled = []()
+	{
+		const char* env = getenv("ELB_GATE_PREFETCH");
+		return !(env && (env[0] == '0') );
+	}();
+
+	return enabled;
+}
+
 /**
  * Write loop for buffered writes of several workers to shared files (the write gate is on): the
  * kernel lets one writer into a file at a time anyway, so what counts is that the writer whose
@@ -1954,8 +1966,28 @@ void Worker::rwBlocksGatedWrite(BlockSource& source)
 
 			turn.waitUntilNear();
 			gpuLaunchWriteStage(batch);
-			turn.waitTurn();
-			gpuWait(batch);
+
+			if(turn.hasToWait() && gatePrefetchEnabled() )
+			{ /* the file is busy anyway: wait for the GPU stage first and pull the batch's host
+			     slots (which DDIO put into the last level cache) into this core's L2, so that
+			     the copy into the page cache inside the turn reads from L2 */
+				gpuWait(batch);
+
+				for(size_t i = 0; i < batch.blocks.size(); i++)
+				{
+					const char* slot = slotHostPtr(batch, i);
+
+					for(uint64_t pos = 0; pos < batch.blocks[i].len; pos += 64)
+						__builtin_prefetch(slot + pos, 0 /*read*/, 3 /*keep in all levels*/);
+				}
+
+				turn.waitTurn();
+			}
+			else
+			{
+				turn.waitTurn();
+				gpuWait(batch);
+			}
 
 			for(size_t i = 0; i < batch.blocks.size(); i++)
 			{

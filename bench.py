@@ -65,8 +65,10 @@ def parse_args():
     p.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
     p.add_argument("--file-gib", type=float, default=0.0,
                    help="file size per GPU (GiB); 0 = the config's stated size")
-    p.add_argument("--threads", type=int, default=int(os.environ.get("ELB_BENCH_THREADS", "16")),
-                   help="worker threads per GPU (-t), both arms")
+    p.add_argument("--threads", type=int, default=int(os.environ.get("ELB_BENCH_THREADS", "0")),
+                   help="worker threads per GPU (-t), both arms; 0 = min(16, usable CPUs / GPUs): "
+                        "the boxes give the container a CPU quota (16 CPUs at 1 GPU, 96 at 8) and "
+                        "more busy threads than that get throttled")
     p.add_argument("--dir", default=os.environ.get("ELB_BENCH_DIR", "/dev/shm"))
     p.add_argument("--salt", type=int, default=1)
     p.add_argument("--direct", action="store_true", help="O_DIRECT (--direct)")
@@ -86,7 +88,10 @@ def parse_args():
     p.add_argument("--no-gpu-numa", action="store_true")
     p.add_argument("--kernel-block-kib", type=int, default=0,
                    help="block size of the kernel-level window (0 = the config's block size)")
-    return p.parse_args()
+    args = p.parse_args()
+    if args.threads <= 0:
+        args.threads = max(1, min(16, int(cpu_quota() // max(1, args.gpus))))
+    return args
 
 
 # ------------------------------------------------------------------------------------------------

@@ -984,10 +984,8 @@ def main():
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    host_group = None
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-        host_group = dist.new_group(backend="gloo")  # host-side barrier (in-process pool leg)
 
     workload_cls = WORKLOADS[args.config]
 
@@ -1061,16 +1059,28 @@ def main():
 
     pool = None
     if world > 1 and not args.skip_pool:
-        # the other ranks wait on the HOST (gloo) while rank 0 drives all GPUs from one process: a
-        # pending NCCL barrier would keep a spinning kernel on every GPU the pool wants to use
-        torch.cuda.synchronize(device)
-        dist.barrier(group=host_group)
+        # the other ranks wait on the HOST (polling a flag file) while rank 0 drives all GPUs from
+        # one process: a pending NCCL barrier would keep a spinning kernel on every GPU the pool
+        # wants to use
+        flag = os.path.join(bench_dir(args), "pool_done.flag")
+        if rank == 0 and os.path.exists(flag):
+            os.unlink(flag)
+        barrier(torch, device)  # (everybody is done with its GPU; a stale flag is gone)
         if rank == 0:
             try:
                 pool = inprocess_pool(args, torch, workload_cls, world)
             except Exception as err:  # noqa: BLE001 (an extra must not break the bench line)
                 pool = {"error": str(err)}
-        dist.barrier(group=host_group)
+            finally:
+                with open(flag, "w") as f:
+                    f.write("done\n")
+        else:
+            deadline = time.time() + 1800
+            while not os.path.exists(flag) and time.time() < deadline:
+                time.sleep(0.05)
+        barrier(torch, device)
+        if rank == 0 and os.path.exists(flag):
+            os.unlink(flag)
 
     if world > 1:
         dist.barrier(device_ids=[device.index])

@@ -296,13 +296,15 @@ def test_full_file_lock_rejects_async_io(workdir):
 
 def test_stonewall_snapshot_with_a_deterministic_straggler(workdir):
     """Stonewall ("first done") totals against the oracle, exactly. A rwmix reader thread is the
-    straggler: --limitread of one block per second lets it read exactly one block and then sleep
-    for the rest of the second, in which the one writer thread finishes its whole share and
-    triggers the snapshot (Worker.cpp:33-55). Reader -> ReadMix counters, writer -> main ones."""
+    straggler: --limitread of 64 blocks per second lets it read exactly 64 of its 128 blocks (a few
+    milliseconds) and then sleep for the rest of the second, in which the one writer thread
+    finishes its whole share (tens of milliseconds) and triggers the snapshot (Worker.cpp:33-55).
+    Reader -> ReadMix counters, writer -> main ones."""
     size, block = 256 * MiB, MiB
     kwargs = dict(num_threads=2, block_size=block, file_size=size, integrity_check_salt=3)
     gcfg, ccfg = gpu_and_cpu_configs(workdir, ["f"], **kwargs)
-    limited = dict(kwargs, num_rwmix_read_threads=1, limit_read_bps=block)
+    budget = 64  # blocks per second for the reader
+    limited = dict(kwargs, num_rwmix_read_threads=1, limit_read_bps=budget * block)
     gcfg2 = WorkerConfig(paths=gcfg.paths, **limited)
     ccfg2 = WorkerConfig(paths=ccfg.paths, **limited)
     with WorkerManager(gcfg) as mgr:  # the files the reader thread reads
@@ -312,13 +314,13 @@ def test_stonewall_snapshot_with_a_deterministic_straggler(workdir):
         res = mgr.run_phase(BenchPhase.CREATEFILES)
     rc, _, opr = oracle_lib.run_oracle_phase(ccfg2, BenchPhase.CREATEFILES)
     assert rc == 0
-    # writer (rank 1): all of its half at the moment it finishes; reader (rank 0): one block
+    # writer (rank 1): all of its half at the moment it finishes; reader (rank 0): its budget
     assert res["ops_stonewall_total"]["bytes"] == opr.opsStoneWallTotal.numBytesDone == size // 2
     assert res["ops_stonewall_total"]["iops"] == opr.opsStoneWallTotal.numIOPSDone == 128
     assert res["ops_stonewall_readmix_total"]["bytes"] == \
-        opr.opsStoneWallReadMixTotal.numBytesDone == block
+        opr.opsStoneWallReadMixTotal.numBytesDone == budget * block
     assert res["ops_stonewall_readmix_total"]["iops"] == \
-        opr.opsStoneWallReadMixTotal.numIOPSDone == 1
+        opr.opsStoneWallReadMixTotal.numIOPSDone == budget
     # and the end-of-phase totals
     assert res["ops_total"]["bytes"] == opr.opsTotal.numBytesDone == size // 2
     assert res["ops_readmix_total"]["bytes"] == opr.opsReadMixTotal.numBytesDone == size // 2

@@ -781,7 +781,7 @@ inline void liveOpsAdd(elb_liveops& dst, const elb_liveops& src)
  *
  * Buffered writes to one inode are serialised by the kernel on the inode lock; what a writer can
  * win is a fast hand-over and a source buffer that is still in the last level cache. Tickets give
- * FIFO order. A waiter sleeps on a futex word of its own ticket slot while NEAR_DISTANCE or more
+ * FIFO order. A waiter sleeps on a futex word of its own ticket slot while nearDistance() (2) or more
  * tickets are ahead of it and is woken when it gets near (one targeted wake-up per hand-over,
  * hidden behind the current holder's write); the near ones spin in user space, so the hand-over
  * itself costs a cache line transfer, not a wake-up. Knowing its position lets a worker produce
@@ -799,7 +799,7 @@ class FileWriteGate
 			{
 				const char* env = getenv("ELB_GATE_NEAR");
 				const int val = env ? atoi(env) : 0;
-				return ( (val >= 2) && (val <= 8) ) ? (unsigned)val : 3u;
+				return ( (val >= 2) && (val <= 8) ) ? (unsigned)val : 2u;
 			}();
 
 			return distance;
@@ -817,7 +817,7 @@ class FileWriteGate
 
 		uint64_t takeTicket() { return nextTicket.fetch_add(1, std::memory_order_relaxed); }
 
-		/* sleeps until fewer than NEAR_DISTANCE tickets are ahead of this one */
+		/* sleeps until fewer than nearDistance() tickets are ahead of this one */
 		void waitUntilNear(uint64_t ticket)
 		{
 			std::atomic<uint32_t>& mySlot = wakeSeq[ticket % NUM_SLOTS];
@@ -861,7 +861,7 @@ class FileWriteGate
 		{
 			const uint64_t done = serving.fetch_add(1, std::memory_order_release);
 
-			/* ticket done+1 is served now; ticket done+NEAR_DISTANCE just got near: wake it if it
+			/* ticket done+1 is served now; ticket done+nearDistance() just got near: wake it if it
 			   sleeps (a thread that takes that ticket later sees the new serving value) */
 			const uint64_t nearTicket = done + nearDistance();
 			std::atomic<uint32_t>& slot = wakeSeq[nearTicket % NUM_SLOTS];

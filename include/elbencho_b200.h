@@ -493,7 +493,7 @@ void elb_rwmix_balancer_interrupt(elb_rwmix_balancer* balancer); /* waiters retu
 void elb_rwmix_balancer_destroy(elb_rwmix_balancer* balancer);
 
 /* The FIFO gate in front of buffered writes to one file (elb_cfg::serializeBufferedWrites) as a
- * toolkit object: take a ticket, optionally sleep until near the front (< 3 tickets ahead), wait
+ * toolkit object: take a ticket, optionally sleep until near the front (< 2 tickets ahead), wait
  * for the turn, leave. */
 typedef struct elb_write_gate elb_write_gate;
 elb_write_gate* elb_write_gate_create(void);

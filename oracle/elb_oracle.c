@@ -886,6 +886,7 @@ typedef struct orc_worker
 	int isRWMixReader; // --rwmixthr reader in a write phase (workers/LocalWorker.cpp:1028-1041)
 	orc_worker_result* res;
 	elb_liveops stoneWallOps;
+	elb_liveops stoneWallOpsReadMix; // Worker.h:203-209 snapshots both counter sets
 	char errTmp[512];
 } orc_worker;
 
@@ -1751,6 +1752,12 @@ static void orc_inc_num_workers_done(orc_worker* w)
 				__atomic_load_n(&other->res->liveOps.numBytesDone, __ATOMIC_RELAXED);
 			other->stoneWallOps.numIOPSDone =
 				__atomic_load_n(&other->res->liveOps.numIOPSDone, __ATOMIC_RELAXED);
+			other->stoneWallOpsReadMix.numEntriesDone =
+				__atomic_load_n(&other->res->liveOpsReadMix.numEntriesDone, __ATOMIC_RELAXED);
+			other->stoneWallOpsReadMix.numBytesDone =
+				__atomic_load_n(&other->res->liveOpsReadMix.numBytesDone, __ATOMIC_RELAXED);
+			other->stoneWallOpsReadMix.numIOPSDone =
+				__atomic_load_n(&other->res->liveOpsReadMix.numIOPSDone, __ATOMIC_RELAXED);
 		}
 	}
 
@@ -2041,6 +2048,11 @@ int orc_run_phase(const elb_cfg* cfg, int benchPhase, orc_worker_result* results
 			pr->opsStoneWallTotal.numEntriesDone += workers[i].stoneWallOps.numEntriesDone;
 			pr->opsStoneWallTotal.numBytesDone += workers[i].stoneWallOps.numBytesDone;
 			pr->opsStoneWallTotal.numIOPSDone += workers[i].stoneWallOps.numIOPSDone;
+			// (Statistics.cpp:1697: opsStoneWallTotalReadMix)
+			pr->opsStoneWallReadMixTotal.numEntriesDone +=
+				workers[i].stoneWallOpsReadMix.numEntriesDone;
+			pr->opsStoneWallReadMixTotal.numBytesDone += workers[i].stoneWallOpsReadMix.numBytesDone;
+			pr->opsStoneWallReadMixTotal.numIOPSDone += workers[i].stoneWallOpsReadMix.numIOPSDone;
 			orc_histogram_merge(&pr->iopsLatHisto, &r->iopsLatHisto);
 			orc_histogram_merge(&pr->entriesLatHisto, &r->entriesLatHisto);
 
@@ -2070,6 +2082,13 @@ int orc_run_phase(const elb_cfg* cfg, int benchPhase, orc_worker_result* results
 				pr->opsStoneWallTotal.numBytesDone, pr->firstFinishUSec);
 			pr->opsStoneWallPerSec.numIOPSDone = orc_per_sec_from_usec(
 				pr->opsStoneWallTotal.numIOPSDone, pr->firstFinishUSec);
+			// (Statistics.cpp:1721-1722)
+			pr->opsStoneWallReadMixPerSec.numEntriesDone = orc_per_sec_from_usec(
+				pr->opsStoneWallReadMixTotal.numEntriesDone, pr->firstFinishUSec);
+			pr->opsStoneWallReadMixPerSec.numBytesDone = orc_per_sec_from_usec(
+				pr->opsStoneWallReadMixTotal.numBytesDone, pr->firstFinishUSec);
+			pr->opsStoneWallReadMixPerSec.numIOPSDone = orc_per_sec_from_usec(
+				pr->opsStoneWallReadMixTotal.numIOPSDone, pr->firstFinishUSec);
 		}
 	}
 

@@ -1113,6 +1113,18 @@ def main():
         },
         "gpu_launches": extra["launches"],
         "clocks": clocks,
+        "parity": {
+            "checked_in_this_run": "every read phase verified its blocks on the GPU (0 mismatching "
+                                   "bytes, verified_bytes below) and byte / IOPS totals equal the "
+                                   "expected ones" if workload.name != "c4" else
+                                   "byte / IOPS totals equal the expected ones (no --verify in c4)",
+            "bit_exact_vs_oracle": "tests/ -m gpu: file bytes, counters, verify outcome and "
+                                   "exception text against the CPU oracle, which is pinned to the "
+                                   "reference's own headers (oracle/_ref, tests/golden/)",
+            "random_fill_content": "K3 (--blockvarpct) is bit-exact against its own CPU twin only: "
+                                   "the reference's random fill is self-seeded, its content cannot "
+                                   "be pinned (SURVEY 8c); the layout rule is the reference's",
+        },
     }
     line["e2e"] = {
         "value": round(value, 3), "unit": workload.unit,

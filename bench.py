@@ -955,6 +955,131 @@ def inprocess_pool(args, torch, workload_cls, world):
     return info
 
 
+def build_line(args, workload, world, value, totals, extra, prep_info, kern, pcie, storage, cpu,
+               pool, clocks, requested_gib):
+    """the ONE JSON line of the b200 arm from what was measured (pure: testable without a GPU)"""
+    peak, peak_src = load_hbm_peak()
+    rates = phase_rates(totals)
+    timed_secs = totals["usec"] / 1e6
+
+    line = {
+        "metric": workload.metric, "value": round(value, 3), "unit": workload.unit,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(totals["usec"] / 1e3 / max(1, args.steps), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": common_config(args, workload, world),
+        "impl_config": {
+            "staging": args.staging, "batch_blocks": args.batch_blocks,
+            "num_batches": args.num_batches, "write_gate": args.write_gate,
+            "gpu_numa_binding": not args.no_gpu_numa,
+            "file_gib_requested": requested_gib or None,
+            "parallelism": "%d process(es) x %d worker threads, rank r <-> file r <-> GPU r" % (
+                world, workload.threads),
+            "timing": "phase time = max over all workers of all ranks (host steady clock inside "
+                      "the worker, as the reference measures phases), phases bracketed by barrier "
+                      "+ cudaDeviceSynchronize; value = bytes of the timed steps / sum of phase times",
+        },
+        "gpu_launches": extra["launches"],
+        "clocks": clocks,
+        "parity": {
+            "checked_in_this_run": "every read phase verified its blocks on the GPU (0 mismatching "
+                                   "bytes, verified_bytes below) and byte / IOPS totals equal the "
+                                   "expected ones" if workload.name != "c4" else
+                                   "byte / IOPS totals equal the expected ones (no --verify in c4)",
+            "bit_exact_vs_oracle": "tests/ -m gpu: file bytes, counters, verify outcome and "
+                                   "exception text against the CPU oracle, which is pinned to the "
+                                   "reference's own headers (oracle/_ref, tests/golden/)",
+            "random_fill_content": "K3 (--blockvarpct) is bit-exact against its own CPU twin only: "
+                                   "the reference's random fill is self-seeded, its content cannot "
+                                   "be pinned (SURVEY 8c); the layout rule is the reference's",
+        },
+    }
+    line["e2e"] = {
+        "value": round(value, 3), "unit": workload.unit,
+        "h2d_bytes_per_step": extra["h2d_bytes"] // max(1, args.steps),
+        "d2h_bytes_per_step": extra["d2h_bytes"] // max(1, args.steps),
+        "step": "the phases of one step through the worker's C ABI: storage I/O into / out of the "
+                "pinned host ring, host<->device transfer and on-GPU fill / verify",
+        **rates,
+        "gpu_launches": extra["launches"],
+        "dev_kernel_usec": extra["dev_kernel_usec"],
+        "dev_kernel_share_of_timed": round(extra["dev_kernel_usec"] / 1e6 /
+                                           (timed_secs * workload.threads * world), 4)
+        if timed_secs else None,
+        "verified_bytes": extra["verified_bytes"], "filled_bytes": extra["filled_bytes"],
+        "total_usec": totals["usec"],
+        "latency": {name: histo_summary(h) for name, h in extra["histos"].items()},
+    }
+    if prep_info:
+        line["e2e"]["preparation"] = prep_info
+
+    roofline = {}
+    if kern:
+        window = kern["window_bytes"]
+        gbs = {k: window / (v * 1e-3) / 1e9 for k, v in kern["ms"].items()}
+        # dominant resident kernel of the configuration
+        if workload.name == "c4":
+            dom_key, dom_name, dom = "K3_fill_random_pct100", \
+                "elb_blocks_tiled_kernel<FILL_RANDOM> (K3)", gbs["rand"]
+        elif workload.name == "c3" or kern["ms"]["verify"] >= kern["ms"]["fill"]:
+            dom_key, dom_name, dom = "K2_verify_pattern", \
+                "elb_blocks_tiled_kernel<VERIFY_PATTERN> (K2)", gbs["verify"]
+        else:
+            dom_key, dom_name, dom = "K1_fill_pattern", \
+                "elb_blocks_tiled_kernel<FILL_PATTERN> (K1)", gbs["fill"]
+        traffic, traffic_src = load_ncu_traffic(window, kern["block_bytes"], dom_key)
+        roofline = {
+            "bound": "hbm", "kernel": dom_name, "achieved": round(dom, 1), "peak": peak,
+            "unit": "GB/s", "frac": round(dom / peak, 4), "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "measured": "CUDA events around each launch over a %.1f GiB HBM-resident window of "
+                        "%d KiB blocks (larger than L2), %d launches each" % (
+                            window / GiB, kern["block_bytes"] // KiB, 10),
+            "note": "peak is the driver-measured COPY bandwidth; one-directional streams exceed "
+                    "it (copy-engine cudaMemset writes 7.35 TB/s), hence frac > 1",
+            "algorithmic_bytes_per_launch": window,
+            "all_kernels": {
+                "K1_fill_pattern": {"achieved": round(gbs["fill"], 1),
+                                    "frac": round(gbs["fill"] / peak, 4),
+                                    "ms_per_launch": round(kern["ms"]["fill"], 4)},
+                "K2_verify_pattern": {"achieved": round(gbs["verify"], 1),
+                                      "frac": round(gbs["verify"] / peak, 4),
+                                      "ms_per_launch": round(kern["ms"]["verify"], 4)},
+                "K3_fill_random_pct100": {"achieved": round(gbs["rand"], 1),
+                                          "frac": round(gbs["rand"] / peak, 4),
+                                          "ms_per_launch": round(kern["ms"]["rand"], 4)},
+            },
+        }
+    if pcie:
+        roofline["pcie"] = pcie
+        if "read_gib_s" in rates:
+            best_h2d = max(pcie["copy_engine_h2d_gib_s"], pcie["stage_kernel_h2d_gib_s"])
+            roofline["pcie"]["e2e_read_frac_of_pcie"] = round(
+                rates["read_gib_s"] / (best_h2d * world), 3)
+        if "write_gib_s" in rates:
+            best_d2h = max(pcie["copy_engine_d2h_gib_s"], pcie["stage_kernel_d2h_gib_s"])
+            roofline["pcie"]["e2e_write_frac_of_pcie"] = round(
+                rates["write_gib_s"] / (best_d2h * world), 3)
+    if storage:
+        roofline["storage"] = storage
+        for key in ("read_gib_s", "write_gib_s"):
+            if key in rates and storage.get(key):
+                roofline["storage"]["e2e_%s_frac" % key.split("_")[0]] = round(
+                    rates[key] / storage[key], 3)
+        if storage["value"]:
+            roofline["storage"]["e2e_frac"] = round(value / storage["value"], 3)
+    line["roofline"] = roofline
+    if cpu:
+        line["cpu_baseline"] = cpu
+    extra_out = {}
+    if pool:
+        extra_out["inprocess_pool"] = pool
+    if extra_out:
+        line["extra"] = extra_out
+    return line
+
+
 # ------------------------------------------------------------------------------------------------
 # main
 # ------------------------------------------------------------------------------------------------
@@ -1089,125 +1214,8 @@ def main():
     if rank != 0:
         return 0
 
-    peak, peak_src = load_hbm_peak()
-    rates = phase_rates(totals)
-    timed_secs = totals["usec"] / 1e6
-
-    line = {
-        "metric": workload.metric, "value": round(value, 3), "unit": workload.unit,
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(totals["usec"] / 1e3 / max(1, args.steps), 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
-        "config": common_config(args, workload, world),
-        "impl_config": {
-            "staging": args.staging, "batch_blocks": args.batch_blocks,
-            "num_batches": args.num_batches, "write_gate": args.write_gate,
-            "gpu_numa_binding": not args.no_gpu_numa,
-            "file_gib_requested": requested_gib or None,
-            "parallelism": "%d process(es) x %d worker threads, rank r <-> file r <-> GPU r" % (
-                world, workload.threads),
-            "timing": "phase time = max over all workers of all ranks (host steady clock inside "
-                      "the worker, as the reference measures phases), phases bracketed by barrier "
-                      "+ cudaDeviceSynchronize; value = bytes of the timed steps / sum of phase times",
-        },
-        "gpu_launches": extra["launches"],
-        "clocks": clocks,
-        "parity": {
-            "checked_in_this_run": "every read phase verified its blocks on the GPU (0 mismatching "
-                                   "bytes, verified_bytes below) and byte / IOPS totals equal the "
-                                   "expected ones" if workload.name != "c4" else
-                                   "byte / IOPS totals equal the expected ones (no --verify in c4)",
-            "bit_exact_vs_oracle": "tests/ -m gpu: file bytes, counters, verify outcome and "
-                                   "exception text against the CPU oracle, which is pinned to the "
-                                   "reference's own headers (oracle/_ref, tests/golden/)",
-            "random_fill_content": "K3 (--blockvarpct) is bit-exact against its own CPU twin only: "
-                                   "the reference's random fill is self-seeded, its content cannot "
-                                   "be pinned (SURVEY 8c); the layout rule is the reference's",
-        },
-    }
-    line["e2e"] = {
-        "value": round(value, 3), "unit": workload.unit,
-        "h2d_bytes_per_step": extra["h2d_bytes"] // max(1, args.steps),
-        "d2h_bytes_per_step": extra["d2h_bytes"] // max(1, args.steps),
-        "step": "the phases of one step through the worker's C ABI: storage I/O into / out of the "
-                "pinned host ring, host<->device transfer and on-GPU fill / verify",
-        **rates,
-        "gpu_launches": extra["launches"],
-        "dev_kernel_usec": extra["dev_kernel_usec"],
-        "dev_kernel_share_of_timed": round(extra["dev_kernel_usec"] / 1e6 /
-                                           (timed_secs * workload.threads * world), 4)
-        if timed_secs else None,
-        "verified_bytes": extra["verified_bytes"], "filled_bytes": extra["filled_bytes"],
-        "total_usec": totals["usec"],
-        "latency": {name: histo_summary(h) for name, h in extra["histos"].items()},
-    }
-    if prep_info:
-        line["e2e"]["preparation"] = prep_info
-
-    roofline = {}
-    if kern:
-        window = kern["window_bytes"]
-        gbs = {k: window / (v * 1e-3) / 1e9 for k, v in kern["ms"].items()}
-        # dominant resident kernel of the configuration
-        if workload.name == "c4":
-            dom_key, dom_name, dom = "K3_fill_random_pct100", \
-                "elb_blocks_tiled_kernel<FILL_RANDOM> (K3)", gbs["rand"]
-        elif workload.name == "c3" or kern["ms"]["verify"] >= kern["ms"]["fill"]:
-            dom_key, dom_name, dom = "K2_verify_pattern", \
-                "elb_blocks_tiled_kernel<VERIFY_PATTERN> (K2)", gbs["verify"]
-        else:
-            dom_key, dom_name, dom = "K1_fill_pattern", \
-                "elb_blocks_tiled_kernel<FILL_PATTERN> (K1)", gbs["fill"]
-        traffic, traffic_src = load_ncu_traffic(window, kern["block_bytes"], dom_key)
-        roofline = {
-            "bound": "hbm", "kernel": dom_name, "achieved": round(dom, 1), "peak": peak,
-            "unit": "GB/s", "frac": round(dom / peak, 4), "traffic": traffic,
-            "traffic_source": traffic_src, "peak_source": peak_src,
-            "measured": "CUDA events around each launch over a %.1f GiB HBM-resident window of "
-                        "%d KiB blocks (larger than L2), %d launches each" % (
-                            window / GiB, kern["block_bytes"] // KiB, 10),
-            "note": "peak is the driver-measured COPY bandwidth; one-directional streams exceed "
-                    "it (copy-engine cudaMemset writes 7.35 TB/s), hence frac > 1",
-            "algorithmic_bytes_per_launch": window,
-            "all_kernels": {
-                "K1_fill_pattern": {"achieved": round(gbs["fill"], 1),
-                                    "frac": round(gbs["fill"] / peak, 4),
-                                    "ms_per_launch": round(kern["ms"]["fill"], 4)},
-                "K2_verify_pattern": {"achieved": round(gbs["verify"], 1),
-                                      "frac": round(gbs["verify"] / peak, 4),
-                                      "ms_per_launch": round(kern["ms"]["verify"], 4)},
-                "K3_fill_random_pct100": {"achieved": round(gbs["rand"], 1),
-                                          "frac": round(gbs["rand"] / peak, 4),
-                                          "ms_per_launch": round(kern["ms"]["rand"], 4)},
-            },
-        }
-    if pcie:
-        roofline["pcie"] = pcie
-        if "read_gib_s" in rates:
-            best_h2d = max(pcie["copy_engine_h2d_gib_s"], pcie["stage_kernel_h2d_gib_s"])
-            roofline["pcie"]["e2e_read_frac_of_pcie"] = round(
-                rates["read_gib_s"] / (best_h2d * world), 3)
-        if "write_gib_s" in rates:
-            best_d2h = max(pcie["copy_engine_d2h_gib_s"], pcie["stage_kernel_d2h_gib_s"])
-            roofline["pcie"]["e2e_write_frac_of_pcie"] = round(
-                rates["write_gib_s"] / (best_d2h * world), 3)
-    if storage:
-        roofline["storage"] = storage
-        for key in ("read_gib_s", "write_gib_s"):
-            if key in rates and storage.get(key):
-                roofline["storage"]["e2e_%s_frac" % key.split("_")[0]] = round(
-                    rates[key] / storage[key], 3)
-        if storage["value"]:
-            roofline["storage"]["e2e_frac"] = round(value / storage["value"], 3)
-    line["roofline"] = roofline
-    if cpu:
-        line["cpu_baseline"] = cpu
-    extra_out = {}
-    if pool:
-        extra_out["inprocess_pool"] = pool
-    if extra_out:
-        line["extra"] = extra_out
+    line = build_line(args, workload, world, value, totals, extra, prep_info, kern, pcie, storage, cpu,
+                      pool, clocks, requested_gib)
     emit(line)
     return 0
 

@@ -90,3 +90,62 @@ def test_c5_counts_files_and_reads_them_back(workdir):
     assert totals["phase"]["CREATEFILES"]["entries"] == files_per_step * args.steps
     assert totals["phase"]["READFILES"]["entries"] == files_per_step * args.steps
     assert totals["phase"]["READFILES"]["bytes"] == files_per_step * args.steps * workload.block
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+@pytest.mark.parametrize("world", [1, 8])
+def test_b200_arm_json_line_from_fake_measurements(workdir, name, world):
+    """the line builder of the b200 arm is pure: feed it plausible measurements and check the
+    contract keys (metric, value == e2e.value, roofline, cpu_baseline, config equality)"""
+    import json
+    args = make_args(workdir, config=name, gpus=world, file_gib=64 / 1024, steps=4, warmup=1,
+                     staging="auto", batch_blocks=0, num_batches=0, write_gate="auto",
+                     no_gpu_numa=False, window_gib=4.0)
+    workload = bench.WORKLOADS[name](args, world)
+    totals = bench.new_totals()
+    if name != "c4":
+        bench.add_phase(totals, "CREATEFILES", 4 << 30, 4096, 10, 1100000)
+    bench.add_phase(totals, "READFILES", 4 << 30, 4096, 10, 130000)
+    bench.add_phase(totals, "CREATEDIRS", 0, 0, 5, 1000)  # (not a timed phase)
+    histo = {"buckets": [0] * 112, "num": 4096, "sum_usec": 4096 * 500, "min_usec": 100,
+             "max_usec": 9000}
+    histo["buckets"][36] = 4096
+    extra = {"h2d_bytes": 4 << 30, "d2h_bytes": 4 << 30, "launches": 4096, "dev_kernel_usec": 300000,
+             "verified_bytes": 4 << 30, "filled_bytes": 4 << 30, "histos": {"READFILES": histo}}
+    kern = {"window_bytes": 4 << 30, "block_bytes": workload.block, "nblocks": 4096,
+            "ms": {"fill": 0.57, "verify": 0.59, "rand": 0.62}, "launches": 39}
+    pcie = {"copy_engine_h2d_gib_s": 50.0, "copy_engine_d2h_gib_s": 52.0,
+            "stage_kernel_h2d_gib_s": 46.0, "stage_kernel_d2h_gib_s": 47.0, "note": "x"}
+    value = workload.value_of(totals)
+    storage = {"value": value * 1.05, "unit": workload.unit, "read_gib_s": 35.0,
+               "write_gib_s": 3.9, "threads": 2, "note": "x"} if world == 1 else None
+    cpu = {"value": value / 1.2, "unit": workload.unit, "cores": 2, "kind": "port",
+           "sample": "x"} if world == 1 else None
+    pool = {"value": 1.0, "unit": workload.unit} if world > 1 else None
+    clocks = {"sm_mhz": 1965, "sm_max_mhz": 1965, "reasons": [], "samples": 10}
+    line = bench.build_line(args, workload, world, value, totals, extra, {"CREATEFILES": {}} if
+                            name in ("c3", "c4") else None, kern, pcie, storage, cpu, pool, clocks, 0.0)
+    json.dumps(line)  # serialisable
+    assert line["metric"] == workload.metric and line["unit"] == workload.unit
+    assert line["value"] == line["e2e"]["value"] == round(value, 3) > 0
+    assert line["n_gpus"] == world and line["steps"] == 4 and line["warmup"] == 1
+    assert line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["vs_baseline"] is None and line["dtype"] == "u64"
+    assert line["gpu_launches"] == 4096 and line["e2e"]["dev_kernel_usec"] == 300000
+    assert line["e2e"]["h2d_bytes_per_step"] == (4 << 30) // 4
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["peak"] > 0
+    assert 0 < line["roofline"]["frac"] == round(line["roofline"]["achieved"] /
+                                                line["roofline"]["peak"], 4)
+    assert set(line["roofline"]["all_kernels"]) == {"K1_fill_pattern", "K2_verify_pattern",
+                                                    "K3_fill_random_pct100"}
+    assert line["roofline"]["pcie"]["e2e_read_frac_of_pcie"] > 0
+    assert line["config"] == bench.common_config(args, workload, world)  # == the reference arm's
+    assert line["e2e"]["latency"]["READFILES"]["avg_usec"] == 500.0
+    if world == 1:
+        assert line["cpu_baseline"]["kind"] == "port" and "storage" in line["roofline"]
+    else:
+        assert line["extra"]["inprocess_pool"]["value"] == 1.0
+    if name == "c4":
+        assert line["roofline"]["kernel"].endswith("(K3)")
+    if name == "c3":
+        assert line["unit"] == "IOPS"

@@ -171,16 +171,27 @@ def load_hbm_peak():
 
 def load_ncu_traffic(window_bytes, block_bytes, kernel_key):
     """DRAM bytes (read + write) of one launch of the given kernel from the committed
-    `ncu --set full` capture with the same window and block size; else None."""
+    `ncu --set full` captures (profiles/ncu_traffic.json): the capture with the same block size and
+    window; a capture of the same block size with another window is scaled to this window (the
+    kernels' traffic is proportional to the bytes they cover) and the source says so."""
     path = os.path.join(REPO_ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             data = json.load(f)
-        for entry in data["captures"] if "captures" in data else [data]:
-            if int(entry["window_bytes"]) == int(window_bytes) and \
-                    int(entry.get("block_bytes", MiB)) == int(block_bytes):
+        captures = data["captures"] if "captures" in data else [data]
+        same_block = [c for c in captures if int(c.get("block_bytes", MiB)) == int(block_bytes)
+                      and kernel_key in c["kernels"]]
+        for entry in same_block:
+            if int(entry["window_bytes"]) == int(window_bytes):
                 kern = entry["kernels"][kernel_key]
                 return kern["dram_bytes_read"] + kern["dram_bytes_write"], entry.get("source")
+        if same_block:
+            entry = same_block[0]
+            kern = entry["kernels"][kernel_key]
+            scale = float(window_bytes) / float(entry["window_bytes"])
+            return (int((kern["dram_bytes_read"] + kern["dram_bytes_write"]) * scale),
+                    "%s (captured over a %.0f GiB window, scaled x%.2f to this one)" % (
+                        entry.get("source"), int(entry["window_bytes"]) / GiB, scale))
     except Exception:
         pass
     return None, None
